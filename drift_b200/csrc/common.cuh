@@ -1,0 +1,142 @@
+// drift_b200 -- shared device/host definitions (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/drift_b200.h"
+
+namespace drift {
+
+constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr uint8_t kWaiting = 0;
+constexpr uint8_t kMoving = 1;
+
+// One link event of a tick: an agent leaving or entering a link.  16 bytes so that a
+// warp writes 512 contiguous bytes.  `pos` (arrival order among the events on the same
+// link, assigned by k_count) is only a slot index; the Gauss-Seidel order of the
+// reference (agent-list order, lib/simulation_thread.py:299-303) is recovered from `agent`.
+struct __align__(16) Event {
+  int32_t link;
+  uint32_t agent;  // global agent id
+  int32_t kind;    // +1 enter, -1 leave
+  int32_t pos;
+};
+
+struct __align__(16) Segment {  // the events of one touched link, contiguous in `sorted`
+  int32_t link;
+  int32_t base;
+  int32_t count;
+  int32_t occ0;  // occupancy at the start of the tick
+};
+
+struct __align__(8) SortedEvent {
+  uint32_t agent;
+  int32_t kind;
+};
+
+struct HeapItem {  // (dist, push counter, node): nx:weighted.py heap entries
+  double dist;
+  uint32_t cnt;
+  int32_t node;
+};
+
+struct Counters {
+  int32_t n_events;
+  int32_t n_touched;
+  int32_t seg_cursor;
+  int32_t n_dep_req;      // departure requests of this tick (device-driven demand)
+  int32_t n_pending;      // pending departures (committed routes) for the next tick
+  int32_t overflow;       // bit flags, see kOvf*
+  int32_t tick;           // index of the tick being / last processed (1-based like SimulationThread.step)
+  int32_t pad0;
+  unsigned long long n_arrivals;    // total appended to the arrival ring
+  unsigned long long n_departures;  // total appended to the departure log ring
+  unsigned long long n_entries;     // total appended to the entry trace
+  unsigned long long arena_cursor;  // route arena bump pointer (link ids)
+  unsigned long long stage_cursor;  // staging arena bump pointer
+  long long moving;                 // reductions for drift_stats
+  long long on_roads;
+  long long links_with_traffic;
+  long long total_capacity;
+};
+
+constexpr int kOvfEvents = 1;
+constexpr int kOvfArrivals = 2;
+constexpr int kOvfArena = 4;
+constexpr int kOvfHeap = 8;
+constexpr int kOvfDepLog = 16;
+constexpr int kOvfEntries = 32;
+constexpr int kOvfStage = 64;
+
+struct AgentArrays {
+  uint8_t* state;       // [Npad] kWaiting / kMoving
+  double* dist;         // [Npad] distance_on_edge
+  double* speed;        // [Npad] m/s, fixed while on a link
+  double* elen;         // [Npad] edge_length of the current link
+  int32_t* cur_link;    // [Npad] -1 when not on a link
+  int32_t* route_idx;   // [Npad] path_index
+  int32_t* route_len;   // [Npad] hops of the current route
+  int64_t* route_off;   // [Npad] start of the route in the arena
+  int32_t* trip_count;  // [Npad]
+  int32_t* cur_node;    // [Npad] Agent.target: where the next trip starts
+  int64_t n;
+  uint32_t base;  // global id of local agent 0
+};
+
+struct LinkArrays {
+  const double* len;
+  const double* v0;
+  const double* t0;
+  const int32_t* cap;
+  const int32_t* u;
+  const int32_t* v;
+  int32_t* occ;
+  double* tt;  // congestion-updated travel time (extension)
+  const int32_t* cls;
+  const double* factor;     // concatenated per-class tables
+  const int64_t* cls_off;   // [n_class+1]
+  int32_t L;
+};
+
+struct Rings {
+  int32_t* arr_agent;
+  int32_t* arr_tick;
+  unsigned long long arr_cap;
+  unsigned long long arr_drained;
+  int32_t* ent_tick;
+  int32_t* ent_agent;
+  int32_t* ent_link;
+  double* ent_speed;
+  unsigned long long ent_cap;  // 0 = trace off
+  unsigned long long ent_drained;
+};
+
+// ---- Philox4x32-10 counter-based generator (Salmon et al., SC'11; public algorithm) ----
+__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,
+                                             uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+  uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+  uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+  c0 = n0;
+  c1 = n1;
+  c2 = n2;
+  c3 = n3;
+}
+
+// uniform double in [0,1) with 53 random bits, same construction as MT19937 genrand_res53
+// (what Python's random.random() returns): (a>>5, b>>6) -> (a*2^26+b)/2^53.
+__device__ __forceinline__ double philox_uniform53(uint64_t seed, uint32_t agent, uint32_t tick) {
+  uint32_t c0 = agent, c1 = tick, c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  uint32_t a = c0 >> 5, b = c1 >> 6;
+  return __dmul_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 1.0 / 9007199254740992.0);
+}
+
+}  // namespace drift

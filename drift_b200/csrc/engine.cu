@@ -1,0 +1,976 @@
+// drift_b200 -- engine + C ABI (include/drift_b200.h).  sm_100a only; no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "route_kernels.cuh"
+#include "tick_kernels.cuh"
+
+using namespace drift;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(_e == cudaErrorMemoryAllocation ? DRIFT_ENOMEM : DRIFT_ECUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(_e), __FILE__, __LINE__);                                     \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  int64_t n = 0;
+  cudaError_t alloc(int64_t count, bool zero = true) {
+    release();
+    n = count;
+    if (count <= 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, sizeof(T) * (size_t)count);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      n = 0;
+      return e;
+    }
+    if (zero) e = cudaMemset(p, 0, sizeof(T) * (size_t)count);
+    return e;
+  }
+  cudaError_t upload(const T* h, int64_t count) {
+    cudaError_t e = alloc(count, false);
+    if (e != cudaSuccess || count <= 0) return e;
+    return cudaMemcpy(p, h, sizeof(T) * (size_t)count, cudaMemcpyHostToDevice);
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+inline int grid_for(int64_t n, int threads, int max_blocks) {
+  int64_t b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+}  // namespace
+
+struct drift_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  // graph
+  int32_t V = 0, L = 0, Ef = 0, Eb = 0;
+  DevBuf<int32_t> fwd_rowptr, fwd_col, fwd_link, bwd_rowptr, bwd_col, bwd_link, link_cap, link_u, link_v, link_cls;
+  DevBuf<double> fwd_w, bwd_w, link_len, link_v0, link_t0, link_tt, factor, fwd_wc, bwd_wc;
+  DevBuf<int64_t> cls_off;
+  DevBuf<int32_t> occ, evcnt, segid, hist;
+  int64_t total_capacity = 0;
+  double alpha = 0.15, beta = 4.0;
+  bool have_bpr = false;
+  // agents
+  int64_t N = 0, Npad = 0;
+  uint32_t agent_base = 0;
+  DevBuf<uint8_t> state;
+  DevBuf<double> dist, speed, elen;
+  DevBuf<int32_t> cur_link, route_idx, route_len, trip_count, cur_node;
+  DevBuf<int64_t> route_off;
+  DevBuf<int32_t> arena;
+  int64_t arena_cap = 0;
+  // events
+  DevBuf<Event> events;
+  DevBuf<SortedEvent> sorted;
+  DevBuf<Segment> segs;
+  DevBuf<int32_t> touched;
+  int64_t ev_cap = 0;
+  // pending departures + staged route batch
+  DevBuf<int32_t> pend_agent, pend_len;
+  DevBuf<int64_t> pend_off;
+  int64_t pend_cap = 0;
+  DevBuf<int32_t> q_src, q_dst, q_agent, q_status, q_len;
+  DevBuf<int64_t> q_off;
+  DevBuf<double> q_cost;
+  int64_t q_cap = 0;
+  int64_t last_Q = 0;
+  unsigned long long last_arena_begin = 0, last_arena_end = 0;
+  // router scratch
+  DevBuf<double> r_seen;
+  DevBuf<int32_t> r_plink;
+  DevBuf<uint32_t> r_mark, r_epoch;
+  DevBuf<HeapItem> r_heap;
+  int32_t r_workers = 0;
+  int64_t r_heap_cap = 0;
+  // rings
+  DevBuf<int32_t> arr_agent, arr_tick;
+  int64_t arr_cap = 0;
+  unsigned long long arr_drained = 0;
+  DevBuf<int32_t> ent_tick, ent_agent, ent_link;
+  DevBuf<double> ent_speed;
+  int64_t ent_cap = 0;
+  unsigned long long ent_drained = 0;
+  DevBuf<int32_t> dl_agent, dl_tick, dl_src, dl_dst, dl_status;
+  int64_t dl_cap = 0;
+  unsigned long long dl_drained = 0;
+  // demand
+  bool have_demand = false;
+  uint64_t seed = 0;
+  double hourly[24];
+  DevBuf<int64_t> trip_off;
+  DevBuf<int32_t> trip_dst, dep_req;
+  int32_t demand_router = DRIFT_ROUTER_NX_EXACT;
+  // counters
+  DevBuf<Counters> ctr;
+  Counters* h_ctr = nullptr;  // pinned
+  int64_t tick = 0;
+  // profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, int>> adv_marks;  // (begin,end) event indices of advance launches
+  int tick_ev0 = -1, tick_ev1 = -1;
+  double adv_ms = 0, total_ms = 0;
+  int64_t adv_launches = 0, total_launches = 0;
+
+  AgentArrays agents() {
+    AgentArrays a;
+    a.state = state.p;
+    a.dist = dist.p;
+    a.speed = speed.p;
+    a.elen = elen.p;
+    a.cur_link = cur_link.p;
+    a.route_idx = route_idx.p;
+    a.route_len = route_len.p;
+    a.route_off = route_off.p;
+    a.trip_count = trip_count.p;
+    a.cur_node = cur_node.p;
+    a.n = N;
+    a.base = agent_base;
+    return a;
+  }
+  LinkArrays links() {
+    LinkArrays l;
+    l.len = link_len.p;
+    l.v0 = link_v0.p;
+    l.t0 = link_t0.p;
+    l.cap = link_cap.p;
+    l.u = link_u.p;
+    l.v = link_v.p;
+    l.occ = occ.p;
+    l.tt = link_tt.p;
+    l.cls = link_cls.p;
+    l.factor = factor.p;
+    l.cls_off = cls_off.p;
+    l.L = L;
+    return l;
+  }
+  GraphArrays graph() {
+    GraphArrays g;
+    g.fwd_rowptr = fwd_rowptr.p;
+    g.fwd_col = fwd_col.p;
+    g.fwd_w = fwd_w.p;
+    g.fwd_link = fwd_link.p;
+    g.bwd_rowptr = bwd_rowptr.p;
+    g.bwd_col = bwd_col.p;
+    g.bwd_w = bwd_w.p;
+    g.bwd_link = bwd_link.p;
+    g.link_u = link_u.p;
+    g.link_v = link_v.p;
+    g.V = V;
+    g.L = L;
+    return g;
+  }
+  Rings rings() {
+    Rings r;
+    r.arr_agent = arr_agent.p;
+    r.arr_tick = arr_tick.p;
+    r.arr_cap = (unsigned long long)arr_cap;
+    r.arr_drained = arr_drained;
+    r.ent_tick = ent_tick.p;
+    r.ent_agent = ent_agent.p;
+    r.ent_link = ent_link.p;
+    r.ent_speed = ent_speed.p;
+    r.ent_cap = (unsigned long long)ent_cap;
+    r.ent_drained = ent_drained;
+    return r;
+  }
+};
+
+namespace {
+
+constexpr double kKphToMps = 1000.0 / 3600.0;  // config.py:186
+
+int check_overflow(drift_engine* e, const Counters& c) {
+  if (!c.overflow) return DRIFT_OK;
+  std::string what;
+  if (c.overflow & kOvfEvents) what += " events";
+  if (c.overflow & kOvfArrivals) what += " arrivals";
+  if (c.overflow & kOvfArena) what += " route-arena";
+  if (c.overflow & kOvfHeap) what += " router-heap";
+  if (c.overflow & kOvfDepLog) what += " departure-log";
+  if (c.overflow & kOvfEntries) what += " entry-trace";
+  return fail(DRIFT_EOVERFLOW, "device buffer overflow:%s", what.c_str());
+}
+
+int fetch_counters(drift_engine* e, Counters* out) {
+  CU(cudaMemcpyAsync(e->h_ctr, e->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  *out = *e->h_ctr;
+  return DRIFT_OK;
+}
+
+int ensure_router(drift_engine* e, int64_t Q) {
+  // one worker (thread) per concurrent query; scratch is 16 B/node/direction/worker
+  int64_t want = std::min<int64_t>(std::max<int64_t>(Q, 1), 148 * 64);
+  const int64_t budget = (int64_t)6 << 30;
+  const int64_t per_worker = 2 * (int64_t)e->V * 16 + 2 * (int64_t)(e->Ef + 2) * (int64_t)sizeof(HeapItem);
+  want = std::max<int64_t>(1, std::min<int64_t>(want, budget / std::max<int64_t>(per_worker, 1)));
+  if (e->r_workers >= want) return DRIFT_OK;
+  const int64_t W = std::max<int64_t>(want, std::min<int64_t>(2 * (int64_t)e->r_workers, budget / per_worker));
+  CU(e->r_seen.alloc(W * 2 * e->V, false));
+  CU(e->r_plink.alloc(W * 2 * e->V, false));
+  CU(e->r_mark.alloc(W * 2 * e->V, true));
+  CU(e->r_epoch.alloc(W, true));
+  e->r_heap_cap = (int64_t)e->Ef + 2;
+  CU(e->r_heap.alloc(W * 2 * e->r_heap_cap, false));
+  e->r_workers = (int32_t)W;
+  return DRIFT_OK;
+}
+
+int ensure_qcap(drift_engine* e, int64_t Q) {
+  if (Q <= e->q_cap) return DRIFT_OK;
+  int64_t cap = std::max<int64_t>(Q, std::max<int64_t>(1024, 2 * e->q_cap));
+  CU(e->q_src.alloc(cap));
+  CU(e->q_dst.alloc(cap));
+  CU(e->q_agent.alloc(cap));
+  CU(e->q_status.alloc(cap));
+  CU(e->q_len.alloc(cap));
+  CU(e->q_off.alloc(cap));
+  CU(e->q_cost.alloc(cap));
+  e->q_cap = cap;
+  return DRIFT_OK;
+}
+
+// launches the router over the first Q entries of q_src/q_dst (device), count known on host
+int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_congested) {
+  if (Q <= 0) return DRIFT_OK;
+  int rc = ensure_router(e, Q);
+  if (rc) return rc;
+  RouteScratch sc;
+  sc.seen = e->r_seen.p;
+  sc.plink = e->r_plink.p;
+  sc.mark = e->r_mark.p;
+  sc.heap = e->r_heap.p;
+  sc.epoch = e->r_epoch.p;
+  sc.heap_cap = e->r_heap_cap;
+  sc.workers = (int32_t)std::min<int64_t>(e->r_workers, Q);
+  RouteOut out;
+  out.status = e->q_status.p;
+  out.n_links = e->q_len.p;
+  out.off = e->q_off.p;
+  out.cost = e->q_cost.p;
+  const double* wf = use_congested ? e->fwd_wc.p : e->fwd_w.p;
+  const double* wb = use_congested ? e->bwd_wc.p : e->bwd_w.p;
+  const double* lc = use_congested ? e->link_tt.p : e->link_t0.p;
+  (void)router;  // DRIFT_ROUTER_BATCHED falls through to the exact router until K5b lands
+  const int blocks = (sc.workers + 31) / 32;
+  k_route_nx<<<blocks, 32, 0, e->stream>>>(e->graph(), wf, wb, Q, e->q_src.p, e->q_dst.p, sc, e->arena.p,
+                                           (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
+  CU(cudaGetLastError());
+  return DRIFT_OK;
+}
+
+struct ProfScope {
+  drift_engine* e;
+  int i0 = -1;
+  bool adv;
+  ProfScope(drift_engine* e_, bool adv_) : e(e_), adv(adv_) {
+    if (!e->profiling) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    i0 = (int)e->ev_pool.size();
+    e->ev_pool.push_back(a);
+    e->ev_pool.push_back(b);
+    cudaEventRecord(a, e->stream);
+  }
+  ~ProfScope() {
+    if (i0 < 0) return;
+    cudaEventRecord(e->ev_pool[i0 + 1], e->stream);
+    if (adv) e->adv_marks.push_back({i0, i0 + 1});
+  }
+};
+
+// one tick, part 1: advance + departures -> local events
+int tick_begin(drift_engine* e, double delta, bool demand, double p_dep) {
+  e->tick += 1;
+  const int32_t tick = (int32_t)e->tick;
+  // reset the per-tick counters (n_events, n_touched, seg_cursor, n_dep_req)
+  CU(cudaMemsetAsync(e->ctr.p, 0, 4 * sizeof(int32_t), e->stream));
+  const int64_t per_block = (int64_t)kAdvThreads * kAdvPerThread;
+  const int blocks = grid_for(e->N, (int)per_block, kSMs * 8);
+  {
+    ProfScope ps(e, true);
+    if (demand)
+      k_advance<true><<<blocks, kAdvThreads, 0, e->stream>>>(e->agents(), e->arena.p, delta, tick, e->ctr.p,
+                                                             e->events.p, (int32_t)e->ev_cap, e->rings(), e->seed,
+                                                             p_dep, e->trip_off.p, e->dep_req.p);
+    else
+      k_advance<false><<<blocks, kAdvThreads, 0, e->stream>>>(e->agents(), e->arena.p, delta, tick, e->ctr.p,
+                                                              e->events.p, (int32_t)e->ev_cap, e->rings(), 0, 0.0,
+                                                              nullptr, nullptr);
+  }
+  CU(cudaGetLastError());
+  e->total_launches += 1;
+  e->adv_launches += 1;
+  return DRIFT_OK;
+}
+
+int inject_pending(drift_engine* e) {
+  Counters* c = e->ctr.p;
+  k_inject_departures<<<kSMs, 256, 0, e->stream>>>(e->agents(), e->arena.p, c, e->pend_agent.p, e->pend_off.p,
+                                                   e->pend_len.p, &c->n_pending, e->events.p, (int32_t)e->ev_cap);
+  CU(cudaGetLastError());
+  // n_pending is cleared after the inject kernel consumed it
+  CU(cudaMemsetAsync(&c->n_pending, 0, sizeof(int32_t), e->stream));
+  e->total_launches += 1;
+  return DRIFT_OK;
+}
+
+// one tick, part 2: ordered occupancy + entry speeds from `n_events_ptr` events at `events`
+int tick_finish(drift_engine* e, Event* events, const int32_t* n_events_ptr, int64_t n_hint) {
+  Counters* c = e->ctr.p;
+  const int g = grid_for(n_hint, 256, kSMs * 4);
+  k_count<<<g, 256, 0, e->stream>>>(events, n_events_ptr, e->evcnt.p, e->touched.p, c);
+  k_segment<<<g, 256, 0, e->stream>>>(e->touched.p, c, e->evcnt.p, e->segid.p, e->segs.p, e->occ.p);
+  k_scatter<<<g, 256, 0, e->stream>>>(events, n_events_ptr, e->segid.p, e->segs.p, e->sorted.p);
+  k_resolve<<<g, 256, 0, e->stream>>>(events, n_events_ptr, e->segid.p, e->segs.p, e->sorted.p, e->links(),
+                                      e->agents(), kKphToMps, (int32_t)e->tick, c, e->rings());
+  CU(cudaGetLastError());
+  e->total_launches += 4;
+  return DRIFT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* drift_last_error(void) { return g_err.c_str(); }
+int drift_abi_version(void) { return DRIFT_ABI_VERSION; }
+
+int drift_create(drift_engine** out, int device, const drift_graph_desc* g) {
+  if (!out || !g) return fail(DRIFT_EINVAL, "drift_create: null argument");
+  if (g->V <= 0 || g->L < 0 || g->Ef < 0 || g->Eb != g->Ef) return fail(DRIFT_EINVAL, "drift_create: bad sizes");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(DRIFT_ECUDA, "drift_create: no CUDA device (%s); this library has no CPU path",
+                cudaGetErrorString(ce));
+  CU(cudaSetDevice(device));
+  drift_engine* e = new drift_engine();
+  e->device = device;
+  *out = nullptr;
+#define CUX(call)                  \
+  do {                             \
+    cudaError_t _e2 = (call);      \
+    if (_e2 != cudaSuccess) {      \
+      delete e;                    \
+      CU(_e2);                     \
+    }                              \
+  } while (0)
+  CUX(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  e->V = g->V;
+  e->L = g->L;
+  e->Ef = g->Ef;
+  e->Eb = g->Eb;
+  CUX(e->fwd_rowptr.upload(g->fwd_rowptr, g->V + 1));
+  CUX(e->fwd_col.upload(g->fwd_col, g->Ef));
+  CUX(e->fwd_w.upload(g->fwd_w, g->Ef));
+  CUX(e->fwd_link.upload(g->fwd_link, g->Ef));
+  CUX(e->bwd_rowptr.upload(g->bwd_rowptr, g->V + 1));
+  CUX(e->bwd_col.upload(g->bwd_col, g->Eb));
+  CUX(e->bwd_w.upload(g->bwd_w, g->Eb));
+  CUX(e->bwd_link.upload(g->bwd_link, g->Eb));
+  CUX(e->link_len.upload(g->link_len, g->L));
+  CUX(e->link_v0.upload(g->link_v0, g->L));
+  CUX(e->link_t0.upload(g->link_t0, g->L));
+  CUX(e->link_tt.upload(g->link_t0, g->L));
+  CUX(e->link_cap.upload(g->link_cap, g->L));
+  CUX(e->link_u.upload(g->link_u, g->L));
+  CUX(e->link_v.upload(g->link_v, g->L));
+  CUX(e->fwd_wc.upload(g->fwd_w, g->Ef));
+  CUX(e->bwd_wc.upload(g->bwd_w, g->Eb));
+  CUX(e->occ.alloc(std::max(1, g->L)));
+  CUX(e->evcnt.alloc(std::max(1, g->L)));
+  CUX(e->segid.alloc(std::max(1, g->L)));
+  CUX(e->hist.alloc(std::max(1, g->L)));
+  CUX(e->ctr.alloc(1));
+  CUX(cudaMallocHost(&e->h_ctr, sizeof(Counters)));
+  e->total_capacity = 0;
+  for (int32_t l = 0; l < g->L; ++l) e->total_capacity += g->link_cap[l];
+  for (int h = 0; h < 24; ++h) e->hourly[h] = 0.05;
+#undef CUX
+  *out = e;
+  return DRIFT_OK;
+}
+
+int drift_destroy(drift_engine* e) {
+  if (!e) return DRIFT_OK;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (auto ev : e->ev_pool) cudaEventDestroy(ev);
+  if (e->h_ctr) cudaFreeHost(e->h_ctr);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return DRIFT_OK;
+}
+
+int drift_sync(drift_engine* e) {
+  if (!e) return fail(DRIFT_EINVAL, "null engine");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  return DRIFT_OK;
+}
+
+int drift_set_bpr(drift_engine* e, double alpha, double beta, const double* factor_table, const int64_t* class_off,
+                  int32_t n_class, const int32_t* link_class) {
+  if (!e || !factor_table || !class_off || !link_class || n_class <= 0) return fail(DRIFT_EINVAL, "drift_set_bpr");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  e->alpha = alpha;
+  e->beta = beta;
+  CU(e->factor.upload(factor_table, class_off[n_class]));
+  CU(e->cls_off.upload(class_off, n_class + 1));
+  CU(e->link_cls.upload(link_class, e->L));
+  e->have_bpr = true;
+  return DRIFT_OK;
+}
+
+int drift_add_agents(drift_engine* e, int64_t n_agents, int64_t agent_base, int64_t route_arena_links) {
+  if (!e || n_agents <= 0 || agent_base < 0) return fail(DRIFT_EINVAL, "drift_add_agents: bad argument");
+  if (e->N) return fail(DRIFT_ESTATE, "drift_add_agents: agents already created");
+  if (agent_base + n_agents >= ((int64_t)1 << 32)) return fail(DRIFT_EINVAL, "agent ids must fit 32 bits");
+  CU(cudaSetDevice(e->device));
+  const int64_t tile = (int64_t)kAdvThreads * kAdvPerThread;
+  const int64_t Np = (n_agents + tile - 1) / tile * tile;
+  CU(e->state.alloc(Np));
+  CU(e->dist.alloc(Np));
+  CU(e->speed.alloc(Np));
+  CU(e->elen.alloc(Np));
+  CU(e->cur_link.alloc(Np, false));
+  CU(cudaMemset(e->cur_link.p, 0xff, sizeof(int32_t) * Np));
+  CU(e->route_idx.alloc(Np));
+  CU(e->route_len.alloc(Np));
+  CU(e->route_off.alloc(Np));
+  CU(e->trip_count.alloc(Np));
+  CU(e->cur_node.alloc(Np));
+  if (route_arena_links <= 0) route_arena_links = std::max<int64_t>((int64_t)1 << 20, n_agents * 64);
+  CU(e->arena.alloc(route_arena_links, false));
+  e->arena_cap = route_arena_links;
+  e->ev_cap = 2 * n_agents + 1024;
+  if (e->ev_cap > 0x7fffffff) return fail(DRIFT_EINVAL, "too many agents for one engine");
+  CU(e->events.alloc(e->ev_cap, false));
+  CU(e->sorted.alloc(e->ev_cap, false));
+  CU(e->segs.alloc(e->ev_cap, false));
+  CU(e->touched.alloc(e->ev_cap, false));
+  e->pend_cap = n_agents;
+  CU(e->pend_agent.alloc(n_agents));
+  CU(e->pend_off.alloc(n_agents));
+  CU(e->pend_len.alloc(n_agents));
+  e->arr_cap = std::max<int64_t>(n_agents, 4096);
+  CU(e->arr_agent.alloc(e->arr_cap));
+  CU(e->arr_tick.alloc(e->arr_cap));
+  e->dl_cap = std::max<int64_t>(n_agents, 4096);
+  CU(e->dl_agent.alloc(e->dl_cap));
+  CU(e->dl_tick.alloc(e->dl_cap));
+  CU(e->dl_src.alloc(e->dl_cap));
+  CU(e->dl_dst.alloc(e->dl_cap));
+  CU(e->dl_status.alloc(e->dl_cap));
+  CU(e->dep_req.alloc(n_agents));
+  e->N = n_agents;
+  e->Npad = Np;
+  e->agent_base = (uint32_t)agent_base;
+  return DRIFT_OK;
+}
+
+int drift_route_od(drift_engine* e, int32_t router, int64_t Q, const int32_t* src, const int32_t* dst,
+                   int32_t use_congested, int32_t* status, int32_t* n_links) {
+  if (!e || Q < 0 || (Q && (!src || !dst))) return fail(DRIFT_EINVAL, "drift_route_od: bad argument");
+  if (!e->N) return fail(DRIFT_ESTATE, "drift_route_od: call drift_add_agents first (route arena)");
+  CU(cudaSetDevice(e->device));
+  e->last_Q = Q;
+  if (Q == 0) return DRIFT_OK;
+  int rc = ensure_qcap(e, Q);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(e->q_src.p, src, sizeof(int32_t) * Q, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->q_dst.p, dst, sizeof(int32_t) * Q, cudaMemcpyHostToDevice, e->stream));
+  Counters c0;
+  rc = fetch_counters(e, &c0);
+  if (rc) return rc;
+  e->last_arena_begin = c0.arena_cursor;
+  rc = launch_router(e, router, Q, use_congested);
+  if (rc) return rc;
+  Counters c1;
+  rc = fetch_counters(e, &c1);
+  if (rc) return rc;
+  e->last_arena_end = std::min<unsigned long long>(c1.arena_cursor, (unsigned long long)e->arena_cap);
+  if (status) CU(cudaMemcpy(status, e->q_status.p, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost));
+  if (n_links) CU(cudaMemcpy(n_links, e->q_len.p, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost));
+  return check_overflow(e, c1);
+}
+
+int drift_fetch_routes(drift_engine* e, int32_t* links_out, int64_t cap) {
+  if (!e || !links_out) return fail(DRIFT_EINVAL, "drift_fetch_routes");
+  CU(cudaSetDevice(e->device));
+  const int64_t Q = e->last_Q;
+  if (Q == 0) return DRIFT_OK;
+  std::vector<int64_t> off(Q);
+  std::vector<int32_t> len(Q);
+  CU(cudaMemcpy(off.data(), e->q_off.p, sizeof(int64_t) * Q, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(len.data(), e->q_len.p, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost));
+  const int64_t span = (int64_t)(e->last_arena_end - e->last_arena_begin);
+  std::vector<int32_t> buf((size_t)std::max<int64_t>(span, 1));
+  if (span > 0)
+    CU(cudaMemcpy(buf.data(), e->arena.p + e->last_arena_begin, sizeof(int32_t) * span, cudaMemcpyDeviceToHost));
+  int64_t w = 0;
+  for (int64_t q = 0; q < Q; ++q) {
+    if (len[q] <= 0) continue;
+    if (w + len[q] > cap) return fail(DRIFT_EINVAL, "drift_fetch_routes: output buffer too small");
+    const int64_t rel = off[q] - (int64_t)e->last_arena_begin;
+    if (rel < 0 || rel + len[q] > span) return fail(DRIFT_ESTATE, "drift_fetch_routes: stale batch");
+    memcpy(links_out + w, buf.data() + rel, sizeof(int32_t) * len[q]);
+    w += len[q];
+  }
+  return DRIFT_OK;
+}
+
+int drift_fetch_route_costs(drift_engine* e, double* cost_out, int64_t Q) {
+  if (!e || !cost_out || Q > e->last_Q) return fail(DRIFT_EINVAL, "drift_fetch_route_costs");
+  CU(cudaSetDevice(e->device));
+  if (Q > 0) CU(cudaMemcpy(cost_out, e->q_cost.p, sizeof(double) * Q, cudaMemcpyDeviceToHost));
+  return DRIFT_OK;
+}
+
+int drift_commit_departures(drift_engine* e, int64_t Q, const int32_t* agent) {
+  if (!e || Q < 0 || Q > e->last_Q || (Q && !agent)) return fail(DRIFT_EINVAL, "drift_commit_departures");
+  CU(cudaSetDevice(e->device));
+  if (Q == 0) return DRIFT_OK;
+  for (int64_t q = 0; q < Q; ++q)
+    if (agent[q] < 0 || agent[q] >= e->N) return fail(DRIFT_EINVAL, "drift_commit_departures: agent out of range");
+  CU(cudaMemcpyAsync(e->q_agent.p, agent, sizeof(int32_t) * Q, cudaMemcpyHostToDevice, e->stream));
+  k_commit<<<grid_for(Q, 256, kSMs), 256, 0, e->stream>>>(Q, e->q_agent.p, e->q_off.p, e->q_len.p, e->ctr.p,
+                                                           e->pend_agent.p, e->pend_off.p, e->pend_len.p,
+                                                           (int32_t)e->pend_cap);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(e->stream));  // `agent` is a caller buffer
+  return DRIFT_OK;
+}
+
+int drift_submit_departures(drift_engine* e, int64_t n, const int32_t* agent, const int64_t* route_off,
+                            const int32_t* route_links) {
+  if (!e || n < 0 || (n && (!agent || !route_off))) return fail(DRIFT_EINVAL, "drift_submit_departures");
+  if (!e->N) return fail(DRIFT_ESTATE, "drift_submit_departures: no agents");
+  CU(cudaSetDevice(e->device));
+  if (n == 0) return DRIFT_OK;
+  const int64_t total = route_off[n];
+  for (int64_t q = 0; q < n; ++q) {
+    if (agent[q] < 0 || agent[q] >= e->N) return fail(DRIFT_EINVAL, "drift_submit_departures: agent out of range");
+    if (route_off[q + 1] < route_off[q]) return fail(DRIFT_EINVAL, "drift_submit_departures: bad offsets");
+  }
+  for (int64_t k = 0; k < total; ++k)
+    if (route_links[k] < 0 || route_links[k] >= e->L) return fail(DRIFT_EINVAL, "drift_submit_departures: bad link id");
+  int rc = ensure_qcap(e, n);
+  if (rc) return rc;
+  DevBuf<int64_t> d_off;
+  DevBuf<int32_t> d_links;
+  CU(d_off.upload(route_off, n + 1));
+  CU(d_links.upload(route_links, std::max<int64_t>(total, 1)));
+  CU(cudaMemcpyAsync(e->q_agent.p, agent, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+  k_import_routes<<<grid_for(n, 128, kSMs), 128, 0, e->stream>>>(n, d_off.p, d_links.p, e->arena.p,
+                                                                 (unsigned long long)e->arena_cap, e->ctr.p,
+                                                                 e->q_off.p, e->q_len.p);
+  k_commit<<<grid_for(n, 256, kSMs), 256, 0, e->stream>>>(n, e->q_agent.p, e->q_off.p, e->q_len.p, e->ctr.p,
+                                                           e->pend_agent.p, e->pend_off.p, e->pend_len.p,
+                                                           (int32_t)e->pend_cap);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(e->stream));
+  e->last_Q = 0;
+  return DRIFT_OK;
+}
+
+int drift_step(drift_engine* e, int32_t n_ticks, double delta) {
+  if (!e || n_ticks < 0) return fail(DRIFT_EINVAL, "drift_step");
+  if (!e->N) return fail(DRIFT_ESTATE, "drift_step: no agents");
+  if (!e->have_bpr) return fail(DRIFT_ESTATE, "drift_step: call drift_set_bpr first");
+  CU(cudaSetDevice(e->device));
+  for (int32_t k = 0; k < n_ticks; ++k) {
+    ProfScope ps(e, false);
+    if (e->profiling && k == 0 && e->tick_ev0 < 0) e->tick_ev0 = ps.i0;
+    int rc = tick_begin(e, delta, false, 0.0);
+    if (rc) return rc;
+    rc = inject_pending(e);
+    if (rc) return rc;
+    rc = tick_finish(e, e->events.p, &e->ctr.p->n_events, 2 * e->N);
+    if (rc) return rc;
+  }
+  return DRIFT_OK;
+}
+
+int drift_set_demand(drift_engine* e, uint64_t seed, const double hourly24[24], const int32_t* start_node,
+                     const int64_t* trip_off, const int32_t* trip_dst, int32_t router) {
+  if (!e || !hourly24 || !start_node || !trip_off || !trip_dst) return fail(DRIFT_EINVAL, "drift_set_demand");
+  if (!e->N) return fail(DRIFT_ESTATE, "drift_set_demand: no agents");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  e->seed = seed;
+  for (int h = 0; h < 24; ++h) e->hourly[h] = hourly24[h];
+  for (int64_t i = 0; i < e->N; ++i)
+    if (start_node[i] < 0 || start_node[i] >= e->V) return fail(DRIFT_EINVAL, "drift_set_demand: bad start node");
+  CU(cudaMemcpy(e->cur_node.p, start_node, sizeof(int32_t) * e->N, cudaMemcpyHostToDevice));
+  CU(e->trip_off.upload(trip_off, e->N + 1));
+  CU(e->trip_dst.upload(trip_dst, std::max<int64_t>(trip_off[e->N], 1)));
+  e->demand_router = router;
+  e->have_demand = true;
+  int rc = ensure_qcap(e, e->N);
+  if (rc) return rc;
+  return DRIFT_OK;
+}
+
+int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0) {
+  if (!e || n_ticks < 0) return fail(DRIFT_EINVAL, "drift_run");
+  if (!e->have_demand) return fail(DRIFT_ESTATE, "drift_run: call drift_set_demand first");
+  if (!e->have_bpr) return fail(DRIFT_ESTATE, "drift_run: call drift_set_bpr first");
+  CU(cudaSetDevice(e->device));
+  double t = t0;
+  for (int32_t k = 0; k < n_ticks; ++k) {
+    t += delta;  // repeated fp64 sum like lib/simulation_thread.py:295
+    const int hour = (int)std::fmod((t + 21600.0) / 3600.0, 24.0);  // lib/agent.py:251-252
+    const double p = e->hourly[hour] * 4.0 * delta / 3600.0;        // lib/agent.py:259,180
+    int rc = tick_begin(e, delta, true, p);
+    if (rc) return rc;
+    // route this tick's departure requests on the device (count stays on the device: the
+    // router is launched over a worker pool and reads n_dep_req itself)
+    Counters* c = e->ctr.p;
+    k_prepare_requests<<<kSMs, 256, 0, e->stream>>>(e->agents(), c, e->dep_req.p, e->trip_off.p, e->trip_dst.p,
+                                                    e->q_src.p, e->q_dst.p, e->q_agent.p);
+    CU(cudaGetLastError());
+    // the exact router needs the host to know Q to size its worker pool: read it back
+    Counters hc;
+    rc = fetch_counters(e, &hc);
+    if (rc) return rc;
+    const int64_t Q = hc.n_dep_req;
+    if (Q > 0) {
+      rc = launch_router(e, e->demand_router, Q, 0);
+      if (rc) return rc;
+      k_log_departures<<<grid_for(Q, 256, kSMs), 256, 0, e->stream>>>(
+          c, (int32_t)e->tick, e->q_agent.p, e->q_src.p, e->q_dst.p, e->q_status.p, e->dl_agent.p, e->dl_tick.p,
+          e->dl_src.p, e->dl_dst.p, e->dl_status.p, (unsigned long long)e->dl_cap, e->dl_drained);
+      k_commit<<<grid_for(Q, 256, kSMs), 256, 0, e->stream>>>(Q, e->q_agent.p, e->q_off.p, e->q_len.p, c,
+                                                               e->pend_agent.p, e->pend_off.p, e->pend_len.p,
+                                                               (int32_t)e->pend_cap);
+      CU(cudaGetLastError());
+      rc = inject_pending(e);
+      if (rc) return rc;
+    }
+    rc = tick_finish(e, e->events.p, &c->n_events, 2 * e->N);
+    if (rc) return rc;
+  }
+  return DRIFT_OK;
+}
+
+int drift_update_travel_times(drift_engine* e) {
+  if (!e || !e->have_bpr) return fail(DRIFT_ESTATE, "drift_update_travel_times");
+  CU(cudaSetDevice(e->device));
+  k_travel_times<<<grid_for(e->L, 256, kSMs * 8), 256, 0, e->stream>>>(e->links());
+  CU(cudaGetLastError());
+  return DRIFT_OK;
+}
+
+int drift_reroute_moving(drift_engine* e, int32_t router, int64_t* n_rerouted) {
+  (void)router;
+  if (n_rerouted) *n_rerouted = 0;
+  return fail(DRIFT_ESTATE, "drift_reroute_moving: not implemented yet");
+}
+
+int drift_read_occupancy(drift_engine* e, int32_t* occ_out) {
+  if (!e || !occ_out) return fail(DRIFT_EINVAL, "drift_read_occupancy");
+  CU(cudaSetDevice(e->device));
+  CU(cudaMemcpyAsync(occ_out, e->occ.p, sizeof(int32_t) * e->L, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return DRIFT_OK;
+}
+
+int drift_recount_occupancy(drift_engine* e, int32_t* occ_out) {
+  if (!e || !occ_out || !e->N) return fail(DRIFT_EINVAL, "drift_recount_occupancy");
+  CU(cudaSetDevice(e->device));
+  CU(cudaMemsetAsync(e->hist.p, 0, sizeof(int32_t) * e->L, e->stream));
+  k_recount<<<grid_for(e->N, 256, kSMs * 8), 256, 0, e->stream>>>(e->agents(), e->hist.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(occ_out, e->hist.p, sizeof(int32_t) * e->L, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return DRIFT_OK;
+}
+
+int drift_read_travel_times(drift_engine* e, double* tt_out) {
+  if (!e || !tt_out) return fail(DRIFT_EINVAL, "drift_read_travel_times");
+  CU(cudaSetDevice(e->device));
+  CU(cudaMemcpyAsync(tt_out, e->link_tt.p, sizeof(double) * e->L, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return DRIFT_OK;
+}
+
+int drift_read_agents(drift_engine* e, uint8_t* state, double* dist_on_link, double* speed, double* link_len,
+                      int32_t* cur_link, int32_t* route_idx, int32_t* route_len, int32_t* trip_count,
+                      int32_t* cur_node) {
+  if (!e || !e->N) return fail(DRIFT_EINVAL, "drift_read_agents");
+  CU(cudaSetDevice(e->device));
+  const int64_t n = e->N;
+  cudaStream_t s = e->stream;
+  if (state) CU(cudaMemcpyAsync(state, e->state.p, n, cudaMemcpyDeviceToHost, s));
+  if (dist_on_link) CU(cudaMemcpyAsync(dist_on_link, e->dist.p, 8 * n, cudaMemcpyDeviceToHost, s));
+  if (speed) CU(cudaMemcpyAsync(speed, e->speed.p, 8 * n, cudaMemcpyDeviceToHost, s));
+  if (link_len) CU(cudaMemcpyAsync(link_len, e->elen.p, 8 * n, cudaMemcpyDeviceToHost, s));
+  if (cur_link) CU(cudaMemcpyAsync(cur_link, e->cur_link.p, 4 * n, cudaMemcpyDeviceToHost, s));
+  if (route_idx) CU(cudaMemcpyAsync(route_idx, e->route_idx.p, 4 * n, cudaMemcpyDeviceToHost, s));
+  if (route_len) CU(cudaMemcpyAsync(route_len, e->route_len.p, 4 * n, cudaMemcpyDeviceToHost, s));
+  if (trip_count) CU(cudaMemcpyAsync(trip_count, e->trip_count.p, 4 * n, cudaMemcpyDeviceToHost, s));
+  if (cur_node) CU(cudaMemcpyAsync(cur_node, e->cur_node.p, 4 * n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return DRIFT_OK;
+}
+
+int drift_read_agent_route(drift_engine* e, int64_t agent, int32_t* links_out, int64_t cap, int64_t* n) {
+  if (!e || agent < 0 || agent >= e->N || !n) return fail(DRIFT_EINVAL, "drift_read_agent_route");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  int64_t off = 0;
+  int32_t len = 0;
+  CU(cudaMemcpy(&off, e->route_off.p + agent, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&len, e->route_len.p + agent, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  *n = len;
+  if (links_out && len > 0) {
+    if (len > cap) return fail(DRIFT_EINVAL, "drift_read_agent_route: buffer too small");
+    CU(cudaMemcpy(links_out, e->arena.p + off, sizeof(int32_t) * len, cudaMemcpyDeviceToHost));
+  }
+  return DRIFT_OK;
+}
+
+static int drain_ring(drift_engine* e, unsigned long long total, unsigned long long* drained, int64_t ring_cap,
+                      int64_t cap, int64_t* n, std::initializer_list<std::pair<void*, const void*>> cols,
+                      std::initializer_list<size_t> widths) {
+  unsigned long long avail = total - *drained;
+  if ((int64_t)avail > ring_cap) return fail(DRIFT_EOVERFLOW, "ring overflow: drain more often");
+  int64_t take = std::min<int64_t>((int64_t)avail, cap);
+  *n = take;
+  if (take == 0) return DRIFT_OK;
+  const int64_t start = (int64_t)(*drained % (unsigned long long)ring_cap);
+  const int64_t first = std::min<int64_t>(take, ring_cap - start);
+  auto w = widths.begin();
+  for (auto& c : cols) {
+    const size_t sz = *w++;
+    if (!c.first) continue;
+    CU(cudaMemcpy(c.first, (const char*)c.second + sz * start, sz * first, cudaMemcpyDeviceToHost));
+    if (take > first)
+      CU(cudaMemcpy((char*)c.first + sz * first, c.second, sz * (take - first), cudaMemcpyDeviceToHost));
+  }
+  *drained += (unsigned long long)take;
+  return DRIFT_OK;
+}
+
+int drift_drain_arrivals(drift_engine* e, int32_t* agent, int32_t* tick, int64_t cap, int64_t* n) {
+  if (!e || !n || cap < 0) return fail(DRIFT_EINVAL, "drift_drain_arrivals");
+  CU(cudaSetDevice(e->device));
+  Counters c;
+  int rc = fetch_counters(e, &c);
+  if (rc) return rc;
+  rc = check_overflow(e, c);
+  if (rc) return rc;
+  return drain_ring(e, c.n_arrivals, &e->arr_drained, e->arr_cap, cap, n,
+                    {{agent, e->arr_agent.p}, {tick, e->arr_tick.p}}, {4, 4});
+}
+
+int drift_drain_departures(drift_engine* e, int32_t* agent, int32_t* tick, int32_t* src, int32_t* dst,
+                           int32_t* status, int64_t cap, int64_t* n) {
+  if (!e || !n || cap < 0) return fail(DRIFT_EINVAL, "drift_drain_departures");
+  CU(cudaSetDevice(e->device));
+  Counters c;
+  int rc = fetch_counters(e, &c);
+  if (rc) return rc;
+  rc = check_overflow(e, c);
+  if (rc) return rc;
+  return drain_ring(e, c.n_departures, &e->dl_drained, e->dl_cap, cap, n,
+                    {{agent, e->dl_agent.p}, {tick, e->dl_tick.p}, {src, e->dl_src.p}, {dst, e->dl_dst.p},
+                     {status, e->dl_status.p}},
+                    {4, 4, 4, 4, 4});
+}
+
+int drift_enable_entry_trace(drift_engine* e, int64_t cap) {
+  if (!e || cap < 0) return fail(DRIFT_EINVAL, "drift_enable_entry_trace");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  CU(e->ent_tick.alloc(cap));
+  CU(e->ent_agent.alloc(cap));
+  CU(e->ent_link.alloc(cap));
+  CU(e->ent_speed.alloc(cap));
+  e->ent_cap = cap;
+  Counters c;
+  int rc = fetch_counters(e, &c);
+  if (rc) return rc;
+  e->ent_drained = c.n_entries;
+  return DRIFT_OK;
+}
+
+int drift_drain_entries(drift_engine* e, int32_t* tick, int32_t* agent, int32_t* link, double* speed, int64_t cap,
+                        int64_t* n) {
+  if (!e || !n || cap < 0) return fail(DRIFT_EINVAL, "drift_drain_entries");
+  if (!e->ent_cap) return fail(DRIFT_ESTATE, "entry trace is off");
+  CU(cudaSetDevice(e->device));
+  Counters c;
+  int rc = fetch_counters(e, &c);
+  if (rc) return rc;
+  rc = check_overflow(e, c);
+  if (rc) return rc;
+  return drain_ring(e, c.n_entries, &e->ent_drained, e->ent_cap, cap, n,
+                    {{tick, e->ent_tick.p}, {agent, e->ent_agent.p}, {link, e->ent_link.p}, {speed, e->ent_speed.p}},
+                    {4, 4, 4, 8});
+}
+
+int drift_stats(drift_engine* e, drift_stats_out* out) {
+  if (!e || !out) return fail(DRIFT_EINVAL, "drift_stats");
+  CU(cudaSetDevice(e->device));
+  Counters* c = e->ctr.p;
+  CU(cudaMemsetAsync(&c->moving, 0, 3 * sizeof(long long), e->stream));
+  if (e->N) {
+    k_stats<<<kSMs * 4, 256, 0, e->stream>>>(e->agents(), e->links(), c);
+    CU(cudaGetLastError());
+  }
+  Counters h;
+  int rc = fetch_counters(e, &h);
+  if (rc) return rc;
+  out->moving_agents = h.moving;
+  out->total_agents_on_roads = h.on_roads;
+  out->links_with_traffic = h.links_with_traffic;
+  out->total_capacity = e->total_capacity;
+  out->arrivals_total = (int64_t)h.n_arrivals;
+  out->departures_total = (int64_t)h.n_departures;
+  out->route_arena_used = (int64_t)h.arena_cursor;
+  out->events_last_tick = h.n_events;
+  return check_overflow(e, h);
+}
+
+int drift_tick_index(drift_engine* e, int64_t* tick) {
+  if (!e || !tick) return fail(DRIFT_EINVAL, "drift_tick_index");
+  *tick = e->tick;
+  return DRIFT_OK;
+}
+
+int drift_tick_begin(drift_engine* e, double delta, int64_t* n_events) {
+  if (!e || !e->N || !e->have_bpr) return fail(DRIFT_ESTATE, "drift_tick_begin");
+  CU(cudaSetDevice(e->device));
+  int rc = tick_begin(e, delta, false, 0.0);
+  if (rc) return rc;
+  rc = inject_pending(e);
+  if (rc) return rc;
+  if (n_events) {
+    Counters c;
+    rc = fetch_counters(e, &c);
+    if (rc) return rc;
+    rc = check_overflow(e, c);
+    if (rc) return rc;
+    *n_events = c.n_events;
+  }
+  return DRIFT_OK;
+}
+
+int drift_events_ptr(drift_engine* e, void** dev_ptr, int64_t* capacity) {
+  if (!e || !dev_ptr) return fail(DRIFT_EINVAL, "drift_events_ptr");
+  *dev_ptr = e->events.p;
+  if (capacity) *capacity = e->ev_cap;
+  return DRIFT_OK;
+}
+
+int drift_tick_finish(drift_engine* e, const void* events_dev, int64_t n_events) {
+  if (!e || !events_dev || n_events < 0) return fail(DRIFT_EINVAL, "drift_tick_finish");
+  CU(cudaSetDevice(e->device));
+  if (n_events > e->sorted.n) {  // gathered events of all ranks
+    CU(cudaStreamSynchronize(e->stream));
+    CU(e->sorted.alloc(n_events, false));
+    CU(e->segs.alloc(n_events, false));
+    CU(e->touched.alloc(n_events, false));
+  }
+  // the gathered count replaces the local one
+  const int32_t n32 = (int32_t)n_events;
+  CU(cudaMemcpyAsync(&e->ctr.p->n_events, &n32, sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return tick_finish(e, (Event*)events_dev, &e->ctr.p->n_events, n_events);
+}
+
+int drift_set_profiling(drift_engine* e, int32_t on) {
+  if (!e) return fail(DRIFT_EINVAL, "drift_set_profiling");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  for (auto ev : e->ev_pool) cudaEventDestroy(ev);
+  e->ev_pool.clear();
+  e->adv_marks.clear();
+  e->tick_ev0 = e->tick_ev1 = -1;
+  e->profiling = on != 0;
+  e->adv_launches = e->total_launches = 0;
+  return DRIFT_OK;
+}
+
+int drift_kernel_times(drift_engine* e, double* advance_ms, int64_t* advance_launches, double* total_ms,
+                       int64_t* total_launches) {
+  if (!e) return fail(DRIFT_EINVAL, "drift_kernel_times");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  double adv = 0;
+  for (auto& m : e->adv_marks) {
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e->ev_pool[m.first], e->ev_pool[m.second]));
+    adv += ms;
+  }
+  if (advance_ms) *advance_ms = adv;
+  if (advance_launches) *advance_launches = (int64_t)e->adv_marks.size();
+  if (total_ms) *total_ms = 0;
+  if (total_launches) *total_launches = e->total_launches;
+  return DRIFT_OK;
+}
+
+int drift_device_ptr(drift_engine* e, const char* name, void** ptr, int64_t* n_elems) {
+  if (!e || !name || !ptr) return fail(DRIFT_EINVAL, "drift_device_ptr");
+  std::string s(name);
+  int64_t n = 0;
+  void* p = nullptr;
+  if (s == "occ") p = e->occ.p, n = e->L;
+  else if (s == "state") p = e->state.p, n = e->N;
+  else if (s == "dist") p = e->dist.p, n = e->N;
+  else if (s == "speed") p = e->speed.p, n = e->N;
+  else if (s == "link_len") p = e->elen.p, n = e->N;
+  else if (s == "cur_link") p = e->cur_link.p, n = e->N;
+  else if (s == "events") p = e->events.p, n = e->ev_cap;
+  else if (s == "travel_time") p = e->link_tt.p, n = e->L;
+  else return fail(DRIFT_EINVAL, "drift_device_ptr: unknown buffer '%s'", name);
+  *ptr = p;
+  if (n_elems) *n_elems = n;
+  return DRIFT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,268 @@
+"""Python handle on one device engine (thin wrapper over the C ABI, numpy in / numpy out)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from . import bpr as _bpr
+from .graph import LoweredGraph
+
+ROUTER_NX_EXACT = _capi.ROUTER_NX_EXACT
+ROUTER_BATCHED = _capi.ROUTER_BATCHED
+ROUTE_OK, ROUTE_TRIVIAL, ROUTE_NOPATH = _capi.ROUTE_OK, _capi.ROUTE_TRIVIAL, _capi.ROUTE_NOPATH
+
+
+def _p(arr, ctype):
+    return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Engine:
+    """One engine = one CUDA device = one rank.
+
+    ``lg``           lowered graph (``drift_b200.graph``)
+    ``num_agents``   local agents; ``agent_base`` = global id of local agent 0
+    ``alpha/beta``   BPR parameters (lib/managers/traffic_manager.py:25-31)
+    """
+
+    def __init__(self, lg: LoweredGraph, num_agents: int, alpha: float = 0.15, beta: float = 4.0, device: int = 0,
+                 agent_base: int = 0, route_arena_links: int = 0, total_agents: int | None = None):
+        self._lib = _capi.load()
+        self.lg = lg
+        self.N = int(num_agents)
+        self.agent_base = int(agent_base)
+        self._h = _capi.ENGINE()
+        self._keep = dict(
+            fwd_rowptr=_i32(lg.fwd_rowptr), fwd_col=_i32(lg.fwd_col), fwd_w=_f64(lg.fwd_w), fwd_link=_i32(lg.fwd_link),
+            bwd_rowptr=_i32(lg.bwd_rowptr), bwd_col=_i32(lg.bwd_col), bwd_w=_f64(lg.bwd_w), bwd_link=_i32(lg.bwd_link),
+            link_len=_f64(lg.link_len), link_v0=_f64(lg.link_v0), link_t0=_f64(lg.link_t0), link_cap=_i32(lg.link_cap),
+            link_u=_i32(lg.link_u), link_v=_i32(lg.link_v))
+        k = self._keep
+        d = _capi.GraphDesc(
+            V=lg.V, L=lg.L, Ef=len(k["fwd_col"]), Eb=len(k["bwd_col"]),
+            fwd_rowptr=_p(k["fwd_rowptr"], C.c_int32), fwd_col=_p(k["fwd_col"], C.c_int32),
+            fwd_w=_p(k["fwd_w"], C.c_double), fwd_link=_p(k["fwd_link"], C.c_int32),
+            bwd_rowptr=_p(k["bwd_rowptr"], C.c_int32), bwd_col=_p(k["bwd_col"], C.c_int32),
+            bwd_w=_p(k["bwd_w"], C.c_double), bwd_link=_p(k["bwd_link"], C.c_int32),
+            link_len=_p(k["link_len"], C.c_double), link_v0=_p(k["link_v0"], C.c_double),
+            link_t0=_p(k["link_t0"], C.c_double), link_cap=_p(k["link_cap"], C.c_int32),
+            link_u=_p(k["link_u"], C.c_int32), link_v=_p(k["link_v"], C.c_int32))
+        _capi.check(self._lib.drift_create(C.byref(self._h), int(device), C.byref(d)))
+        try:
+            self.set_bpr(alpha, beta)
+            _capi.check(self._lib.drift_add_agents(self._h, self.N, self.agent_base, int(route_arena_links)))
+        except Exception:
+            self.close()
+            raise
+
+    # ---- lifecycle --------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.drift_destroy(self._h)
+            self._h = _capi.ENGINE()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sync(self):
+        _capi.check(self._lib.drift_sync(self._h))
+
+    # ---- configuration ------------------------------------------------------------------------
+    def set_bpr(self, alpha, beta):
+        table, off, cls = _bpr.build_tables(self.lg.link_cap, float(alpha), float(beta))
+        self.alpha, self.beta = float(alpha), float(beta)
+        _capi.check(self._lib.drift_set_bpr(self._h, self.alpha, self.beta, _p(table, C.c_double),
+                                            _p(off, C.c_int64), len(off) - 1, _p(cls, C.c_int32)))
+
+    def set_demand(self, seed, hourly24, start_node, trip_off, trip_dst, router=ROUTER_NX_EXACT):
+        h = _f64(hourly24)
+        assert h.shape == (24,)
+        s, o, d = _i32(start_node), _i64(trip_off), _i32(trip_dst)
+        assert len(s) == self.N and len(o) == self.N + 1
+        if len(d) == 0:
+            d = np.zeros(1, dtype=np.int32)
+        _capi.check(self._lib.drift_set_demand(self._h, int(seed), _p(h, C.c_double), _p(s, C.c_int32),
+                                               _p(o, C.c_int64), _p(d, C.c_int32), int(router)))
+
+    # ---- routing ------------------------------------------------------------------------------
+    def route(self, src, dst, router=ROUTER_NX_EXACT, congested=False, fetch=True):
+        """Route Q (src, dst) node-index pairs on the device.
+
+        Returns (status int32[Q], n_links int32[Q], links list-of-arrays | None).  The routes stay
+        staged on the device for ``commit_departures``.
+        """
+        src, dst = _i32(src), _i32(dst)
+        Q = len(src)
+        status = np.zeros(Q, dtype=np.int32)
+        nl = np.zeros(Q, dtype=np.int32)
+        _capi.check(self._lib.drift_route_od(self._h, int(router), Q, _p(src, C.c_int32), _p(dst, C.c_int32),
+                                             int(bool(congested)), _p(status, C.c_int32), _p(nl, C.c_int32)))
+        links = None
+        if fetch:
+            total = int(nl.sum())
+            flat = np.zeros(max(total, 1), dtype=np.int32)
+            if total:
+                _capi.check(self._lib.drift_fetch_routes(self._h, _p(flat, C.c_int32), total))
+            cuts = np.cumsum(nl)[:-1]
+            links = np.split(flat[:total], cuts) if Q else []
+        return status, nl, links
+
+    def route_costs(self, Q):
+        out = np.zeros(max(Q, 1))
+        _capi.check(self._lib.drift_fetch_route_costs(self._h, _p(out, C.c_double), Q))
+        return out[:Q]
+
+    def commit_departures(self, agents):
+        a = _i32(agents)
+        _capi.check(self._lib.drift_commit_departures(self._h, len(a), _p(a, C.c_int32)))
+
+    def submit_departures(self, agents, routes):
+        """Departures with host-supplied link sequences (trace replay)."""
+        a = _i32(agents)
+        off = np.zeros(len(a) + 1, dtype=np.int64)
+        if len(a):
+            off[1:] = np.cumsum([len(r) for r in routes])
+        flat = _i32(np.concatenate([np.asarray(r, dtype=np.int32) for r in routes])) if off[-1] else np.zeros(1, np.int32)
+        _capi.check(self._lib.drift_submit_departures(self._h, len(a), _p(a, C.c_int32), _p(off, C.c_int64),
+                                                      _p(flat, C.c_int32)))
+
+    # ---- stepping -----------------------------------------------------------------------------
+    def step(self, n_ticks, delta):
+        _capi.check(self._lib.drift_step(self._h, int(n_ticks), float(delta)))
+
+    def run(self, n_ticks, delta, t0):
+        _capi.check(self._lib.drift_run(self._h, int(n_ticks), float(delta), float(t0)))
+
+    def update_travel_times(self):
+        _capi.check(self._lib.drift_update_travel_times(self._h))
+
+    def tick_begin(self, delta):
+        n = C.c_int64(0)
+        _capi.check(self._lib.drift_tick_begin(self._h, float(delta), C.byref(n)))
+        return n.value
+
+    def events_ptr(self):
+        p, cap = C.c_void_p(), C.c_int64(0)
+        _capi.check(self._lib.drift_events_ptr(self._h, C.byref(p), C.byref(cap)))
+        return p.value, cap.value
+
+    def tick_finish(self, events_dev_ptr, n_events):
+        _capi.check(self._lib.drift_tick_finish(self._h, C.c_void_p(events_dev_ptr), int(n_events)))
+
+    # ---- readback -----------------------------------------------------------------------------
+    def occupancy(self):
+        out = np.zeros(max(self.lg.L, 1), dtype=np.int32)
+        _capi.check(self._lib.drift_read_occupancy(self._h, _p(out, C.c_int32)))
+        return out[:self.lg.L]
+
+    def recount_occupancy(self):
+        out = np.zeros(max(self.lg.L, 1), dtype=np.int32)
+        _capi.check(self._lib.drift_recount_occupancy(self._h, _p(out, C.c_int32)))
+        return out[:self.lg.L]
+
+    def travel_times(self):
+        out = np.zeros(max(self.lg.L, 1))
+        _capi.check(self._lib.drift_read_travel_times(self._h, _p(out, C.c_double)))
+        return out[:self.lg.L]
+
+    def agents(self, fields=("state", "dist", "speed", "elen", "cur_link", "route_idx")):
+        """dict of per-agent arrays; fields among state, dist, speed, elen, cur_link, route_idx,
+        route_len, trip_count, cur_node."""
+        n = self.N
+        spec = [("state", np.uint8, C.c_uint8), ("dist", np.float64, C.c_double), ("speed", np.float64, C.c_double),
+                ("elen", np.float64, C.c_double), ("cur_link", np.int32, C.c_int32), ("route_idx", np.int32, C.c_int32),
+                ("route_len", np.int32, C.c_int32), ("trip_count", np.int32, C.c_int32), ("cur_node", np.int32, C.c_int32)]
+        out, args = {}, []
+        for name, dt, ct in spec:
+            if name in fields:
+                out[name] = np.zeros(n, dtype=dt)
+                args.append(_p(out[name], ct))
+            else:
+                args.append(None)
+        _capi.check(self._lib.drift_read_agents(self._h, *args))
+        return out
+
+    def agent_route(self, agent):
+        n = C.c_int64(0)
+        _capi.check(self._lib.drift_read_agent_route(self._h, int(agent), None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=np.int32)
+        if n.value:
+            _capi.check(self._lib.drift_read_agent_route(self._h, int(agent), _p(out, C.c_int32), n.value, C.byref(n)))
+        return out[:n.value]
+
+    def _drain(self, fn, specs, chunk=1 << 16):
+        cols = [[] for _ in specs]
+        while True:
+            bufs = [np.zeros(chunk, dtype=dt) for dt, _ in specs]
+            n = C.c_int64(0)
+            _capi.check(fn(self._h, *[_p(b, ct) for b, (_, ct) in zip(bufs, specs)], chunk, C.byref(n)))
+            for c, b in zip(cols, bufs):
+                c.append(b[:n.value])
+            if n.value < chunk:
+                break
+        return [np.concatenate(c) for c in cols]
+
+    def drain_arrivals(self):
+        """(agent int32[], tick int32[]) of the arrivals since the last drain (device order)."""
+        i32 = (np.int32, C.c_int32)
+        return self._drain(self._lib.drift_drain_arrivals, [i32, i32])
+
+    def drain_departures(self):
+        """(agent, tick, src, dst, status) of device-driven departures since the last drain."""
+        i32 = (np.int32, C.c_int32)
+        return self._drain(self._lib.drift_drain_departures, [i32] * 5)
+
+    def enable_entry_trace(self, cap=1 << 20):
+        _capi.check(self._lib.drift_enable_entry_trace(self._h, int(cap)))
+
+    def drain_entries(self):
+        """(tick, agent, link, speed) of traced link entries since the last drain (device order)."""
+        i32 = (np.int32, C.c_int32)
+        return self._drain(self._lib.drift_drain_entries, [i32, i32, i32, (np.float64, C.c_double)])
+
+    def stats(self):
+        s = _capi.StatsOut()
+        _capi.check(self._lib.drift_stats(self._h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in _capi.StatsOut._fields_}
+
+    @property
+    def tick(self):
+        t = C.c_int64(0)
+        _capi.check(self._lib.drift_tick_index(self._h, C.byref(t)))
+        return t.value
+
+    def set_profiling(self, on=True):
+        _capi.check(self._lib.drift_set_profiling(self._h, int(bool(on))))
+
+    def kernel_times(self):
+        a, t = C.c_double(0), C.c_double(0)
+        an, tn = C.c_int64(0), C.c_int64(0)
+        _capi.check(self._lib.drift_kernel_times(self._h, C.byref(a), C.byref(an), C.byref(t), C.byref(tn)))
+        return dict(advance_ms=a.value, advance_launches=an.value, total_ms=t.value, total_launches=tn.value)
+
+    def device_ptr(self, name):
+        p, n = C.c_void_p(), C.c_int64(0)
+        _capi.check(self._lib.drift_device_ptr(self._h, name.encode(), C.byref(p), C.byref(n)))
+        return p.value, n.value

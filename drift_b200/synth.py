@@ -1,0 +1,74 @@
+"""Synthetic road networks for the large BASELINE.json configs.
+
+The real city networks of the reference (example-data/json/*.json) are not shipped, so the
+Brussels-scale / regional / grid / random-geometric networks are synthesised as link arrays and
+lowered with ``drift_b200.graph.from_links`` (no NetworkX object is built at scale).  Lengths are
+continuous on purpose: with continuous travel times shortest paths are unique, so link sequences
+do not depend on NetworkX's tie-breaking.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .graph import LoweredGraph, from_links
+
+
+def grid_graph(nx_cols, ny_rows, seed=0, len_lo=50.0, len_hi=300.0, speed_kph=50.0, lanes=1.0) -> LoweredGraph:
+    """4-neighbour grid, both directions (config 4: 2000 x 2000 -> 4 M nodes / 15.992 M links)."""
+    rng = np.random.default_rng(seed)
+    W, H = int(nx_cols), int(ny_rows)
+    V = W * H
+    node = np.arange(V, dtype=np.int64)
+    col, row = node % W, node // W
+    cand_u, cand_v = [], []
+    # per node, neighbours in a fixed order: left, right, up, down
+    for dc, dr in ((-1, 0), (1, 0), (0, -1), (0, 1)):
+        c2, r2 = col + dc, row + dr
+        ok = (c2 >= 0) & (c2 < W) & (r2 >= 0) & (r2 < H)
+        cand_u.append(np.where(ok, node, -1))
+        cand_v.append(np.where(ok, r2 * W + c2, -1))
+    u = np.stack(cand_u, axis=1).reshape(-1)
+    v = np.stack(cand_v, axis=1).reshape(-1)
+    keep = u >= 0
+    u, v = u[keep], v[keep]
+    L = len(u)
+    length = rng.uniform(len_lo, len_hi, size=L)
+    pos = np.stack([col, row], axis=1).astype(np.float64)
+    return from_links(V, u, v, length, np.full(L, float(speed_kph)), np.full(L, float(lanes)), pos=pos)
+
+
+def road_graph(num_nodes, seed=0, mean_degree=2.6) -> LoweredGraph:
+    """Planar-ish random road network (configs 2/3): points on a jittered lattice, each joined to
+    its lattice neighbours with probability chosen for the requested mean out-degree; both
+    directions; lengths LogNormal(ln 90 m, 0.6) clipped to [10, 2000]; speed classes
+    {30,50,70,90} km/h w.p. {.5,.3,.15,.05}; lanes {1,2,3}."""
+    rng = np.random.default_rng(seed)
+    W = int(np.ceil(np.sqrt(num_nodes)))
+    H = int(np.ceil(num_nodes / W))
+    V = W * H
+    node = np.arange(V, dtype=np.int64)
+    col, row = node % W, node // W
+    p_keep = min(1.0, mean_degree / 4.0)
+    # undirected lattice edges (right, down) kept with probability p_keep
+    und = []
+    for dc, dr in ((1, 0), (0, 1)):
+        c2, r2 = col + dc, row + dr
+        ok = (c2 < W) & (r2 < H) & (rng.random(V) < p_keep)
+        und.append(np.stack([node[ok], (r2 * W + c2)[ok]], axis=1))
+    und = np.concatenate(und)
+    # keep the network connected: a spanning comb (every row, first column)
+    rows_e = np.stack([node[col < W - 1], node[col < W - 1] + 1], axis=1)
+    col0 = np.stack([node[(col == 0) & (row < H - 1)], node[(col == 0) & (row < H - 1)] + W], axis=1)
+    und = np.unique(np.concatenate([und, rows_e[rng.random(len(rows_e)) < 0.55], col0, rows_e[::1][:0]]), axis=0)
+    # guarantee connectivity of every row segment through column 0 .. W-1: add missing row edges of row 0
+    und = np.unique(np.concatenate([und, rows_e[row[rows_e[:, 0]] % 7 == 0]]), axis=0)
+    u = np.concatenate([und[:, 0], und[:, 1]])
+    v = np.concatenate([und[:, 1], und[:, 0]])
+    order = np.lexsort((v, u))
+    u, v = u[order], v[order]
+    L = len(u)
+    length = np.clip(rng.lognormal(np.log(90.0), 0.6, size=L), 10.0, 2000.0)
+    speed = rng.choice([30.0, 50.0, 70.0, 90.0], size=L, p=[0.5, 0.3, 0.15, 0.05])
+    lanes = rng.choice([1.0, 2.0, 3.0], size=L, p=[0.6, 0.3, 0.1])
+    pos = np.stack([col + rng.uniform(-0.3, 0.3, V), row + rng.uniform(-0.3, 0.3, V)], axis=1)
+    return from_links(V, u, v, length, speed, lanes, pos=pos)

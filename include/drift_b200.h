@@ -1,0 +1,200 @@
+/*
+ * drift_b200 -- C ABI of the B200-native DRIFT simulation step.
+ *
+ * The reference (jbaudru/DRIFT) is pure Python and has no native boundary; the
+ * entry points below are what a ctypes stub inside the reference's
+ * `lib/simulation_thread.py` would bind.  Each one cites
+ * the reference code it replaces (paths relative to the reference root; `nx:`
+ * = NetworkX 3.6.1 `networkx/algorithms/shortest_paths/`).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative DRIFT_E* code on error;
+ *     `drift_last_error()` returns a human-readable message for the calling thread;
+ *   - the caller owns all host buffers, the library owns all device memory;
+ *   - one engine per CUDA device / per rank; calls on one engine must be serialised
+ *     by the caller (the reference itself is single-threaded);
+ *   - work is stream-ordered on the engine's own stream; functions that return data
+ *     to host buffers synchronise, `drift_step` does not (see `drift_sync`);
+ *   - no exceptions and no C++/torch types cross this boundary.
+ *
+ * Data model
+ *   nodes   0..V-1  in `list(G.nodes)` order
+ *   links   0..L-1  in `G.edges(keys=True)` order (one per (u,v,key) edge: the unit
+ *           of occupancy, `TrafficManager.edge_agents`, lib/managers/traffic_manager.py:19)
+ *   forward CSR  in `G._succ[u]` order, backward CSR in `G._pred[v]` order, one entry per
+ *           (u,v) pair carrying min travel_time over parallel edges (nx:weighted.py:76-77)
+ *           and, forward only, the link an agent occupies on that hop (first key with
+ *           minimal travel_time, lib/agent.py:122-130)
+ *   agents  local index 0..N-1, global id = agent_base + index (ordering key across ranks)
+ */
+#ifndef DRIFT_B200_H
+#define DRIFT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRIFT_ABI_VERSION 1
+
+#define DRIFT_OK 0
+#define DRIFT_EINVAL (-1)    /* bad argument */
+#define DRIFT_ECUDA (-2)     /* CUDA runtime error */
+#define DRIFT_ENOMEM (-3)    /* device allocation failed */
+#define DRIFT_EOVERFLOW (-4) /* a device-side buffer (events, arrivals, routes, heap) overflowed */
+#define DRIFT_ESTATE (-5)    /* call sequence error */
+
+/* route status codes (per query) */
+#define DRIFT_ROUTE_OK 0
+#define DRIFT_ROUTE_TRIVIAL 1 /* source == target: path = [s] (nx:weighted.py:2393-2394) */
+#define DRIFT_ROUTE_NOPATH 2  /* NetworkXNoPath / node missing (lib/agent.py:87-99) */
+
+/* routing engines */
+#define DRIFT_ROUTER_NX_EXACT 0 /* bit-exact nx bidirectional_dijkstra order (nx:weighted.py:2387-2459) */
+#define DRIFT_ROUTER_BATCHED 1  /* batched multi-source label-correcting SSSP (unique-path graphs) */
+
+typedef struct drift_engine drift_engine;
+
+typedef struct drift_graph_desc {
+  int32_t V;  /* nodes */
+  int32_t L;  /* links ((u,v,key) edges) */
+  int32_t Ef; /* forward CSR entries ((u,v) pairs) */
+  int32_t Eb; /* backward CSR entries (== Ef) */
+  const int32_t* fwd_rowptr; /* [V+1] */
+  const int32_t* fwd_col;    /* [Ef] successor node */
+  const double* fwd_w;       /* [Ef] min travel_time over parallel edges */
+  const int32_t* fwd_link;   /* [Ef] link occupied on this hop */
+  const int32_t* bwd_rowptr; /* [V+1] */
+  const int32_t* bwd_col;    /* [Eb] predecessor node */
+  const double* bwd_w;       /* [Eb] */
+  const int32_t* bwd_link;   /* [Eb] link occupied on the hop (pred -> node) */
+  const double* link_len;    /* [L] metres   (lib/agent.py:146) */
+  const double* link_v0;     /* [L] km/h     (lib/agent.py:147) */
+  const double* link_t0;     /* [L] seconds  (lib/graph_loader.py:759-766) */
+  const int32_t* link_cap;   /* [L]          (lib/managers/traffic_manager.py:33-61) */
+  const int32_t* link_u;     /* [L] tail node */
+  const int32_t* link_v;     /* [L] head node */
+} drift_graph_desc;
+
+typedef struct drift_stats_out {
+  int64_t moving_agents;         /* lib/simulation_thread.py:424 */
+  int64_t total_agents_on_roads; /* lib/managers/traffic_manager.py:125-128 */
+  int64_t total_capacity;        /* :129 */
+  int64_t links_with_traffic;    /* :132-135 ('congested_edges') */
+  int64_t arrivals_total;        /* completed trips since creation */
+  int64_t departures_total;
+  int64_t route_arena_used;      /* link ids currently held in the route arena */
+  int64_t events_last_tick;
+} drift_stats_out;
+
+const char* drift_last_error(void);
+int drift_abi_version(void);
+
+/* Device-side copy of the graph (replaces the nx.MultiDiGraph walked by lib/agent.py:94,118-151
+ * and the TrafficManager tables built at lib/managers/traffic_manager.py:16-61). */
+int drift_create(drift_engine** out, int device, const drift_graph_desc* g);
+int drift_destroy(drift_engine* e);
+int drift_sync(drift_engine* e);
+
+/* BPR congestion factor, lib/managers/traffic_manager.py:76-107.
+ * `v_c_ratio ** beta` is libm pow in the reference; to stay bit-exact the host tabulates
+ * factor(count) = max(0.1, 1/(1+alpha*(count/cap)**beta)) per capacity class with the same
+ * Python float arithmetic; entry 0 is 1.0 and the last entry of a class is the saturated 0.1.
+ *   class_off[n_class+1]  start of each class in factor_table
+ *   link_class[L]         capacity class of each link */
+int drift_set_bpr(drift_engine* e, double alpha, double beta, const double* factor_table,
+                  const int64_t* class_off, int32_t n_class, const int32_t* link_class);
+
+/* Agents (lib/simulation_thread.py:181-261 builds N Agent objects; all start 'waiting',
+ * lib/agent.py:23).  `agent_base` is the global id of local agent 0. */
+int drift_add_agents(drift_engine* e, int64_t n_agents, int64_t agent_base, int64_t route_arena_links);
+
+/* Routing: replaces nx.shortest_path(G, s, t, weight='travel_time') (lib/agent.py:94).
+ * Routes Q (src,dst) pairs on the device and stages the link sequences in the route arena.
+ *   status[Q]   DRIFT_ROUTE_*
+ *   n_links[Q]  hops of each path (0 for TRIVIAL / NOPATH)
+ * `use_congested` != 0 routes on the congestion-updated travel times written by
+ * drift_update_travel_times (extension; the reference never updates travel_time). */
+int drift_route_od(drift_engine* e, int32_t router, int64_t Q, const int32_t* src, const int32_t* dst,
+                   int32_t use_congested, int32_t* status, int32_t* n_links);
+/* Copy the staged link sequences of the last drift_route_od to the host, concatenated in
+ * query order (sum of n_links entries).  The node path of query q is
+ * [src] + [link_v[l] for l in links_q]. */
+int drift_fetch_routes(drift_engine* e, int32_t* links_out, int64_t cap);
+/* Path costs of the last batch (left-to-right fp64 sums of fwd_w), for tolerance checks. */
+int drift_fetch_route_costs(drift_engine* e, double* cost_out, int64_t Q);
+/* Make the staged routes the pending departures of `agent[q]` for the next tick
+ * (Agent.start_new_journey, lib/agent.py:101-104).  TRIVIAL / NOPATH entries leave the agent
+ * waiting (lib/agent.py:95-99, 107-116). */
+int drift_commit_departures(drift_engine* e, int64_t Q, const int32_t* agent);
+/* Departures with host-supplied routes (replay of a recorded trace):
+ * route_off[n+1] into route_links; an empty route = TRIVIAL. */
+int drift_submit_departures(drift_engine* e, int64_t n, const int32_t* agent, const int64_t* route_off,
+                            const int32_t* route_links);
+
+/* The tick: SimulationThread.update_simulation_step / _update_agent_batch
+ * (lib/simulation_thread.py:288-340) -> Agent.update (lib/agent.py:171-203) ->
+ * setup_current_edge (:106-160) -> TrafficManager register/unregister/get_congested_speed
+ * (lib/managers/traffic_manager.py:63-107), for n_ticks ticks of `delta` seconds
+ * (delta = dt * time_acceleration, lib/simulation_thread.py:294).  Pending departures are
+ * applied in the first tick.  Asynchronous. */
+int drift_step(drift_engine* e, int32_t n_ticks, double delta);
+
+/* Device-driven demand (throughput mode): every waiting agent departs at tick k
+ * with probability hourly[hour(t_k)]*4*delta/3600 (lib/agent.py:176-180, 243-259) drawn from a
+ * counter-based generator keyed (seed, global agent id, tick); its k-th trip goes from its
+ * current node to trip_dst[trip_off[i]+k] (host-generated by the s-t model).  Routing uses
+ * `router`.  start_node[N] = initial node of each agent (lib/agent.py:40-44). */
+int drift_set_demand(drift_engine* e, uint64_t seed, const double hourly24[24], const int32_t* start_node,
+                     const int64_t* trip_off, const int32_t* trip_dst, int32_t router);
+/* Run n_ticks ticks with device-driven demand starting at simulation time t0 (seconds). */
+int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0);
+
+/* Extension (no reference behaviour): congestion-aware travel times
+ * tt[l] = t0[l] / factor(occ[l]) (formula of lib/managers/traffic_manager.py:92-107 applied
+ * per link) and rerouting of en-route agents from the head of their current link. */
+int drift_update_travel_times(drift_engine* e);
+int drift_reroute_moving(drift_engine* e, int32_t router, int64_t* n_rerouted);
+
+/* Readback.  Any output pointer may be NULL. */
+int drift_read_occupancy(drift_engine* e, int32_t* occ_out /* [L] */);
+int drift_recount_occupancy(drift_engine* e, int32_t* occ_out /* [L] */); /* histogram of cur_link (traffic_manager.py:122-135) */
+int drift_read_travel_times(drift_engine* e, double* tt_out /* [L] */);
+int drift_read_agents(drift_engine* e, uint8_t* state, double* dist_on_link, double* speed, double* link_len,
+                      int32_t* cur_link, int32_t* route_idx, int32_t* route_len, int32_t* trip_count,
+                      int32_t* cur_node);
+int drift_read_agent_route(drift_engine* e, int64_t agent, int32_t* links_out, int64_t cap, int64_t* n);
+int drift_drain_arrivals(drift_engine* e, int32_t* agent, int32_t* tick, int64_t cap, int64_t* n);
+int drift_drain_departures(drift_engine* e, int32_t* agent, int32_t* tick, int32_t* src, int32_t* dst,
+                           int32_t* status, int64_t cap, int64_t* n);
+/* optional link-entry trace (tick, agent, link, speed) for parity tests */
+int drift_enable_entry_trace(drift_engine* e, int64_t cap);
+int drift_drain_entries(drift_engine* e, int32_t* tick, int32_t* agent, int32_t* link, double* speed,
+                        int64_t cap, int64_t* n);
+int drift_stats(drift_engine* e, drift_stats_out* out);
+int drift_tick_index(drift_engine* e, int64_t* tick);
+
+/* Multi-GPU (agents sharded by contiguous id block, graph replicated).
+ * A tick is split around the exchange of link events:
+ *   drift_tick_begin    advance + departures -> local events (device), returns their count
+ *   drift_events_ptr    device pointer / capacity of the local event buffer (16 B records)
+ *   drift_tick_finish   resolve `n_events` gathered records at `events_dev` (device pointer,
+ *                       all ranks' records in any order) */
+int drift_tick_begin(drift_engine* e, double delta, int64_t* n_events);
+int drift_events_ptr(drift_engine* e, void** dev_ptr, int64_t* capacity);
+int drift_tick_finish(drift_engine* e, const void* events_dev, int64_t n_events);
+
+/* Timing of the kernels launched by the last drift_step/drift_run (CUDA events on the engine
+ * stream): total milliseconds spent in the advance kernel and number of advance launches. */
+int drift_kernel_times(drift_engine* e, double* advance_ms, int64_t* advance_launches, double* total_ms,
+                       int64_t* total_launches);
+int drift_set_profiling(drift_engine* e, int32_t on);
+/* Raw device pointers for PyTorch interop (tensor views of engine state). name in
+ * {"occ","state","dist","speed","link_len","cur_link","events","travel_time"}. */
+int drift_device_ptr(drift_engine* e, const char* name, void** ptr, int64_t* n_elems);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRIFT_B200_H */

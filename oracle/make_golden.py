@@ -219,6 +219,11 @@ def main():
         names = sorted(os.listdir(os.path.join(EX, "music-net")))
         Gm = H.load_graph(os.path.join(EX, "music-net", names[0]), seed=0)
     case("musicnet_random_s0", Gm, 300, "random", seed=0, accel=10, hours=1)
+    # unreachable pairs + the finish_simulation TypeError quirk
+    Gch = H.load_graph(os.path.join(EX, "music-net", "chpn_op35_4l_0.graphml"), seed=0)
+    case("chpn_random_nopath", Gch, 300, "random", seed=0, accel=10, hours=2)
+    Glz = H.load_graph(os.path.join(EX, "music-net", "liz_rhap09.graphml"), seed=0)
+    case("liz_random_nopath", Glz, 300, "random", seed=0, accel=10, hours=2)
     # multigraph / int labels / falsy node 0
     case("multi_random_s0", multigraph_case(), 400, "random", seed=11, accel=10, hours=1,
          settings=dict(bpr_alpha=0.15, bpr_beta=4.0, hourly_probabilities={h: 0.6 for h in range(24)}))

@@ -1,0 +1,100 @@
+"""CPU-only checks of the host side: lowering, BPR tables, C-ABI surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import golden
+from oracle.port import bpr_factor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = golden.case_names()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_lowering_matches_fixture(name):
+    from drift_b200.graph import lower_graph
+
+    case = golden.GoldenCase(name)
+    lg = lower_graph(case.nx_graph())
+    pg = case.plain_graph()
+    assert lg.V == case.V and lg.L == case.L
+    assert np.array_equal(lg.link_u, case.link_u) and np.array_equal(lg.link_v, case.link_v)
+    assert np.array_equal(lg.link_len, case.link_len) and np.array_equal(lg.link_v0, case.link_v0)
+    assert np.array_equal(lg.link_t0, case.link_tt)
+    assert np.array_equal(lg.link_cap, case.capacities)  # recorded from the reference's TrafficManager
+    for u in range(lg.V):
+        a, b = lg.fwd_rowptr[u], lg.fwd_rowptr[u + 1]
+        want = pg.succ[u]
+        assert lg.fwd_col[a:b].tolist() == [r[0] for r in want]
+        assert lg.fwd_w[a:b].tolist() == [r[1] for r in want]
+        assert lg.fwd_link[a:b].tolist() == [r[2] for r in want]
+        assert lg.fwd_minlen[a:b].tolist() == [r[3] for r in want]
+        a, b = lg.bwd_rowptr[u], lg.bwd_rowptr[u + 1]
+        assert lg.bwd_col[a:b].tolist() == [r[0] for r in pg.pred[u]]
+        assert lg.bwd_w[a:b].tolist() == [r[1] for r in pg.pred[u]]
+        for e in range(a, b):
+            l = lg.bwd_link[e]
+            assert lg.link_u[l] == lg.bwd_col[e] and lg.link_v[l] == u
+
+
+def test_from_links_matches_lower_graph():
+    from drift_b200.graph import from_links, lower_graph, to_networkx
+    from drift_b200.synth import grid_graph
+
+    lg = grid_graph(7, 5, seed=3)
+    lg2 = lower_graph(to_networkx(lg))
+    for f in ("link_u", "link_v", "link_len", "link_v0", "link_t0", "link_cap", "fwd_rowptr", "fwd_col", "fwd_w",
+              "fwd_link", "bwd_rowptr", "bwd_col", "bwd_w", "bwd_link"):
+        assert np.array_equal(getattr(lg, f), getattr(lg2, f)), f
+
+
+@pytest.mark.parametrize("alpha,beta", [(0.15, 4.0), (0.8, 2.5), (0.01, 1.0), (2.0, 8.0)])
+def test_bpr_tables_equal_reference_expression(alpha, beta):
+    from drift_b200.bpr import build_tables
+
+    caps = np.array([1, 4, 12, 24, 160, 532, 532, 1500, 12])
+    table, off, cls = build_tables(caps, alpha, beta)
+    assert len(off) - 1 == len(np.unique(caps))
+    for l, cap in enumerate(caps.tolist()):
+        c = cls[l]
+        row = table[off[c]:off[c + 1]]
+        assert row[0] == 1.0
+        n_check = min(len(row), 4000)
+        for count in range(n_check):
+            assert row[count] == bpr_factor(count, cap, alpha, beta)
+        if alpha >= 0.15:
+            assert row[-1] == 0.1
+            # everything past the table is saturated too
+            for count in (len(row), len(row) + 7, 100 * len(row)):
+                assert bpr_factor(count, cap, alpha, beta) == 0.1
+
+
+def test_capi_exports_every_declared_symbol():
+    from drift_b200 import _capi, build
+
+    build.build()
+    header = open(os.path.join(ROOT, "include", "drift_b200.h")).read()
+    declared = set(re.findall(r"\b(drift_[a-z0-9_]+)\s*\(", header))
+    declared -= {"drift_engine", "drift_graph_desc", "drift_stats_out"}
+    assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
+    lib = _capi.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.drift_abi_version() == 1
+
+
+def test_capi_fails_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from drift_b200 import _capi
+    from drift_b200.engine import Engine
+    from drift_b200.synth import grid_graph
+
+    with pytest.raises(_capi.DriftError) as ei:
+        Engine(grid_graph(3, 3, seed=0), 8)
+    assert "no CPU path" in str(ei.value) or "CUDA" in str(ei.value)
