@@ -55,6 +55,7 @@ SIGNATURES = {
     "drift_submit_departures": (C.c_int, [ENGINE, C.c_int64, c_i32p, c_i64p, c_i32p]),
     "drift_step": (C.c_int, [ENGINE, C.c_int32, C.c_double]),
     "drift_set_demand": (C.c_int, [ENGINE, C.c_uint64, c_f64p, c_i32p, c_i64p, c_i32p, C.c_int32]),
+    "drift_push_trips": (C.c_int, [ENGINE, c_i64p, c_i32p]),
     "drift_run": (C.c_int, [ENGINE, C.c_int32, C.c_double, C.c_double]),
     "drift_update_travel_times": (C.c_int, [ENGINE]),
     "drift_reroute_moving": (C.c_int, [ENGINE, C.c_int32, c_i64p]),

@@ -79,6 +79,7 @@ struct AgentArrays {
   int64_t* route_off;   // [Npad] start of the route in the arena
   int32_t* trip_count;  // [Npad]
   int32_t* cur_node;    // [Npad] Agent.target: where the next trip starts
+  int32_t* chain_pos;   // [Npad] next entry of the agent's host-generated trip chain
   int64_t n;
   uint32_t base;  // global id of local agent 0
 };

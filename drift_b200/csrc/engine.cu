@@ -93,7 +93,7 @@ struct drift_engine {
   uint32_t agent_base = 0;
   DevBuf<uint8_t> state;
   DevBuf<double> dist, speed, elen;
-  DevBuf<int32_t> cur_link, route_idx, route_len, trip_count, cur_node;
+  DevBuf<int32_t> cur_link, route_idx, route_len, trip_count, cur_node, chain_pos;
   DevBuf<int64_t> route_off;
   DevBuf<int32_t> arena;
   int64_t arena_cap = 0;
@@ -120,6 +120,14 @@ struct drift_engine {
   DevBuf<HeapItem> r_heap;
   int32_t r_workers = 0;
   int64_t r_heap_cap = 0;
+  // tree cache + tree builder scratch (batched router)
+  DevBuf<int32_t> t_slot_of, t_next, t_job_dst, t_job_slot, t_ctl;  // t_ctl: n_slots, n_jobs, job_cursor
+  DevBuf<unsigned long long> t_dist;
+  DevBuf<uint32_t> t_stamp, t_infar, t_iter;
+  DevBuf<int32_t> t_lists;
+  int32_t t_max_slots = 0, t_blocks = 0;
+  double t_delta = 1.0;
+  int64_t tree_budget_bytes = (int64_t)48 << 30;
   // rings
   DevBuf<int32_t> arr_agent, arr_tick;
   int64_t arr_cap = 0;
@@ -162,6 +170,7 @@ struct drift_engine {
     a.route_off = route_off.p;
     a.trip_count = trip_count.p;
     a.cur_node = cur_node.p;
+    a.chain_pos = chain_pos.p;
     a.n = N;
     a.base = agent_base;
     return a;
@@ -227,6 +236,7 @@ int check_overflow(drift_engine* e, const Counters& c) {
   if (c.overflow & kOvfHeap) what += " router-heap";
   if (c.overflow & kOvfDepLog) what += " departure-log";
   if (c.overflow & kOvfEntries) what += " entry-trace";
+  if (c.overflow & kOvfStage) what += " tree-cache";
   return fail(DRIFT_EOVERFLOW, "device buffer overflow:%s", what.c_str());
 }
 
@@ -269,9 +279,77 @@ int ensure_qcap(drift_engine* e, int64_t Q) {
   return DRIFT_OK;
 }
 
-// launches the router over the first Q entries of q_src/q_dst (device), count known on host
-int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_congested) {
+int ensure_trees(drift_engine* e) {
+  if (e->t_max_slots) return DRIFT_OK;
+  const int64_t V = e->V;
+  int64_t slots = std::min<int64_t>(V, e->tree_budget_bytes / (4 * V));
+  slots = std::max<int64_t>(slots, 1);
+  // resident builder blocks: 32 B of scratch per node each
+  int64_t blocks = std::min<int64_t>(kSMs * 6, ((int64_t)8 << 30) / (32 * V));
+  blocks = std::max<int64_t>(blocks, 1);
+  CU(e->t_slot_of.alloc(V, false));
+  CU(cudaMemset(e->t_slot_of.p, 0xff, sizeof(int32_t) * V));
+  CU(e->t_next.alloc(slots * V, false));
+  CU(e->t_job_dst.alloc(slots));
+  CU(e->t_job_slot.alloc(slots));
+  CU(e->t_ctl.alloc(4));
+  CU(e->t_dist.alloc(blocks * V, false));
+  CU(e->t_stamp.alloc(blocks * V, true));
+  CU(e->t_infar.alloc(blocks * V, true));
+  CU(e->t_iter.alloc(blocks, true));
+  CU(e->t_lists.alloc(blocks * 4 * V, false));
+  e->t_max_slots = (int32_t)slots;
+  e->t_blocks = (int32_t)blocks;
+  return DRIFT_OK;
+}
+
+int invalidate_trees(drift_engine* e) {
+  if (!e->t_max_slots) return DRIFT_OK;
+  CU(cudaMemsetAsync(e->t_slot_of.p, 0xff, sizeof(int32_t) * e->V, e->stream));
+  CU(cudaMemsetAsync(e->t_ctl.p, 0, 4 * sizeof(int32_t), e->stream));
+  return DRIFT_OK;
+}
+
+// launches the router over the staged q_src/q_dst (device).  Q is the host-known batch size or an
+// upper bound; when n_dev != nullptr the kernels read the actual size from device memory.
+int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_congested, const int32_t* n_dev = nullptr) {
   if (Q <= 0) return DRIFT_OK;
+  RouteOut out;
+  out.status = e->q_status.p;
+  out.n_links = e->q_len.p;
+  out.off = e->q_off.p;
+  out.cost = e->q_cost.p;
+  const double* wf = use_congested ? e->fwd_wc.p : e->fwd_w.p;
+  const double* wb = use_congested ? e->bwd_wc.p : e->bwd_w.p;
+  const double* lc = use_congested ? e->link_tt.p : e->link_t0.p;
+  if (router == DRIFT_ROUTER_BATCHED) {
+    int rc = ensure_trees(e);
+    if (rc) return rc;
+    TreeCache tc;
+    tc.slot_of = e->t_slot_of.p;
+    tc.next_link = e->t_next.p;
+    tc.n_slots = e->t_ctl.p + 0;
+    tc.n_jobs = e->t_ctl.p + 1;
+    tc.job_cursor = e->t_ctl.p + 2;
+    tc.max_slots = e->t_max_slots;
+    tc.job_dst = e->t_job_dst.p;
+    tc.job_slot = e->t_job_slot.p;
+    TreeScratch ts;
+    ts.dist = e->t_dist.p;
+    ts.stamp = e->t_stamp.p;
+    ts.infar = e->t_infar.p;
+    ts.lists = e->t_lists.p;
+    ts.iter = e->t_iter.p;
+    CU(cudaMemsetAsync(e->t_ctl.p + 1, 0, 2 * sizeof(int32_t), e->stream));
+    const int gq = grid_for(Q, 256, kSMs * 4);
+    k_tree_requests<<<gq, 256, 0, e->stream>>>(Q, e->q_dst.p, e->V, tc, e->ctr.p, n_dev);
+    k_build_trees<<<e->t_blocks, kTreeThreads, 0, e->stream>>>(e->graph(), wb, wf, e->t_delta, tc, ts);
+    k_extract_paths<<<gq, 256, 0, e->stream>>>(e->graph(), Q, n_dev, e->q_src.p, e->q_dst.p, tc, e->arena.p,
+                                                (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
+    CU(cudaGetLastError());
+    e->total_launches += 3;
+    return DRIFT_OK;
+  }
   int rc = ensure_router(e, Q);
   if (rc) return rc;
   RouteScratch sc;
@@ -282,19 +360,11 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
   sc.epoch = e->r_epoch.p;
   sc.heap_cap = e->r_heap_cap;
   sc.workers = (int32_t)std::min<int64_t>(e->r_workers, Q);
-  RouteOut out;
-  out.status = e->q_status.p;
-  out.n_links = e->q_len.p;
-  out.off = e->q_off.p;
-  out.cost = e->q_cost.p;
-  const double* wf = use_congested ? e->fwd_wc.p : e->fwd_w.p;
-  const double* wb = use_congested ? e->bwd_wc.p : e->bwd_w.p;
-  const double* lc = use_congested ? e->link_tt.p : e->link_t0.p;
-  (void)router;  // DRIFT_ROUTER_BATCHED falls through to the exact router until K5b lands
   const int blocks = (sc.workers + 31) / 32;
   k_route_nx<<<blocks, 32, 0, e->stream>>>(e->graph(), wf, wb, Q, e->q_src.p, e->q_dst.p, sc, e->arena.p,
-                                           (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
+                                           (unsigned long long)e->arena_cap, e->ctr.p, out, lc, n_dev);
   CU(cudaGetLastError());
+  e->total_launches += 1;
   return DRIFT_OK;
 }
 
@@ -426,6 +496,12 @@ int drift_create(drift_engine** out, int device, const drift_graph_desc* g) {
   CUX(cudaMallocHost(&e->h_ctr, sizeof(Counters)));
   e->total_capacity = 0;
   for (int32_t l = 0; l < g->L; ++l) e->total_capacity += g->link_cap[l];
+  {  // bucket width of the near-far tree builder: a few average hops
+    double sum = 0;
+    for (int32_t k = 0; k < g->Ef; ++k) sum += g->fwd_w[k];
+    e->t_delta = g->Ef ? 4.0 * sum / g->Ef : 1.0;
+    if (!(e->t_delta > 0)) e->t_delta = 1.0;
+  }
   for (int h = 0; h < 24; ++h) e->hourly[h] = 0.05;
 #undef CUX
   *out = e;
@@ -482,6 +558,7 @@ int drift_add_agents(drift_engine* e, int64_t n_agents, int64_t agent_base, int6
   CU(e->route_off.alloc(Np));
   CU(e->trip_count.alloc(Np));
   CU(e->cur_node.alloc(Np));
+  CU(e->chain_pos.alloc(Np));
   if (route_arena_links <= 0) route_arena_links = std::max<int64_t>((int64_t)1 << 20, n_agents * 64);
   CU(e->arena.alloc(route_arena_links, false));
   e->arena_cap = route_arena_links;
@@ -578,7 +655,7 @@ int drift_commit_departures(drift_engine* e, int64_t Q, const int32_t* agent) {
   CU(cudaMemcpyAsync(e->q_agent.p, agent, sizeof(int32_t) * Q, cudaMemcpyHostToDevice, e->stream));
   k_commit<<<grid_for(Q, 256, kSMs), 256, 0, e->stream>>>(Q, e->q_agent.p, e->q_off.p, e->q_len.p, e->ctr.p,
                                                            e->pend_agent.p, e->pend_off.p, e->pend_len.p,
-                                                           (int32_t)e->pend_cap);
+                                                           (int32_t)e->pend_cap, nullptr);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(e->stream));  // `agent` is a caller buffer
   return DRIFT_OK;
@@ -609,7 +686,7 @@ int drift_submit_departures(drift_engine* e, int64_t n, const int32_t* agent, co
                                                                  e->q_off.p, e->q_len.p);
   k_commit<<<grid_for(n, 256, kSMs), 256, 0, e->stream>>>(n, e->q_agent.p, e->q_off.p, e->q_len.p, e->ctr.p,
                                                            e->pend_agent.p, e->pend_off.p, e->pend_len.p,
-                                                           (int32_t)e->pend_cap);
+                                                           (int32_t)e->pend_cap, nullptr);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(e->stream));
   e->last_Q = 0;
@@ -636,7 +713,7 @@ int drift_step(drift_engine* e, int32_t n_ticks, double delta) {
 
 int drift_set_demand(drift_engine* e, uint64_t seed, const double hourly24[24], const int32_t* start_node,
                      const int64_t* trip_off, const int32_t* trip_dst, int32_t router) {
-  if (!e || !hourly24 || !start_node || !trip_off || !trip_dst) return fail(DRIFT_EINVAL, "drift_set_demand");
+  if (!e || !hourly24 || !start_node) return fail(DRIFT_EINVAL, "drift_set_demand");
   if (!e->N) return fail(DRIFT_ESTATE, "drift_set_demand: no agents");
   CU(cudaSetDevice(e->device));
   CU(cudaStreamSynchronize(e->stream));
@@ -645,12 +722,32 @@ int drift_set_demand(drift_engine* e, uint64_t seed, const double hourly24[24], 
   for (int64_t i = 0; i < e->N; ++i)
     if (start_node[i] < 0 || start_node[i] >= e->V) return fail(DRIFT_EINVAL, "drift_set_demand: bad start node");
   CU(cudaMemcpy(e->cur_node.p, start_node, sizeof(int32_t) * e->N, cudaMemcpyHostToDevice));
-  CU(e->trip_off.upload(trip_off, e->N + 1));
-  CU(e->trip_dst.upload(trip_dst, std::max<int64_t>(trip_off[e->N], 1)));
   e->demand_router = router;
-  e->have_demand = true;
   int rc = ensure_qcap(e, e->N);
   if (rc) return rc;
+  if (trip_off && trip_dst) {
+    rc = drift_push_trips(e, trip_off, trip_dst);
+    if (rc) return rc;
+  }
+  e->have_demand = true;
+  return DRIFT_OK;
+}
+
+int drift_push_trips(drift_engine* e, const int64_t* trip_off, const int32_t* trip_dst) {
+  if (!e || !trip_off || !trip_dst) return fail(DRIFT_EINVAL, "drift_push_trips");
+  if (!e->N) return fail(DRIFT_ESTATE, "drift_push_trips: no agents");
+  CU(cudaSetDevice(e->device));
+  const int64_t total = trip_off[e->N];
+  if (trip_off[0] != 0 || total < 0) return fail(DRIFT_EINVAL, "drift_push_trips: bad offsets");
+  if (e->trip_off.n < e->N + 1) CU(e->trip_off.alloc(e->N + 1, false));
+  if (e->trip_dst.n < std::max<int64_t>(total, 1)) {
+    CU(cudaStreamSynchronize(e->stream));
+    CU(e->trip_dst.alloc(std::max<int64_t>(total, 1) * 5 / 4 + 16, false));
+  }
+  CU(cudaMemcpyAsync(e->trip_off.p, trip_off, sizeof(int64_t) * (e->N + 1), cudaMemcpyHostToDevice, e->stream));
+  if (total)
+    CU(cudaMemcpyAsync(e->trip_dst.p, trip_dst, sizeof(int32_t) * total, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemsetAsync(e->chain_pos.p, 0, sizeof(int32_t) * e->Npad, e->stream));
   return DRIFT_OK;
 }
 
@@ -672,24 +769,20 @@ int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0) {
     k_prepare_requests<<<kSMs, 256, 0, e->stream>>>(e->agents(), c, e->dep_req.p, e->trip_off.p, e->trip_dst.p,
                                                     e->q_src.p, e->q_dst.p, e->q_agent.p);
     CU(cudaGetLastError());
-    // the exact router needs the host to know Q to size its worker pool: read it back
-    Counters hc;
-    rc = fetch_counters(e, &hc);
+    // batch size stays on the device: every kernel below reads n_dep_req itself (no host sync)
+    const int64_t Qmax = std::min<int64_t>(e->N, e->q_cap);
+    rc = launch_router(e, e->demand_router, Qmax, 0, &c->n_dep_req);
     if (rc) return rc;
-    const int64_t Q = hc.n_dep_req;
-    if (Q > 0) {
-      rc = launch_router(e, e->demand_router, Q, 0);
-      if (rc) return rc;
-      k_log_departures<<<grid_for(Q, 256, kSMs), 256, 0, e->stream>>>(
-          c, (int32_t)e->tick, e->q_agent.p, e->q_src.p, e->q_dst.p, e->q_status.p, e->dl_agent.p, e->dl_tick.p,
-          e->dl_src.p, e->dl_dst.p, e->dl_status.p, (unsigned long long)e->dl_cap, e->dl_drained);
-      k_commit<<<grid_for(Q, 256, kSMs), 256, 0, e->stream>>>(Q, e->q_agent.p, e->q_off.p, e->q_len.p, c,
-                                                               e->pend_agent.p, e->pend_off.p, e->pend_len.p,
-                                                               (int32_t)e->pend_cap);
-      CU(cudaGetLastError());
-      rc = inject_pending(e);
-      if (rc) return rc;
-    }
+    k_log_departures<<<kSMs, 256, 0, e->stream>>>(c, (int32_t)e->tick, e->q_agent.p, e->q_src.p, e->q_dst.p,
+                                                  e->q_status.p, e->dl_agent.p, e->dl_tick.p, e->dl_src.p,
+                                                  e->dl_dst.p, e->dl_status.p, (unsigned long long)e->dl_cap,
+                                                  e->dl_drained);
+    k_commit<<<kSMs, 256, 0, e->stream>>>(Qmax, e->q_agent.p, e->q_off.p, e->q_len.p, c, e->pend_agent.p,
+                                          e->pend_off.p, e->pend_len.p, (int32_t)e->pend_cap, &c->n_dep_req);
+    CU(cudaGetLastError());
+    e->total_launches += 3;
+    rc = inject_pending(e);
+    if (rc) return rc;
     rc = tick_finish(e, e->events.p, &c->n_events, 2 * e->N);
     if (rc) return rc;
   }
@@ -700,8 +793,10 @@ int drift_update_travel_times(drift_engine* e) {
   if (!e || !e->have_bpr) return fail(DRIFT_ESTATE, "drift_update_travel_times");
   CU(cudaSetDevice(e->device));
   k_travel_times<<<grid_for(e->L, 256, kSMs * 8), 256, 0, e->stream>>>(e->links());
+  k_refresh_weights<<<grid_for(e->Ef, 256, kSMs * 8), 256, 0, e->stream>>>(e->Ef, e->link_tt.p, e->fwd_link.p,
+                                                                           e->bwd_link.p, e->fwd_wc.p, e->bwd_wc.p);
   CU(cudaGetLastError());
-  return DRIFT_OK;
+  return invalidate_trees(e);  // cached trees were built on the old weights
 }
 
 int drift_reroute_moving(drift_engine* e, int32_t router, int64_t* n_rerouted) {

@@ -81,9 +81,11 @@ __global__ void __launch_bounds__(32) k_route_nx(GraphArrays g, const double* __
                                                   const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                                                   RouteScratch sc, int32_t* __restrict__ arena,
                                                   unsigned long long arena_cap, Counters* ctr, RouteOut out,
-                                                  const double* __restrict__ link_cost) {
+                                                  const double* __restrict__ link_cost,
+                                                  const int32_t* __restrict__ n_dev) {
   const int worker = blockIdx.x * blockDim.x + threadIdx.x;
   if (worker >= sc.workers) return;
+  if (n_dev) Q = *n_dev;  // device-side batch size (device-driven demand)
   const int64_t V = g.V;
   double* seen[2] = {sc.seen + ((int64_t)worker * 2 + 0) * V, sc.seen + ((int64_t)worker * 2 + 1) * V};
   int32_t* plink[2] = {sc.plink + ((int64_t)worker * 2 + 0) * V, sc.plink + ((int64_t)worker * 2 + 1) * V};
@@ -228,7 +230,9 @@ __global__ void k_import_routes(int64_t n, const int64_t* __restrict__ route_off
 // Pending departures of the next tick: (agent, arena offset, hops) from the staged batch.
 __global__ void k_commit(int64_t Q, const int32_t* __restrict__ agent, const int64_t* __restrict__ q_off,
                          const int32_t* __restrict__ q_len, Counters* ctr, int32_t* __restrict__ pend_agent,
-                         int64_t* __restrict__ pend_off, int32_t* __restrict__ pend_len, int32_t pend_cap) {
+                         int64_t* __restrict__ pend_off, int32_t* __restrict__ pend_len, int32_t pend_cap,
+                         const int32_t* __restrict__ n_dev) {
+  if (n_dev) Q = *n_dev;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
     if (q_len[q] <= 0) continue;
     const int p = atomicAdd(&ctr->n_pending, 1);
@@ -249,10 +253,11 @@ __global__ void k_prepare_requests(AgentArrays a, Counters* ctr, const int32_t* 
   const int n = ctr->n_dep_req;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
     const int32_t i = dep_req[r];
-    const int32_t tc = a.trip_count[i];
+    const int32_t cp = a.chain_pos[i];
     const int32_t s = a.cur_node[i];
-    const int32_t t = trip_dst[trip_off[i] + tc];
-    a.trip_count[i] = tc + 1;
+    const int32_t t = trip_dst[trip_off[i] + cp];
+    a.chain_pos[i] = cp + 1;
+    a.trip_count[i] += 1;
     a.cur_node[i] = t;  // agent.py:51: target is overwritten even if routing fails
     q_src[r] = s;
     q_dst[r] = t;
@@ -279,6 +284,263 @@ __global__ void k_log_departures(Counters* ctr, int32_t tick, const int32_t* __r
     } else {
       atomicOr(&ctr->overflow, kOvfDepLog);
     }
+  }
+}
+
+// =====================================================================================
+// K5b: batched multi-source SSSP -- one reverse shortest-path tree per destination.
+//
+// DRIFT's s-t models concentrate trips on few destinations (activity pools, hubs, zones:
+// lib/st_selection.py), and the reference's travel_time never changes, so a tree
+// "first link of the shortest path from every node to destination t" is built once per
+// distinct t and cached in HBM; a route is then a pointer walk.  Trees are built many at a
+// time: one thread block per tree (near-far / delta-stepping worklists, block-level
+// barriers only), blocks pull jobs from a device queue so no host round trip is needed.
+// Distances are accumulated from the destination side (dist[u] = dist[v] + w(u,v)), so the
+// path equals NetworkX's wherever the shortest path is unique; cost parity 1e-9 relative.
+// =====================================================================================
+
+struct TreeScratch {   // per resident block
+  unsigned long long* dist;  // [blocks][V] fp64 bit patterns (non-negative doubles order like u64)
+  uint32_t* stamp;           // [blocks][V] near-list dedupe stamp
+  uint32_t* infar;           // [blocks][V] node is queued in the far list
+  int32_t* lists;            // [blocks][4][V] nearA, nearB, farA, farB
+  uint32_t* iter;            // [blocks] running stamp
+};
+
+struct TreeCache {
+  int32_t* slot_of;    // [V] destination node -> slot, -1 = not cached
+  int32_t* next_link;  // [slots][V] first link towards the destination, -1 = none
+  int32_t* n_slots;    // allocated slots (device counter)
+  int32_t max_slots;
+  int32_t* job_dst;    // [max_slots] trees to build
+  int32_t* job_slot;
+  int32_t* n_jobs;
+  int32_t* job_cursor;
+};
+
+constexpr unsigned long long kInfBits = 0x7FF0000000000000ULL;
+constexpr int kTreeThreads = 256;
+
+// Make sure every destination of the batch has a slot; new ones become build jobs.
+__global__ void k_tree_requests(int64_t Q, const int32_t* __restrict__ dst, int32_t V, TreeCache tc, Counters* ctr,
+                                const int32_t* __restrict__ n_dev) {
+  const int64_t n = n_dev ? (int64_t)*n_dev : Q;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t t = dst[q];
+    if (t < 0 || t >= V) continue;
+    if (atomicCAS(&tc.slot_of[t], -1, -2) == -1) {  // first requester allocates
+      const int32_t s = atomicAdd(tc.n_slots, 1);
+      if (s < tc.max_slots) {
+        const int32_t j = atomicAdd(tc.n_jobs, 1);
+        tc.job_dst[j] = t;
+        tc.job_slot[j] = s;
+        tc.slot_of[t] = s;
+      } else {
+        tc.slot_of[t] = -1;
+        atomicOr(&ctr->overflow, kOvfStage);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, unsigned long long* s_min) {
+  for (int o = 16; o; o >>= 1) {
+    const unsigned long long x = __shfl_xor_sync(0xffffffffu, v, o);
+    v = x < v ? x : v;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMin(s_min, v);
+  __syncthreads();
+  return *s_min;
+}
+
+__global__ void __launch_bounds__(kTreeThreads) k_build_trees(GraphArrays g, const double* __restrict__ w_bwd,
+                                                              const double* __restrict__ w_fwd, double delta,
+                                                              TreeCache tc, TreeScratch sc) {
+  __shared__ int s_job, s_near_n, s_next_n, s_far_n, s_far2_n;
+  __shared__ unsigned long long s_min;
+  const int64_t V = g.V;
+  unsigned long long* dist = sc.dist + (int64_t)blockIdx.x * V;
+  uint32_t* stamp = sc.stamp + (int64_t)blockIdx.x * V;
+  uint32_t* infar = sc.infar + (int64_t)blockIdx.x * V;
+  int32_t* nearA = sc.lists + ((int64_t)blockIdx.x * 4 + 0) * V;
+  int32_t* nearB = sc.lists + ((int64_t)blockIdx.x * 4 + 1) * V;
+  int32_t* farA = sc.lists + ((int64_t)blockIdx.x * 4 + 2) * V;
+  int32_t* farB = sc.lists + ((int64_t)blockIdx.x * 4 + 3) * V;
+  uint32_t iter = sc.iter[blockIdx.x];
+  const int n_jobs = *tc.n_jobs;
+  for (;;) {
+    if (threadIdx.x == 0) s_job = atomicAdd(tc.job_cursor, 1);
+    __syncthreads();
+    const int job = s_job;
+    __syncthreads();
+    if (job >= n_jobs) break;
+    const int32_t dest = tc.job_dst[job];
+    int32_t* next_link = tc.next_link + (int64_t)tc.job_slot[job] * V;
+    for (int64_t v = threadIdx.x; v < V; v += blockDim.x) {
+      dist[v] = kInfBits;
+      infar[v] = 0;
+    }
+    if (threadIdx.x == 0) {
+      s_near_n = 1;
+      s_next_n = 0;
+      s_far_n = 0;
+      s_far2_n = 0;
+      nearA[0] = dest;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) dist[dest] = 0ULL;
+    double T_old = -1.0, T = delta;
+    __syncthreads();
+    for (;;) {
+      const int n = s_near_n;
+      if (n == 0) {
+        const int nf = s_far_n;
+        if (nf == 0) break;
+        // next threshold: skip empty buckets
+        if (threadIdx.x == 0) s_min = kInfBits;
+        __syncthreads();
+        unsigned long long m = kInfBits;
+        for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+          const unsigned long long d = dist[farA[i]];
+          m = d < m ? d : m;
+        }
+        const double minfar = __longlong_as_double((long long)block_min_u64(m, &s_min));
+        T_old = T;
+        T = (minfar > T ? minfar : T) + delta;
+        for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+          const int32_t u = farA[i];
+          const double d = __longlong_as_double((long long)dist[u]);
+          if (d <= T_old) {
+            infar[u] = 0;  // already expanded as a near node
+          } else if (d <= T) {
+            infar[u] = 0;
+            nearA[atomicAdd(&s_near_n, 1)] = u;
+          } else {
+            farB[atomicAdd(&s_far2_n, 1)] = u;
+          }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          s_far_n = s_far2_n;
+          s_far2_n = 0;
+        }
+        int32_t* t = farA;
+        farA = farB;
+        farB = t;
+        __syncthreads();
+        continue;
+      }
+      ++iter;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int32_t v = nearA[i];
+        const double dv = __longlong_as_double((long long)dist[v]);
+        const int32_t e1 = g.bwd_rowptr[v + 1];
+        for (int32_t e = g.bwd_rowptr[v]; e < e1; ++e) {
+          const int32_t u = g.bwd_col[e];
+          const double cand = __dadd_rn(dv, w_bwd[e]);
+          const unsigned long long cb = (unsigned long long)__double_as_longlong(cand);
+          const unsigned long long old = atomicMin(&dist[u], cb);
+          if (cb < old) {
+            if (cand <= T) {
+              if (atomicExch(&stamp[u], iter) != iter) nearB[atomicAdd(&s_next_n, 1)] = u;
+            } else if (atomicExch(&infar[u], 1u) == 0u) {
+              farA[atomicAdd(&s_far_n, 1)] = u;  // at most one far entry per node: <= V entries
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        s_near_n = s_next_n;
+        s_next_n = 0;
+      }
+      int32_t* t = nearA;
+      nearA = nearB;
+      nearB = t;
+      __syncthreads();
+    }
+    // first link of the shortest path u -> dest: first forward entry (CSR order) that attains dist[u]
+    for (int64_t u = threadIdx.x; u < V; u += blockDim.x) {
+      int32_t nl = -1;
+      const unsigned long long du = dist[u];
+      if (u != dest && du != kInfBits) {
+        const int32_t e1 = g.fwd_rowptr[u + 1];
+        for (int32_t e = g.fwd_rowptr[u]; e < e1; ++e) {
+          const unsigned long long dvb = dist[g.fwd_col[e]];
+          if (dvb == kInfBits) continue;
+          const double c = __dadd_rn(__longlong_as_double((long long)dvb), w_fwd[e]);
+          if ((unsigned long long)__double_as_longlong(c) == du) {
+            nl = g.fwd_link[e];
+            break;
+          }
+        }
+      }
+      next_link[u] = nl;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sc.iter[blockIdx.x] = iter;
+}
+
+// Pointer walk over the cached trees: route of every query into the arena.
+__global__ void k_extract_paths(GraphArrays g, int64_t Q, const int32_t* __restrict__ n_dev,
+                                const int32_t* __restrict__ src, const int32_t* __restrict__ dst, TreeCache tc,
+                                int32_t* __restrict__ arena, unsigned long long arena_cap, Counters* ctr,
+                                RouteOut out, const double* __restrict__ link_cost) {
+  const int64_t n = n_dev ? (int64_t)*n_dev : Q;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t s = src[q], t = dst[q];
+    out.off[q] = 0;
+    out.cost[q] = 0.0;
+    out.n_links[q] = 0;
+    if (s < 0 || t < 0 || s >= g.V || t >= g.V) {
+      out.status[q] = DRIFT_ROUTE_NOPATH;
+      continue;
+    }
+    if (s == t) {
+      out.status[q] = DRIFT_ROUTE_TRIVIAL;
+      continue;
+    }
+    const int32_t slot = tc.slot_of[t];
+    if (slot < 0) {
+      out.status[q] = DRIFT_ROUTE_NOPATH;
+      continue;
+    }
+    const int32_t* next_link = tc.next_link + (int64_t)slot * g.V;
+    int hops = 0;
+    int32_t x = s;
+    while (x != t) {
+      const int32_t l = next_link[x];
+      if (l < 0 || hops > g.V) {
+        hops = -1;
+        break;
+      }
+      ++hops;
+      x = g.link_v[l];
+    }
+    if (hops < 0) {
+      out.status[q] = DRIFT_ROUTE_NOPATH;
+      continue;
+    }
+    const unsigned long long off = atomicAdd(&ctr->arena_cursor, (unsigned long long)hops);
+    if (off + hops > arena_cap) {
+      atomicOr(&ctr->overflow, kOvfArena);
+      out.status[q] = DRIFT_ROUTE_NOPATH;
+      continue;
+    }
+    double c = 0.0;
+    x = s;
+    for (int k = 0; k < hops; ++k) {
+      const int32_t l = next_link[x];
+      arena[off + k] = l;
+      c = __dadd_rn(c, link_cost[l]);
+      x = g.link_v[l];
+    }
+    out.status[q] = DRIFT_ROUTE_OK;
+    out.n_links[q] = hops;
+    out.off[q] = (int64_t)off;
+    out.cost[q] = c;
   }
 }
 

@@ -115,8 +115,7 @@ __global__ void __launch_bounds__(kAdvThreads) k_advance(AgentArrays a, const in
         for (int j = 0; j < kAdvPerThread; ++j) {
           const int64_t i = i0 + j;
           if (st[j] == kWaiting && i < a.n) {  // an agent arriving this tick draws from the next tick on
-            const int32_t tc = a.trip_count[i];
-            if (trip_off[i] + tc < trip_off[i + 1]) {
+            if (trip_off[i] + a.chain_pos[i] < trip_off[i + 1]) {
               const double u = philox_uniform53(seed, a.base + (uint32_t)i, (uint32_t)tick);
               if (u < p_dep) dep_req[atomicAdd(&ctr->n_dep_req, 1)] = (int32_t)i;
             }
@@ -305,6 +304,16 @@ __global__ void k_travel_times(LinkArrays lk) {
     const int32_t c = lk.occ[l];
     const double f = (c == 0) ? 1.0 : bpr_factor_lookup(lk, l, c);
     lk.tt[l] = __ddiv_rn(lk.t0[l], f);
+  }
+}
+
+// per-CSR-entry routing weights from the per-link travel times (extension mode)
+__global__ void k_refresh_weights(int32_t E, const double* __restrict__ tt, const int32_t* __restrict__ fwd_link,
+                                  const int32_t* __restrict__ bwd_link, double* __restrict__ fwd_wc,
+                                  double* __restrict__ bwd_wc) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    fwd_wc[e] = tt[fwd_link[e]];
+    bwd_wc[e] = tt[bwd_link[e]];
   }
 }
 

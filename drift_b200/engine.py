@@ -106,6 +106,15 @@ class Engine:
         _capi.check(self._lib.drift_set_demand(self._h, int(seed), _p(h, C.c_double), _p(s, C.c_int32),
                                                _p(o, C.c_int64), _p(d, C.c_int32), int(router)))
 
+    def push_trips(self, trip_off, trip_dst):
+        """Replace the trip chains (asynchronous; the arrays are kept alive by the engine object)."""
+        o, d = _i64(trip_off), _i32(trip_dst)
+        assert len(o) == self.N + 1
+        if len(d) == 0:
+            d = np.zeros(1, dtype=np.int32)
+        self._trip_keep = (o, d)
+        _capi.check(self._lib.drift_push_trips(self._h, _p(o, C.c_int64), _p(d, C.c_int32)))
+
     # ---- routing ------------------------------------------------------------------------------
     def route(self, src, dst, router=ROUTER_NX_EXACT, congested=False, fetch=True):
         """Route Q (src, dst) node-index pairs on the device.

@@ -148,6 +148,10 @@ int drift_step(drift_engine* e, int32_t n_ticks, double delta);
  * `router`.  start_node[N] = initial node of each agent (lib/agent.py:40-44). */
 int drift_set_demand(drift_engine* e, uint64_t seed, const double hourly24[24], const int32_t* start_node,
                      const int64_t* trip_off, const int32_t* trip_dst, int32_t router);
+/* Replace every agent's trip chain (host buffers, asynchronous: keep them alive until the next
+ * synchronising call); the chain position restarts at 0.  Lets the host stream demand block by
+ * block instead of generating a whole horizon up front. */
+int drift_push_trips(drift_engine* e, const int64_t* trip_off, const int32_t* trip_dst);
 /* Run n_ticks ticks with device-driven demand starting at simulation time t0 (seconds). */
 int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0);
 

@@ -105,3 +105,92 @@ def test_live_networkx_tie_breaking(kind):
         assert got == want
         n_ok += 1
     assert n_ok > Q // 3
+
+
+def _unique_path_graph(seed, n=400, m=1400):
+    """Continuous random weights: shortest paths are unique."""
+    import networkx as nx
+
+    rng = random.Random(seed)
+    G = nx.MultiDiGraph()
+    G.add_nodes_from(range(n))
+    for i in range(n):
+        G.add_edge(i, (i + 1) % n, length=rng.uniform(50, 300), speed_kph=50.0)
+    for _ in range(m):
+        a, b = rng.randrange(n), rng.randrange(n)
+        if a != b and not G.has_edge(a, b):
+            G.add_edge(a, b, length=rng.uniform(50, 300), speed_kph=rng.choice([30.0, 50.0, 70.0]))
+    for u, v, k, d in G.edges(keys=True, data=True):
+        d["travel_time"] = (d["length"] / 1000.0) / d["speed_kph"] * 3600
+    for i in range(5):  # a few nodes nobody can reach / leave
+        G.add_node(n + i)
+    G.add_edge(n, 0, length=100.0, speed_kph=30.0, travel_time=12.0)
+    G.add_edge(1, n + 1, length=100.0, speed_kph=30.0, travel_time=12.0)
+    return G
+
+
+def test_batched_router_unique_paths_match_networkx():
+    import networkx as nx
+    from drift_b200.engine import Engine, ROUTE_OK, ROUTE_TRIVIAL, ROUTE_NOPATH, ROUTER_BATCHED, ROUTER_NX_EXACT
+    from drift_b200.graph import lower_graph
+
+    G = _unique_path_graph(3)
+    lg = lower_graph(G)
+    rng = random.Random(4)
+    nodes = list(G.nodes)
+    Q = 3000
+    dests = [rng.randrange(len(nodes)) for _ in range(60)]
+    pairs = [(rng.randrange(len(nodes)), rng.choice(dests)) for _ in range(Q)]
+    src, dst = [p[0] for p in pairs], [p[1] for p in pairs]
+    with Engine(lg, 8, route_arena_links=1 << 22) as eng:
+        st_b, nl_b, links_b = eng.route(src, dst, router=ROUTER_BATCHED)
+        cost_b = eng.route_costs(Q)
+        st_x, nl_x, links_x = eng.route(src, dst, router=ROUTER_NX_EXACT)
+        cost_x = eng.route_costs(Q)
+        # second batch hits the tree cache
+        st_c, nl_c, links_c = eng.route(src[:500], dst[:500], router=ROUTER_BATCHED)
+    assert np.array_equal(st_b, st_x)
+    n_ok = 0
+    for q, ((s, t), st) in enumerate(zip(pairs, st_b)):
+        try:
+            want = nx.shortest_path(G, nodes[s], nodes[t], weight="travel_time")
+        except nx.NetworkXNoPath:
+            assert st == ROUTE_NOPATH
+            continue
+        if s == t:
+            assert st == ROUTE_TRIVIAL
+            continue
+        assert st == ROUTE_OK
+        assert [nodes[i] for i in lg.links_to_nodes(s, links_b[q])] == want  # unique shortest path
+        assert links_b[q].tolist() == links_x[q].tolist()
+        assert abs(cost_b[q] - cost_x[q]) <= 1e-9 * abs(cost_x[q])  # tolerance stated by north_star
+        if q < 500:
+            assert links_c[q].tolist() == links_b[q].tolist()
+        n_ok += 1
+    assert n_ok > Q // 2
+
+
+@pytest.mark.parametrize("name", ["g100_random_s0", "musicnet_random_s0", "multi_random_s0"])
+def test_batched_router_costs_on_tie_graphs(name):
+    """With ties the batched router may pick another shortest path; its cost must be the optimum."""
+    from drift_b200.engine import Engine, ROUTE_OK, ROUTER_BATCHED, ROUTER_NX_EXACT
+    from drift_b200.graph import lower_graph
+
+    case = golden.GoldenCase(name)
+    lg = lower_graph(case.nx_graph())
+    rng = random.Random(1)
+    Q = 800
+    src = [rng.randrange(lg.V) for _ in range(Q)]
+    dst = [rng.randrange(lg.V) for _ in range(Q)]
+    with Engine(lg, 8, route_arena_links=1 << 22) as eng:
+        st_b, nl_b, links_b = eng.route(src, dst, router=ROUTER_BATCHED)
+        cost_b = eng.route_costs(Q)
+        st_x, nl_x, links_x = eng.route(src, dst, router=ROUTER_NX_EXACT)
+        cost_x = eng.route_costs(Q)
+    assert np.array_equal(st_b, st_x)
+    ok = st_x == ROUTE_OK
+    assert np.all(np.abs(cost_b[ok] - cost_x[ok]) <= 1e-9 * np.abs(cost_x[ok]))
+    for q in np.nonzero(ok)[0]:  # a valid walk from src to dst
+        nodes = lg.links_to_nodes(src[q], links_b[q])
+        assert nodes[0] == src[q] and nodes[-1] == dst[q]
+        assert all(lg.link_u[l] == a for l, a in zip(links_b[q], nodes[:-1]))
