@@ -123,7 +123,9 @@ struct drift_engine {
   // tree cache + tree builder scratch (batched router)
   DevBuf<int32_t> t_slot_of, t_next, t_job_dst, t_job_slot, t_ctl;  // t_ctl: n_slots, n_jobs, job_cursor
   DevBuf<unsigned long long> t_dist;
-  DevBuf<uint32_t> t_stamp, t_infar, t_iter;
+  DevBuf<uint32_t> t_stamp, t_infar, t_iter, t_slot_stamp;
+  DevBuf<int32_t> t_slot_owner;
+  uint32_t t_batch = 0;
   DevBuf<int32_t> t_lists;
   int32_t t_max_slots = 0, t_blocks = 0;
   double t_delta = 1.0;
@@ -290,6 +292,9 @@ int ensure_trees(drift_engine* e) {
   CU(e->t_slot_of.alloc(V, false));
   CU(cudaMemset(e->t_slot_of.p, 0xff, sizeof(int32_t) * V));
   CU(e->t_next.alloc(slots * V, false));
+  CU(e->t_slot_owner.alloc(slots, false));
+  CU(cudaMemset(e->t_slot_owner.p, 0xff, sizeof(int32_t) * slots));
+  CU(e->t_slot_stamp.alloc(slots, true));
   CU(e->t_job_dst.alloc(slots));
   CU(e->t_job_slot.alloc(slots));
   CU(e->t_ctl.alloc(4));
@@ -306,6 +311,7 @@ int ensure_trees(drift_engine* e) {
 int invalidate_trees(drift_engine* e) {
   if (!e->t_max_slots) return DRIFT_OK;
   CU(cudaMemsetAsync(e->t_slot_of.p, 0xff, sizeof(int32_t) * e->V, e->stream));
+  CU(cudaMemsetAsync(e->t_slot_owner.p, 0xff, sizeof(int32_t) * e->t_max_slots, e->stream));
   CU(cudaMemsetAsync(e->t_ctl.p, 0, 4 * sizeof(int32_t), e->stream));
   return DRIFT_OK;
 }
@@ -328,7 +334,10 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     TreeCache tc;
     tc.slot_of = e->t_slot_of.p;
     tc.next_link = e->t_next.p;
-    tc.n_slots = e->t_ctl.p + 0;
+    tc.ring_cursor = e->t_ctl.p + 0;
+    tc.slot_owner = e->t_slot_owner.p;
+    tc.slot_stamp = e->t_slot_stamp.p;
+    tc.batch = ++e->t_batch;
     tc.n_jobs = e->t_ctl.p + 1;
     tc.job_cursor = e->t_ctl.p + 2;
     tc.max_slots = e->t_max_slots;
@@ -342,12 +351,13 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     ts.iter = e->t_iter.p;
     CU(cudaMemsetAsync(e->t_ctl.p + 1, 0, 2 * sizeof(int32_t), e->stream));
     const int gq = grid_for(Q, 256, kSMs * 4);
+    k_tree_hits<<<gq, 256, 0, e->stream>>>(Q, e->q_dst.p, e->V, tc, n_dev);
     k_tree_requests<<<gq, 256, 0, e->stream>>>(Q, e->q_dst.p, e->V, tc, e->ctr.p, n_dev);
     k_build_trees<<<e->t_blocks, kTreeThreads, 0, e->stream>>>(e->graph(), wb, wf, e->t_delta, tc, ts);
     k_extract_paths<<<gq, 256, 0, e->stream>>>(e->graph(), Q, n_dev, e->q_src.p, e->q_dst.p, tc, e->arena.p,
                                                 (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
     CU(cudaGetLastError());
-    e->total_launches += 3;
+    e->total_launches += 4;
     return DRIFT_OK;
   }
   int rc = ensure_router(e, Q);
@@ -1046,6 +1056,20 @@ int drift_kernel_times(drift_engine* e, double* advance_ms, int64_t* advance_lau
   if (advance_launches) *advance_launches = (int64_t)e->adv_marks.size();
   if (total_ms) *total_ms = 0;
   if (total_launches) *total_launches = e->total_launches;
+  return DRIFT_OK;
+}
+
+int drift_set_option(drift_engine* e, const char* name, double value) {
+  if (!e || !name) return fail(DRIFT_EINVAL, "drift_set_option");
+  std::string s(name);
+  if (s == "tree_cache_bytes") {
+    if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_cache_bytes must be set before the first batched route");
+    e->tree_budget_bytes = (int64_t)value;
+  } else if (s == "tree_delta_scale") {
+    e->t_delta *= value;
+  } else {
+    return fail(DRIFT_EINVAL, "drift_set_option: unknown option '%s'", name);
+  }
   return DRIFT_OK;
 }
 

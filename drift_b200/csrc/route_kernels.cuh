@@ -309,38 +309,63 @@ struct TreeScratch {   // per resident block
 };
 
 struct TreeCache {
-  int32_t* slot_of;    // [V] destination node -> slot, -1 = not cached
-  int32_t* next_link;  // [slots][V] first link towards the destination, -1 = none
-  int32_t* n_slots;    // allocated slots (device counter)
+  int32_t* slot_of;      // [V] destination node -> slot, -1 = not cached
+  int32_t* slot_owner;   // [max_slots] destination held by the slot, -1 = free
+  uint32_t* slot_stamp;  // [max_slots] last batch that used the slot (never evicted within that batch)
+  int32_t* next_link;    // [slots][V] first link towards the destination, -1 = none
+  int32_t* ring_cursor;  // FIFO allocation cursor (device counter)
   int32_t max_slots;
-  int32_t* job_dst;    // [max_slots] trees to build
+  int32_t* job_dst;      // [max_slots] trees to build
   int32_t* job_slot;
   int32_t* n_jobs;
   int32_t* job_cursor;
+  uint32_t batch;        // id of this batch
 };
 
 constexpr unsigned long long kInfBits = 0x7FF0000000000000ULL;
 constexpr int kTreeThreads = 256;
 
-// Make sure every destination of the batch has a slot; new ones become build jobs.
+// Pass 1: destinations already cached pin their slot for this batch.
+__global__ void k_tree_hits(int64_t Q, const int32_t* __restrict__ dst, int32_t V, TreeCache tc,
+                            const int32_t* __restrict__ n_dev) {
+  const int64_t n = n_dev ? (int64_t)*n_dev : Q;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t t = dst[q];
+    if (t < 0 || t >= V) continue;
+    const int32_t s = tc.slot_of[t];
+    if (s >= 0) tc.slot_stamp[s] = tc.batch;
+  }
+}
+
+// Pass 2: every other destination gets a slot from the FIFO ring (evicting the oldest tree that is
+// not used by this batch) and becomes a build job.
 __global__ void k_tree_requests(int64_t Q, const int32_t* __restrict__ dst, int32_t V, TreeCache tc, Counters* ctr,
                                 const int32_t* __restrict__ n_dev) {
   const int64_t n = n_dev ? (int64_t)*n_dev : Q;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
     const int32_t t = dst[q];
     if (t < 0 || t >= V) continue;
-    if (atomicCAS(&tc.slot_of[t], -1, -2) == -1) {  // first requester allocates
-      const int32_t s = atomicAdd(tc.n_slots, 1);
-      if (s < tc.max_slots) {
-        const int32_t j = atomicAdd(tc.n_jobs, 1);
-        tc.job_dst[j] = t;
-        tc.job_slot[j] = s;
-        tc.slot_of[t] = s;
-      } else {
-        tc.slot_of[t] = -1;
-        atomicOr(&ctr->overflow, kOvfStage);
+    if (atomicCAS(&tc.slot_of[t], -1, -2) != -1) continue;  // cached, or another thread is allocating it
+    int32_t s = -1;
+    for (int tries = 0; tries < tc.max_slots; ++tries) {
+      const int32_t c = (int32_t)((uint32_t)atomicAdd(tc.ring_cursor, 1) % (uint32_t)tc.max_slots);
+      if (atomicExch(&tc.slot_stamp[c], tc.batch) != tc.batch) {  // not used by this batch: take it
+        s = c;
+        break;
       }
     }
+    if (s < 0) {  // more distinct destinations in one batch than slots
+      tc.slot_of[t] = -1;
+      atomicOr(&ctr->overflow, kOvfStage);
+      continue;
+    }
+    const int32_t old = tc.slot_owner[s];
+    if (old >= 0) tc.slot_of[old] = -1;  // evicted (old != any destination of this batch: its slot is stamped)
+    tc.slot_owner[s] = t;
+    const int32_t j = atomicAdd(tc.n_jobs, 1);
+    tc.job_dst[j] = t;
+    tc.job_slot[j] = s;
+    tc.slot_of[t] = s;
   }
 }
 

@@ -1,0 +1,158 @@
+"""Vectorised trip-chain generators for the device-driven demand mode (synthetic workloads).
+
+In the reference every departure calls the s-t plugin once
+(``get_source_target(agent_type, current_location, trip_count) -> (source, target)``,
+lib/st_selection.py:23-35) and ``source`` is always the previous target (lib/agent.py:47-53).  A
+trip chain is therefore just the sequence of targets; these generators produce, for all agents at
+once, chains with the same structure as the five reference models so that the large BASELINE.json
+configs can be driven without a Python call per departure.  They are workload generators, not
+parity objects: bit-exact parity runs use the reference's own selector objects through
+``drift_b200.simulation_thread`` or recorded traces.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _no_self(rng, dst, prev, V):
+    """Redraw targets equal to the trip's source (st_selection.py:47-49)."""
+    bad = dst == prev
+    while bad.any():
+        dst[bad] = rng.integers(0, V, size=int(bad.sum()))
+        bad = dst == prev
+    return dst
+
+
+def random_chains(rng, V, start, k):
+    """RandomSelection (st_selection.py:37-51): uniform target != source."""
+    N = len(start)
+    dst = np.empty((N, k), dtype=np.int32)
+    prev = np.asarray(start, dtype=np.int64).copy()
+    for j in range(k):
+        d = _no_self(rng, rng.integers(0, V, size=N), prev, V)
+        dst[:, j] = d
+        prev = d
+    return np.arange(N + 1, dtype=np.int64) * k, dst.reshape(-1)
+
+
+def hub_chains(rng, lg, start, k, hub_trip_probability=0.3, hub_percentage=0.1):
+    """HubAndSpokeSelection (st_selection.py:469-648) structure: hubs = top ``hub_percentage`` nodes
+    by degree; a trip goes to a hub with probability ``hub_trip_probability``, else anywhere."""
+    V = lg.V
+    deg = np.diff(lg.fwd_rowptr) + np.diff(lg.bwd_rowptr)
+    n_hubs = max(1, int(V * hub_percentage))
+    hubs = np.argsort(-deg, kind="stable")[:n_hubs]
+    N = len(start)
+    dst = np.empty((N, k), dtype=np.int32)
+    prev = np.asarray(start, dtype=np.int64).copy()
+    for j in range(k):
+        to_hub = rng.random(N) < hub_trip_probability
+        d = rng.integers(0, V, size=N)
+        d[to_hub] = hubs[rng.integers(0, n_hubs, size=int(to_hub.sum()))]
+        d = _no_self(rng, d, prev, V)
+        dst[:, j] = d
+        prev = d
+    return np.arange(N + 1, dtype=np.int64) * k, dst.reshape(-1)
+
+
+def activity_chains(rng, lg, start, k):
+    """ActivityBasedSelection (st_selection.py:650-1082) structure: trips run between small pools of
+    home / work / business / activity / distribution nodes whose sizes are capped by config.py:294-303
+    (100/100/80/50/20), picked by distance ring from the network centre; agent types commuter /
+    leisure / business / delivery with shares .4/.3/.2/.1 (config.py:323-328)."""
+    V = lg.V
+    pos = lg.pos if lg.pos is not None else rng.random((V, 2))
+    c = pos.mean(axis=0)
+    r = np.hypot(pos[:, 0] - c[0], pos[:, 1] - c[1])
+    rn = r / max(r.max(), 1e-12)
+    centre = np.nonzero(rn < 0.3)[0]
+    middle = np.nonzero((rn >= 0.3) & (rn < 0.7))[0]
+    border = np.nonzero(rn >= 0.7)[0]
+
+    def pick(pool, n):
+        pool = pool if len(pool) else np.arange(V)
+        return rng.choice(pool, size=min(n, len(pool)), replace=False)
+
+    homes = np.concatenate([pick(centre, 5), pick(middle, 35), pick(border, 60)])
+    works = np.concatenate([pick(centre, 20), pick(middle, 40), pick(border, 40)])
+    business = np.concatenate([pick(centre, 56), pick(middle, 24)])
+    leisure = np.concatenate([pick(centre, 40), pick(middle, 10)])
+    depots = np.concatenate([pick(middle, 10), pick(border, 10)])
+    N = len(start)
+    typ = rng.choice(4, size=N, p=[0.4, 0.3, 0.2, 0.1])
+    home = homes[rng.integers(0, len(homes), size=N)]
+    work = works[rng.integers(0, len(works), size=N)]
+    dst = np.empty((N, k), dtype=np.int32)
+    for j in range(k):
+        out = np.where(j % 2 == 0, 1, 0)  # even legs go out, odd legs return home
+        d = np.empty(N, dtype=np.int64)
+        com, lei, bus, dly = typ == 0, typ == 1, typ == 2, typ == 3
+        d[com] = work[com] if out else home[com]
+        d[lei] = leisure[rng.integers(0, len(leisure), size=int(lei.sum()))] if out else home[lei]
+        d[bus] = business[rng.integers(0, len(business), size=int(bus.sum()))]
+        d[dly] = depots[rng.integers(0, len(depots), size=int(dly.sum()))] if not out else \
+            rng.integers(0, V, size=int(dly.sum()))
+        dst[:, j] = d
+    return np.arange(N + 1, dtype=np.int64) * k, dst.reshape(-1)
+
+
+def zone_chains(rng, lg, start, k, intra_zone_probability=0.7, grid=3):
+    """ZoneBasedSelection (st_selection.py:1084-1252) structure: 3 x 3 position zones; a trip stays
+    in the source's zone with probability 0.7 (config.py:283)."""
+    V = lg.V
+    pos = lg.pos if lg.pos is not None else rng.random((V, 2))
+    lo, hi = pos.min(axis=0), pos.max(axis=0)
+    cell = np.minimum(((pos - lo) / np.maximum(hi - lo, 1e-12) * grid).astype(np.int64), grid - 1)
+    zone = cell[:, 1] * grid + cell[:, 0]
+    order = np.argsort(zone, kind="stable")
+    zstart = np.searchsorted(zone[order], np.arange(grid * grid + 1))
+    N = len(start)
+    dst = np.empty((N, k), dtype=np.int32)
+    prev = np.asarray(start, dtype=np.int64).copy()
+    for j in range(k):
+        intra = rng.random(N) < intra_zone_probability
+        z = np.where(intra, zone[prev], rng.integers(0, grid * grid, size=N))
+        lo_i, hi_i = zstart[z], zstart[z + 1]
+        empty = hi_i <= lo_i
+        pick = lo_i + (rng.random(N) * np.maximum(hi_i - lo_i, 1)).astype(np.int64)
+        d = np.where(empty, rng.integers(0, V, size=N), order[np.minimum(pick, V - 1)])
+        dst[:, j] = d
+        prev = d
+    return np.arange(N + 1, dtype=np.int64) * k, dst.reshape(-1)
+
+
+def gravity_chains(rng, lg, start, k, alpha=1.0, beta=2.0, candidates=32):
+    """GravitySelection (st_selection.py:53-466) structure, sampled: T_ij ~ A_j / d_ij^beta with
+    A_j = 0.01 + alpha * degree centrality (:288-303) and Euclidean d_ij (:327-363); the target is
+    drawn among ``candidates`` uniformly pre-drawn nodes instead of all V (the exact model is
+    O(V) per draw)."""
+    V = lg.V
+    pos = lg.pos if lg.pos is not None else rng.random((V, 2))
+    deg = (np.diff(lg.fwd_rowptr) + np.diff(lg.bwd_rowptr)) / max(V - 1, 1)
+    attr = 0.01 + alpha * deg
+    N = len(start)
+    dst = np.empty((N, k), dtype=np.int32)
+    prev = np.asarray(start, dtype=np.int64).copy()
+    for j in range(k):
+        cand = rng.integers(0, V, size=(N, candidates))
+        dx = pos[cand, 0] - pos[prev, 0][:, None]
+        dy = pos[cand, 1] - pos[prev, 1][:, None]
+        dij = np.maximum(np.hypot(dx, dy), 0.1)
+        w = attr[cand] / dij ** beta
+        w[cand == prev[:, None]] = 0.0
+        cw = np.cumsum(w, axis=1)
+        u = rng.random(N) * cw[:, -1]
+        pickj = np.minimum((cw < u[:, None]).sum(axis=1), candidates - 1)
+        d = cand[np.arange(N), pickj]
+        dst[:, j] = d
+        prev = d
+    return np.arange(N + 1, dtype=np.int64) * k, dst.reshape(-1)
+
+
+MODELS = {
+    "random": lambda rng, lg, start, k: random_chains(rng, lg.V, start, k),
+    "hub": hub_chains,
+    "activity": activity_chains,
+    "zone": zone_chains,
+    "gravity": gravity_chains,
+}

@@ -262,6 +262,9 @@ class Engine:
         _capi.check(self._lib.drift_tick_index(self._h, C.byref(t)))
         return t.value
 
+    def set_option(self, name, value):
+        _capi.check(self._lib.drift_set_option(self._h, name.encode(), float(value)))
+
     def set_profiling(self, on=True):
         _capi.check(self._lib.drift_set_profiling(self._h, int(bool(on))))
 

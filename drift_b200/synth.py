@@ -38,30 +38,33 @@ def grid_graph(nx_cols, ny_rows, seed=0, len_lo=50.0, len_hi=300.0, speed_kph=50
 
 
 def road_graph(num_nodes, seed=0, mean_degree=2.6) -> LoweredGraph:
-    """Planar-ish random road network (configs 2/3): points on a jittered lattice, each joined to
-    its lattice neighbours with probability chosen for the requested mean out-degree; both
-    directions; lengths LogNormal(ln 90 m, 0.6) clipped to [10, 2000]; speed classes
-    {30,50,70,90} km/h w.p. {.5,.3,.15,.05}; lanes {1,2,3}."""
+    """Planar random road network (configs 2/3): nodes on a jittered lattice, lattice edges kept at
+    random to reach the requested mean out-degree, both directions, largest connected component
+    kept.  Lengths LogNormal(ln 90 m, 0.6) clipped to [10, 2000] (continuous => unique shortest
+    paths); speed classes {30,50,70,90} km/h w.p. {.5,.3,.15,.05}; lanes {1,2,3}."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+
     rng = np.random.default_rng(seed)
-    W = int(np.ceil(np.sqrt(num_nodes)))
-    H = int(np.ceil(num_nodes / W))
-    V = W * H
-    node = np.arange(V, dtype=np.int64)
+    W = int(np.ceil(np.sqrt(num_nodes * 1.08)))
+    H = int(np.ceil(num_nodes * 1.08 / W))
+    V0 = W * H
+    node = np.arange(V0, dtype=np.int64)
     col, row = node % W, node // W
-    p_keep = min(1.0, mean_degree / 4.0)
-    # undirected lattice edges (right, down) kept with probability p_keep
+    p_keep = min(1.0, mean_degree / 4.0 * 1.04)
     und = []
     for dc, dr in ((1, 0), (0, 1)):
-        c2, r2 = col + dc, row + dr
-        ok = (c2 < W) & (r2 < H) & (rng.random(V) < p_keep)
-        und.append(np.stack([node[ok], (r2 * W + c2)[ok]], axis=1))
+        ok = (col + dc < W) & (row + dr < H) & (rng.random(V0) < p_keep)
+        und.append(np.stack([node[ok], ((row + dr) * W + col + dc)[ok]], axis=1))
     und = np.concatenate(und)
-    # keep the network connected: a spanning comb (every row, first column)
-    rows_e = np.stack([node[col < W - 1], node[col < W - 1] + 1], axis=1)
-    col0 = np.stack([node[(col == 0) & (row < H - 1)], node[(col == 0) & (row < H - 1)] + W], axis=1)
-    und = np.unique(np.concatenate([und, rows_e[rng.random(len(rows_e)) < 0.55], col0, rows_e[::1][:0]]), axis=0)
-    # guarantee connectivity of every row segment through column 0 .. W-1: add missing row edges of row 0
-    und = np.unique(np.concatenate([und, rows_e[row[rows_e[:, 0]] % 7 == 0]]), axis=0)
+    adj = coo_matrix((np.ones(len(und), dtype=np.int8), (und[:, 0], und[:, 1])), shape=(V0, V0))
+    _, lab = connected_components(adj, directed=False)
+    big = np.argmax(np.bincount(lab))
+    keep = lab == big
+    new_id = np.cumsum(keep) - 1
+    und = und[keep[und[:, 0]] & keep[und[:, 1]]]
+    und = np.stack([new_id[und[:, 0]], new_id[und[:, 1]]], axis=1)
+    V = int(keep.sum())
     u = np.concatenate([und[:, 0], und[:, 1]])
     v = np.concatenate([und[:, 1], und[:, 0]])
     order = np.lexsort((v, u))
@@ -70,5 +73,5 @@ def road_graph(num_nodes, seed=0, mean_degree=2.6) -> LoweredGraph:
     length = np.clip(rng.lognormal(np.log(90.0), 0.6, size=L), 10.0, 2000.0)
     speed = rng.choice([30.0, 50.0, 70.0, 90.0], size=L, p=[0.5, 0.3, 0.15, 0.05])
     lanes = rng.choice([1.0, 2.0, 3.0], size=L, p=[0.6, 0.3, 0.1])
-    pos = np.stack([col + rng.uniform(-0.3, 0.3, V), row + rng.uniform(-0.3, 0.3, V)], axis=1)
+    pos = np.stack([col[keep] + rng.uniform(-0.3, 0.3, V), row[keep] + rng.uniform(-0.3, 0.3, V)], axis=1)
     return from_links(V, u, v, length, speed, lanes, pos=pos)

@@ -194,6 +194,9 @@ int drift_tick_finish(drift_engine* e, const void* events_dev, int64_t n_events)
 int drift_kernel_times(drift_engine* e, double* advance_ms, int64_t* advance_launches, double* total_ms,
                        int64_t* total_launches);
 int drift_set_profiling(drift_engine* e, int32_t on);
+/* Tunables: "tree_cache_bytes" (HBM budget of the destination-tree cache, before first use),
+ * "tree_delta_scale" (multiplies the near-far bucket width). */
+int drift_set_option(drift_engine* e, const char* name, double value);
 /* Raw device pointers for PyTorch interop (tensor views of engine state). name in
  * {"occ","state","dist","speed","link_len","cur_link","events","travel_time"}. */
 int drift_device_ptr(drift_engine* e, const char* name, void** ptr, int64_t* n_elems);

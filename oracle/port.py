@@ -180,7 +180,7 @@ class PortSim:
 
     def __init__(self, pg: PlainGraph, num_agents, selector=None, hourly=None, alpha=0.15, beta=4.0,
                  accel=10, hours=1, departure_trace=None, init_nodes=None, agent_types=None,
-                 route_fn=None, record_entries=False):
+                 route_fn=None, record_entries=False, chains=None):
         self.pg = pg
         self.alpha, self.beta = alpha, beta
         self.hourly = DEFAULT_HOURLY if hourly is None else hourly
@@ -191,6 +191,8 @@ class PortSim:
         self.step = 0
         self.trace = departure_trace
         self.selector = selector
+        self.chains = chains  # (trip_off, trip_dst): host-generated target chains instead of a selector
+        self.chain_pos = [0] * num_agents
         self.route_fn = route_fn or (lambda s, t: bidirectional_route(pg, s, t))
         self.occ = [0] * pg.L
         self.trips = []
@@ -280,6 +282,11 @@ class PortSim:
         pg = self.pg
         if self.trace is not None:
             s, t, path = self.trace[self.step][a.idx]
+        elif self.chains is not None:
+            off, dst = self.chains
+            s, t = a.target, int(dst[off[a.idx] + self.chain_pos[a.idx]])
+            self.chain_pos[a.idx] += 1
+            path = "route"
         else:
             sl, tl = self.selector.get_source_target(a.agent_type, pg.nodes[a.target], a.trip_count)
             s, t = pg.node_index.get(sl, -1), pg.node_index.get(tl, -1)
@@ -322,6 +329,8 @@ class PortSim:
             if old == 0:
                 if self.trace is not None:
                     go = trace_now is not None and a.idx in trace_now
+                elif self.chains is not None and self.chains[0][a.idx] + self.chain_pos[a.idx] >= self.chains[0][a.idx + 1]:
+                    go = False  # chain exhausted
                 else:
                     go = _random.random() < p_dep
                 if go:
@@ -361,3 +370,15 @@ class PortSim:
         sp = np.fromiter((a.speed for a in self.agents), dtype=np.float64, count=n)
         pi = np.fromiter((a.pidx for a in self.agents), dtype=np.int32, count=n)
         return st, d, sp, pi
+
+
+def plain_from_arrays(nodes, link_u, link_v, link_len, link_v0, link_tt, link_cap, fwd_rowptr, fwd_col, fwd_w,
+                      fwd_link, fwd_minlen, bwd_rowptr, bwd_col, bwd_w):
+    """PlainGraph from CSR arrays (synthetic networks that never existed as a NetworkX object)."""
+    V = len(fwd_rowptr) - 1
+    succ = [[(int(fwd_col[e]), float(fwd_w[e]), int(fwd_link[e]), float(fwd_minlen[e]))
+             for e in range(fwd_rowptr[u], fwd_rowptr[u + 1])] for u in range(V)]
+    pred = [[(int(bwd_col[e]), float(bwd_w[e])) for e in range(bwd_rowptr[v], bwd_rowptr[v + 1])] for v in range(V)]
+    links = [(nodes[u], nodes[v], 0) for u, v in zip(link_u.tolist(), link_v.tolist())]
+    return PlainGraph(list(nodes), links, np.asarray(link_len, dtype=np.float64), np.asarray(link_v0, dtype=np.float64),
+                      np.asarray(link_tt, dtype=np.float64), np.asarray(link_cap, dtype=np.int64), succ, pred)

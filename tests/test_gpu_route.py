@@ -194,3 +194,29 @@ def test_batched_router_costs_on_tie_graphs(name):
         nodes = lg.links_to_nodes(src[q], links_b[q])
         assert nodes[0] == src[q] and nodes[-1] == dst[q]
         assert all(lg.link_u[l] == a for l, a in zip(links_b[q], nodes[:-1]))
+
+
+def test_tree_cache_eviction():
+    """A cache that holds 8 trees serves batches with many more destinations over time."""
+    import networkx as nx
+    from drift_b200.engine import Engine, ROUTE_OK, ROUTER_BATCHED
+    from drift_b200.graph import lower_graph
+
+    G = _unique_path_graph(11, n=200, m=600)
+    lg = lower_graph(G)
+    nodes = list(G.nodes)
+    rng = random.Random(2)
+    with Engine(lg, 8, route_arena_links=1 << 22) as eng:
+        eng.set_option("tree_cache_bytes", 8 * 4 * lg.V)
+        for rnd in range(12):
+            dests = [rng.randrange(200) for _ in range(6)] + [0, 1]  # 0 and 1 stay hot, others churn
+            pairs = [(rng.randrange(200), rng.choice(dests)) for _ in range(300)]
+            st, nl, links = eng.route([p[0] for p in pairs], [p[1] for p in pairs], router=ROUTER_BATCHED)
+            for (s, t), stt, ln in zip(pairs, st, links):
+                if s == t:
+                    continue
+                want = nx.shortest_path(G, nodes[s], nodes[t], weight="travel_time")
+                assert stt == ROUTE_OK and [nodes[i] for i in lg.links_to_nodes(s, ln)] == want
+        from drift_b200._capi import DriftError
+        with pytest.raises(DriftError):  # 20 distinct destinations cannot fit 8 slots in one batch
+            eng.route(list(range(20, 40)), list(range(100, 120)), router=ROUTER_BATCHED)
