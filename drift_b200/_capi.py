@@ -54,8 +54,10 @@ SIGNATURES = {
     "drift_commit_departures": (C.c_int, [ENGINE, C.c_int64, c_i32p]),
     "drift_submit_departures": (C.c_int, [ENGINE, C.c_int64, c_i32p, c_i64p, c_i32p]),
     "drift_step": (C.c_int, [ENGINE, C.c_int32, C.c_double]),
-    "drift_set_demand": (C.c_int, [ENGINE, C.c_uint64, c_f64p, c_i32p, c_i64p, c_i32p, C.c_int32]),
-    "drift_push_trips": (C.c_int, [ENGINE, c_i64p, c_i32p]),
+    "drift_set_demand": (C.c_int, [ENGINE, C.c_uint64, c_f64p, c_i32p, C.c_int32, C.c_int32]),
+    "drift_push_trips": (C.c_int, [ENGINE, c_i32p, C.c_int32]),
+    "drift_store_trip_pool": (C.c_int, [ENGINE, c_i32p, C.c_int32, C.c_int32]),
+    "drift_refill_from_pool": (C.c_int, [ENGINE, C.c_int32]),
     "drift_run": (C.c_int, [ENGINE, C.c_int32, C.c_double, C.c_double]),
     "drift_update_travel_times": (C.c_int, [ENGINE]),
     "drift_reroute_moving": (C.c_int, [ENGINE, C.c_int32, c_i64p]),

@@ -48,7 +48,7 @@ struct Counters {
   int32_t n_pending;      // pending departures (committed routes) for the next tick
   int32_t overflow;       // bit flags, see kOvf*
   int32_t tick;           // index of the tick being / last processed (1-based like SimulationThread.step)
-  int32_t pad0;
+  int32_t n_plan;         // route requests of the current planning batch
   unsigned long long n_arrivals;    // total appended to the arrival ring
   unsigned long long n_departures;  // total appended to the departure log ring
   unsigned long long n_entries;     // total appended to the entry trace
@@ -79,7 +79,17 @@ struct AgentArrays {
   int64_t* route_off;   // [Npad] start of the route in the arena
   int32_t* trip_count;  // [Npad]
   int32_t* cur_node;    // [Npad] Agent.target: where the next trip starts
-  int32_t* chain_pos;   // [Npad] next entry of the agent's host-generated trip chain
+  // host-generated trip chain: a small ring of upcoming destinations per agent, topped up by
+  // drift_push_trips; entry k of agent i is chain_dst[i * chain_cap + (chain_head[i] + k) % chain_cap]
+  int32_t* chain_dst;    // [N][chain_cap]
+  uint8_t* chain_head;   // [Npad]
+  uint8_t* chain_cnt;    // [Npad] destinations available
+  int32_t chain_cap;
+  // prefetched routes of the next two trips (device-driven demand): slot k at [k * npad + i]
+  int64_t* next_off;     // [2][Npad] arena offset
+  int32_t* next_len;     // [2][Npad] hops
+  int32_t* next_status;  // [2][Npad] 0 = none, 1 + DRIFT_ROUTE_* otherwise
+  int64_t npad;
   int64_t n;
   uint32_t base;  // global id of local agent 0
 };
@@ -97,6 +107,19 @@ struct LinkArrays {
   const double* factor;     // concatenated per-class tables
   const int64_t* cls_off;   // [n_class+1]
   int32_t L;
+};
+
+struct DemandArgs {  // device-driven demand (drift_run)
+  uint64_t seed;
+  double p_dep;                // hourly[h] * 4 * delta / 3600 (agent.py:180,259)
+  int32_t* dep_req;            // departures that found no prefetched route (routed within the tick)
+  int32_t* log_agent;          // departure log ring
+  int32_t* log_tick;
+  int32_t* log_src;
+  int32_t* log_dst;
+  int32_t* log_status;
+  unsigned long long log_cap;
+  unsigned long long log_drained;
 };
 
 struct Rings {

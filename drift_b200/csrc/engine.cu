@@ -93,7 +93,13 @@ struct drift_engine {
   uint32_t agent_base = 0;
   DevBuf<uint8_t> state;
   DevBuf<double> dist, speed, elen;
-  DevBuf<int32_t> cur_link, route_idx, route_len, trip_count, cur_node, chain_pos;
+  DevBuf<int32_t> cur_link, route_idx, route_len, trip_count, cur_node, chain_dst, next_len, next_status;
+  DevBuf<uint8_t> chain_head, chain_cnt;
+  DevBuf<int64_t> next_off;
+  int32_t chain_cap = 4;
+  int32_t route_window = 300;
+  DevBuf<int32_t> trip_stage, trip_pool;
+  int64_t pool_blocks = 0, pool_k = 0;
   DevBuf<int64_t> route_off;
   DevBuf<int32_t> arena;
   int64_t arena_cap = 0;
@@ -145,13 +151,14 @@ struct drift_engine {
   bool have_demand = false;
   uint64_t seed = 0;
   double hourly[24];
-  DevBuf<int64_t> trip_off;
-  DevBuf<int32_t> trip_dst, dep_req;
+  DevBuf<int32_t> dep_req;
   int32_t demand_router = DRIFT_ROUTER_NX_EXACT;
   // counters
   DevBuf<Counters> ctr;
   Counters* h_ctr = nullptr;  // pinned
   int64_t tick = 0;
+  int32_t ticks_since_plan = 0;
+  int64_t routes_planned = 0;
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -172,7 +179,14 @@ struct drift_engine {
     a.route_off = route_off.p;
     a.trip_count = trip_count.p;
     a.cur_node = cur_node.p;
-    a.chain_pos = chain_pos.p;
+    a.chain_dst = chain_dst.p;
+    a.chain_head = chain_head.p;
+    a.chain_cnt = chain_cnt.p;
+    a.chain_cap = chain_cap;
+    a.next_off = next_off.p;
+    a.next_len = next_len.p;
+    a.next_status = next_status.p;
+    a.npad = Npad;
     a.n = N;
     a.base = agent_base;
     return a;
@@ -318,13 +332,16 @@ int invalidate_trees(drift_engine* e) {
 
 // launches the router over the staged q_src/q_dst (device).  Q is the host-known batch size or an
 // upper bound; when n_dev != nullptr the kernels read the actual size from device memory.
-int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_congested, const int32_t* n_dev = nullptr) {
+int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_congested, const int32_t* n_dev = nullptr,
+                  int64_t q0 = 0) {
   if (Q <= 0) return DRIFT_OK;
   RouteOut out;
-  out.status = e->q_status.p;
-  out.n_links = e->q_len.p;
-  out.off = e->q_off.p;
-  out.cost = e->q_cost.p;
+  out.status = e->q_status.p + q0;
+  out.n_links = e->q_len.p + q0;
+  out.off = e->q_off.p + q0;
+  out.cost = e->q_cost.p + q0;
+  const int32_t* qs = e->q_src.p + q0;
+  const int32_t* qd = e->q_dst.p + q0;
   const double* wf = use_congested ? e->fwd_wc.p : e->fwd_w.p;
   const double* wb = use_congested ? e->bwd_wc.p : e->bwd_w.p;
   const double* lc = use_congested ? e->link_tt.p : e->link_t0.p;
@@ -351,10 +368,10 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     ts.iter = e->t_iter.p;
     CU(cudaMemsetAsync(e->t_ctl.p + 1, 0, 2 * sizeof(int32_t), e->stream));
     const int gq = grid_for(Q, 256, kSMs * 4);
-    k_tree_hits<<<gq, 256, 0, e->stream>>>(Q, e->q_dst.p, e->V, tc, n_dev);
-    k_tree_requests<<<gq, 256, 0, e->stream>>>(Q, e->q_dst.p, e->V, tc, e->ctr.p, n_dev);
+    k_tree_hits<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, n_dev);
+    k_tree_requests<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, e->ctr.p, n_dev);
     k_build_trees<<<e->t_blocks, kTreeThreads, 0, e->stream>>>(e->graph(), wb, wf, e->t_delta, tc, ts);
-    k_extract_paths<<<gq, 256, 0, e->stream>>>(e->graph(), Q, n_dev, e->q_src.p, e->q_dst.p, tc, e->arena.p,
+    k_extract_paths<<<gq, 256, 0, e->stream>>>(e->graph(), Q, n_dev, qs, qd, tc, e->arena.p,
                                                 (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
     CU(cudaGetLastError());
     e->total_launches += 4;
@@ -371,7 +388,7 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
   sc.heap_cap = e->r_heap_cap;
   sc.workers = (int32_t)std::min<int64_t>(e->r_workers, Q);
   const int blocks = (sc.workers + 31) / 32;
-  k_route_nx<<<blocks, 32, 0, e->stream>>>(e->graph(), wf, wb, Q, e->q_src.p, e->q_dst.p, sc, e->arena.p,
+  k_route_nx<<<blocks, 32, 0, e->stream>>>(e->graph(), wf, wb, Q, qs, qd, sc, e->arena.p,
                                            (unsigned long long)e->arena_cap, e->ctr.p, out, lc, n_dev);
   CU(cudaGetLastError());
   e->total_launches += 1;
@@ -409,14 +426,25 @@ int tick_begin(drift_engine* e, double delta, bool demand, double p_dep) {
   const int blocks = grid_for(e->N, (int)per_block, kSMs * 8);
   {
     ProfScope ps(e, true);
-    if (demand)
+    DemandArgs dm;
+    memset(&dm, 0, sizeof(dm));
+    if (demand) {
+      dm.seed = e->seed;
+      dm.p_dep = p_dep;
+      dm.dep_req = e->dep_req.p;
+      dm.log_agent = e->dl_agent.p;
+      dm.log_tick = e->dl_tick.p;
+      dm.log_src = e->dl_src.p;
+      dm.log_dst = e->dl_dst.p;
+      dm.log_status = e->dl_status.p;
+      dm.log_cap = (unsigned long long)e->dl_cap;
+      dm.log_drained = e->dl_drained;
       k_advance<true><<<blocks, kAdvThreads, 0, e->stream>>>(e->agents(), e->arena.p, delta, tick, e->ctr.p,
-                                                             e->events.p, (int32_t)e->ev_cap, e->rings(), e->seed,
-                                                             p_dep, e->trip_off.p, e->dep_req.p);
-    else
+                                                             e->events.p, (int32_t)e->ev_cap, e->rings(), dm);
+    } else {
       k_advance<false><<<blocks, kAdvThreads, 0, e->stream>>>(e->agents(), e->arena.p, delta, tick, e->ctr.p,
-                                                              e->events.p, (int32_t)e->ev_cap, e->rings(), 0, 0.0,
-                                                              nullptr, nullptr);
+                                                              e->events.p, (int32_t)e->ev_cap, e->rings(), dm);
+    }
   }
   CU(cudaGetLastError());
   e->total_launches += 1;
@@ -568,7 +596,11 @@ int drift_add_agents(drift_engine* e, int64_t n_agents, int64_t agent_base, int6
   CU(e->route_off.alloc(Np));
   CU(e->trip_count.alloc(Np));
   CU(e->cur_node.alloc(Np));
-  CU(e->chain_pos.alloc(Np));
+  CU(e->chain_head.alloc(Np));
+  CU(e->chain_cnt.alloc(Np));
+  CU(e->next_off.alloc(2 * Np));
+  CU(e->next_len.alloc(2 * Np));
+  CU(e->next_status.alloc(2 * Np));
   if (route_arena_links <= 0) route_arena_links = std::max<int64_t>((int64_t)1 << 20, n_agents * 64);
   CU(e->arena.alloc(route_arena_links, false));
   e->arena_cap = route_arena_links;
@@ -722,9 +754,10 @@ int drift_step(drift_engine* e, int32_t n_ticks, double delta) {
 }
 
 int drift_set_demand(drift_engine* e, uint64_t seed, const double hourly24[24], const int32_t* start_node,
-                     const int64_t* trip_off, const int32_t* trip_dst, int32_t router) {
+                     int32_t chain_capacity, int32_t router) {
   if (!e || !hourly24 || !start_node) return fail(DRIFT_EINVAL, "drift_set_demand");
   if (!e->N) return fail(DRIFT_ESTATE, "drift_set_demand: no agents");
+  if (chain_capacity < 2 || chain_capacity > 64) return fail(DRIFT_EINVAL, "chain_capacity must be in [2, 64]");
   CU(cudaSetDevice(e->device));
   CU(cudaStreamSynchronize(e->stream));
   e->seed = seed;
@@ -732,32 +765,86 @@ int drift_set_demand(drift_engine* e, uint64_t seed, const double hourly24[24], 
   for (int64_t i = 0; i < e->N; ++i)
     if (start_node[i] < 0 || start_node[i] >= e->V) return fail(DRIFT_EINVAL, "drift_set_demand: bad start node");
   CU(cudaMemcpy(e->cur_node.p, start_node, sizeof(int32_t) * e->N, cudaMemcpyHostToDevice));
+  e->chain_cap = chain_capacity;
+  CU(e->chain_dst.alloc(e->N * (int64_t)chain_capacity));
+  CU(cudaMemset(e->chain_head.p, 0, e->Npad));
+  CU(cudaMemset(e->chain_cnt.p, 0, e->Npad));
+  CU(cudaMemset(e->next_status.p, 0, sizeof(int32_t) * 2 * e->Npad));
   e->demand_router = router;
-  int rc = ensure_qcap(e, e->N);
+  int rc = ensure_qcap(e, 2 * e->N);
   if (rc) return rc;
-  if (trip_off && trip_dst) {
-    rc = drift_push_trips(e, trip_off, trip_dst);
-    if (rc) return rc;
-  }
   e->have_demand = true;
   return DRIFT_OK;
 }
 
-int drift_push_trips(drift_engine* e, const int64_t* trip_off, const int32_t* trip_dst) {
-  if (!e || !trip_off || !trip_dst) return fail(DRIFT_EINVAL, "drift_push_trips");
-  if (!e->N) return fail(DRIFT_ESTATE, "drift_push_trips: no agents");
+static int refill_from(drift_engine* e, const int32_t* cand_dev, int32_t k) {
+  k_refill_chains<<<grid_for(e->N, 256, kSMs * 8), 256, 0, e->stream>>>(e->agents(), cand_dev, k);
+  CU(cudaGetLastError());
+  e->total_launches += 1;
+  return DRIFT_OK;
+}
+
+int drift_push_trips(drift_engine* e, const int32_t* candidates, int32_t k) {
+  if (!e || !candidates || k <= 0) return fail(DRIFT_EINVAL, "drift_push_trips");
+  if (!e->have_demand) return fail(DRIFT_ESTATE, "drift_push_trips: call drift_set_demand first");
   CU(cudaSetDevice(e->device));
-  const int64_t total = trip_off[e->N];
-  if (trip_off[0] != 0 || total < 0) return fail(DRIFT_EINVAL, "drift_push_trips: bad offsets");
-  if (e->trip_off.n < e->N + 1) CU(e->trip_off.alloc(e->N + 1, false));
-  if (e->trip_dst.n < std::max<int64_t>(total, 1)) {
+  const int64_t total = e->N * (int64_t)k;
+  if (e->trip_stage.n < total) {
     CU(cudaStreamSynchronize(e->stream));
-    CU(e->trip_dst.alloc(std::max<int64_t>(total, 1) * 5 / 4 + 16, false));
+    CU(e->trip_stage.alloc(total, false));
   }
-  CU(cudaMemcpyAsync(e->trip_off.p, trip_off, sizeof(int64_t) * (e->N + 1), cudaMemcpyHostToDevice, e->stream));
-  if (total)
-    CU(cudaMemcpyAsync(e->trip_dst.p, trip_dst, sizeof(int32_t) * total, cudaMemcpyHostToDevice, e->stream));
-  CU(cudaMemsetAsync(e->chain_pos.p, 0, sizeof(int32_t) * e->Npad, e->stream));
+  CU(cudaMemcpyAsync(e->trip_stage.p, candidates, sizeof(int32_t) * total, cudaMemcpyHostToDevice, e->stream));
+  return refill_from(e, e->trip_stage.p, k);
+}
+
+int drift_store_trip_pool(drift_engine* e, const int32_t* candidates, int32_t n_blocks, int32_t k) {
+  if (!e || !candidates || k <= 0 || n_blocks <= 0) return fail(DRIFT_EINVAL, "drift_store_trip_pool");
+  if (!e->have_demand) return fail(DRIFT_ESTATE, "drift_store_trip_pool: call drift_set_demand first");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  CU(e->trip_pool.upload(candidates, (int64_t)n_blocks * e->N * k));
+  e->pool_blocks = n_blocks;
+  e->pool_k = k;
+  return DRIFT_OK;
+}
+
+int drift_refill_from_pool(drift_engine* e, int32_t block) {
+  if (!e || block < 0 || block >= e->pool_blocks) return fail(DRIFT_EINVAL, "drift_refill_from_pool");
+  CU(cudaSetDevice(e->device));
+  return refill_from(e, e->trip_pool.p + (int64_t)block * e->N * e->pool_k, (int32_t)e->pool_k);
+}
+
+// Window planning: route, as one large batch, every missing prefetched route (next two trips of
+// every agent).  One host sync per window to learn the batch size.
+static int plan_window(drift_engine* e) {
+  Counters* c = e->ctr.p;
+  CU(cudaMemsetAsync(&c->n_plan, 0, sizeof(int32_t), e->stream));
+  k_plan_requests<<<grid_for(e->N, 256, kSMs * 8), 256, 0, e->stream>>>(e->agents(), c, e->q_src.p, e->q_dst.p,
+                                                                         e->q_agent.p, (int32_t)e->q_cap);
+  CU(cudaGetLastError());
+  e->total_launches += 1;
+  Counters hc;
+  int rc = fetch_counters(e, &hc);
+  if (rc) return rc;
+  const int64_t Q = std::min<int64_t>(hc.n_plan, e->q_cap);
+  e->routes_planned += Q;
+  int64_t chunk = Q;
+  if (e->demand_router == DRIFT_ROUTER_BATCHED) {
+    rc = ensure_trees(e);
+    if (rc) return rc;
+    chunk = std::max<int64_t>(1, e->t_max_slots);  // a chunk never needs more distinct trees than slots
+  }
+  for (int64_t q0 = 0; q0 < Q; q0 += chunk) {
+    const int64_t n = std::min(chunk, Q - q0);
+    rc = launch_router(e, e->demand_router, n, 0, nullptr, q0);
+    if (rc) return rc;
+  }
+  if (Q > 0) {
+    k_store_prefetch<<<grid_for(Q, 256, kSMs * 8), 256, 0, e->stream>>>(Q, e->q_agent.p, e->q_off.p, e->q_len.p,
+                                                                       e->q_status.p, e->agents());
+    CU(cudaGetLastError());
+    e->total_launches += 1;
+  }
   return DRIFT_OK;
 }
 
@@ -768,27 +855,29 @@ int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0) {
   CU(cudaSetDevice(e->device));
   double t = t0;
   for (int32_t k = 0; k < n_ticks; ++k) {
+    if (e->ticks_since_plan <= 0) {
+      int rc = plan_window(e);
+      if (rc) return rc;
+      e->ticks_since_plan = e->route_window;
+    }
+    e->ticks_since_plan -= 1;
     t += delta;  // repeated fp64 sum like lib/simulation_thread.py:295
     const int hour = (int)std::fmod((t + 21600.0) / 3600.0, 24.0);  // lib/agent.py:251-252
     const double p = e->hourly[hour] * 4.0 * delta / 3600.0;        // lib/agent.py:259,180
     int rc = tick_begin(e, delta, true, p);
     if (rc) return rc;
-    // route this tick's departure requests on the device (count stays on the device: the
-    // router is launched over a worker pool and reads n_dep_req itself)
+    // Departures that found no prefetched route (an agent that completed two trips inside one
+    // window) are routed here, inside the tick; the batch size stays on the device, the kernels
+    // return at once when it is zero.
     Counters* c = e->ctr.p;
-    k_prepare_requests<<<kSMs, 256, 0, e->stream>>>(e->agents(), c, e->dep_req.p, e->trip_off.p, e->trip_dst.p,
-                                                    e->q_src.p, e->q_dst.p, e->q_agent.p);
-    CU(cudaGetLastError());
-    // batch size stays on the device: every kernel below reads n_dep_req itself (no host sync)
-    const int64_t Qmax = std::min<int64_t>(e->N, e->q_cap);
-    rc = launch_router(e, e->demand_router, Qmax, 0, &c->n_dep_req);
+    k_prepare_requests<<<1, 256, 0, e->stream>>>(e->agents(), c, e->dep_req.p, e->q_src.p, e->q_dst.p, e->q_agent.p);
+    rc = launch_router(e, e->demand_router, 256, 0, &c->n_dep_req);
     if (rc) return rc;
-    k_log_departures<<<kSMs, 256, 0, e->stream>>>(c, (int32_t)e->tick, e->q_agent.p, e->q_src.p, e->q_dst.p,
-                                                  e->q_status.p, e->dl_agent.p, e->dl_tick.p, e->dl_src.p,
-                                                  e->dl_dst.p, e->dl_status.p, (unsigned long long)e->dl_cap,
-                                                  e->dl_drained);
-    k_commit<<<kSMs, 256, 0, e->stream>>>(Qmax, e->q_agent.p, e->q_off.p, e->q_len.p, c, e->pend_agent.p,
-                                          e->pend_off.p, e->pend_len.p, (int32_t)e->pend_cap, &c->n_dep_req);
+    k_log_departures<<<1, 256, 0, e->stream>>>(c, (int32_t)e->tick, e->q_agent.p, e->q_src.p, e->q_dst.p,
+                                               e->q_status.p, e->dl_agent.p, e->dl_tick.p, e->dl_src.p, e->dl_dst.p,
+                                               e->dl_status.p, (unsigned long long)e->dl_cap, e->dl_drained);
+    k_commit<<<1, 256, 0, e->stream>>>(e->N, e->q_agent.p, e->q_off.p, e->q_len.p, c, e->pend_agent.p, e->pend_off.p,
+                                       e->pend_len.p, (int32_t)e->pend_cap, &c->n_dep_req);
     CU(cudaGetLastError());
     e->total_launches += 3;
     rc = inject_pending(e);
@@ -1065,6 +1154,11 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
   if (s == "tree_cache_bytes") {
     if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_cache_bytes must be set before the first batched route");
     e->tree_budget_bytes = (int64_t)value;
+  } else if (s == "route_window") {
+    if (value < 1) return fail(DRIFT_EINVAL, "route_window must be >= 1");
+    e->route_window = (int32_t)value;
+  } else if (s == "replan") {
+    e->ticks_since_plan = 0;
   } else if (s == "tree_delta_scale") {
     e->t_delta *= value;
   } else {

@@ -247,21 +247,55 @@ __global__ void k_commit(int64_t Q, const int32_t* __restrict__ agent, const int
 // Device-driven demand: turn this tick's departure requests into (src, dst) queries
 // (Agent.start_new_journey, agent.py:46-83: source = previous target, trip_count += 1).
 __global__ void k_prepare_requests(AgentArrays a, Counters* ctr, const int32_t* __restrict__ dep_req,
-                                   const int64_t* __restrict__ trip_off, const int32_t* __restrict__ trip_dst,
                                    int32_t* __restrict__ q_src, int32_t* __restrict__ q_dst,
                                    int32_t* __restrict__ q_agent) {
   const int n = ctr->n_dep_req;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
     const int32_t i = dep_req[r];
-    const int32_t cp = a.chain_pos[i];
+    const int head = a.chain_head[i];
     const int32_t s = a.cur_node[i];
-    const int32_t t = trip_dst[trip_off[i] + cp];
-    a.chain_pos[i] = cp + 1;
+    const int32_t t = a.chain_dst[(int64_t)i * a.chain_cap + head];
+    a.chain_head[i] = (uint8_t)((head + 1) % a.chain_cap);
+    a.chain_cnt[i] -= 1;
     a.trip_count[i] += 1;
     a.cur_node[i] = t;  // agent.py:51: target is overwritten even if routing fails
     q_src[r] = s;
     q_dst[r] = t;
     q_agent[r] = i;
+  }
+}
+
+// Window planning: every agent missing a prefetched route for one of its next two trips asks
+// for it (source of trip k+1 = destination of trip k, known from the chain).
+__global__ void k_plan_requests(AgentArrays a, Counters* ctr, int32_t* __restrict__ q_src,
+                                int32_t* __restrict__ q_dst, int32_t* __restrict__ q_agent, int32_t q_cap) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cnt = a.chain_cnt[i], head = a.chain_head[i];
+    const int32_t* ring = a.chain_dst + i * a.chain_cap;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k >= cnt) break;
+      if (a.next_status[k * a.npad + i] != 0) continue;
+      const int32_t s = k == 0 ? a.cur_node[i] : ring[head];
+      const int r = atomicAdd(&ctr->n_plan, 1);
+      if (r < q_cap) {
+        q_src[r] = s;
+        q_dst[r] = ring[(head + k) % a.chain_cap];
+        q_agent[r] = (int32_t)i * 2 + k;
+      }
+    }
+  }
+}
+
+__global__ void k_store_prefetch(int64_t Q, const int32_t* __restrict__ q_agent, const int64_t* __restrict__ q_off,
+                                 const int32_t* __restrict__ q_len, const int32_t* __restrict__ q_status,
+                                 AgentArrays a) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t code = q_agent[q];
+    const int64_t idx = (int64_t)(code & 1) * a.npad + (code >> 1);
+    a.next_off[idx] = q_off[q];
+    a.next_len[idx] = q_len[q];
+    a.next_status[idx] = 1 + q_status[q];
   }
 }
 

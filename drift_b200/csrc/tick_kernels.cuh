@@ -45,9 +45,7 @@ template <bool DEMAND>
 __global__ void __launch_bounds__(kAdvThreads) k_advance(AgentArrays a, const int32_t* __restrict__ arena,
                                                           double delta, int32_t tick, Counters* ctr,
                                                           Event* __restrict__ events, int32_t ev_cap, Rings rg,
-                                                          uint64_t seed, double p_dep,
-                                                          const int64_t* __restrict__ trip_off,
-                                                          int32_t* __restrict__ dep_req) {
+                                                          DemandArgs dm) {
   __shared__ int s_cnt, s_base;
   const int64_t tiles = (a.n + (int64_t)kAdvThreads * kAdvPerThread - 1) / ((int64_t)kAdvThreads * kAdvPerThread);
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -58,6 +56,8 @@ __global__ void __launch_bounds__(kAdvThreads) k_advance(AgentArrays a, const in
     if (i0 < a.n) {
       const uchar4 st4 = *reinterpret_cast<const uchar4*>(a.state + i0);
       const uint8_t st[4] = {st4.x, st4.y, st4.z, st4.w};
+      uint8_t nst[4] = {st[0], st[1], st[2], st[3]};
+      bool state_changed = false;
       if (st4.x | st4.y | st4.z | st4.w) {
         const double2 d01 = *reinterpret_cast<const double2*>(a.dist + i0);
         const double2 d23 = *reinterpret_cast<const double2*>(a.dist + i0 + 2);
@@ -68,8 +68,6 @@ __global__ void __launch_bounds__(kAdvThreads) k_advance(AgentArrays a, const in
         double d[4] = {d01.x, d01.y, d23.x, d23.y};
         const double sp[4] = {s01.x, s01.y, s23.x, s23.y};
         const double el[4] = {e01.x, e01.y, e23.x, e23.y};
-        uint8_t nst[4] = {st[0], st[1], st[2], st[3]};
-        bool any_arrival = false;
 #pragma unroll
         for (int j = 0; j < kAdvPerThread; ++j) {
           if (st[j] == kMoving) {
@@ -92,7 +90,7 @@ __global__ void __launch_bounds__(kAdvThreads) k_advance(AgentArrays a, const in
               } else {  // agent.py:107-116: arrived
                 a.cur_link[i] = -1;
                 nst[j] = kWaiting;
-                any_arrival = true;
+                state_changed = true;
                 const unsigned long long slot = atomicAdd(&ctr->n_arrivals, 1ULL);
                 if (slot - rg.arr_drained < rg.arr_cap) {
                   rg.arr_agent[slot % rg.arr_cap] = (int32_t)i;
@@ -108,20 +106,61 @@ __global__ void __launch_bounds__(kAdvThreads) k_advance(AgentArrays a, const in
         }
         *reinterpret_cast<double2*>(a.dist + i0) = make_double2(d[0], d[1]);
         *reinterpret_cast<double2*>(a.dist + i0 + 2) = make_double2(d[2], d[3]);
-        if (any_arrival) *reinterpret_cast<uchar4*>(a.state + i0) = make_uchar4(nst[0], nst[1], nst[2], nst[3]);
       }
       if (DEMAND) {
 #pragma unroll
         for (int j = 0; j < kAdvPerThread; ++j) {
           const int64_t i = i0 + j;
-          if (st[j] == kWaiting && i < a.n) {  // an agent arriving this tick draws from the next tick on
-            if (trip_off[i] + a.chain_pos[i] < trip_off[i + 1]) {
-              const double u = philox_uniform53(seed, a.base + (uint32_t)i, (uint32_t)tick);
-              if (u < p_dep) dep_req[atomicAdd(&ctr->n_dep_req, 1)] = (int32_t)i;
-            }
+          if (st[j] != kWaiting || i >= a.n) continue;  // an agent arriving this tick draws from the next tick on
+          const int cnt = a.chain_cnt[i];
+          if (cnt == 0) continue;  // no destination available (chain exhausted)
+          const double u = philox_uniform53(dm.seed, a.base + (uint32_t)i, (uint32_t)tick);
+          if (!(u < dm.p_dep)) continue;  // agent.py:180
+          const int32_t ns = a.next_status[i];
+          if (ns == 0) {  // no prefetched route: routed inside this tick (rare)
+            dm.dep_req[atomicAdd(&ctr->n_dep_req, 1)] = (int32_t)i;
+            continue;
+          }
+          // Agent.start_new_journey (agent.py:46-104) with the prefetched route
+          const int head = a.chain_head[i];
+          const int32_t src = a.cur_node[i], dst = a.chain_dst[i * a.chain_cap + head];
+          a.chain_head[i] = (uint8_t)((head + 1) % a.chain_cap);
+          a.chain_cnt[i] = (uint8_t)(cnt - 1);
+          a.trip_count[i] += 1;
+          a.cur_node[i] = dst;
+          const int64_t noff = a.next_off[i];
+          const int32_t nlen = a.next_len[i];
+          a.next_status[i] = a.next_status[a.npad + i];  // shift the second prefetched route up
+          a.next_off[i] = a.next_off[a.npad + i];
+          a.next_len[i] = a.next_len[a.npad + i];
+          a.next_status[a.npad + i] = 0;
+          const unsigned long long slot = atomicAdd(&ctr->n_departures, 1ULL);
+          if (slot - dm.log_drained < dm.log_cap) {
+            const unsigned long long k = slot % dm.log_cap;
+            dm.log_agent[k] = (int32_t)i;
+            dm.log_tick[k] = tick;
+            dm.log_src[k] = src;
+            dm.log_dst[k] = dst;
+            dm.log_status[k] = ns - 1;
+          } else {
+            atomicOr(&ctr->overflow, kOvfDepLog);
+          }
+          if (ns == 1 + DRIFT_ROUTE_OK) {
+            const int32_t fl = arena[noff];
+            a.route_off[i] = noff;
+            a.route_len[i] = nlen;
+            a.route_idx[i] = 0;
+            a.dist[i] = 0.0;
+            a.cur_link[i] = fl;
+            nst[j] = kMoving;
+            state_changed = true;
+            ev_link[nev] = fl;
+            ev_kind_agent[nev] = j | 256;
+            ++nev;
           }
         }
       }
+      if (state_changed) *reinterpret_cast<uchar4*>(a.state + i0) = make_uchar4(nst[0], nst[1], nst[2], nst[3]);
     }
     const int slot0 = block_alloc(nev, &ctr->n_events, &s_cnt, &s_base);
     if (nev) {
@@ -304,6 +343,18 @@ __global__ void k_travel_times(LinkArrays lk) {
     const int32_t c = lk.occ[l];
     const double f = (c == 0) ? 1.0 : bpr_factor_lookup(lk, l, c);
     lk.tt[l] = __ddiv_rn(lk.t0[l], f);
+  }
+}
+
+// Top up every agent's chain ring from a block of host-generated candidate destinations
+// (k per agent, row-major); candidates that do not fit are dropped.
+__global__ void k_refill_chains(AgentArrays a, const int32_t* __restrict__ cand, int32_t k) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    int cnt = a.chain_cnt[i];
+    const int head = a.chain_head[i];
+    for (int j = 0; j < k && cnt < a.chain_cap; ++j, ++cnt)
+      a.chain_dst[i * a.chain_cap + (head + cnt) % a.chain_cap] = cand[i * k + j];
+    a.chain_cnt[i] = (uint8_t)cnt;
   }
 }
 

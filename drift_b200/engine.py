@@ -96,24 +96,30 @@ class Engine:
         _capi.check(self._lib.drift_set_bpr(self._h, self.alpha, self.beta, _p(table, C.c_double),
                                             _p(off, C.c_int64), len(off) - 1, _p(cls, C.c_int32)))
 
-    def set_demand(self, seed, hourly24, start_node, trip_off, trip_dst, router=ROUTER_NX_EXACT):
+    def set_demand(self, seed, hourly24, start_node, chain_capacity=4, router=ROUTER_NX_EXACT):
         h = _f64(hourly24)
         assert h.shape == (24,)
-        s, o, d = _i32(start_node), _i64(trip_off), _i32(trip_dst)
-        assert len(s) == self.N and len(o) == self.N + 1
-        if len(d) == 0:
-            d = np.zeros(1, dtype=np.int32)
+        s = _i32(start_node)
+        assert len(s) == self.N
         _capi.check(self._lib.drift_set_demand(self._h, int(seed), _p(h, C.c_double), _p(s, C.c_int32),
-                                               _p(o, C.c_int64), _p(d, C.c_int32), int(router)))
+                                               int(chain_capacity), int(router)))
 
-    def push_trips(self, trip_off, trip_dst):
-        """Replace the trip chains (asynchronous; the arrays are kept alive by the engine object)."""
-        o, d = _i64(trip_off), _i32(trip_dst)
-        assert len(o) == self.N + 1
-        if len(d) == 0:
-            d = np.zeros(1, dtype=np.int32)
-        self._trip_keep = (o, d)
-        _capi.check(self._lib.drift_push_trips(self._h, _p(o, C.c_int64), _p(d, C.c_int32)))
+    def push_trips(self, candidates):
+        """Top up the per-agent destination rings from an [N, k] int32 host array (asynchronous copy;
+        the array is kept alive by the engine object)."""
+        c = _i32(candidates)
+        assert c.ndim == 2 and c.shape[0] == self.N
+        self._trip_keep = c
+        _capi.check(self._lib.drift_push_trips(self._h, _p(c, C.c_int32), c.shape[1]))
+
+    def store_trip_pool(self, pool):
+        """Upload [n_blocks, N, k] candidate destinations once; ``refill_from_pool(b)`` tops up from block b."""
+        c = _i32(pool)
+        assert c.ndim == 3 and c.shape[1] == self.N
+        _capi.check(self._lib.drift_store_trip_pool(self._h, _p(c, C.c_int32), c.shape[0], c.shape[2]))
+
+    def refill_from_pool(self, block):
+        _capi.check(self._lib.drift_refill_from_pool(self._h, int(block)))
 
     # ---- routing ------------------------------------------------------------------------------
     def route(self, src, dst, router=ROUTER_NX_EXACT, congested=False, fetch=True):

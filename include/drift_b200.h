@@ -143,15 +143,22 @@ int drift_step(drift_engine* e, int32_t n_ticks, double delta);
 
 /* Device-driven demand (throughput mode): every waiting agent departs at tick k
  * with probability hourly[hour(t_k)]*4*delta/3600 (lib/agent.py:176-180, 243-259) drawn from a
- * counter-based generator keyed (seed, global agent id, tick); its k-th trip goes from its
- * current node to trip_dst[trip_off[i]+k] (host-generated by the s-t model).  Routing uses
- * `router`.  start_node[N] = initial node of each agent (lib/agent.py:40-44). */
+ * counter-based generator keyed (seed, global agent id, tick).  Its trips go from its current
+ * node (lib/agent.py:47: source = previous target) to the destinations the host pushes into a
+ * per-agent ring of `chain_capacity` upcoming targets (generated by the s-t model on the host).
+ * Routes of the next two trips of every agent are prefetched as one large batch every
+ * "route_window" ticks (option; the reference's travel_time is static, so a route does not
+ * depend on when it is computed); `router` selects the engine.  start_node[N] = initial node of
+ * each agent (lib/agent.py:40-44). */
 int drift_set_demand(drift_engine* e, uint64_t seed, const double hourly24[24], const int32_t* start_node,
-                     const int64_t* trip_off, const int32_t* trip_dst, int32_t router);
-/* Replace every agent's trip chain (host buffers, asynchronous: keep them alive until the next
- * synchronising call); the chain position restarts at 0.  Lets the host stream demand block by
- * block instead of generating a whole horizon up front. */
-int drift_push_trips(drift_engine* e, const int64_t* trip_off, const int32_t* trip_dst);
+                     int32_t chain_capacity, int32_t router);
+/* Top up every agent's ring from `k` candidate destinations per agent (row-major [N][k] host
+ * buffer, copied asynchronously: keep it alive until the next synchronising call).  Candidates
+ * that do not fit are dropped. */
+int drift_push_trips(drift_engine* e, const int32_t* candidates, int32_t k);
+/* Same, from a pool kept in HBM: n_blocks blocks of [N][k] candidates uploaded once. */
+int drift_store_trip_pool(drift_engine* e, const int32_t* candidates, int32_t n_blocks, int32_t k);
+int drift_refill_from_pool(drift_engine* e, int32_t block);
 /* Run n_ticks ticks with device-driven demand starting at simulation time t0 (seconds). */
 int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0);
 

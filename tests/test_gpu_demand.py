@@ -14,14 +14,9 @@ from oracle.port import DEFAULT_HOURLY, PortSim, travel_probability
 pytestmark = pytest.mark.gpu
 
 
-def _chains(rng, N, V, start, per_agent):
-    off = np.arange(N + 1, dtype=np.int64) * per_agent
-    dst = rng.integers(0, V, size=N * per_agent).astype(np.int32)
-    return off, dst
-
-
-@pytest.mark.parametrize("name,router", [("g40_congested", 0), ("g100_random_s0", 0), ("multi_random_s0", 0)])
-def test_device_demand_matches_port(name, router):
+@pytest.mark.parametrize("name,router,window", [("g40_congested", 0, 25), ("g100_random_s0", 0, 300),
+                                                ("multi_random_s0", 0, 7), ("g40_congested", 0, 1)])
+def test_device_demand_matches_port(name, router, window):
     from drift_b200.engine import Engine
     from drift_b200.graph import lower_graph
 
@@ -32,12 +27,14 @@ def test_device_demand_matches_port(name, router):
     N, V = 3000, lg.V
     start = rng.integers(0, V, size=N).astype(np.int32)
     per_agent = 6
-    off, dst = _chains(rng, N, V, start, per_agent)
+    cands = rng.integers(0, V, size=(N, per_agent)).astype(np.int32)
     hourly = {h: 0.9 for h in range(24)}
     h24 = np.array([hourly[h] for h in range(24)])
     seed, delta, blocks, ticks_per_block = 1234567, 1.0, 12, 50
     with Engine(lg, N, alpha=0.15, beta=4.0) as eng:
-        eng.set_demand(seed, h24, start, off, dst, router=router)
+        eng.set_demand(seed, h24, start, chain_capacity=per_agent, router=router)
+        eng.set_option("route_window", window)
+        eng.push_trips(cands)
         occs, t = [], 0.0
         dep_log = []
         arr_log = []
