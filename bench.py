@@ -218,7 +218,7 @@ def run_b200(args):
     trips_per_step = 2
     delta = 1.0
     eng = Engine(lg, n_local, device=local_rank, agent_base=rank * n_local,
-                 route_arena_links=max(1 << 24, n_local * 256))
+                 route_arena_links=max(1 << 24, n_local * 1536))
     # HBM-resident pass: candidate destinations of all warm-up + timed steps uploaded once
     total_steps = W + K
     _, dst_all = make_chains(model, rng, lg, start, 4 + trips_per_step * total_steps)
