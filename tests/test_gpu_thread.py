@@ -55,13 +55,18 @@ def test_thread_matches_reference_run(name, tmp_path):
         want = case.trips
         got = th.data_logger.trips_data
         id2idx = {"A%06d" % id(a): a.index for a in th.agents}
+        if case.finish_error:
+            # the reference's finish_simulation dies with a TypeError half way through the flush
+            # (SURVEY.md 0-9a); the drop-in guards it, so only the rows up to the crash compare
+            assert len(got) > len(want)
+            got = got[:len(want)]
         assert len(got) == len(want)
         for g, w in zip(got, want):
             g = dict(g)
             g["agent_index"] = id2idx[g.pop("agent_id")]
             assert g == w
         stats = th.data_logger.get_statistics()
-        for k, v in case.stats.items():
+        for k, v in (case.stats or {}).items():
             assert stats[k] == v
         assert np.array_equal(np.array([a.trip_count for a in th.agents]), case.z["trip_counts"])
         # the CSV on disk has the reference's header and one row per trip
@@ -71,7 +76,7 @@ def test_thread_matches_reference_run(name, tmp_path):
             rows = list(csv.reader(fh))
         assert rows[0] == ["trip_id", "agent_id", "start_time", "end_time", "origin_node", "destination_node",
                            "route_taken", "trip_distance_km", "trip_duration_min", "average_speed_kmh"]
-        assert len(rows) == len(want) + 1
+        assert len(rows) == len(th.data_logger.trips_data) + 1
         assert rows[1][0] == want[0]["trip_id"] and rows[1][6] == want[0]["route_taken"]
         assert rows[1][8] == repr(want[0]["trip_duration_min"])
     finally:
