@@ -217,8 +217,14 @@ def run_b200(args):
     K, W, TPS = args.steps, args.warmup, args.ticks_per_step
     trips_per_step = 2
     delta = 1.0
-    eng = Engine(lg, n_local, device=local_rank, agent_base=rank * n_local,
-                 route_arena_links=max(1 << 24, n_local * 1536))
+    sharded = None
+    if world > 1:
+        from drift_b200.dist import ShardedEngine
+
+        sharded = ShardedEngine(lg, n_local * world, device=local_rank, route_arena_links=max(1 << 24, n_local * 1536))
+        eng = sharded.engine
+    else:
+        eng = Engine(lg, n_local, device=local_rank, agent_base=0, route_arena_links=max(1 << 24, n_local * 1536))
     # HBM-resident pass: candidate destinations of all warm-up + timed steps uploaded once
     total_steps = W + K
     _, dst_all = make_chains(model, rng, lg, start, 4 + trips_per_step * total_steps)
@@ -246,9 +252,12 @@ def run_b200(args):
         if resident:
             eng.refill_from_pool(step_no[0])
             step_no[0] += 1
-        eng.run(TPS, delta, t_sim)
-        for _ in range(TPS):
-            t_sim += delta
+        if sharded is not None:
+            t_sim = sharded.run(TPS, delta, t_sim)
+        else:
+            eng.run(TPS, delta, t_sim)
+            for _ in range(TPS):
+                t_sim += delta
 
     for _ in range(W):
         run_block()
@@ -302,7 +311,10 @@ def run_b200(args):
     stm0 = eng.stats()
     eng.set_profiling(True)
     prof_ticks = min(TPS, 100)
-    eng.run(prof_ticks, delta, t_sim)
+    if sharded is not None:
+        sharded.run(prof_ticks, delta, t_sim)
+    else:
+        eng.run(prof_ticks, delta, t_sim)
     kt = eng.kernel_times()
     eng.set_profiling(False)
     stm1 = eng.stats()
@@ -328,7 +340,8 @@ def run_b200(args):
                         router="batched reverse-tree SSSP + destination cache", clock="08:00 peak",
                         l2="agent state (%.0f MB) and link arrays exceed L2 only for >= 4M agents; the tick loop touches "
                            "all of it every tick, no flush" % (n_local * 45 / 1e6),
-                        multi_gpu="replicas (link-event exchange not in this build)" if world > 1 else "n/a"),
+                        multi_gpu=("agents sharded by id block, graph replicated, per-tick all-gather of link events "
+                                   "(NCCL), every rank resolves the global event set") if world > 1 else "n/a"),
             routes_per_s=routes / dt, routes_in_timed_region=int(routes),
             moving_fraction=float(moving / n_local),
             e2e=dict(value=e2e_value, unit="agent-steps/s", h2d_bytes_per_step=int(h2d),

@@ -73,6 +73,7 @@ SIGNATURES = {
     "drift_stats": (C.c_int, [ENGINE, C.POINTER(StatsOut)]),
     "drift_tick_index": (C.c_int, [ENGINE, c_i64p]),
     "drift_tick_begin": (C.c_int, [ENGINE, C.c_double, c_i64p]),
+    "drift_tick_begin_demand": (C.c_int, [ENGINE, C.c_double, C.c_double, c_i64p]),
     "drift_events_ptr": (C.c_int, [ENGINE, C.POINTER(C.c_void_p), c_i64p]),
     "drift_tick_finish": (C.c_int, [ENGINE, C.c_void_p, C.c_int64]),
     "drift_kernel_times": (C.c_int, [ENGINE, c_f64p, c_i64p, c_f64p, c_i64p]),

@@ -848,6 +848,35 @@ static int plan_window(drift_engine* e) {
   return DRIFT_OK;
 }
 
+// one tick of device-driven demand up to (not including) the event resolution
+static int demand_tick_begin(drift_engine* e, double delta, double t) {
+  if (e->ticks_since_plan <= 0) {
+    int rc = plan_window(e);
+    if (rc) return rc;
+    e->ticks_since_plan = e->route_window;
+  }
+  e->ticks_since_plan -= 1;
+  const int hour = (int)std::fmod((t + 21600.0) / 3600.0, 24.0);  // lib/agent.py:251-252
+  const double p = e->hourly[hour] * 4.0 * delta / 3600.0;        // lib/agent.py:259,180
+  int rc = tick_begin(e, delta, true, p);
+  if (rc) return rc;
+  // Departures that found no prefetched route (an agent that completed two trips inside one
+  // window) are routed here, inside the tick; the batch size stays on the device, the kernels
+  // return at once when it is zero.
+  Counters* c = e->ctr.p;
+  k_prepare_requests<<<1, 256, 0, e->stream>>>(e->agents(), c, e->dep_req.p, e->q_src.p, e->q_dst.p, e->q_agent.p);
+  rc = launch_router(e, e->demand_router, 256, 0, &c->n_dep_req);
+  if (rc) return rc;
+  k_log_departures<<<1, 256, 0, e->stream>>>(c, (int32_t)e->tick, e->q_agent.p, e->q_src.p, e->q_dst.p,
+                                             e->q_status.p, e->dl_agent.p, e->dl_tick.p, e->dl_src.p, e->dl_dst.p,
+                                             e->dl_status.p, (unsigned long long)e->dl_cap, e->dl_drained);
+  k_commit<<<1, 256, 0, e->stream>>>(e->N, e->q_agent.p, e->q_off.p, e->q_len.p, c, e->pend_agent.p, e->pend_off.p,
+                                     e->pend_len.p, (int32_t)e->pend_cap, &c->n_dep_req);
+  CU(cudaGetLastError());
+  e->total_launches += 3;
+  return inject_pending(e);
+}
+
 int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0) {
   if (!e || n_ticks < 0) return fail(DRIFT_EINVAL, "drift_run");
   if (!e->have_demand) return fail(DRIFT_ESTATE, "drift_run: call drift_set_demand first");
@@ -855,35 +884,27 @@ int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0) {
   CU(cudaSetDevice(e->device));
   double t = t0;
   for (int32_t k = 0; k < n_ticks; ++k) {
-    if (e->ticks_since_plan <= 0) {
-      int rc = plan_window(e);
-      if (rc) return rc;
-      e->ticks_since_plan = e->route_window;
-    }
-    e->ticks_since_plan -= 1;
     t += delta;  // repeated fp64 sum like lib/simulation_thread.py:295
-    const int hour = (int)std::fmod((t + 21600.0) / 3600.0, 24.0);  // lib/agent.py:251-252
-    const double p = e->hourly[hour] * 4.0 * delta / 3600.0;        // lib/agent.py:259,180
-    int rc = tick_begin(e, delta, true, p);
+    int rc = demand_tick_begin(e, delta, t);
     if (rc) return rc;
-    // Departures that found no prefetched route (an agent that completed two trips inside one
-    // window) are routed here, inside the tick; the batch size stays on the device, the kernels
-    // return at once when it is zero.
-    Counters* c = e->ctr.p;
-    k_prepare_requests<<<1, 256, 0, e->stream>>>(e->agents(), c, e->dep_req.p, e->q_src.p, e->q_dst.p, e->q_agent.p);
-    rc = launch_router(e, e->demand_router, 256, 0, &c->n_dep_req);
+    rc = tick_finish(e, e->events.p, &e->ctr.p->n_events, 2 * e->N);
     if (rc) return rc;
-    k_log_departures<<<1, 256, 0, e->stream>>>(c, (int32_t)e->tick, e->q_agent.p, e->q_src.p, e->q_dst.p,
-                                               e->q_status.p, e->dl_agent.p, e->dl_tick.p, e->dl_src.p, e->dl_dst.p,
-                                               e->dl_status.p, (unsigned long long)e->dl_cap, e->dl_drained);
-    k_commit<<<1, 256, 0, e->stream>>>(e->N, e->q_agent.p, e->q_off.p, e->q_len.p, c, e->pend_agent.p, e->pend_off.p,
-                                       e->pend_len.p, (int32_t)e->pend_cap, &c->n_dep_req);
-    CU(cudaGetLastError());
-    e->total_launches += 3;
-    rc = inject_pending(e);
+  }
+  return DRIFT_OK;
+}
+
+int drift_tick_begin_demand(drift_engine* e, double delta, double t, int64_t* n_events) {
+  if (!e || !e->have_demand || !e->have_bpr) return fail(DRIFT_ESTATE, "drift_tick_begin_demand");
+  CU(cudaSetDevice(e->device));
+  int rc = demand_tick_begin(e, delta, t);
+  if (rc) return rc;
+  if (n_events) {
+    Counters c;
+    rc = fetch_counters(e, &c);
     if (rc) return rc;
-    rc = tick_finish(e, e->events.p, &c->n_events, 2 * e->N);
+    rc = check_overflow(e, c);
     if (rc) return rc;
+    *n_events = c.n_events;
   }
   return DRIFT_OK;
 }

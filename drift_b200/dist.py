@@ -1,0 +1,95 @@
+"""Multi-GPU: agents sharded by contiguous id block, graph replicated, one exchange per tick.
+
+An agent on rank r entering link l must see the events of all lower-index agents of the same
+tick, i.e. of lower ranks (a sum-only all-reduce of volumes gives wrong entry
+speeds from tick 4).  So the ranks exchange their *link events* (16 B each, a few thousand per
+tick) instead of a dense per-link vector (4*L bytes): every rank then resolves the global event
+set -- occupancy stays replicated and identical everywhere, speeds are written for local agents
+only.  The collective is an all-gather over ``torch.distributed`` (NCCL on GPUs; gloo in the CPU
+tests of this module's host logic).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+EVENT_WORDS = 4  # one event = 4 x int32: link, agent (global id), kind, pos
+
+
+def shard_bounds(n_total, rank, world):
+    """Contiguous block of agent ids owned by ``rank`` (lower rank <=> lower agent index)."""
+    base = n_total // world
+    rem = n_total % world
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class _DevPtr:
+    """Expose a raw device pointer to torch through the CUDA array interface (no copy)."""
+
+    def __init__(self, ptr, n_words):
+        self.__cuda_array_interface__ = dict(shape=(n_words,), typestr="<i4", data=(ptr, False), version=2)
+
+
+def exchange_events(local: torch.Tensor, n_local: int, group=None):
+    """All-gather variable-length event lists.  ``local``: int32 tensor [cap, 4] whose first
+    ``n_local`` rows are valid.  Returns (events [n_total, 4] in rank order, counts list)."""
+    world = dist.get_world_size(group)
+    cnt = torch.tensor([n_local], dtype=torch.int64, device=local.device)
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt, group=group)
+    counts = [int(c.item()) for c in counts]
+    m = max(counts)
+    if m == 0:
+        return local[:0], counts
+    if local.shape[0] >= m:
+        send = local[:m].contiguous()  # rows past n_local are padding
+    else:
+        send = torch.zeros((m, EVENT_WORDS), dtype=local.dtype, device=local.device)
+        send[:n_local] = local[:n_local]
+    recv = torch.empty((world, m, EVENT_WORDS), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group) if local.is_cuda else \
+        dist.all_gather(list(recv.unbind(0)), send, group=group)
+    parts = [recv[r, :counts[r]] for r in range(world) if counts[r]]
+    return torch.cat(parts, dim=0), counts
+
+
+class ShardedEngine:
+    """One rank of a sharded run: wraps a local ``Engine`` and performs the per-tick exchange."""
+
+    def __init__(self, lg, n_total, alpha=0.15, beta=4.0, device=0, route_arena_links=0, group=None):
+        from .engine import Engine
+
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.lo, self.hi = shard_bounds(n_total, self.rank, self.world)
+        self.n_total = n_total
+        self.engine = Engine(lg, self.hi - self.lo, alpha=alpha, beta=beta, device=device, agent_base=self.lo,
+                             route_arena_links=route_arena_links)
+        ptr, cap = self.engine.events_ptr()
+        self._events = torch.as_tensor(_DevPtr(ptr, cap * EVENT_WORDS), device="cuda:%d" % device).view(cap, EVENT_WORDS)
+        self._keep = None
+
+    def _finish(self, n_local):
+        events, counts = exchange_events(self._events, n_local, self.group)
+        self._keep = events  # alive until the next tick's kernels are done with it
+        torch.cuda.current_stream().synchronize()
+        self.engine.tick_finish(events.data_ptr() if events.numel() else self._events.data_ptr(), int(sum(counts)))
+        return counts
+
+    def step(self, delta):
+        """Trace / host-driven mode: pending departures were submitted to the local engine."""
+        return self._finish(self.engine.tick_begin(delta))
+
+    def run(self, n_ticks, delta, t0):
+        """Device-driven demand, ``n_ticks`` ticks starting at clock ``t0``."""
+        t = t0
+        for _ in range(n_ticks):
+            t += delta
+            self._finish(self.engine.tick_begin_demand(delta, t))
+        return t
+
+    def close(self):
+        self.engine.close()

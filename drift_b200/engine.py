@@ -178,6 +178,11 @@ class Engine:
         _capi.check(self._lib.drift_tick_begin(self._h, float(delta), C.byref(n)))
         return n.value
 
+    def tick_begin_demand(self, delta, t):
+        n = C.c_int64(0)
+        _capi.check(self._lib.drift_tick_begin_demand(self._h, float(delta), float(t), C.byref(n)))
+        return n.value
+
     def events_ptr(self):
         p, cap = C.c_void_p(), C.c_int64(0)
         _capi.check(self._lib.drift_events_ptr(self._h, C.byref(p), C.byref(cap)))

@@ -193,6 +193,7 @@ int drift_tick_index(drift_engine* e, int64_t* tick);
  *   drift_tick_finish   resolve `n_events` gathered records at `events_dev` (device pointer,
  *                       all ranks' records in any order) */
 int drift_tick_begin(drift_engine* e, double delta, int64_t* n_events);
+int drift_tick_begin_demand(drift_engine* e, double delta, double t, int64_t* n_events); /* same, device-driven demand at clock t */
 int drift_events_ptr(drift_engine* e, void** dev_ptr, int64_t* capacity);
 int drift_tick_finish(drift_engine* e, const void* events_dev, int64_t n_events);
 

@@ -1,0 +1,114 @@
+"""World-size-2 gloo tests (CPU) of the multi-rank host logic: shard bounds, the variable-length
+event exchange, and the rank-prefix semantics of the sharded tick using the oracle's event model."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker_exchange(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from drift_b200.dist import exchange_events, shard_bounds
+
+    try:
+        assert shard_bounds(10, 0, 3) == (0, 4) and shard_bounds(10, 1, 3) == (4, 7) and shard_bounds(10, 2, 3) == (7, 10)
+        for trial, n_local in enumerate([3 + 2 * rank, 0 if rank == 0 else 5, 0]):
+            local = torch.full((16, 4), -1, dtype=torch.int32)
+            for i in range(n_local):
+                local[i] = torch.tensor([100 * rank + i, rank, 1, trial], dtype=torch.int32)
+            ev, counts = exchange_events(local, n_local)
+            want = []
+            for r in range(world):
+                n_r = [3 + 2 * r, 0 if r == 0 else 5, 0][trial]
+                want += [[100 * r + i, r, 1, trial] for i in range(n_r)]
+            assert counts == [[3 + 2 * r, 0 if r == 0 else 5, 0][trial] for r in range(world)]
+            assert ev.tolist() == want
+        out.put((rank, "ok"))
+    except Exception as exc:  # pragma: no cover
+        out.put((rank, repr(exc)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_event_exchange_gloo_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_exchange, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")]
+
+
+def _worker_sharded_port(rank, world, port, out):
+    """Each rank advances its own agent block with the oracle's event model and resolves the
+    all-gathered events; the result must equal the sequential single-process port."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from drift_b200.dist import exchange_events, shard_bounds
+        from oracle import golden
+        from oracle.event_model import EventModel
+        from oracle.port import PortSim
+
+        case = golden.GoldenCase("g40_congested_bpr")
+        pg = case.plain_graph()
+        trace = case.departure_trace()
+        ticks = 300
+        lo, hi = shard_bounds(case.N, rank, world)
+        em = EventModel(pg, case.N, lo, hi, alpha=case.alpha, beta=case.beta)
+        ref = PortSim(pg, case.N, hourly=case.hourly, alpha=case.alpha, beta=case.beta, accel=case.accel,
+                      hours=case.hours, departure_trace=trace, init_nodes=case.init_nodes)
+        for k in range(1, ticks + 1):
+            deps = {a: v for a, v in trace.get(k, {}).items() if lo <= a < hi}
+            local = em.tick_begin(1.0, deps)
+            buf = torch.zeros((max(len(local), 1), 4), dtype=torch.int32)
+            if len(local):
+                buf[:len(local)] = torch.from_numpy(local)
+            ev, counts = exchange_events(buf, len(local))
+            em.tick_finish(ev.numpy())
+            ref.tick()
+            assert np.array_equal(em.occ, np.asarray(ref.occ)), "volumes differ at tick %d" % k
+        st, d, sp, pi = ref.snapshot()
+        mv = st[lo:hi] == 1
+        assert np.array_equal(em.state, st[lo:hi])
+        assert np.array_equal(em.dist[mv], d[lo:hi][mv]) and np.array_equal(em.speed[mv], sp[lo:hi][mv])
+        out.put((rank, "ok"))
+    except Exception as exc:  # pragma: no cover
+        import traceback
+
+        out.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_tick_semantics_gloo(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sharded_port, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
