@@ -11,27 +11,15 @@ constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
 constexpr uint8_t kWaiting = 0;
 constexpr uint8_t kMoving = 1;
 
-// One link event of a tick: an agent leaving or entering a link.  16 bytes so that a
-// warp writes 512 contiguous bytes.  `pos` (arrival order among the events on the same
-// link, assigned by k_count) is only a slot index; the Gauss-Seidel order of the
+// One link event of a tick: an agent leaving or entering a link.  16 bytes so that a warp
+// writes 512 contiguous bytes.  The events of one link form a singly linked list threaded through
+// `aux` (head in LinkArrays::head); list order is arbitrary, the Gauss-Seidel order of the
 // reference (agent-list order, lib/simulation_thread.py:299-303) is recovered from `agent`.
 struct __align__(16) Event {
   int32_t link;
   uint32_t agent;  // global agent id
   int32_t kind;    // +1 enter, -1 leave
-  int32_t pos;
-};
-
-struct __align__(16) Segment {  // the events of one touched link, contiguous in `sorted`
-  int32_t link;
-  int32_t base;
-  int32_t count;
-  int32_t occ0;  // occupancy at the start of the tick
-};
-
-struct __align__(8) SortedEvent {
-  uint32_t agent;
-  int32_t kind;
+  int32_t aux;     // >= 0: next event of the same link; < 0: last one, carries -(occ_start) - 1
 };
 
 struct HeapItem {  // (dist, push counter, node): nx:weighted.py heap entries
@@ -41,23 +29,22 @@ struct HeapItem {  // (dist, push counter, node): nx:weighted.py heap entries
 };
 
 struct Counters {
-  int32_t n_events;
-  int32_t n_touched;
-  int32_t seg_cursor;
-  int32_t n_dep_req;      // departure requests of this tick (device-driven demand)
+  int32_t n_events[2];    // indexed by tick parity: tick k resets the slot of tick k+1
+  int32_t n_dep_req[2];   // departures of this tick that found no prefetched route
   int32_t n_pending;      // pending departures (committed routes) for the next tick
   int32_t overflow;       // bit flags, see kOvf*
-  int32_t tick;           // index of the tick being / last processed (1-based like SimulationThread.step)
   int32_t n_plan;         // route requests of the current planning batch
+  int32_t pad0;
   unsigned long long n_arrivals;    // total appended to the arrival ring
   unsigned long long n_departures;  // total appended to the departure log ring
   unsigned long long n_entries;     // total appended to the entry trace
   unsigned long long arena_cursor;  // route arena bump pointer (link ids)
-  unsigned long long stage_cursor;  // staging arena bump pointer
+  unsigned long long stage_cursor;
   long long moving;                 // reductions for drift_stats
   long long on_roads;
   long long links_with_traffic;
   long long total_capacity;
+  unsigned long long phase_ns[4];   // persistent kernel: accumulated %globaltimer time per phase
 };
 
 constexpr int kOvfEvents = 1;
@@ -102,6 +89,7 @@ struct LinkArrays {
   const int32_t* u;
   const int32_t* v;
   int32_t* occ;
+  unsigned long long* head;  // [L] (tick << 32 | event index): head of the link's event list this tick
   double* tt;  // congestion-updated travel time (extension)
   const int32_t* cls;
   const double* factor;     // concatenated per-class tables

@@ -84,7 +84,8 @@ struct drift_engine {
   DevBuf<int32_t> fwd_rowptr, fwd_col, fwd_link, bwd_rowptr, bwd_col, bwd_link, link_cap, link_u, link_v, link_cls;
   DevBuf<double> fwd_w, bwd_w, link_len, link_v0, link_t0, link_tt, factor, fwd_wc, bwd_wc;
   DevBuf<int64_t> cls_off;
-  DevBuf<int32_t> occ, evcnt, segid, hist;
+  DevBuf<int32_t> occ, hist;
+  DevBuf<unsigned long long> head;
   int64_t total_capacity = 0;
   double alpha = 0.15, beta = 4.0;
   bool have_bpr = false;
@@ -105,10 +106,18 @@ struct drift_engine {
   int64_t arena_cap = 0;
   // events
   DevBuf<Event> events;
-  DevBuf<SortedEvent> sorted;
-  DevBuf<Segment> segs;
-  DevBuf<int32_t> touched;
   int64_t ev_cap = 0;
+  // in-tick fallback router scratch (device-driven demand)
+  DevBuf<double> f_seen;
+  DevBuf<int32_t> f_plink;
+  DevBuf<uint32_t> f_mark, f_epoch;
+  DevBuf<HeapItem> f_heap;
+  int32_t f_workers = 0;
+  int64_t f_heap_cap = 0;
+  // persistent tick loop
+  bool persistent = true;
+  int coop_blocks_per_sm = 2;
+  int num_sms = kSMs;
   // pending departures + staged route batch
   DevBuf<int32_t> pend_agent, pend_len;
   DevBuf<int64_t> pend_off;
@@ -157,6 +166,7 @@ struct drift_engine {
   DevBuf<Counters> ctr;
   Counters* h_ctr = nullptr;  // pinned
   int64_t tick = 0;
+  double last_delta = 1.0;
   int32_t ticks_since_plan = 0;
   int64_t routes_planned = 0;
   // profiling
@@ -200,6 +210,7 @@ struct drift_engine {
     l.u = link_u.p;
     l.v = link_v.p;
     l.occ = occ.p;
+    l.head = head.p;
     l.tt = link_tt.p;
     l.cls = link_cls.p;
     l.factor = factor.p;
@@ -416,64 +427,103 @@ struct ProfScope {
   }
 };
 
-// one tick, part 1: advance + departures -> local events
+TickArgs make_tick_args(drift_engine* e, double delta, bool demand) {
+  TickArgs p;
+  memset(&p, 0, sizeof(p));
+  p.a = e->agents();
+  p.lk = e->links();
+  p.g = e->graph();
+  p.rg = e->rings();
+  if (demand) {
+    p.dm.seed = e->seed;
+    p.dm.dep_req = e->dep_req.p;
+    p.dm.log_agent = e->dl_agent.p;
+    p.dm.log_tick = e->dl_tick.p;
+    p.dm.log_src = e->dl_src.p;
+    p.dm.log_dst = e->dl_dst.p;
+    p.dm.log_status = e->dl_status.p;
+    p.dm.log_cap = (unsigned long long)e->dl_cap;
+    p.dm.log_drained = e->dl_drained;
+    p.fsc.seen = e->f_seen.p;
+    p.fsc.plink = e->f_plink.p;
+    p.fsc.mark = e->f_mark.p;
+    p.fsc.heap = e->f_heap.p;
+    p.fsc.epoch = e->f_epoch.p;
+    p.fsc.heap_cap = e->f_heap_cap;
+    p.fsc.workers = e->f_workers;
+  }
+  p.w_fwd = e->fwd_w.p;
+  p.w_bwd = e->bwd_w.p;
+  p.link_cost = e->link_t0.p;
+  p.arena = e->arena.p;
+  p.arena_cap = (unsigned long long)e->arena_cap;
+  p.ctr = e->ctr.p;
+  p.events = e->events.p;
+  p.ev_cap = (int32_t)e->ev_cap;
+  p.pend_agent = e->pend_agent.p;
+  p.pend_off = e->pend_off.p;
+  p.pend_len = e->pend_len.p;
+  p.delta = delta;
+  p.kph_to_mps = kKphToMps;
+  p.demand = demand ? 1 : 0;
+  return p;
+}
+
+// one tick as separate kernels, phases A + A2: advance, departures -> local events
 int tick_begin(drift_engine* e, double delta, bool demand, double p_dep) {
   e->tick += 1;
   const int32_t tick = (int32_t)e->tick;
-  // reset the per-tick counters (n_events, n_touched, seg_cursor, n_dep_req)
-  CU(cudaMemsetAsync(e->ctr.p, 0, 4 * sizeof(int32_t), e->stream));
+  const TickArgs p = make_tick_args(e, delta, demand);
   const int64_t per_block = (int64_t)kAdvThreads * kAdvPerThread;
-  const int blocks = grid_for(e->N, (int)per_block, kSMs * 8);
+  const int blocks = grid_for(e->N, (int)per_block, e->num_sms * 8);
   {
     ProfScope ps(e, true);
-    DemandArgs dm;
-    memset(&dm, 0, sizeof(dm));
-    if (demand) {
-      dm.seed = e->seed;
-      dm.p_dep = p_dep;
-      dm.dep_req = e->dep_req.p;
-      dm.log_agent = e->dl_agent.p;
-      dm.log_tick = e->dl_tick.p;
-      dm.log_src = e->dl_src.p;
-      dm.log_dst = e->dl_dst.p;
-      dm.log_status = e->dl_status.p;
-      dm.log_cap = (unsigned long long)e->dl_cap;
-      dm.log_drained = e->dl_drained;
-      k_advance<true><<<blocks, kAdvThreads, 0, e->stream>>>(e->agents(), e->arena.p, delta, tick, e->ctr.p,
-                                                             e->events.p, (int32_t)e->ev_cap, e->rings(), dm);
-    } else {
-      k_advance<false><<<blocks, kAdvThreads, 0, e->stream>>>(e->agents(), e->arena.p, delta, tick, e->ctr.p,
-                                                              e->events.p, (int32_t)e->ev_cap, e->rings(), dm);
-    }
+    if (demand)
+      k_advance<true><<<blocks, kAdvThreads, 0, e->stream>>>(p, tick, p_dep);
+    else
+      k_advance<false><<<blocks, kAdvThreads, 0, e->stream>>>(p, tick, p_dep);
   }
+  k_inject<<<std::max(1, std::min(e->num_sms, (int)((e->pend_cap + 255) / 256))), 256, 0, e->stream>>>(p, tick);
   CU(cudaGetLastError());
-  e->total_launches += 1;
+  e->total_launches += 2;
   e->adv_launches += 1;
   return DRIFT_OK;
 }
 
-int inject_pending(drift_engine* e) {
-  Counters* c = e->ctr.p;
-  k_inject_departures<<<kSMs, 256, 0, e->stream>>>(e->agents(), e->arena.p, c, e->pend_agent.p, e->pend_off.p,
-                                                   e->pend_len.p, &c->n_pending, e->events.p, (int32_t)e->ev_cap);
+// phase C as a separate kernel.  gathered = events of all ranks (re-linked first); n_events < 0 = local
+int tick_finish(drift_engine* e, Event* events, int64_t n_events, bool gathered, double delta) {
+  const TickArgs p = make_tick_args(e, delta, e->have_demand);
+  const int32_t tick = (int32_t)e->tick;
+  const int64_t hint = n_events < 0 ? 2 * e->N : n_events;
+  const int g = grid_for(std::max<int64_t>(hint, 1), 256, e->num_sms * 4);
+  if (gathered && n_events > 0) {
+    k_link_events<<<g, 256, 0, e->stream>>>(e->links(), events, (int)n_events, tick);
+    e->total_launches += 1;
+  }
+  k_resolve<<<g, 256, 0, e->stream>>>(p, events, (int)n_events, tick);
   CU(cudaGetLastError());
-  // n_pending is cleared after the inject kernel consumed it
-  CU(cudaMemsetAsync(&c->n_pending, 0, sizeof(int32_t), e->stream));
   e->total_launches += 1;
   return DRIFT_OK;
 }
 
-// one tick, part 2: ordered occupancy + entry speeds from `n_events_ptr` events at `events`
-int tick_finish(drift_engine* e, Event* events, const int32_t* n_events_ptr, int64_t n_hint) {
-  Counters* c = e->ctr.p;
-  const int g = grid_for(n_hint, 256, kSMs * 4);
-  k_count<<<g, 256, 0, e->stream>>>(events, n_events_ptr, e->evcnt.p, e->touched.p, c);
-  k_segment<<<g, 256, 0, e->stream>>>(e->touched.p, c, e->evcnt.p, e->segid.p, e->segs.p, e->occ.p);
-  k_scatter<<<g, 256, 0, e->stream>>>(events, n_events_ptr, e->segid.p, e->segs.p, e->sorted.p);
-  k_resolve<<<g, 256, 0, e->stream>>>(events, n_events_ptr, e->segid.p, e->segs.p, e->sorted.p, e->links(),
-                                      e->agents(), kKphToMps, (int32_t)e->tick, c, e->rings());
-  CU(cudaGetLastError());
-  e->total_launches += 4;
+// n_ticks ticks in one cooperative launch (k_tick_loop): p_dep and the window plan are constant inside
+int run_tick_loop(drift_engine* e, int32_t n_ticks, double delta, bool demand, double p_dep) {
+  if (n_ticks <= 0) return DRIFT_OK;
+  TickArgs p = make_tick_args(e, delta, demand);
+  int32_t tick0 = (int32_t)e->tick + 1;
+  static int max_per_sm = 0;
+  if (!max_per_sm) {
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_per_sm, k_tick_loop, kAdvThreads, 0));
+    if (max_per_sm < 1) return fail(DRIFT_ECUDA, "k_tick_loop does not fit on an SM");
+  }
+  const int64_t tiles = (e->N + (int64_t)kAdvThreads * kAdvPerThread - 1) / ((int64_t)kAdvThreads * kAdvPerThread);
+  int blocks = e->num_sms * std::min(max_per_sm, e->coop_blocks_per_sm);
+  if (tiles < blocks) blocks = (int)std::max<int64_t>(tiles, 1);
+  void* args[] = {(void*)&p, (void*)&tick0, (void*)&n_ticks, (void*)&p_dep};
+  CU(cudaLaunchCooperativeKernel((void*)k_tick_loop, dim3(blocks), dim3(kAdvThreads), args, 0, e->stream));
+  e->tick += n_ticks;
+  e->total_launches += 1;
+  e->adv_launches += n_ticks;
   return DRIFT_OK;
 }
 
@@ -527,8 +577,12 @@ int drift_create(drift_engine** out, int device, const drift_graph_desc* g) {
   CUX(e->fwd_wc.upload(g->fwd_w, g->Ef));
   CUX(e->bwd_wc.upload(g->bwd_w, g->Eb));
   CUX(e->occ.alloc(std::max(1, g->L)));
-  CUX(e->evcnt.alloc(std::max(1, g->L)));
-  CUX(e->segid.alloc(std::max(1, g->L)));
+  CUX(e->head.alloc(std::max(1, g->L)));
+  {
+    cudaDeviceProp prop;
+    CUX(cudaGetDeviceProperties(&prop, device));
+    e->num_sms = prop.multiProcessorCount;
+  }
   CUX(e->hist.alloc(std::max(1, g->L)));
   CUX(e->ctr.alloc(1));
   CUX(cudaMallocHost(&e->h_ctr, sizeof(Counters)));
@@ -607,9 +661,6 @@ int drift_add_agents(drift_engine* e, int64_t n_agents, int64_t agent_base, int6
   e->ev_cap = 2 * n_agents + 1024;
   if (e->ev_cap > 0x7fffffff) return fail(DRIFT_EINVAL, "too many agents for one engine");
   CU(e->events.alloc(e->ev_cap, false));
-  CU(e->sorted.alloc(e->ev_cap, false));
-  CU(e->segs.alloc(e->ev_cap, false));
-  CU(e->touched.alloc(e->ev_cap, false));
   e->pend_cap = n_agents;
   CU(e->pend_agent.alloc(n_agents));
   CU(e->pend_off.alloc(n_agents));
@@ -740,14 +791,11 @@ int drift_step(drift_engine* e, int32_t n_ticks, double delta) {
   if (!e->N) return fail(DRIFT_ESTATE, "drift_step: no agents");
   if (!e->have_bpr) return fail(DRIFT_ESTATE, "drift_step: call drift_set_bpr first");
   CU(cudaSetDevice(e->device));
+  if (e->persistent && !e->profiling) return run_tick_loop(e, n_ticks, delta, false, 0.0);
   for (int32_t k = 0; k < n_ticks; ++k) {
-    ProfScope ps(e, false);
-    if (e->profiling && k == 0 && e->tick_ev0 < 0) e->tick_ev0 = ps.i0;
     int rc = tick_begin(e, delta, false, 0.0);
     if (rc) return rc;
-    rc = inject_pending(e);
-    if (rc) return rc;
-    rc = tick_finish(e, e->events.p, &e->ctr.p->n_events, 2 * e->N);
+    rc = tick_finish(e, e->events.p, -1, false, delta);
     if (rc) return rc;
   }
   return DRIFT_OK;
@@ -773,6 +821,18 @@ int drift_set_demand(drift_engine* e, uint64_t seed, const double hourly24[24], 
   e->demand_router = router;
   int rc = ensure_qcap(e, 2 * e->N);
   if (rc) return rc;
+  {  // scratch of the in-tick fallback router: a few NetworkX-exact workers
+    const int64_t per_worker = 2 * (int64_t)e->V * 16 + 2 * (int64_t)(e->Ef + 2) * (int64_t)sizeof(HeapItem);
+    int64_t F = std::min<int64_t>(64, ((int64_t)2 << 30) / std::max<int64_t>(per_worker, 1));
+    F = std::max<int64_t>(F, 1);
+    CU(e->f_seen.alloc(F * 2 * e->V, false));
+    CU(e->f_plink.alloc(F * 2 * e->V, false));
+    CU(e->f_mark.alloc(F * 2 * e->V, true));
+    CU(e->f_epoch.alloc(F, true));
+    e->f_heap_cap = (int64_t)e->Ef + 2;
+    CU(e->f_heap.alloc(F * 2 * e->f_heap_cap, false));
+    e->f_workers = (int32_t)F;
+  }
   e->have_demand = true;
   return DRIFT_OK;
 }
@@ -848,6 +908,11 @@ static int plan_window(drift_engine* e) {
   return DRIFT_OK;
 }
 
+static double departure_probability(drift_engine* e, double t, double delta) {
+  const int hour = (int)std::fmod((t + 21600.0) / 3600.0, 24.0);  // lib/agent.py:251-252
+  return e->hourly[hour] * 4.0 * delta / 3600.0;                 // lib/agent.py:259,180
+}
+
 // one tick of device-driven demand up to (not including) the event resolution
 static int demand_tick_begin(drift_engine* e, double delta, double t) {
   if (e->ticks_since_plan <= 0) {
@@ -856,25 +921,7 @@ static int demand_tick_begin(drift_engine* e, double delta, double t) {
     e->ticks_since_plan = e->route_window;
   }
   e->ticks_since_plan -= 1;
-  const int hour = (int)std::fmod((t + 21600.0) / 3600.0, 24.0);  // lib/agent.py:251-252
-  const double p = e->hourly[hour] * 4.0 * delta / 3600.0;        // lib/agent.py:259,180
-  int rc = tick_begin(e, delta, true, p);
-  if (rc) return rc;
-  // Departures that found no prefetched route (an agent that completed two trips inside one
-  // window) are routed here, inside the tick; the batch size stays on the device, the kernels
-  // return at once when it is zero.
-  Counters* c = e->ctr.p;
-  k_prepare_requests<<<1, 256, 0, e->stream>>>(e->agents(), c, e->dep_req.p, e->q_src.p, e->q_dst.p, e->q_agent.p);
-  rc = launch_router(e, e->demand_router, 256, 0, &c->n_dep_req);
-  if (rc) return rc;
-  k_log_departures<<<1, 256, 0, e->stream>>>(c, (int32_t)e->tick, e->q_agent.p, e->q_src.p, e->q_dst.p,
-                                             e->q_status.p, e->dl_agent.p, e->dl_tick.p, e->dl_src.p, e->dl_dst.p,
-                                             e->dl_status.p, (unsigned long long)e->dl_cap, e->dl_drained);
-  k_commit<<<1, 256, 0, e->stream>>>(e->N, e->q_agent.p, e->q_off.p, e->q_len.p, c, e->pend_agent.p, e->pend_off.p,
-                                     e->pend_len.p, (int32_t)e->pend_cap, &c->n_dep_req);
-  CU(cudaGetLastError());
-  e->total_launches += 3;
-  return inject_pending(e);
+  return tick_begin(e, delta, true, departure_probability(e, t, delta));
 }
 
 int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0) {
@@ -883,11 +930,37 @@ int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0) {
   if (!e->have_bpr) return fail(DRIFT_ESTATE, "drift_run: call drift_set_bpr first");
   CU(cudaSetDevice(e->device));
   double t = t0;
+  if (e->persistent && !e->profiling) {
+    // split into runs of ticks that share the departure probability and do not cross a planning boundary
+    int32_t k = 0;
+    while (k < n_ticks) {
+      if (e->ticks_since_plan <= 0) {
+        int rc = plan_window(e);
+        if (rc) return rc;
+        e->ticks_since_plan = e->route_window;
+      }
+      double tt = t + delta;  // repeated fp64 sum like lib/simulation_thread.py:295
+      const double p = departure_probability(e, tt, delta);
+      int32_t n = 1;
+      while (k + n < n_ticks && n < e->ticks_since_plan) {
+        const double t_next = tt + delta;
+        if (departure_probability(e, t_next, delta) != p) break;
+        tt = t_next;
+        ++n;
+      }
+      int rc = run_tick_loop(e, n, delta, true, p);
+      if (rc) return rc;
+      e->ticks_since_plan -= n;
+      t = tt;
+      k += n;
+    }
+    return DRIFT_OK;
+  }
   for (int32_t k = 0; k < n_ticks; ++k) {
-    t += delta;  // repeated fp64 sum like lib/simulation_thread.py:295
+    t += delta;
     int rc = demand_tick_begin(e, delta, t);
     if (rc) return rc;
-    rc = tick_finish(e, e->events.p, &e->ctr.p->n_events, 2 * e->N);
+    rc = tick_finish(e, e->events.p, -1, false, delta);
     if (rc) return rc;
   }
   return DRIFT_OK;
@@ -898,13 +971,14 @@ int drift_tick_begin_demand(drift_engine* e, double delta, double t, int64_t* n_
   CU(cudaSetDevice(e->device));
   int rc = demand_tick_begin(e, delta, t);
   if (rc) return rc;
+  e->last_delta = delta;
   if (n_events) {
     Counters c;
     rc = fetch_counters(e, &c);
     if (rc) return rc;
     rc = check_overflow(e, c);
     if (rc) return rc;
-    *n_events = c.n_events;
+    *n_events = c.n_events[e->tick & 1];
   }
   return DRIFT_OK;
 }
@@ -1087,7 +1161,7 @@ int drift_stats(drift_engine* e, drift_stats_out* out) {
   out->arrivals_total = (int64_t)h.n_arrivals;
   out->departures_total = (int64_t)h.n_departures;
   out->route_arena_used = (int64_t)h.arena_cursor;
-  out->events_last_tick = h.n_events;
+  out->events_last_tick = h.n_events[e->tick & 1];
   return check_overflow(e, h);
 }
 
@@ -1102,15 +1176,14 @@ int drift_tick_begin(drift_engine* e, double delta, int64_t* n_events) {
   CU(cudaSetDevice(e->device));
   int rc = tick_begin(e, delta, false, 0.0);
   if (rc) return rc;
-  rc = inject_pending(e);
-  if (rc) return rc;
+  e->last_delta = delta;
   if (n_events) {
     Counters c;
     rc = fetch_counters(e, &c);
     if (rc) return rc;
     rc = check_overflow(e, c);
     if (rc) return rc;
-    *n_events = c.n_events;
+    *n_events = c.n_events[e->tick & 1];
   }
   return DRIFT_OK;
 }
@@ -1124,18 +1197,9 @@ int drift_events_ptr(drift_engine* e, void** dev_ptr, int64_t* capacity) {
 
 int drift_tick_finish(drift_engine* e, const void* events_dev, int64_t n_events) {
   if (!e || !events_dev || n_events < 0) return fail(DRIFT_EINVAL, "drift_tick_finish");
+  if (n_events > 0x7fffffff) return fail(DRIFT_EINVAL, "drift_tick_finish: too many events");
   CU(cudaSetDevice(e->device));
-  if (n_events > e->sorted.n) {  // gathered events of all ranks
-    CU(cudaStreamSynchronize(e->stream));
-    CU(e->sorted.alloc(n_events, false));
-    CU(e->segs.alloc(n_events, false));
-    CU(e->touched.alloc(n_events, false));
-  }
-  // the gathered count replaces the local one
-  const int32_t n32 = (int32_t)n_events;
-  CU(cudaMemcpyAsync(&e->ctr.p->n_events, &n32, sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-  CU(cudaStreamSynchronize(e->stream));
-  return tick_finish(e, (Event*)events_dev, &e->ctr.p->n_events, n_events);
+  return tick_finish(e, (Event*)events_dev, n_events, true, e->last_delta);
 }
 
 int drift_set_profiling(drift_engine* e, int32_t on) {
@@ -1175,6 +1239,10 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
   if (s == "tree_cache_bytes") {
     if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_cache_bytes must be set before the first batched route");
     e->tree_budget_bytes = (int64_t)value;
+  } else if (s == "persistent") {
+    e->persistent = value != 0;
+  } else if (s == "coop_blocks_per_sm") {
+    e->coop_blocks_per_sm = std::max(1, (int)value);
   } else if (s == "route_window") {
     if (value < 1) return fail(DRIFT_EINVAL, "route_window must be >= 1");
     e->route_window = (int32_t)value;

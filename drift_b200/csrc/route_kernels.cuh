@@ -75,7 +75,129 @@ __device__ __forceinline__ HeapItem heap_pop(HeapItem* h, int& n) {
   return top;
 }
 
-// w_fwd / w_bwd: per-CSR-entry weights (static travel_time, or congestion-updated).
+struct RouteResult {
+  int32_t status;
+  int32_t n_links;
+  int64_t off;
+  double cost;
+};
+
+// One NetworkX-exact query by one thread.  w_fwd / w_bwd: per-CSR-entry weights (static
+// travel_time, or congestion-updated).  `worker` selects the private scratch.
+__device__ inline RouteResult route_nx_one(const GraphArrays& g, const double* __restrict__ w_fwd,
+                                           const double* __restrict__ w_bwd, int32_t s, int32_t t,
+                                           const RouteScratch& sc, int worker, uint32_t& epoch,
+                                           int32_t* __restrict__ arena, unsigned long long arena_cap, Counters* ctr,
+                                           const double* __restrict__ link_cost) {
+  RouteResult res;
+  res.status = DRIFT_ROUTE_NOPATH;
+  res.n_links = 0;
+  res.off = 0;
+  res.cost = 0.0;
+  if (s < 0 || t < 0 || s >= g.V || t >= g.V) return res;  // agent.py:87-91
+  if (s == t) {  // weighted.py:2393-2394
+    res.status = DRIFT_ROUTE_TRIVIAL;
+    return res;
+  }
+  const int64_t V = g.V;
+  double* seen[2] = {sc.seen + ((int64_t)worker * 2 + 0) * V, sc.seen + ((int64_t)worker * 2 + 1) * V};
+  int32_t* plink[2] = {sc.plink + ((int64_t)worker * 2 + 0) * V, sc.plink + ((int64_t)worker * 2 + 1) * V};
+  uint32_t* mark[2] = {sc.mark + ((int64_t)worker * 2 + 0) * V, sc.mark + ((int64_t)worker * 2 + 1) * V};
+  HeapItem* heap[2] = {sc.heap + ((int64_t)worker * 2 + 0) * sc.heap_cap,
+                       sc.heap + ((int64_t)worker * 2 + 1) * sc.heap_cap};
+  ++epoch;
+  const uint32_t seen_tag = epoch << 1;
+  int hn[2] = {0, 0};
+  uint32_t pushes = 2;
+  seen[0][s] = 0.0;
+  mark[0][s] = seen_tag;
+  plink[0][s] = -1;
+  seen[1][t] = 0.0;
+  mark[1][t] = seen_tag;
+  plink[1][t] = -1;
+  heap_push(heap[0], hn[0], HeapItem{0.0, 0u, s});
+  heap_push(heap[1], hn[1], HeapItem{0.0, 1u, t});
+  bool have_best = false;
+  double best = 0.0;
+  int32_t meet = -1;
+  int dir = 1;
+  bool found = false, overflow = false;
+  while (hn[0] > 0 && hn[1] > 0) {
+    dir = 1 - dir;  // forward first, strict alternation; a stale pop still uses the turn
+    const HeapItem it = heap_pop(heap[dir], hn[dir]);
+    const int32_t v = it.node;
+    if (mark[dir][v] == (seen_tag | 1u)) continue;
+    mark[dir][v] = seen_tag | 1u;
+    if (mark[1 - dir][v] == (seen_tag | 1u)) {
+      found = true;
+      break;
+    }
+    const int32_t* rowptr = dir == 0 ? g.fwd_rowptr : g.bwd_rowptr;
+    const int32_t* col = dir == 0 ? g.fwd_col : g.bwd_col;
+    const double* wts = dir == 0 ? w_fwd : w_bwd;
+    const int32_t* lnk = dir == 0 ? g.fwd_link : g.bwd_link;
+    const int32_t e1 = rowptr[v + 1];
+    for (int32_t e = rowptr[v]; e < e1; ++e) {
+      const int32_t w = col[e];
+      const double cand = __dadd_rn(it.dist, wts[e]);
+      const uint32_t mw = mark[dir][w];
+      if (mw == (seen_tag | 1u)) continue;  // finalised in this direction
+      if (mw != seen_tag || cand < seen[dir][w]) {
+        seen[dir][w] = cand;
+        mark[dir][w] = seen_tag;
+        plink[dir][w] = lnk[e];
+        if (hn[dir] >= sc.heap_cap) {
+          overflow = true;
+          break;
+        }
+        heap_push(heap[dir], hn[dir], HeapItem{cand, pushes++, w});
+        if ((mark[1 - dir][w] >> 1) == epoch) {
+          const double tot = __dadd_rn(cand, seen[1 - dir][w]);
+          if (!have_best || best > tot) {
+            have_best = true;
+            best = tot;
+            meet = w;
+          }
+        }
+      }
+    }
+    if (overflow) break;
+  }
+  if (overflow) {
+    atomicOr(&ctr->overflow, kOvfHeap);
+    return res;
+  }
+  if (!found) return res;  // weighted.py:2459 NetworkXNoPath
+  int nf = 0, nb = 0;
+  for (int32_t x = meet; x != s; x = g.link_u[plink[0][x]]) ++nf;
+  for (int32_t x = meet; x != t; x = g.link_v[plink[1][x]]) ++nb;
+  const int n = nf + nb;
+  const unsigned long long off = atomicAdd(&ctr->arena_cursor, (unsigned long long)n);
+  if (off + n > arena_cap) {
+    atomicOr(&ctr->overflow, kOvfArena);
+    return res;
+  }
+  int k = nf;
+  for (int32_t x = meet; x != s;) {
+    const int32_t l = plink[0][x];
+    arena[off + (--k)] = l;
+    x = g.link_u[l];
+  }
+  k = nf;
+  for (int32_t x = meet; x != t;) {
+    const int32_t l = plink[1][x];
+    arena[off + (k++)] = l;
+    x = g.link_v[l];
+  }
+  double c = 0.0;
+  for (int j = 0; j < n; ++j) c = __dadd_rn(c, link_cost[arena[off + j]]);
+  res.status = DRIFT_ROUTE_OK;
+  res.n_links = n;
+  res.off = (int64_t)off;
+  res.cost = c;
+  return res;
+}
+
 __global__ void __launch_bounds__(32) k_route_nx(GraphArrays g, const double* __restrict__ w_fwd,
                                                   const double* __restrict__ w_bwd, int64_t Q,
                                                   const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
@@ -85,123 +207,15 @@ __global__ void __launch_bounds__(32) k_route_nx(GraphArrays g, const double* __
                                                   const int32_t* __restrict__ n_dev) {
   const int worker = blockIdx.x * blockDim.x + threadIdx.x;
   if (worker >= sc.workers) return;
-  if (n_dev) Q = *n_dev;  // device-side batch size (device-driven demand)
-  const int64_t V = g.V;
-  double* seen[2] = {sc.seen + ((int64_t)worker * 2 + 0) * V, sc.seen + ((int64_t)worker * 2 + 1) * V};
-  int32_t* plink[2] = {sc.plink + ((int64_t)worker * 2 + 0) * V, sc.plink + ((int64_t)worker * 2 + 1) * V};
-  uint32_t* mark[2] = {sc.mark + ((int64_t)worker * 2 + 0) * V, sc.mark + ((int64_t)worker * 2 + 1) * V};
-  HeapItem* heap[2] = {sc.heap + ((int64_t)worker * 2 + 0) * sc.heap_cap,
-                       sc.heap + ((int64_t)worker * 2 + 1) * sc.heap_cap};
+  if (n_dev) Q = *n_dev;  // device-side batch size
   uint32_t epoch = sc.epoch[worker];
-
   for (int64_t q = worker; q < Q; q += sc.workers) {
-    const int32_t s = src[q], t = dst[q];
-    out.off[q] = 0;
-    out.cost[q] = 0.0;
-    out.n_links[q] = 0;
-    if (s < 0 || t < 0 || s >= g.V || t >= g.V) {  // agent.py:87-91
-      out.status[q] = DRIFT_ROUTE_NOPATH;
-      continue;
-    }
-    if (s == t) {  // weighted.py:2393-2394
-      out.status[q] = DRIFT_ROUTE_TRIVIAL;
-      continue;
-    }
-    ++epoch;
-    const uint32_t seen_tag = epoch << 1;
-    int hn[2] = {0, 0};
-    uint32_t pushes = 2;
-    seen[0][s] = 0.0;
-    mark[0][s] = seen_tag;
-    plink[0][s] = -1;
-    seen[1][t] = 0.0;
-    mark[1][t] = seen_tag;
-    plink[1][t] = -1;
-    heap_push(heap[0], hn[0], HeapItem{0.0, 0u, s});
-    heap_push(heap[1], hn[1], HeapItem{0.0, 1u, t});
-    bool have_best = false;
-    double best = 0.0;
-    int32_t meet = -1;
-    int dir = 1;
-    bool found = false, overflow = false;
-    while (hn[0] > 0 && hn[1] > 0) {
-      dir = 1 - dir;  // forward first, strict alternation; a stale pop still uses the turn
-      const HeapItem it = heap_pop(heap[dir], hn[dir]);
-      const int32_t v = it.node;
-      if (mark[dir][v] == (seen_tag | 1u)) continue;
-      mark[dir][v] = seen_tag | 1u;
-      if (mark[1 - dir][v] == (seen_tag | 1u)) {
-        found = true;
-        break;
-      }
-      const int32_t* rowptr = dir == 0 ? g.fwd_rowptr : g.bwd_rowptr;
-      const int32_t* col = dir == 0 ? g.fwd_col : g.bwd_col;
-      const double* wts = dir == 0 ? w_fwd : w_bwd;
-      const int32_t* lnk = dir == 0 ? g.fwd_link : g.bwd_link;
-      const int32_t e1 = rowptr[v + 1];
-      for (int32_t e = rowptr[v]; e < e1; ++e) {
-        const int32_t w = col[e];
-        const double cand = __dadd_rn(it.dist, wts[e]);
-        const uint32_t mw = mark[dir][w];
-        if (mw == (seen_tag | 1u)) continue;  // finalised in this direction
-        if (mw != seen_tag || cand < seen[dir][w]) {
-          seen[dir][w] = cand;
-          mark[dir][w] = seen_tag;
-          plink[dir][w] = lnk[e];
-          if (hn[dir] >= sc.heap_cap) {
-            overflow = true;
-            break;
-          }
-          heap_push(heap[dir], hn[dir], HeapItem{cand, pushes++, w});
-          if ((mark[1 - dir][w] >> 1) == epoch) {
-            const double tot = __dadd_rn(cand, seen[1 - dir][w]);
-            if (!have_best || best > tot) {
-              have_best = true;
-              best = tot;
-              meet = w;
-            }
-          }
-        }
-      }
-      if (overflow) break;
-    }
-    if (overflow) {
-      atomicOr(&ctr->overflow, kOvfHeap);
-      out.status[q] = DRIFT_ROUTE_NOPATH;
-      continue;
-    }
-    if (!found) {  // weighted.py:2459 NetworkXNoPath
-      out.status[q] = DRIFT_ROUTE_NOPATH;
-      continue;
-    }
-    int nf = 0, nb = 0;
-    for (int32_t x = meet; x != s; x = g.link_u[plink[0][x]]) ++nf;
-    for (int32_t x = meet; x != t; x = g.link_v[plink[1][x]]) ++nb;
-    const int n = nf + nb;
-    const unsigned long long off = atomicAdd(&ctr->arena_cursor, (unsigned long long)n);
-    if (off + n > arena_cap) {
-      atomicOr(&ctr->overflow, kOvfArena);
-      out.status[q] = DRIFT_ROUTE_NOPATH;
-      continue;
-    }
-    int k = nf;
-    for (int32_t x = meet; x != s;) {
-      const int32_t l = plink[0][x];
-      arena[off + (--k)] = l;
-      x = g.link_u[l];
-    }
-    k = nf;
-    for (int32_t x = meet; x != t;) {
-      const int32_t l = plink[1][x];
-      arena[off + (k++)] = l;
-      x = g.link_v[l];
-    }
-    double c = 0.0;
-    for (int j = 0; j < n; ++j) c = __dadd_rn(c, link_cost[arena[off + j]]);
-    out.status[q] = DRIFT_ROUTE_OK;
-    out.n_links[q] = n;
-    out.off[q] = (int64_t)off;
-    out.cost[q] = c;
+    const RouteResult r = route_nx_one(g, w_fwd, w_bwd, src[q], dst[q], sc, worker, epoch, arena, arena_cap, ctr,
+                                       link_cost);
+    out.status[q] = r.status;
+    out.n_links[q] = r.n_links;
+    out.off[q] = r.off;
+    out.cost[q] = r.cost;
   }
   sc.epoch[worker] = epoch;
 }
@@ -244,27 +258,6 @@ __global__ void k_commit(int64_t Q, const int32_t* __restrict__ agent, const int
   }
 }
 
-// Device-driven demand: turn this tick's departure requests into (src, dst) queries
-// (Agent.start_new_journey, agent.py:46-83: source = previous target, trip_count += 1).
-__global__ void k_prepare_requests(AgentArrays a, Counters* ctr, const int32_t* __restrict__ dep_req,
-                                   int32_t* __restrict__ q_src, int32_t* __restrict__ q_dst,
-                                   int32_t* __restrict__ q_agent) {
-  const int n = ctr->n_dep_req;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-    const int32_t i = dep_req[r];
-    const int head = a.chain_head[i];
-    const int32_t s = a.cur_node[i];
-    const int32_t t = a.chain_dst[(int64_t)i * a.chain_cap + head];
-    a.chain_head[i] = (uint8_t)((head + 1) % a.chain_cap);
-    a.chain_cnt[i] -= 1;
-    a.trip_count[i] += 1;
-    a.cur_node[i] = t;  // agent.py:51: target is overwritten even if routing fails
-    q_src[r] = s;
-    q_dst[r] = t;
-    q_agent[r] = i;
-  }
-}
-
 // Window planning: every agent missing a prefetched route for one of its next two trips asks
 // for it (source of trip k+1 = destination of trip k, known from the chain).
 __global__ void k_plan_requests(AgentArrays a, Counters* ctr, int32_t* __restrict__ q_src,
@@ -296,28 +289,6 @@ __global__ void k_store_prefetch(int64_t Q, const int32_t* __restrict__ q_agent,
     a.next_off[idx] = q_off[q];
     a.next_len[idx] = q_len[q];
     a.next_status[idx] = 1 + q_status[q];
-  }
-}
-
-__global__ void k_log_departures(Counters* ctr, int32_t tick, const int32_t* __restrict__ q_agent,
-                                 const int32_t* __restrict__ q_src, const int32_t* __restrict__ q_dst,
-                                 const int32_t* __restrict__ q_status, int32_t* __restrict__ log_agent,
-                                 int32_t* __restrict__ log_tick, int32_t* __restrict__ log_src,
-                                 int32_t* __restrict__ log_dst, int32_t* __restrict__ log_status,
-                                 unsigned long long cap, unsigned long long drained) {
-  const int n = ctr->n_dep_req;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-    const unsigned long long slot = atomicAdd(&ctr->n_departures, 1ULL);
-    if (slot - drained < cap) {
-      const unsigned long long k = slot % cap;
-      log_agent[k] = q_agent[r];
-      log_tick[k] = tick;
-      log_src[k] = q_src[r];
-      log_dst[k] = q_dst[r];
-      log_status[k] = q_status[r];
-    } else {
-      atomicOr(&ctr->overflow, kOvfDepLog);
-    }
   }
 }
 

@@ -8,10 +8,49 @@
 // Parallel formulation (validated bit-exact against the sequential order):
 //   every crossing/departure becomes a link event; the BPR count an entering agent `a` sees on
 //   link l is   occ_start[l] + #{enter events on l with agent <= a} - #{leave events on l with agent < a}.
+//
+// A tick is three phases separated by grid-wide barriers:
+//   A  advance every agent, emit + link the events of crossers and of prefetched departures
+//   A2 (only when needed) inject host-committed departures, route + inject departures that had
+//      no prefetched route
+//   C  resolve: every event walks the event list of its link
+// run either as separate kernels (multi-rank exchange between A2 and C, profiling) or inside one
+// persistent cooperative kernel that loops over many ticks (k_tick_loop).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+#include "route_kernels.cuh"
 
 namespace drift {
+
+namespace cg = cooperative_groups;
+
+constexpr int kAdvThreads = 256;
+constexpr int kAdvPerThread = 4;
+
+struct TickArgs {
+  AgentArrays a;
+  LinkArrays lk;
+  GraphArrays g;
+  Rings rg;
+  DemandArgs dm;
+  RouteScratch fsc;         // scratch of the in-tick fallback router
+  const double* w_fwd;      // routing weights of the fallback router
+  const double* w_bwd;
+  const double* link_cost;
+  int32_t* arena;
+  unsigned long long arena_cap;
+  Counters* ctr;
+  Event* events;
+  int32_t ev_cap;
+  const int32_t* pend_agent;
+  const int64_t* pend_off;
+  const int32_t* pend_len;
+  double delta;
+  double kph_to_mps;
+  int32_t demand;           // device-driven departures on/off
+};
 
 // Block-level slot allocation: every thread asks for `n` consecutive slots of a global
 // bump counter; one global atomic per block (single-address L2 atomics serialise at
@@ -36,17 +75,31 @@ __device__ __forceinline__ double bpr_factor_lookup(const LinkArrays& lk, int32_
   return lk.factor[idx];
 }
 
-constexpr int kAdvThreads = 256;
-constexpr int kAdvPerThread = 4;
+// Write event `slot` and push it on the event list of its link.  The first event of a link in
+// this tick snapshots the link's start-of-tick occupancy (occ is only written in phase C).
+// `tag` identifies the list generation: the tick number for local lists, tick | 2^31 for the
+// lists rebuilt over the events gathered from all ranks.
+__device__ __forceinline__ void emit_event(const LinkArrays& lk, Event* __restrict__ events, int slot, int32_t link,
+                                           uint32_t agent, int32_t kind, uint32_t tag) {
+  const unsigned long long mine = ((unsigned long long)tag << 32) | (uint32_t)slot;
+  const unsigned long long prev = atomicExch(&lk.head[link], mine);
+  Event e;
+  e.link = link;
+  e.agent = agent;
+  e.kind = kind;
+  e.aux = ((uint32_t)(prev >> 32) == tag) ? (int32_t)(prev & 0xffffffffu) : -lk.occ[link] - 1;
+  events[slot] = e;
+}
 
-// K1+K2: advance every agent by one tick and emit the link events of the crossers.
-// DEMAND: waiting agents also draw their Bernoulli departure (agent.py:176-183).
+// ---- phase A ------------------------------------------------------------------------------------
+// K1+K2: advance every agent by one tick, emit the link events of the crossers; with device-driven
+// demand waiting agents also draw their Bernoulli departure (agent.py:176-183) and leave on their
+// prefetched route.
 template <bool DEMAND>
-__global__ void __launch_bounds__(kAdvThreads) k_advance(AgentArrays a, const int32_t* __restrict__ arena,
-                                                          double delta, int32_t tick, Counters* ctr,
-                                                          Event* __restrict__ events, int32_t ev_cap, Rings rg,
-                                                          DemandArgs dm) {
-  __shared__ int s_cnt, s_base;
+__device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, double p_dep, int* s_cnt, int* s_base) {
+  const AgentArrays& a = p.a;
+  Counters* ctr = p.ctr;
+  const int par = tick & 1;
   const int64_t tiles = (a.n + (int64_t)kAdvThreads * kAdvPerThread - 1) / ((int64_t)kAdvThreads * kAdvPerThread);
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t i0 = (tile * kAdvThreads + threadIdx.x) * kAdvPerThread;
@@ -72,7 +125,7 @@ __global__ void __launch_bounds__(kAdvThreads) k_advance(AgentArrays a, const in
         for (int j = 0; j < kAdvPerThread; ++j) {
           if (st[j] == kMoving) {
             // two roundings, never contracted to an FMA (agent.py:197-198)
-            const double nd = __dadd_rn(d[j], __dmul_rn(sp[j], delta));
+            const double nd = __dadd_rn(d[j], __dmul_rn(sp[j], p.delta));
             if (nd >= el[j]) {  // agent.py:200-203: at most one link per tick, overshoot dropped
               const int64_t i = i0 + j;
               const int32_t ri = a.route_idx[i] + 1;
@@ -82,7 +135,7 @@ __global__ void __launch_bounds__(kAdvThreads) k_advance(AgentArrays a, const in
               ev_kind_agent[nev] = j;  // leave
               ++nev;
               if (ri < a.route_len[i]) {
-                const int32_t nl = arena[a.route_off[i] + ri];
+                const int32_t nl = p.arena[a.route_off[i] + ri];
                 a.cur_link[i] = nl;
                 ev_link[nev] = nl;
                 ev_kind_agent[nev] = j | 256;  // enter
@@ -92,9 +145,9 @@ __global__ void __launch_bounds__(kAdvThreads) k_advance(AgentArrays a, const in
                 nst[j] = kWaiting;
                 state_changed = true;
                 const unsigned long long slot = atomicAdd(&ctr->n_arrivals, 1ULL);
-                if (slot - rg.arr_drained < rg.arr_cap) {
-                  rg.arr_agent[slot % rg.arr_cap] = (int32_t)i;
-                  rg.arr_tick[slot % rg.arr_cap] = tick;
+                if (slot - p.rg.arr_drained < p.rg.arr_cap) {
+                  p.rg.arr_agent[slot % p.rg.arr_cap] = (int32_t)i;
+                  p.rg.arr_tick[slot % p.rg.arr_cap] = tick;
                 } else {
                   atomicOr(&ctr->overflow, kOvfArrivals);
                 }
@@ -108,17 +161,19 @@ __global__ void __launch_bounds__(kAdvThreads) k_advance(AgentArrays a, const in
         *reinterpret_cast<double2*>(a.dist + i0 + 2) = make_double2(d[2], d[3]);
       }
       if (DEMAND) {
+        const uchar4 cn4 = *reinterpret_cast<const uchar4*>(a.chain_cnt + i0);
+        const uint8_t cn[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
 #pragma unroll
         for (int j = 0; j < kAdvPerThread; ++j) {
           const int64_t i = i0 + j;
           if (st[j] != kWaiting || i >= a.n) continue;  // an agent arriving this tick draws from the next tick on
-          const int cnt = a.chain_cnt[i];
+          const int cnt = cn[j];
           if (cnt == 0) continue;  // no destination available (chain exhausted)
-          const double u = philox_uniform53(dm.seed, a.base + (uint32_t)i, (uint32_t)tick);
-          if (!(u < dm.p_dep)) continue;  // agent.py:180
+          const double u = philox_uniform53(p.dm.seed, a.base + (uint32_t)i, (uint32_t)tick);
+          if (!(u < p_dep)) continue;  // agent.py:180
           const int32_t ns = a.next_status[i];
-          if (ns == 0) {  // no prefetched route: routed inside this tick (rare)
-            dm.dep_req[atomicAdd(&ctr->n_dep_req, 1)] = (int32_t)i;
+          if (ns == 0) {  // no prefetched route: routed in phase A2 of this tick (rare)
+            p.dm.dep_req[atomicAdd(&ctr->n_dep_req[par], 1)] = (int32_t)i;
             continue;
           }
           // Agent.start_new_journey (agent.py:46-104) with the prefetched route
@@ -135,18 +190,18 @@ __global__ void __launch_bounds__(kAdvThreads) k_advance(AgentArrays a, const in
           a.next_len[i] = a.next_len[a.npad + i];
           a.next_status[a.npad + i] = 0;
           const unsigned long long slot = atomicAdd(&ctr->n_departures, 1ULL);
-          if (slot - dm.log_drained < dm.log_cap) {
-            const unsigned long long k = slot % dm.log_cap;
-            dm.log_agent[k] = (int32_t)i;
-            dm.log_tick[k] = tick;
-            dm.log_src[k] = src;
-            dm.log_dst[k] = dst;
-            dm.log_status[k] = ns - 1;
+          if (slot - p.dm.log_drained < p.dm.log_cap) {
+            const unsigned long long k = slot % p.dm.log_cap;
+            p.dm.log_agent[k] = (int32_t)i;
+            p.dm.log_tick[k] = tick;
+            p.dm.log_src[k] = src;
+            p.dm.log_dst[k] = dst;
+            p.dm.log_status[k] = ns - 1;
           } else {
             atomicOr(&ctr->overflow, kOvfDepLog);
           }
           if (ns == 1 + DRIFT_ROUTE_OK) {
-            const int32_t fl = arena[noff];
+            const int32_t fl = p.arena[noff];
             a.route_off[i] = noff;
             a.route_len[i] = nlen;
             a.route_idx[i] = 0;
@@ -162,17 +217,12 @@ __global__ void __launch_bounds__(kAdvThreads) k_advance(AgentArrays a, const in
       }
       if (state_changed) *reinterpret_cast<uchar4*>(a.state + i0) = make_uchar4(nst[0], nst[1], nst[2], nst[3]);
     }
-    const int slot0 = block_alloc(nev, &ctr->n_events, &s_cnt, &s_base);
+    const int slot0 = block_alloc(nev, &ctr->n_events[par], s_cnt, s_base);
     if (nev) {
-      if (slot0 + nev <= ev_cap) {
-        for (int k = 0; k < nev; ++k) {
-          Event e;
-          e.link = ev_link[k];
-          e.agent = a.base + (uint32_t)(i0 + (ev_kind_agent[k] & 255));
-          e.kind = (ev_kind_agent[k] & 256) ? 1 : -1;
-          e.pos = 0;
-          events[slot0 + k] = e;
-        }
+      if (slot0 + nev <= p.ev_cap) {
+        for (int k = 0; k < nev; ++k)
+          emit_event(p.lk, p.events, slot0 + k, ev_link[k], a.base + (uint32_t)(i0 + (ev_kind_agent[k] & 255)),
+                     (ev_kind_agent[k] & 256) ? 1 : -1, (uint32_t)tick);
       } else {
         atomicOr(&ctr->overflow, kOvfEvents);
       }
@@ -180,131 +230,90 @@ __global__ void __launch_bounds__(kAdvThreads) k_advance(AgentArrays a, const in
   }
 }
 
-// Agent.start_new_journey tail (agent.py:101-104) for the routed pending departures: the agent
-// becomes 'moving' on the first link of its route and emits the enter event of that link.
-__global__ void k_inject_departures(AgentArrays a, const int32_t* __restrict__ arena, Counters* ctr,
-                                    const int32_t* __restrict__ pend_agent, const int64_t* __restrict__ pend_off,
-                                    const int32_t* __restrict__ pend_len, const int32_t* __restrict__ n_pending_ptr,
-                                    Event* __restrict__ events, int32_t ev_cap) {
-  __shared__ int s_cnt, s_base;
-  const int n_pending = *n_pending_ptr;
-  for (int p0 = blockIdx.x * blockDim.x; p0 < n_pending; p0 += gridDim.x * blockDim.x) {
-    const int p = p0 + threadIdx.x;
-    int nev = 0;
-    int32_t link = -1;
-    int32_t i = -1;
-    if (p < n_pending && pend_len[p] > 0) {
-      i = pend_agent[p];
-      link = arena[pend_off[p]];
-      a.state[i] = kMoving;
-      a.route_off[i] = pend_off[p];
-      a.route_len[i] = pend_len[p];
-      a.route_idx[i] = 0;
-      a.dist[i] = 0.0;
-      a.cur_link[i] = link;
-      nev = 1;
-    }
-    const int slot = block_alloc(nev, &ctr->n_events, &s_cnt, &s_base);
-    if (nev) {
-      if (slot < ev_cap) {
-        Event e;
-        e.link = link;
-        e.agent = a.base + (uint32_t)i;
-        e.kind = 1;
-        e.pos = 0;
-        events[slot] = e;
+// ---- phase A2 -----------------------------------------------------------------------------------
+__device__ __forceinline__ void start_on_route(const TickArgs& p, int32_t i, int64_t off, int32_t len, int32_t tick) {
+  const AgentArrays& a = p.a;
+  const int32_t link = p.arena[off];
+  a.state[i] = kMoving;
+  a.route_off[i] = off;
+  a.route_len[i] = len;
+  a.route_idx[i] = 0;
+  a.dist[i] = 0.0;
+  a.cur_link[i] = link;
+  const int slot = atomicAdd(&p.ctr->n_events[tick & 1], 1);
+  if (slot < p.ev_cap)
+    emit_event(p.lk, p.events, slot, link, a.base + (uint32_t)i, 1, (uint32_t)tick);
+  else
+    atomicOr(&p.ctr->overflow, kOvfEvents);
+}
+
+// Agent.start_new_journey tail (agent.py:101-104) for host-committed departures, and the whole of
+// it (selector output = next ring entry, NetworkX-exact route, one thread per agent) for device
+// departures that had no prefetched route.
+__device__ __forceinline__ void phase_inject(const TickArgs& p, int32_t tick, int n_pending, int n_urgent) {
+  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = gtid; q < n_pending; q += gsz)
+    if (p.pend_len[q] > 0) start_on_route(p, p.pend_agent[q], p.pend_off[q], p.pend_len[q], tick);
+  if (n_urgent > 0 && gtid < p.fsc.workers) {
+    const AgentArrays& a = p.a;
+    uint32_t epoch = p.fsc.epoch[gtid];
+    for (int r = (int)gtid; r < n_urgent; r += p.fsc.workers) {
+      const int32_t i = p.dm.dep_req[r];
+      const int head = a.chain_head[i];
+      const int32_t s = a.cur_node[i];
+      const int32_t t = a.chain_dst[(int64_t)i * a.chain_cap + head];
+      a.chain_head[i] = (uint8_t)((head + 1) % a.chain_cap);
+      a.chain_cnt[i] -= 1;
+      a.trip_count[i] += 1;
+      a.cur_node[i] = t;  // agent.py:51: target is overwritten even if routing fails
+      const RouteResult rr = route_nx_one(p.g, p.w_fwd, p.w_bwd, s, t, p.fsc, (int)gtid, epoch, p.arena, p.arena_cap,
+                                          p.ctr, p.link_cost);
+      const unsigned long long slot = atomicAdd(&p.ctr->n_departures, 1ULL);
+      if (slot - p.dm.log_drained < p.dm.log_cap) {
+        const unsigned long long k = slot % p.dm.log_cap;
+        p.dm.log_agent[k] = i;
+        p.dm.log_tick[k] = tick;
+        p.dm.log_src[k] = s;
+        p.dm.log_dst[k] = t;
+        p.dm.log_status[k] = rr.status;
       } else {
-        atomicOr(&ctr->overflow, kOvfEvents);
+        atomicOr(&p.ctr->overflow, kOvfDepLog);
       }
+      if (rr.status == DRIFT_ROUTE_OK) start_on_route(p, i, rr.off, rr.n_links, tick);
     }
+    p.fsc.epoch[gtid] = epoch;
   }
 }
 
-// K3 step 1: slot of every event inside its link (arrival order, only used as an address)
-// and the list of touched links.
-__global__ void k_count(Event* __restrict__ events, const int32_t* __restrict__ n_events_ptr,
-                        int32_t* __restrict__ evcnt, int32_t* __restrict__ touched, Counters* ctr) {
-  __shared__ int s_cnt, s_base;
-  const int n = *n_events_ptr;
-  for (int e0 = blockIdx.x * blockDim.x; e0 < n; e0 += gridDim.x * blockDim.x) {
-    const int e = e0 + threadIdx.x;
-    int first = 0;
-    int32_t link = -1;
-    if (e < n) {
-      link = events[e].link;
-      const int pos = atomicAdd(&evcnt[link], 1);
-      events[e].pos = pos;
-      first = (pos == 0);
-    }
-    const int slot = block_alloc(first, &ctr->n_touched, &s_cnt, &s_base);
-    if (first) touched[slot] = link;
-  }
-}
-
-// K3 step 2: one contiguous segment per touched link; snapshot of its start-of-tick occupancy.
-__global__ void k_segment(const int32_t* __restrict__ touched, Counters* ctr, int32_t* __restrict__ evcnt,
-                          int32_t* __restrict__ segid, Segment* __restrict__ segs,
-                          const int32_t* __restrict__ occ) {
-  __shared__ int s_cnt, s_base;
-  const int n = ctr->n_touched;
-  for (int t0 = blockIdx.x * blockDim.x; t0 < n; t0 += gridDim.x * blockDim.x) {
-    const int t = t0 + threadIdx.x;
-    int m = 0;
-    int32_t link = -1;
-    if (t < n) {
-      link = touched[t];
-      m = evcnt[link];
-      evcnt[link] = 0;  // ready for the next tick
-    }
-    const int base = block_alloc(m, &ctr->seg_cursor, &s_cnt, &s_base);
-    if (t < n) {
-      Segment s;
-      s.link = link;
-      s.base = base;
-      s.count = m;
-      s.occ0 = occ[link];
-      segs[t] = s;
-      segid[link] = t;
-    }
-  }
-}
-
-__global__ void k_scatter(const Event* __restrict__ events, const int32_t* __restrict__ n_events_ptr,
-                          const int32_t* __restrict__ segid, const Segment* __restrict__ segs,
-                          SortedEvent* __restrict__ sorted) {
-  const int n = *n_events_ptr;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+// ---- phase C ------------------------------------------------------------------------------------
+// K3: ordered running count -> BPR factor -> entry speed (agent.py:154-160), and the end-of-tick
+// occupancy of every touched link.  Each event walks the list of its link.
+__device__ __forceinline__ void phase_resolve(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
+                                              const Event* __restrict__ events, int n_events, int32_t tick,
+                                              double kph_to_mps, const Rings& rg) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_events; e += gridDim.x * blockDim.x) {
     const Event ev = events[e];
-    const Segment s = segs[segid[ev.link]];
-    SortedEvent o;
-    o.agent = ev.agent;
-    o.kind = ev.kind;
-    sorted[s.base + ev.pos] = o;
-  }
-}
-
-// K3 step 3: ordered running count -> BPR factor -> entry speed (agent.py:154-160), and the
-// end-of-tick occupancy of every touched link.
-__global__ void k_resolve(const Event* __restrict__ events, const int32_t* __restrict__ n_events_ptr,
-                          const int32_t* __restrict__ segid, const Segment* __restrict__ segs,
-                          const SortedEvent* __restrict__ sorted, LinkArrays lk, AgentArrays a, double kph_to_mps,
-                          int32_t tick, Counters* ctr, Rings rg) {
-  const int n = *n_events_ptr;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const Event ev = events[e];
-    const Segment s = segs[segid[ev.link]];
-    int before = 0;  // sum of deltas of events ordered before this one (Gauss-Seidel order)
+    const int first = (int)(lk.head[ev.link] & 0xffffffffu);
+    int before = 0;  // sum of the deltas of events ordered before this one (agent-list order)
     int net = 0;
-    for (int j = 0; j < s.count; ++j) {
-      const SortedEvent o = sorted[s.base + j];
+    int occ0 = 0;
+    int j = first;
+    for (;;) {
+      const Event o = events[j];
       net += o.kind;
       if (o.agent < ev.agent) before += o.kind;
+      if (o.aux < 0) {
+        occ0 = -o.aux - 1;
+        break;
+      }
+      j = o.aux;
     }
-    if (ev.pos == 0) lk.occ[ev.link] = s.occ0 + net;
+    if (first == e) lk.occ[ev.link] = occ0 + net;
     if (ev.kind > 0) {
       const uint32_t li = ev.agent - a.base;
       if (ev.agent >= a.base && (int64_t)li < a.n) {
-        const int32_t count = s.occ0 + before + 1;  // includes the entering agent itself
+        const int32_t count = occ0 + before + 1;  // includes the entering agent itself
         const double f = bpr_factor_lookup(lk, ev.link, count);
         const double sp = __dmul_rn(__dmul_rn(lk.v0[ev.link], f), kph_to_mps);
         a.speed[li] = sp;
@@ -326,6 +335,88 @@ __global__ void k_resolve(const Event* __restrict__ events, const int32_t* __res
   }
 }
 
+// ---- standalone kernels (multi-rank exchange between A2 and C; per-kernel profiling) -----------------
+template <bool DEMAND>
+__global__ void __launch_bounds__(kAdvThreads) k_advance(TickArgs p, int32_t tick, double p_dep) {
+  __shared__ int s_cnt, s_base;
+  phase_advance<DEMAND>(p, tick, p_dep, &s_cnt, &s_base);
+}
+
+__global__ void __launch_bounds__(256) k_inject(TickArgs p, int32_t tick) {
+  const int par = tick & 1;
+  phase_inject(p, tick, p.ctr->n_pending, p.ctr->n_dep_req[par]);
+}
+
+// Events that arrived from other ranks (link, agent, kind): push them on the link lists.
+__global__ void k_link_events(LinkArrays lk, Event* __restrict__ events, int n_events, int32_t tick) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_events; e += gridDim.x * blockDim.x) {
+    const Event ev = events[e];
+    emit_event(lk, events, e, ev.link, ev.agent, ev.kind, (uint32_t)tick | 0x80000000u);
+  }
+}
+
+// n_events < 0: take the local count of this tick from the counters.
+__global__ void k_resolve(TickArgs p, const Event* __restrict__ events, int n_events, int32_t tick) {
+  const int par = tick & 1;
+  if (n_events < 0) n_events = p.ctr->n_events[par];
+  phase_resolve(p.lk, p.a, p.ctr, events, n_events, tick, p.kph_to_mps, p.rg);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // counters of the next tick
+    p.ctr->n_events[par ^ 1] = 0;
+    p.ctr->n_dep_req[par ^ 1] = 0;
+    p.ctr->n_pending = 0;
+  }
+}
+
+// ---- the persistent tick loop ---------------------------------------------------------------------
+// One cooperative launch runs `n_ticks` ticks: 2 grid barriers per tick (3 when phase A2 has work).
+__global__ void __launch_bounds__(kAdvThreads) k_tick_loop(TickArgs p, int32_t tick0, int32_t n_ticks, double p_dep) {
+  __shared__ int s_cnt, s_base;
+  cg::grid_group grid = cg::this_grid();
+  Counters* ctr = p.ctr;
+  const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long t0 = 0;
+  for (int32_t k = 0; k < n_ticks; ++k) {
+    const int32_t tick = tick0 + k;
+    const int par = tick & 1;
+    if (lead) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    if (p.demand)
+      phase_advance<true>(p, tick, p_dep, &s_cnt, &s_base);
+    else
+      phase_advance<false>(p, tick, p_dep, &s_cnt, &s_base);
+    grid.sync();
+    if (lead) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      ctr->phase_ns[0] += t1 - t0;
+      t0 = t1;
+    }
+    const int n_pending = ctr->n_pending, n_urgent = ctr->n_dep_req[par];
+    if (n_pending | n_urgent) {  // uniform across the grid
+      phase_inject(p, tick, n_pending, n_urgent);
+      grid.sync();
+      if (lead) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        ctr->phase_ns[1] += t1 - t0;
+        t0 = t1;
+      }
+    }
+    phase_resolve(p.lk, p.a, ctr, p.events, ctr->n_events[par], tick, p.kph_to_mps, p.rg);
+    if (lead) {
+      ctr->n_events[par ^ 1] = 0;
+      ctr->n_dep_req[par ^ 1] = 0;
+    }
+    grid.sync();
+    if (lead) {
+      ctr->n_pending = 0;
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      ctr->phase_ns[2] += t1 - t0;
+    }
+  }
+}
+
+// ---- auxiliary passes -------------------------------------------------------------------------------
 // K3': per-link volume recount = histogram of cur_link over moving agents
 // (traffic_manager.py:122-135: total_agents_on_roads / per-link list lengths).
 __global__ void k_recount(AgentArrays a, int32_t* __restrict__ hist) {

@@ -14,9 +14,10 @@ from oracle.port import DEFAULT_HOURLY, PortSim, travel_probability
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,router,window", [("g40_congested", 0, 25), ("g100_random_s0", 0, 300),
-                                                ("multi_random_s0", 0, 7), ("g40_congested", 0, 1)])
-def test_device_demand_matches_port(name, router, window):
+@pytest.mark.parametrize("name,router,window,persistent", [
+    ("g40_congested", 0, 25, 1), ("g100_random_s0", 0, 300, 1), ("multi_random_s0", 0, 7, 1), ("g40_congested", 0, 1, 1),
+    ("g40_congested", 0, 25, 0), ("multi_random_s0", 0, 300, 0)])
+def test_device_demand_matches_port(name, router, window, persistent):
     from drift_b200.engine import Engine
     from drift_b200.graph import lower_graph
 
@@ -34,6 +35,7 @@ def test_device_demand_matches_port(name, router, window):
     with Engine(lg, N, alpha=0.15, beta=4.0) as eng:
         eng.set_demand(seed, h24, start, chain_capacity=per_agent, router=router)
         eng.set_option("route_window", window)
+        eng.set_option("persistent", persistent)
         eng.push_trips(cands)
         occs, t = [], 0.0
         dep_log = []

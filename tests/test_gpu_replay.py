@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 CASES = golden.case_names()
 
 
-def _replay(case, use_device_router):
+def _replay(case, use_device_router, persistent=True):
     from drift_b200.engine import Engine, ROUTE_OK, ROUTE_TRIVIAL, ROUTE_NOPATH
     from drift_b200.graph import lower_graph
 
@@ -24,6 +24,7 @@ def _replay(case, use_device_router):
     snaps = case.snapshots()
     with Engine(lg, case.N, alpha=case.alpha, beta=case.beta) as eng:
         eng.enable_entry_trace(1 << 18)
+        eng.set_option("persistent", 1 if persistent else 0)
         arr, ent = [], []
 
         def drain():
@@ -85,3 +86,9 @@ def test_replay_host_routes(name):
     "g100_random_s0", "g40_congested_bpr", "chpn_random_nopath", "multi_random_s0", "g100_activity_s0")])
 def test_replay_device_routes(name):
     _replay(golden.GoldenCase(name), use_device_router=True)
+
+
+@pytest.mark.parametrize("name", ["g40_congested", "multi_random_s0", "g100_random_accel7"])
+def test_replay_separate_kernels(name):
+    """Same tick as three separate kernels (the path the multi-rank exchange and the profiler use)."""
+    _replay(golden.GoldenCase(name), use_device_router=False, persistent=False)
