@@ -61,6 +61,7 @@ struct AgentArrays {
   double* speed;        // [Npad] m/s, fixed while on a link
   double* elen;         // [Npad] edge_length of the current link
   int32_t* cur_link;    // [Npad] -1 when not on a link
+  int32_t* next_link;   // [Npad] link after cur_link on the route, -1 = cur_link is the last one
   int32_t* route_idx;   // [Npad] path_index
   int32_t* route_len;   // [Npad] hops of the current route
   int64_t* route_off;   // [Npad] start of the route in the arena

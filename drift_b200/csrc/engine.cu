@@ -94,7 +94,7 @@ struct drift_engine {
   uint32_t agent_base = 0;
   DevBuf<uint8_t> state;
   DevBuf<double> dist, speed, elen;
-  DevBuf<int32_t> cur_link, route_idx, route_len, trip_count, cur_node, chain_dst, next_len, next_status;
+  DevBuf<int32_t> cur_link, next_link, route_idx, route_len, trip_count, cur_node, chain_dst, next_len, next_status;
   DevBuf<uint8_t> chain_head, chain_cnt;
   DevBuf<int64_t> next_off;
   int32_t chain_cap = 4;
@@ -184,6 +184,7 @@ struct drift_engine {
     a.speed = speed.p;
     a.elen = elen.p;
     a.cur_link = cur_link.p;
+    a.next_link = next_link.p;
     a.route_idx = route_idx.p;
     a.route_len = route_len.p;
     a.route_off = route_off.p;
@@ -645,6 +646,8 @@ int drift_add_agents(drift_engine* e, int64_t n_agents, int64_t agent_base, int6
   CU(e->elen.alloc(Np));
   CU(e->cur_link.alloc(Np, false));
   CU(cudaMemset(e->cur_link.p, 0xff, sizeof(int32_t) * Np));
+  CU(e->next_link.alloc(Np, false));
+  CU(cudaMemset(e->next_link.p, 0xff, sizeof(int32_t) * Np));
   CU(e->route_idx.alloc(Np));
   CU(e->route_len.alloc(Np));
   CU(e->route_off.alloc(Np));

@@ -82,12 +82,13 @@ __device__ __forceinline__ double bpr_factor_lookup(const LinkArrays& lk, int32_
 __device__ __forceinline__ void emit_event(const LinkArrays& lk, Event* __restrict__ events, int slot, int32_t link,
                                            uint32_t agent, int32_t kind, uint32_t tag) {
   const unsigned long long mine = ((unsigned long long)tag << 32) | (uint32_t)slot;
+  const int32_t occ0 = lk.occ[link];  // issued alongside the exchange: only the first event needs it
   const unsigned long long prev = atomicExch(&lk.head[link], mine);
   Event e;
   e.link = link;
   e.agent = agent;
   e.kind = kind;
-  e.aux = ((uint32_t)(prev >> 32) == tag) ? (int32_t)(prev & 0xffffffffu) : -lk.occ[link] - 1;
+  e.aux = ((uint32_t)(prev >> 32) == tag) ? (int32_t)(prev & 0xffffffffu) : -occ0 - 1;
   events[slot] = e;
 }
 
@@ -95,23 +96,107 @@ __device__ __forceinline__ void emit_event(const LinkArrays& lk, Event* __restri
 // K1+K2: advance every agent by one tick, emit the link events of the crossers; with device-driven
 // demand waiting agents also draw their Bernoulli departure (agent.py:176-183) and leave on their
 // prefetched route.
-template <bool DEMAND>
-__device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, double p_dep, int* s_cnt, int* s_base) {
+//
+// The hot loop touches state (1 B) for every agent and dist/speed/elen (24 B read, 8 B written) for
+// moving ones, 4 agents per thread with 16-byte loads.  Crossings and departures are rare: they run
+// in out-of-line handlers that stage their events in shared memory; at the end of a tile the block
+// reserves the slots with ONE global atomic (single-address L2 atomics serialise at ~1 op/cycle
+// chip-wide) and all threads write + link the staged events.
+constexpr int kStageCap = 2 * kAdvThreads * kAdvPerThread;  // every agent of a tile emits <= 2 events
+
+struct AdvSmem {
+  int n;
+  int base;
+  uint32_t link_kind[kStageCap];  // link | (enter ? 2^31 : 0)
+  uint32_t agent[kStageCap];
+};
+
+__device__ __forceinline__ void stage_event(AdvSmem& sm, int32_t link, uint32_t agent, bool enter) {
+  const int k = atomicAdd(&sm.n, 1);
+  sm.link_kind[k] = (uint32_t)link | (enter ? 0x80000000u : 0u);
+  sm.agent[k] = agent;
+}
+
+// Agent crosses to the next link of its route or arrives (agent.py:200-203, 107-116).  Returns true on arrival.
+__device__ __noinline__ bool cross_agent(const TickArgs& p, int64_t i, int32_t tick, AdvSmem& sm) {
+  const AgentArrays& a = p.a;
+  const int32_t old_link = a.cur_link[i], nl = a.next_link[i];
+  a.route_idx[i] += 1;
+  stage_event(sm, old_link, a.base + (uint32_t)i, false);
+  if (nl >= 0) {  // next_link is refreshed in phase C when the enter event is resolved
+    a.cur_link[i] = nl;
+    stage_event(sm, nl, a.base + (uint32_t)i, true);
+    return false;
+  }
+  a.cur_link[i] = -1;
+  const unsigned long long slot = atomicAdd(&p.ctr->n_arrivals, 1ULL);
+  if (slot - p.rg.arr_drained < p.rg.arr_cap) {
+    p.rg.arr_agent[slot % p.rg.arr_cap] = (int32_t)i;
+    p.rg.arr_tick[slot % p.rg.arr_cap] = tick;
+  } else {
+    atomicOr(&p.ctr->overflow, kOvfArrivals);
+  }
+  return true;
+}
+
+// Agent.start_new_journey (agent.py:46-104) with the prefetched route.  Returns true if the agent is now moving.
+__device__ __noinline__ bool depart_agent(const TickArgs& p, int64_t i, int cnt, int32_t tick, AdvSmem& sm) {
   const AgentArrays& a = p.a;
   Counters* ctr = p.ctr;
+  const int32_t ns = a.next_status[i];
+  if (ns == 0) {  // no prefetched route: routed in phase A2 of this tick (rare)
+    p.dm.dep_req[atomicAdd(&ctr->n_dep_req[tick & 1], 1)] = (int32_t)i;
+    return false;
+  }
+  const int head = a.chain_head[i];
+  const int32_t src = a.cur_node[i], dst = a.chain_dst[i * a.chain_cap + head];
+  a.chain_head[i] = (uint8_t)((head + 1) % a.chain_cap);
+  a.chain_cnt[i] = (uint8_t)(cnt - 1);
+  a.trip_count[i] += 1;
+  a.cur_node[i] = dst;
+  const int64_t noff = a.next_off[i];
+  const int32_t nlen = a.next_len[i];
+  a.next_status[i] = a.next_status[a.npad + i];  // shift the second prefetched route up
+  a.next_off[i] = a.next_off[a.npad + i];
+  a.next_len[i] = a.next_len[a.npad + i];
+  a.next_status[a.npad + i] = 0;
+  const unsigned long long slot = atomicAdd(&ctr->n_departures, 1ULL);
+  if (slot - p.dm.log_drained < p.dm.log_cap) {
+    const unsigned long long k = slot % p.dm.log_cap;
+    p.dm.log_agent[k] = (int32_t)i;
+    p.dm.log_tick[k] = tick;
+    p.dm.log_src[k] = src;
+    p.dm.log_dst[k] = dst;
+    p.dm.log_status[k] = ns - 1;
+  } else {
+    atomicOr(&ctr->overflow, kOvfDepLog);
+  }
+  if (ns != 1 + DRIFT_ROUTE_OK) return false;
+  const int32_t fl = p.arena[noff];
+  a.route_off[i] = noff;
+  a.route_len[i] = nlen;
+  a.route_idx[i] = 0;
+  a.dist[i] = 0.0;
+  a.cur_link[i] = fl;
+  stage_event(sm, fl, a.base + (uint32_t)i, true);
+  return true;
+}
+
+template <bool DEMAND>
+__device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, double p_dep, AdvSmem& sm) {
+  const AgentArrays& a = p.a;
   const int par = tick & 1;
   const int64_t tiles = (a.n + (int64_t)kAdvThreads * kAdvPerThread - 1) / ((int64_t)kAdvThreads * kAdvPerThread);
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    if (threadIdx.x == 0) sm.n = 0;
+    __syncthreads();
     const int64_t i0 = (tile * kAdvThreads + threadIdx.x) * kAdvPerThread;
-    int32_t ev_link[2 * kAdvPerThread];
-    int32_t ev_kind_agent[2 * kAdvPerThread];  // local agent offset (0..3) | kind in bit 8
-    int nev = 0;
     if (i0 < a.n) {
-      const uchar4 st4 = *reinterpret_cast<const uchar4*>(a.state + i0);
-      const uint8_t st[4] = {st4.x, st4.y, st4.z, st4.w};
-      uint8_t nst[4] = {st[0], st[1], st[2], st[3]};
-      bool state_changed = false;
-      if (st4.x | st4.y | st4.z | st4.w) {
+      const uint32_t st4 = *reinterpret_cast<const uint32_t*>(a.state + i0);
+      uint32_t cn4 = 0;
+      if (DEMAND) cn4 = *reinterpret_cast<const uint32_t*>(a.chain_cnt + i0);  // independent of the state load
+      uint32_t nst4 = st4;
+      if (st4) {  // at least one of the four agents is moving
         const double2 d01 = *reinterpret_cast<const double2*>(a.dist + i0);
         const double2 d23 = *reinterpret_cast<const double2*>(a.dist + i0 + 2);
         const double2 s01 = *reinterpret_cast<const double2*>(a.speed + i0);
@@ -121,112 +206,54 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
         double d[4] = {d01.x, d01.y, d23.x, d23.y};
         const double sp[4] = {s01.x, s01.y, s23.x, s23.y};
         const double el[4] = {e01.x, e01.y, e23.x, e23.y};
+        uint32_t cross = 0;
 #pragma unroll
         for (int j = 0; j < kAdvPerThread; ++j) {
-          if (st[j] == kMoving) {
+          if ((st4 >> (8 * j)) & 0xffu) {
             // two roundings, never contracted to an FMA (agent.py:197-198)
             const double nd = __dadd_rn(d[j], __dmul_rn(sp[j], p.delta));
-            if (nd >= el[j]) {  // agent.py:200-203: at most one link per tick, overshoot dropped
-              const int64_t i = i0 + j;
-              const int32_t ri = a.route_idx[i] + 1;
-              a.route_idx[i] = ri;
-              d[j] = 0.0;
-              ev_link[nev] = a.cur_link[i];
-              ev_kind_agent[nev] = j;  // leave
-              ++nev;
-              if (ri < a.route_len[i]) {
-                const int32_t nl = p.arena[a.route_off[i] + ri];
-                a.cur_link[i] = nl;
-                ev_link[nev] = nl;
-                ev_kind_agent[nev] = j | 256;  // enter
-                ++nev;
-              } else {  // agent.py:107-116: arrived
-                a.cur_link[i] = -1;
-                nst[j] = kWaiting;
-                state_changed = true;
-                const unsigned long long slot = atomicAdd(&ctr->n_arrivals, 1ULL);
-                if (slot - p.rg.arr_drained < p.rg.arr_cap) {
-                  p.rg.arr_agent[slot % p.rg.arr_cap] = (int32_t)i;
-                  p.rg.arr_tick[slot % p.rg.arr_cap] = tick;
-                } else {
-                  atomicOr(&ctr->overflow, kOvfArrivals);
-                }
-              }
-            } else {
-              d[j] = nd;
-            }
+            const bool c = nd >= el[j];  // agent.py:200-203: at most one link per tick, overshoot dropped
+            d[j] = c ? 0.0 : nd;
+            cross |= (c ? 1u : 0u) << j;
           }
         }
         *reinterpret_cast<double2*>(a.dist + i0) = make_double2(d[0], d[1]);
         *reinterpret_cast<double2*>(a.dist + i0 + 2) = make_double2(d[2], d[3]);
-      }
-      if (DEMAND) {
-        const uchar4 cn4 = *reinterpret_cast<const uchar4*>(a.chain_cnt + i0);
-        const uint8_t cn[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
-#pragma unroll
-        for (int j = 0; j < kAdvPerThread; ++j) {
-          const int64_t i = i0 + j;
-          if (st[j] != kWaiting || i >= a.n) continue;  // an agent arriving this tick draws from the next tick on
-          const int cnt = cn[j];
-          if (cnt == 0) continue;  // no destination available (chain exhausted)
-          const double u = philox_uniform53(p.dm.seed, a.base + (uint32_t)i, (uint32_t)tick);
-          if (!(u < p_dep)) continue;  // agent.py:180
-          const int32_t ns = a.next_status[i];
-          if (ns == 0) {  // no prefetched route: routed in phase A2 of this tick (rare)
-            p.dm.dep_req[atomicAdd(&ctr->n_dep_req[par], 1)] = (int32_t)i;
-            continue;
-          }
-          // Agent.start_new_journey (agent.py:46-104) with the prefetched route
-          const int head = a.chain_head[i];
-          const int32_t src = a.cur_node[i], dst = a.chain_dst[i * a.chain_cap + head];
-          a.chain_head[i] = (uint8_t)((head + 1) % a.chain_cap);
-          a.chain_cnt[i] = (uint8_t)(cnt - 1);
-          a.trip_count[i] += 1;
-          a.cur_node[i] = dst;
-          const int64_t noff = a.next_off[i];
-          const int32_t nlen = a.next_len[i];
-          a.next_status[i] = a.next_status[a.npad + i];  // shift the second prefetched route up
-          a.next_off[i] = a.next_off[a.npad + i];
-          a.next_len[i] = a.next_len[a.npad + i];
-          a.next_status[a.npad + i] = 0;
-          const unsigned long long slot = atomicAdd(&ctr->n_departures, 1ULL);
-          if (slot - p.dm.log_drained < p.dm.log_cap) {
-            const unsigned long long k = slot % p.dm.log_cap;
-            p.dm.log_agent[k] = (int32_t)i;
-            p.dm.log_tick[k] = tick;
-            p.dm.log_src[k] = src;
-            p.dm.log_dst[k] = dst;
-            p.dm.log_status[k] = ns - 1;
-          } else {
-            atomicOr(&ctr->overflow, kOvfDepLog);
-          }
-          if (ns == 1 + DRIFT_ROUTE_OK) {
-            const int32_t fl = p.arena[noff];
-            a.route_off[i] = noff;
-            a.route_len[i] = nlen;
-            a.route_idx[i] = 0;
-            a.dist[i] = 0.0;
-            a.cur_link[i] = fl;
-            nst[j] = kMoving;
-            state_changed = true;
-            ev_link[nev] = fl;
-            ev_kind_agent[nev] = j | 256;
-            ++nev;
-          }
+        while (cross) {
+          const int j = __ffs(cross) - 1;
+          cross &= cross - 1;
+          if (cross_agent(p, i0 + j, tick, sm)) nst4 &= ~(0xffu << (8 * j));  // arrived: waiting again
         }
       }
-      if (state_changed) *reinterpret_cast<uchar4*>(a.state + i0) = make_uchar4(nst[0], nst[1], nst[2], nst[3]);
+      if (DEMAND) {
+#pragma unroll
+        for (int j = 0; j < kAdvPerThread; ++j) {
+          // an agent arriving this tick draws from the next tick on: test the state at tick start
+          const int cnt = (cn4 >> (8 * j)) & 0xffu;
+          if (((st4 >> (8 * j)) & 0xffu) != kWaiting || cnt == 0 || i0 + j >= a.n) continue;
+          const double u = philox_uniform53(p.dm.seed, a.base + (uint32_t)(i0 + j), (uint32_t)tick);
+          if (u < p_dep && depart_agent(p, i0 + j, cnt, tick, sm)) nst4 |= (uint32_t)kMoving << (8 * j);  // agent.py:180
+        }
+      }
+      if (nst4 != st4) *reinterpret_cast<uint32_t*>(a.state + i0) = nst4;
     }
-    const int slot0 = block_alloc(nev, &ctr->n_events[par], s_cnt, s_base);
-    if (nev) {
-      if (slot0 + nev <= p.ev_cap) {
-        for (int k = 0; k < nev; ++k)
-          emit_event(p.lk, p.events, slot0 + k, ev_link[k], a.base + (uint32_t)(i0 + (ev_kind_agent[k] & 255)),
-                     (ev_kind_agent[k] & 256) ? 1 : -1, (uint32_t)tick);
-      } else {
-        atomicOr(&ctr->overflow, kOvfEvents);
+    __syncthreads();
+    const int n = sm.n;
+    if (threadIdx.x == 0 && n) sm.base = atomicAdd(&p.ctr->n_events[par], n);
+    __syncthreads();
+    if (n) {
+      const int base = sm.base;
+      if (base + n <= p.ev_cap) {
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+          const uint32_t lkd = sm.link_kind[k];
+          emit_event(p.lk, p.events, base + k, (int32_t)(lkd & 0x7fffffffu), sm.agent[k], (lkd >> 31) ? 1 : -1,
+                     (uint32_t)tick);
+        }
+      } else if (threadIdx.x == 0) {
+        atomicOr(&p.ctr->overflow, kOvfEvents);
       }
     }
+    __syncthreads();
   }
 }
 
@@ -291,7 +318,7 @@ __device__ __forceinline__ void phase_inject(const TickArgs& p, int32_t tick, in
 // occupancy of every touched link.  Each event walks the list of its link.
 __device__ __forceinline__ void phase_resolve(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
                                               const Event* __restrict__ events, int n_events, int32_t tick,
-                                              double kph_to_mps, const Rings& rg) {
+                                              double kph_to_mps, const Rings& rg, const int32_t* __restrict__ arena) {
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_events; e += gridDim.x * blockDim.x) {
     const Event ev = events[e];
     const int first = (int)(lk.head[ev.link] & 0xffffffffu);
@@ -318,6 +345,8 @@ __device__ __forceinline__ void phase_resolve(const LinkArrays& lk, const AgentA
         const double sp = __dmul_rn(__dmul_rn(lk.v0[ev.link], f), kph_to_mps);
         a.speed[li] = sp;
         a.elen[li] = lk.len[ev.link];
+        const int32_t ri = a.route_idx[li] + 1;
+        a.next_link[li] = ri < a.route_len[li] ? arena[a.route_off[li] + ri] : -1;
         if (rg.ent_cap) {
           const unsigned long long slot = atomicAdd(&ctr->n_entries, 1ULL);
           if (slot - rg.ent_drained < rg.ent_cap) {
@@ -337,12 +366,12 @@ __device__ __forceinline__ void phase_resolve(const LinkArrays& lk, const AgentA
 
 // ---- standalone kernels (multi-rank exchange between A2 and C; per-kernel profiling) -----------------
 template <bool DEMAND>
-__global__ void __launch_bounds__(kAdvThreads) k_advance(TickArgs p, int32_t tick, double p_dep) {
-  __shared__ int s_cnt, s_base;
-  phase_advance<DEMAND>(p, tick, p_dep, &s_cnt, &s_base);
+__global__ void __launch_bounds__(kAdvThreads, 6) k_advance(const __grid_constant__ TickArgs p, int32_t tick, double p_dep) {
+  __shared__ AdvSmem sm;
+  phase_advance<DEMAND>(p, tick, p_dep, sm);
 }
 
-__global__ void __launch_bounds__(256) k_inject(TickArgs p, int32_t tick) {
+__global__ void __launch_bounds__(256) k_inject(const __grid_constant__ TickArgs p, int32_t tick) {
   const int par = tick & 1;
   phase_inject(p, tick, p.ctr->n_pending, p.ctr->n_dep_req[par]);
 }
@@ -356,10 +385,10 @@ __global__ void k_link_events(LinkArrays lk, Event* __restrict__ events, int n_e
 }
 
 // n_events < 0: take the local count of this tick from the counters.
-__global__ void k_resolve(TickArgs p, const Event* __restrict__ events, int n_events, int32_t tick) {
+__global__ void k_resolve(const __grid_constant__ TickArgs p, const Event* __restrict__ events, int n_events, int32_t tick) {
   const int par = tick & 1;
   if (n_events < 0) n_events = p.ctr->n_events[par];
-  phase_resolve(p.lk, p.a, p.ctr, events, n_events, tick, p.kph_to_mps, p.rg);
+  phase_resolve(p.lk, p.a, p.ctr, events, n_events, tick, p.kph_to_mps, p.rg, p.arena);
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // counters of the next tick
     p.ctr->n_events[par ^ 1] = 0;
     p.ctr->n_dep_req[par ^ 1] = 0;
@@ -369,8 +398,8 @@ __global__ void k_resolve(TickArgs p, const Event* __restrict__ events, int n_ev
 
 // ---- the persistent tick loop ---------------------------------------------------------------------
 // One cooperative launch runs `n_ticks` ticks: 2 grid barriers per tick (3 when phase A2 has work).
-__global__ void __launch_bounds__(kAdvThreads) k_tick_loop(TickArgs p, int32_t tick0, int32_t n_ticks, double p_dep) {
-  __shared__ int s_cnt, s_base;
+__global__ void __launch_bounds__(kAdvThreads, 4) k_tick_loop(const __grid_constant__ TickArgs p, int32_t tick0, int32_t n_ticks, double p_dep) {
+  __shared__ AdvSmem sm;
   cg::grid_group grid = cg::this_grid();
   Counters* ctr = p.ctr;
   const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
@@ -380,9 +409,9 @@ __global__ void __launch_bounds__(kAdvThreads) k_tick_loop(TickArgs p, int32_t t
     const int par = tick & 1;
     if (lead) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     if (p.demand)
-      phase_advance<true>(p, tick, p_dep, &s_cnt, &s_base);
+      phase_advance<true>(p, tick, p_dep, sm);
     else
-      phase_advance<false>(p, tick, p_dep, &s_cnt, &s_base);
+      phase_advance<false>(p, tick, p_dep, sm);
     grid.sync();
     if (lead) {
       unsigned long long t1;
@@ -401,7 +430,7 @@ __global__ void __launch_bounds__(kAdvThreads) k_tick_loop(TickArgs p, int32_t t
         t0 = t1;
       }
     }
-    phase_resolve(p.lk, p.a, ctr, p.events, ctr->n_events[par], tick, p.kph_to_mps, p.rg);
+    phase_resolve(p.lk, p.a, ctr, p.events, ctr->n_events[par], tick, p.kph_to_mps, p.rg, p.arena);
     if (lead) {
       ctr->n_events[par ^ 1] = 0;
       ctr->n_dep_req[par ^ 1] = 0;
