@@ -231,6 +231,8 @@ def run_b200(args):
     dst_all = dst_all.reshape(n_local, -1)
     eng.set_demand(args.seed, HOURLY, start, chain_capacity=4, router=ROUTER_BATCHED)
     eng.set_option("route_window", TPS)
+    if args.coop_blocks:
+        eng.set_option("coop_blocks_per_sm", args.coop_blocks)
     eng.push_trips(dst_all[:, :4])
     pool = np.ascontiguousarray(dst_all[:, 4:].reshape(n_local, total_steps, trips_per_step).transpose(1, 0, 2))
     eng.store_trip_pool(pool)
@@ -264,6 +266,8 @@ def run_b200(args):
     barrier()
     launches0 = eng.kernel_times()["total_launches"]
     st0 = eng.stats()
+    eng.set_option("time_plan", 1)
+    eng.phase_times(reset=True)
     with ClockSampler(local_rank) as clk:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -272,6 +276,8 @@ def run_b200(args):
         barrier()
         dt = time.perf_counter() - t0
     st1 = eng.stats()
+    phases = eng.phase_times(reset=True)
+    eng.set_option("time_plan", 0)
     launches = eng.kernel_times()["total_launches"] - launches0
     if dist is not None:
         tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
@@ -346,7 +352,10 @@ def run_b200(args):
             moving_fraction=float(moving / n_local),
             e2e=dict(value=e2e_value, unit="agent-steps/s", h2d_bytes_per_step=int(h2d),
                      d2h_bytes_per_step=int(d2h_total / K), ms_per_step=1e3 * dt_e2e / K),
-            gpu_launches=int(launches), roofline=roof, clocks=clk.summary())
+            gpu_launches=int(launches), roofline=roof, clocks=clk.summary(),
+            phases=dict(note="timed region: per-tick phase times of the persistent kernel (%globaltimer, barriers "
+                             "included) and total ms in route-planning batches",
+                        **{k: (round(v, 3) if isinstance(v, float) else v) for k, v in phases.items()}))
         if cpu is not None:
             line["cpu_baseline"] = dict(
                 value=cpu["agent_steps_per_s"], unit="agent-steps/s", cores=1, kind="port",
@@ -374,6 +383,7 @@ def main():
     ap.add_argument("--ticks-per-step", type=int, default=300)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg (0 = skip)")
+    ap.add_argument("--coop-blocks", type=int, default=0, help="blocks per SM of the persistent tick kernel (0 = default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

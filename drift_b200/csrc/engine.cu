@@ -139,7 +139,9 @@ struct drift_engine {
   DevBuf<int32_t> t_slot_of, t_next, t_job_dst, t_job_slot, t_ctl;  // t_ctl: n_slots, n_jobs, job_cursor
   DevBuf<unsigned long long> t_dist;
   DevBuf<uint32_t> t_stamp, t_infar, t_iter, t_slot_stamp;
-  DevBuf<int32_t> t_slot_owner;
+  DevBuf<int32_t> t_slot_owner, t_slot_job, t_job_qhead, t_job_cnt, t_q_next;
+  DevBuf<uint32_t> t_slot_job_batch;
+  int32_t t_bounded_max = kMaxBounded;
   uint32_t t_batch = 0;
   DevBuf<int32_t> t_lists;
   int32_t t_max_slots = 0, t_blocks = 0;
@@ -167,6 +169,9 @@ struct drift_engine {
   Counters* h_ctr = nullptr;  // pinned
   int64_t tick = 0;
   double last_delta = 1.0;
+  double plan_ms = 0;
+  int64_t loop_ticks = 0;
+  bool time_plan = false;
   int32_t ticks_since_plan = 0;
   int64_t routes_planned = 0;
   // profiling
@@ -321,6 +326,10 @@ int ensure_trees(drift_engine* e) {
   CU(e->t_slot_owner.alloc(slots, false));
   CU(cudaMemset(e->t_slot_owner.p, 0xff, sizeof(int32_t) * slots));
   CU(e->t_slot_stamp.alloc(slots, true));
+  CU(e->t_slot_job.alloc(slots));
+  CU(e->t_slot_job_batch.alloc(slots, true));
+  CU(e->t_job_qhead.alloc(slots));
+  CU(e->t_job_cnt.alloc(slots));
   CU(e->t_job_dst.alloc(slots));
   CU(e->t_job_slot.alloc(slots));
   CU(e->t_ctl.alloc(4));
@@ -367,6 +376,17 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     tc.slot_owner = e->t_slot_owner.p;
     tc.slot_stamp = e->t_slot_stamp.p;
     tc.batch = ++e->t_batch;
+    if (e->t_q_next.n < Q + q0) {
+      CU(cudaStreamSynchronize(e->stream));
+      CU(e->t_q_next.alloc(std::max<int64_t>(e->q_cap, Q + q0), false));
+    }
+    tc.slot_job = e->t_slot_job.p;
+    tc.slot_job_batch = e->t_slot_job_batch.p;
+    tc.job_qhead = e->t_job_qhead.p;
+    tc.job_cnt = e->t_job_cnt.p;
+    tc.q_next = e->t_q_next.p;  // indexed by the query number inside this call
+    tc.bounded_max = e->t_bounded_max;
+    CU(cudaMemsetAsync(out.status, 0xff, sizeof(int32_t) * Q, e->stream));  // -1 = not answered yet
     tc.n_jobs = e->t_ctl.p + 1;
     tc.job_cursor = e->t_ctl.p + 2;
     tc.max_slots = e->t_max_slots;
@@ -382,11 +402,13 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     const int gq = grid_for(Q, 256, kSMs * 4);
     k_tree_hits<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, n_dev);
     k_tree_requests<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, e->ctr.p, n_dev);
-    k_build_trees<<<e->t_blocks, kTreeThreads, 0, e->stream>>>(e->graph(), wb, wf, e->t_delta, tc, ts);
+    k_link_queries<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, n_dev);
+    k_build_trees<<<e->t_blocks, kTreeThreads, 0, e->stream>>>(e->graph(), wb, wf, e->t_delta, tc, ts, qs, e->arena.p,
+                                                               (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
     k_extract_paths<<<gq, 256, 0, e->stream>>>(e->graph(), Q, n_dev, qs, qd, tc, e->arena.p,
                                                 (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
     CU(cudaGetLastError());
-    e->total_launches += 4;
+    e->total_launches += 5;
     return DRIFT_OK;
   }
   int rc = ensure_router(e, Q);
@@ -523,6 +545,7 @@ int run_tick_loop(drift_engine* e, int32_t n_ticks, double delta, bool demand, d
   void* args[] = {(void*)&p, (void*)&tick0, (void*)&n_ticks, (void*)&p_dep};
   CU(cudaLaunchCooperativeKernel((void*)k_tick_loop, dim3(blocks), dim3(kAdvThreads), args, 0, e->stream));
   e->tick += n_ticks;
+  e->loop_ticks += n_ticks;
   e->total_launches += 1;
   e->adv_launches += n_ticks;
   return DRIFT_OK;
@@ -881,6 +904,12 @@ int drift_refill_from_pool(drift_engine* e, int32_t block) {
 // every agent).  One host sync per window to learn the batch size.
 static int plan_window(drift_engine* e) {
   Counters* c = e->ctr.p;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (e->time_plan) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, e->stream);
+  }
   CU(cudaMemsetAsync(&c->n_plan, 0, sizeof(int32_t), e->stream));
   k_plan_requests<<<grid_for(e->N, 256, kSMs * 8), 256, 0, e->stream>>>(e->agents(), c, e->q_src.p, e->q_dst.p,
                                                                          e->q_agent.p, (int32_t)e->q_cap);
@@ -907,6 +936,15 @@ static int plan_window(drift_engine* e) {
                                                                        e->q_status.p, e->agents());
     CU(cudaGetLastError());
     e->total_launches += 1;
+  }
+  if (ev0) {
+    cudaEventRecord(ev1, e->stream);
+    cudaEventSynchronize(ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    e->plan_ms += ms;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
   }
   return DRIFT_OK;
 }
@@ -1236,12 +1274,34 @@ int drift_kernel_times(drift_engine* e, double* advance_ms, int64_t* advance_lau
   return DRIFT_OK;
 }
 
+int drift_phase_times(drift_engine* e, double* advance_ns, double* inject_ns, double* resolve_ns, double* plan_ms,
+                      int64_t* ticks, int32_t reset) {
+  if (!e) return fail(DRIFT_EINVAL, "drift_phase_times");
+  CU(cudaSetDevice(e->device));
+  Counters c;
+  int rc = fetch_counters(e, &c);
+  if (rc) return rc;
+  if (advance_ns) *advance_ns = (double)c.phase_ns[0];
+  if (inject_ns) *inject_ns = (double)c.phase_ns[1];
+  if (resolve_ns) *resolve_ns = (double)c.phase_ns[2];
+  if (plan_ms) *plan_ms = e->plan_ms;
+  if (ticks) *ticks = e->loop_ticks;
+  if (reset) {
+    CU(cudaMemsetAsync(&e->ctr.p->phase_ns[0], 0, 4 * sizeof(unsigned long long), e->stream));
+    e->plan_ms = 0;
+    e->loop_ticks = 0;
+  }
+  return DRIFT_OK;
+}
+
 int drift_set_option(drift_engine* e, const char* name, double value) {
   if (!e || !name) return fail(DRIFT_EINVAL, "drift_set_option");
   std::string s(name);
   if (s == "tree_cache_bytes") {
     if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_cache_bytes must be set before the first batched route");
     e->tree_budget_bytes = (int64_t)value;
+  } else if (s == "time_plan") {
+    e->time_plan = value != 0;
   } else if (s == "persistent") {
     e->persistent = value != 0;
   } else if (s == "coop_blocks_per_sm") {
@@ -1251,6 +1311,8 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
     e->route_window = (int32_t)value;
   } else if (s == "replan") {
     e->ticks_since_plan = 0;
+  } else if (s == "bounded_max") {
+    e->t_bounded_max = std::max(0, std::min((int)value, kMaxBounded));
   } else if (s == "tree_delta_scale") {
     e->t_delta *= value;
   } else {

@@ -325,7 +325,16 @@ struct TreeCache {
   int32_t* n_jobs;
   int32_t* job_cursor;
   uint32_t batch;        // id of this batch
+  // queries of the batch hanging off the job that builds their destination (bounded search)
+  int32_t* slot_job;        // [max_slots] job that fills the slot ...
+  uint32_t* slot_job_batch; // [max_slots] ... in this batch
+  int32_t* job_qhead;       // [max_slots] head of the job's query list
+  int32_t* job_cnt;         // [max_slots] queries on that list
+  int32_t* q_next;          // [Q]
+  int32_t bounded_max;      // jobs with <= this many queries search only until their sources are settled (0 = off)
 };
+
+constexpr int kMaxBounded = 8;
 
 constexpr unsigned long long kInfBits = 0x7FF0000000000000ULL;
 constexpr int kTreeThreads = 256;
@@ -370,7 +379,26 @@ __global__ void k_tree_requests(int64_t Q, const int32_t* __restrict__ dst, int3
     const int32_t j = atomicAdd(tc.n_jobs, 1);
     tc.job_dst[j] = t;
     tc.job_slot[j] = s;
+    tc.job_qhead[j] = -1;
+    tc.job_cnt[j] = 0;
+    tc.slot_job[s] = j;
+    tc.slot_job_batch[s] = tc.batch;
     tc.slot_of[t] = s;
+  }
+}
+
+// Pass 3: hang every query whose destination is being built in this batch on that job's list.
+__global__ void k_link_queries(int64_t Q, const int32_t* __restrict__ dst, int32_t V, TreeCache tc,
+                               const int32_t* __restrict__ n_dev) {
+  const int64_t n = n_dev ? (int64_t)*n_dev : Q;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t t = dst[q];
+    if (t < 0 || t >= V) continue;
+    const int32_t s = tc.slot_of[t];
+    if (s < 0 || tc.slot_job_batch[s] != tc.batch) continue;
+    const int32_t j = tc.slot_job[s];
+    tc.q_next[q] = atomicExch(&tc.job_qhead[j], (int32_t)q);
+    atomicAdd(&tc.job_cnt[j], 1);
   }
 }
 
@@ -384,10 +412,18 @@ __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v
   return *s_min;
 }
 
+// Jobs whose destination is wanted by at most tc.bounded_max queries of the batch ("cold"
+// destinations) stop as soon as all their sources are settled, write those routes themselves
+// (walking dist[] from the source) and do not keep a tree; the others build and cache the tree.
 __global__ void __launch_bounds__(kTreeThreads) k_build_trees(GraphArrays g, const double* __restrict__ w_bwd,
                                                               const double* __restrict__ w_fwd, double delta,
-                                                              TreeCache tc, TreeScratch sc) {
-  __shared__ int s_job, s_near_n, s_next_n, s_far_n, s_far2_n;
+                                                              TreeCache tc, TreeScratch sc,
+                                                              const int32_t* __restrict__ q_src,
+                                                              int32_t* __restrict__ arena, unsigned long long arena_cap,
+                                                              Counters* ctr, RouteOut out,
+                                                              const double* __restrict__ link_cost) {
+  __shared__ int s_job, s_near_n, s_next_n, s_far_n, s_far2_n, s_done;
+  __shared__ int s_bsrc[kMaxBounded], s_bq[kMaxBounded];
   __shared__ unsigned long long s_min;
   const int64_t V = g.V;
   unsigned long long* dist = sc.dist + (int64_t)blockIdx.x * V;
@@ -407,6 +443,15 @@ __global__ void __launch_bounds__(kTreeThreads) k_build_trees(GraphArrays g, con
     if (job >= n_jobs) break;
     const int32_t dest = tc.job_dst[job];
     int32_t* next_link = tc.next_link + (int64_t)tc.job_slot[job] * V;
+    const int nb = tc.job_cnt[job];
+    const bool bounded = nb > 0 && nb <= tc.bounded_max;
+    if (bounded && threadIdx.x == 0) {
+      int k = 0;
+      for (int32_t q = tc.job_qhead[job]; q >= 0 && k < kMaxBounded; q = tc.q_next[q], ++k) {
+        s_bq[k] = q;
+        s_bsrc[k] = q_src[q];
+      }
+    }
     for (int64_t v = threadIdx.x; v < V; v += blockDim.x) {
       dist[v] = kInfBits;
       infar[v] = 0;
@@ -427,6 +472,20 @@ __global__ void __launch_bounds__(kTreeThreads) k_build_trees(GraphArrays g, con
       if (n == 0) {
         const int nf = s_far_n;
         if (nf == 0) break;
+        if (bounded) {  // every node with dist <= T is final: stop once all sources are
+          if (threadIdx.x == 0) {
+            int done = 1;
+            for (int k = 0; k < nb; ++k) {
+              const int32_t sn = s_bsrc[k];
+              if (sn >= 0 && sn < V && __longlong_as_double((long long)dist[sn]) > T) done = 0;
+            }
+            s_done = done;
+          }
+          __syncthreads();
+          const int done = s_done;
+          __syncthreads();
+          if (done) break;
+        }
         // next threshold: skip empty buckets
         if (threadIdx.x == 0) s_min = kInfBits;
         __syncthreads();
@@ -490,6 +549,73 @@ __global__ void __launch_bounds__(kTreeThreads) k_build_trees(GraphArrays g, con
       nearB = t;
       __syncthreads();
     }
+    if (bounded) {
+      // routes of the few sources, straight from dist[]: at x follow the first forward entry (CSR
+      // order) with dist[head] + w == dist[x]; every node on the way is already final
+      if (threadIdx.x < nb) {
+        const int32_t q = s_bq[threadIdx.x];
+        const int32_t sn = s_bsrc[threadIdx.x];
+        int32_t status = DRIFT_ROUTE_NOPATH, hops = 0;
+        int64_t off = 0;
+        double cost = 0.0;
+        if (sn == dest) {
+          status = DRIFT_ROUTE_TRIVIAL;
+        } else if (sn >= 0 && sn < V && dist[sn] != kInfBits) {
+          for (int pass = 0; pass < 2; ++pass) {
+            int32_t x = sn;
+            int k = 0;
+            while (x != dest) {
+              const unsigned long long dx = dist[x];
+              int32_t nl = -1, nx = -1;
+              const int32_t e1 = g.fwd_rowptr[x + 1];
+              for (int32_t e = g.fwd_rowptr[x]; e < e1; ++e) {
+                const unsigned long long dvb = dist[g.fwd_col[e]];
+                if (dvb == kInfBits) continue;
+                const double c = __dadd_rn(__longlong_as_double((long long)dvb), w_fwd[e]);
+                if ((unsigned long long)__double_as_longlong(c) == dx) {
+                  nl = g.fwd_link[e];
+                  nx = g.fwd_col[e];
+                  break;
+                }
+              }
+              if (nl < 0 || k > V) {
+                k = -1;
+                break;
+              }
+              if (pass) {
+                arena[off + k] = nl;
+                cost = __dadd_rn(cost, link_cost[nl]);
+              }
+              ++k;
+              x = nx;
+            }
+            if (k < 0) break;
+            if (!pass) {
+              hops = k;
+              const unsigned long long o = atomicAdd(&ctr->arena_cursor, (unsigned long long)hops);
+              if (o + hops > arena_cap) {
+                atomicOr(&ctr->overflow, kOvfArena);
+                hops = 0;
+                break;
+              }
+              off = (int64_t)o;
+            } else {
+              status = DRIFT_ROUTE_OK;
+            }
+          }
+        }
+        out.status[q] = status;
+        out.n_links[q] = status == DRIFT_ROUTE_OK ? hops : 0;
+        out.off[q] = status == DRIFT_ROUTE_OK ? off : 0;
+        out.cost[q] = cost;
+      }
+      if (threadIdx.x == 0) {  // no tree was kept
+        tc.slot_of[dest] = -1;
+        tc.slot_owner[tc.job_slot[job]] = -1;
+      }
+      __syncthreads();
+      continue;
+    }
     // first link of the shortest path u -> dest: first forward entry (CSR order) that attains dist[u]
     for (int64_t u = threadIdx.x; u < V; u += blockDim.x) {
       int32_t nl = -1;
@@ -521,6 +647,7 @@ __global__ void k_extract_paths(GraphArrays g, int64_t Q, const int32_t* __restr
   const int64_t n = n_dev ? (int64_t)*n_dev : Q;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
     const int32_t s = src[q], t = dst[q];
+    if (out.status[q] >= 0) continue;  // answered by a bounded search
     out.off[q] = 0;
     out.cost[q] = 0.0;
     out.n_links[q] = 0;

@@ -273,6 +273,15 @@ class Engine:
         _capi.check(self._lib.drift_tick_index(self._h, C.byref(t)))
         return t.value
 
+    def phase_times(self, reset=True):
+        a, i, r, pl = C.c_double(0), C.c_double(0), C.c_double(0), C.c_double(0)
+        n = C.c_int64(0)
+        _capi.check(self._lib.drift_phase_times(self._h, C.byref(a), C.byref(i), C.byref(r), C.byref(pl), C.byref(n),
+                                                int(bool(reset))))
+        t = max(n.value, 1)
+        return dict(ticks=n.value, advance_us_per_tick=a.value / t / 1e3, inject_us_per_tick=i.value / t / 1e3,
+                    resolve_us_per_tick=r.value / t / 1e3, plan_ms=pl.value)
+
     def set_option(self, name, value):
         _capi.check(self._lib.drift_set_option(self._h, name.encode(), float(value)))
 

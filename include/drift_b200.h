@@ -202,6 +202,11 @@ int drift_tick_finish(drift_engine* e, const void* events_dev, int64_t n_events)
 int drift_kernel_times(drift_engine* e, double* advance_ms, int64_t* advance_launches, double* total_ms,
                        int64_t* total_launches);
 int drift_set_profiling(drift_engine* e, int32_t on);
+/* Phase breakdown of the persistent tick kernel since the last reset: %globaltimer nanoseconds spent
+ * in advance / inject / resolve (barriers included) over `ticks` ticks, and milliseconds spent in the
+ * route-planning batches (CUDA events; needs option "time_plan" = 1). */
+int drift_phase_times(drift_engine* e, double* advance_ns, double* inject_ns, double* resolve_ns, double* plan_ms,
+                      int64_t* ticks, int32_t reset);
 /* Tunables: "tree_cache_bytes" (HBM budget of the destination-tree cache, before first use),
  * "tree_delta_scale" (multiplies the near-far bucket width). */
 int drift_set_option(drift_engine* e, const char* name, double value);

@@ -220,3 +220,41 @@ def test_tree_cache_eviction():
         from drift_b200._capi import DriftError
         with pytest.raises(DriftError):  # 20 distinct destinations cannot fit 8 slots in one batch
             eng.route(list(range(20, 40)), list(range(100, 120)), router=ROUTER_BATCHED)
+
+
+@pytest.mark.parametrize("bounded_max", [8, 0])
+def test_batched_router_cold_destinations(bounded_max):
+    """Random (s, t) pairs: most destinations are wanted by a handful of queries, so the builder
+    stops as soon as their sources are settled and writes the routes itself (bounded search)."""
+    import networkx as nx
+    from drift_b200.engine import Engine, ROUTE_OK, ROUTE_TRIVIAL, ROUTE_NOPATH, ROUTER_BATCHED
+
+    from drift_b200.graph import lower_graph
+
+    G = _unique_path_graph(21, n=600, m=1500)
+    lg = lower_graph(G)
+    nodes = list(G.nodes)
+    rng = random.Random(8)
+    Q = 2500
+    pairs = [(rng.randrange(len(nodes)), rng.randrange(len(nodes))) for _ in range(Q)]
+    pairs += [(7, 7), (len(nodes) - 4, 3), (3, len(nodes) - 4)]  # trivial, and the unreachable / dead-end extras
+    with Engine(lg, 8, route_arena_links=1 << 22) as eng:
+        eng.set_option("bounded_max", bounded_max)
+        for rnd in range(2):
+            st, nl, links = eng.route([p[0] for p in pairs], [p[1] for p in pairs], router=ROUTER_BATCHED)
+            costs = eng.route_costs(len(pairs))
+            for q, ((s, t), stt) in enumerate(zip(pairs, st)):
+                if s == t:
+                    assert stt == ROUTE_TRIVIAL
+                    continue
+                try:
+                    want = nx.shortest_path(G, nodes[s], nodes[t], weight="travel_time")
+                except nx.NetworkXNoPath:
+                    assert stt == ROUTE_NOPATH, (q, s, t)
+                    continue
+                assert stt == ROUTE_OK, (q, s, t)
+                assert [nodes[i] for i in lg.links_to_nodes(s, links[q])] == want
+                c = 0.0
+                for l in links[q]:
+                    c += lg.link_t0[l]
+                assert costs[q] == c
