@@ -229,6 +229,9 @@ def run_b200(args):
     total_steps = W + K
     _, dst_all = make_chains(model, rng, lg, start, 4 + trips_per_step * total_steps)
     dst_all = dst_all.reshape(n_local, -1)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, float(v))
     eng.set_demand(args.seed, HOURLY, start, chain_capacity=4, router=ROUTER_BATCHED)
     eng.set_option("route_window", TPS)
     if args.coop_blocks:
@@ -383,6 +386,7 @@ def main():
     ap.add_argument("--ticks-per-step", type=int, default=300)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg (0 = skip)")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
     ap.add_argument("--coop-blocks", type=int, default=0, help="blocks per SM of the persistent tick kernel (0 = default)")
     args = ap.parse_args()
     if args.impl == "reference":

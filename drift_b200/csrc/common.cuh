@@ -28,8 +28,12 @@ struct HeapItem {  // (dist, push counter, node): nx:weighted.py heap entries
   int32_t node;
 };
 
+// The event buffer is split into kEvSub sub-buffers with their own counters so that the warps of
+// phase A do not all hit one address when they reserve slots.
+constexpr int kEvSub = 16;
+
 struct Counters {
-  int32_t n_events[2];    // indexed by tick parity: tick k resets the slot of tick k+1
+  int32_t n_events[2][kEvSub];  // [tick parity][sub-buffer]: tick k resets the slots of tick k+1
   int32_t n_dep_req[2];   // departures of this tick that found no prefetched route
   int32_t n_pending;      // pending departures (committed routes) for the next tick
   int32_t overflow;       // bit flags, see kOvf*

@@ -105,8 +105,9 @@ struct drift_engine {
   DevBuf<int32_t> arena;
   int64_t arena_cap = 0;
   // events
-  DevBuf<Event> events;
-  int64_t ev_cap = 0;
+  DevBuf<Event> events, send;  // kEvSub sub-buffers of ev_sub_cap records; contiguous copy for the rank exchange
+  int64_t ev_cap = 0, ev_sub_cap = 0;
+  DevBuf<int32_t> send_n;
   // in-tick fallback router scratch (device-driven demand)
   DevBuf<double> f_seen;
   DevBuf<int32_t> f_plink;
@@ -141,7 +142,9 @@ struct drift_engine {
   DevBuf<uint32_t> t_stamp, t_infar, t_iter, t_slot_stamp;
   DevBuf<int32_t> t_slot_owner, t_slot_job, t_job_qhead, t_job_cnt, t_q_next;
   DevBuf<uint32_t> t_slot_job_batch;
-  int32_t t_bounded_max = kMaxBounded;
+  int32_t t_bounded_max = -1;  // -1 = automatic: bounded search only when the cache cannot hold every destination
+  int32_t t_threads = 256;
+  int64_t tree_scratch_bytes = (int64_t)24 << 30;
   uint32_t t_batch = 0;
   DevBuf<int32_t> t_lists;
   int32_t t_max_slots = 0, t_blocks = 0;
@@ -318,7 +321,7 @@ int ensure_trees(drift_engine* e) {
   int64_t slots = std::min<int64_t>(V, e->tree_budget_bytes / (4 * V));
   slots = std::max<int64_t>(slots, 1);
   // resident builder blocks: 32 B of scratch per node each
-  int64_t blocks = std::min<int64_t>(kSMs * 6, ((int64_t)8 << 30) / (32 * V));
+  int64_t blocks = std::min<int64_t>((int64_t)e->num_sms * (2048 / e->t_threads), e->tree_scratch_bytes / (32 * V));
   blocks = std::max<int64_t>(blocks, 1);
   CU(e->t_slot_of.alloc(V, false));
   CU(cudaMemset(e->t_slot_of.p, 0xff, sizeof(int32_t) * V));
@@ -385,7 +388,7 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     tc.job_qhead = e->t_job_qhead.p;
     tc.job_cnt = e->t_job_cnt.p;
     tc.q_next = e->t_q_next.p;  // indexed by the query number inside this call
-    tc.bounded_max = e->t_bounded_max;
+    tc.bounded_max = e->t_bounded_max >= 0 ? e->t_bounded_max : (e->t_max_slots >= e->V ? 0 : kMaxBounded);
     CU(cudaMemsetAsync(out.status, 0xff, sizeof(int32_t) * Q, e->stream));  // -1 = not answered yet
     tc.n_jobs = e->t_ctl.p + 1;
     tc.job_cursor = e->t_ctl.p + 2;
@@ -403,7 +406,7 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     k_tree_hits<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, n_dev);
     k_tree_requests<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, e->ctr.p, n_dev);
     k_link_queries<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, n_dev);
-    k_build_trees<<<e->t_blocks, kTreeThreads, 0, e->stream>>>(e->graph(), wb, wf, e->t_delta, tc, ts, qs, e->arena.p,
+    k_build_trees<<<e->t_blocks, e->t_threads, 0, e->stream>>>(e->graph(), wb, wf, e->t_delta, tc, ts, qs, e->arena.p,
                                                                (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
     k_extract_paths<<<gq, 256, 0, e->stream>>>(e->graph(), Q, n_dev, qs, qd, tc, e->arena.p,
                                                 (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
@@ -482,7 +485,7 @@ TickArgs make_tick_args(drift_engine* e, double delta, bool demand) {
   p.arena_cap = (unsigned long long)e->arena_cap;
   p.ctr = e->ctr.p;
   p.events = e->events.p;
-  p.ev_cap = (int32_t)e->ev_cap;
+  p.ev_cap = (int32_t)e->ev_sub_cap;
   p.pend_agent = e->pend_agent.p;
   p.pend_off = e->pend_off.p;
   p.pend_len = e->pend_len.p;
@@ -524,8 +527,9 @@ int tick_finish(drift_engine* e, Event* events, int64_t n_events, bool gathered,
     e->total_launches += 1;
   }
   k_resolve<<<g, 256, 0, e->stream>>>(p, events, (int)n_events, tick);
+  k_reset_counters<<<1, 32, 0, e->stream>>>(e->ctr.p, tick);
   CU(cudaGetLastError());
-  e->total_launches += 1;
+  e->total_launches += 2;
   return DRIFT_OK;
 }
 
@@ -615,7 +619,7 @@ int drift_create(drift_engine** out, int device, const drift_graph_desc* g) {
   {  // bucket width of the near-far tree builder: a few average hops
     double sum = 0;
     for (int32_t k = 0; k < g->Ef; ++k) sum += g->fwd_w[k];
-    e->t_delta = g->Ef ? 4.0 * sum / g->Ef : 1.0;
+    e->t_delta = g->Ef ? 8.0 * sum / g->Ef : 1.0;
     if (!(e->t_delta > 0)) e->t_delta = 1.0;
   }
   for (int h = 0; h < 24; ++h) e->hourly[h] = 0.05;
@@ -684,9 +688,13 @@ int drift_add_agents(drift_engine* e, int64_t n_agents, int64_t agent_base, int6
   if (route_arena_links <= 0) route_arena_links = std::max<int64_t>((int64_t)1 << 20, n_agents * 64);
   CU(e->arena.alloc(route_arena_links, false));
   e->arena_cap = route_arena_links;
-  e->ev_cap = 2 * n_agents + 1024;
+  // every sub-buffer can hold all events of a tick in the worst case only if the warps spread evenly;
+  // sized with a 4x margin over the even share and checked at run time (overflow flag)
+  e->ev_sub_cap = std::min<int64_t>(2 * n_agents + 1024, (2 * n_agents * 4) / kEvSub + 4096);
+  e->ev_cap = e->ev_sub_cap * kEvSub;
   if (e->ev_cap > 0x7fffffff) return fail(DRIFT_EINVAL, "too many agents for one engine");
   CU(e->events.alloc(e->ev_cap, false));
+  CU(e->send_n.alloc(1));
   e->pend_cap = n_agents;
   CU(e->pend_agent.alloc(n_agents));
   CU(e->pend_off.alloc(n_agents));
@@ -1007,21 +1015,31 @@ int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0) {
   return DRIFT_OK;
 }
 
+// local events of the tick -> contiguous send buffer; returns their number
+static int compact_for_exchange(drift_engine* e, int64_t* n_events) {
+  if (e->send.n < e->ev_cap) CU(e->send.alloc(e->ev_cap, false));
+  k_compact_events<<<e->num_sms, 256, 0, e->stream>>>(e->events.p, (int32_t)e->ev_sub_cap, e->ctr.p, (int32_t)e->tick,
+                                                     e->send.p, e->send_n.p);
+  CU(cudaGetLastError());
+  e->total_launches += 1;
+  Counters c;
+  int rc = fetch_counters(e, &c);
+  if (rc) return rc;
+  rc = check_overflow(e, c);
+  if (rc) return rc;
+  int64_t tot = 0;
+  for (int s = 0; s < kEvSub; ++s) tot += c.n_events[e->tick & 1][s];
+  if (n_events) *n_events = tot;
+  return DRIFT_OK;
+}
+
 int drift_tick_begin_demand(drift_engine* e, double delta, double t, int64_t* n_events) {
   if (!e || !e->have_demand || !e->have_bpr) return fail(DRIFT_ESTATE, "drift_tick_begin_demand");
   CU(cudaSetDevice(e->device));
   int rc = demand_tick_begin(e, delta, t);
   if (rc) return rc;
   e->last_delta = delta;
-  if (n_events) {
-    Counters c;
-    rc = fetch_counters(e, &c);
-    if (rc) return rc;
-    rc = check_overflow(e, c);
-    if (rc) return rc;
-    *n_events = c.n_events[e->tick & 1];
-  }
-  return DRIFT_OK;
+  return compact_for_exchange(e, n_events);
 }
 
 int drift_update_travel_times(drift_engine* e) {
@@ -1202,7 +1220,8 @@ int drift_stats(drift_engine* e, drift_stats_out* out) {
   out->arrivals_total = (int64_t)h.n_arrivals;
   out->departures_total = (int64_t)h.n_departures;
   out->route_arena_used = (int64_t)h.arena_cursor;
-  out->events_last_tick = h.n_events[e->tick & 1];
+  out->events_last_tick = 0;
+  for (int sb = 0; sb < kEvSub; ++sb) out->events_last_tick += h.n_events[e->tick & 1][sb];
   return check_overflow(e, h);
 }
 
@@ -1218,20 +1237,13 @@ int drift_tick_begin(drift_engine* e, double delta, int64_t* n_events) {
   int rc = tick_begin(e, delta, false, 0.0);
   if (rc) return rc;
   e->last_delta = delta;
-  if (n_events) {
-    Counters c;
-    rc = fetch_counters(e, &c);
-    if (rc) return rc;
-    rc = check_overflow(e, c);
-    if (rc) return rc;
-    *n_events = c.n_events[e->tick & 1];
-  }
-  return DRIFT_OK;
+  return compact_for_exchange(e, n_events);
 }
 
 int drift_events_ptr(drift_engine* e, void** dev_ptr, int64_t* capacity) {
   if (!e || !dev_ptr) return fail(DRIFT_EINVAL, "drift_events_ptr");
-  *dev_ptr = e->events.p;
+  if (e->send.n < e->ev_cap) CU(e->send.alloc(e->ev_cap, false));
+  *dev_ptr = e->send.p;
   if (capacity) *capacity = e->ev_cap;
   return DRIFT_OK;
 }
@@ -1311,6 +1323,14 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
     e->route_window = (int32_t)value;
   } else if (s == "replan") {
     e->ticks_since_plan = 0;
+  } else if (s == "tree_scratch_bytes") {
+    if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_scratch_bytes must be set before the first batched route");
+    e->tree_scratch_bytes = (int64_t)value;
+  } else if (s == "tree_threads") {
+    if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_threads must be set before the first batched route");
+    const int v = (int)value;
+    if (v != 128 && v != 256 && v != 512 && v != 1024) return fail(DRIFT_EINVAL, "tree_threads: 128/256/512/1024");
+    e->t_threads = v;
   } else if (s == "bounded_max") {
     e->t_bounded_max = std::max(0, std::min((int)value, kMaxBounded));
   } else if (s == "tree_delta_scale") {
@@ -1332,7 +1352,7 @@ int drift_device_ptr(drift_engine* e, const char* name, void** ptr, int64_t* n_e
   else if (s == "speed") p = e->speed.p, n = e->N;
   else if (s == "link_len") p = e->elen.p, n = e->N;
   else if (s == "cur_link") p = e->cur_link.p, n = e->N;
-  else if (s == "events") p = e->events.p, n = e->ev_cap;
+  else if (s == "events") p = e->send.p, n = e->send.n;
   else if (s == "travel_time") p = e->link_tt.p, n = e->L;
   else return fail(DRIFT_EINVAL, "drift_device_ptr: unknown buffer '%s'", name);
   *ptr = p;

@@ -337,7 +337,7 @@ struct TreeCache {
 constexpr int kMaxBounded = 8;
 
 constexpr unsigned long long kInfBits = 0x7FF0000000000000ULL;
-constexpr int kTreeThreads = 256;
+constexpr int kTreeThreadsMax = 1024;
 
 // Pass 1: destinations already cached pin their slot for this batch.
 __global__ void k_tree_hits(int64_t Q, const int32_t* __restrict__ dst, int32_t V, TreeCache tc,
@@ -415,7 +415,7 @@ __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v
 // Jobs whose destination is wanted by at most tc.bounded_max queries of the batch ("cold"
 // destinations) stop as soon as all their sources are settled, write those routes themselves
 // (walking dist[] from the source) and do not keep a tree; the others build and cache the tree.
-__global__ void __launch_bounds__(kTreeThreads) k_build_trees(GraphArrays g, const double* __restrict__ w_bwd,
+__global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, const double* __restrict__ w_bwd,
                                                               const double* __restrict__ w_fwd, double delta,
                                                               TreeCache tc, TreeScratch sc,
                                                               const int32_t* __restrict__ q_src,

@@ -43,7 +43,7 @@ struct TickArgs {
   unsigned long long arena_cap;
   Counters* ctr;
   Event* events;
-  int32_t ev_cap;
+  int32_t ev_cap;      // capacity of one sub-buffer; sub-buffer b starts at events + b * ev_cap
   const int32_t* pend_agent;
   const int64_t* pend_off;
   const int32_t* pend_len;
@@ -102,19 +102,20 @@ __device__ __forceinline__ void emit_event(const LinkArrays& lk, Event* __restri
 // in out-of-line handlers that stage their events in shared memory; at the end of a tile the block
 // reserves the slots with ONE global atomic (single-address L2 atomics serialise at ~1 op/cycle
 // chip-wide) and all threads write + link the staged events.
-constexpr int kStageCap = 2 * kAdvThreads * kAdvPerThread;  // every agent of a tile emits <= 2 events
+constexpr int kAdvWarps = kAdvThreads / 32;
+constexpr int kStageCap = 2 * 32 * kAdvPerThread;  // every agent of a warp's slice emits <= 2 events
 
-struct AdvSmem {
-  int n;
-  int base;
-  uint32_t link_kind[kStageCap];  // link | (enter ? 2^31 : 0)
-  uint32_t agent[kStageCap];
+struct AdvSmem {  // per-warp staging: no block-wide barrier in phase A
+  int n[kAdvWarps];
+  uint32_t link_kind[kAdvWarps][kStageCap];  // link | (enter ? 2^31 : 0)
+  uint32_t agent[kAdvWarps][kStageCap];
 };
 
 __device__ __forceinline__ void stage_event(AdvSmem& sm, int32_t link, uint32_t agent, bool enter) {
-  const int k = atomicAdd(&sm.n, 1);
-  sm.link_kind[k] = (uint32_t)link | (enter ? 0x80000000u : 0u);
-  sm.agent[k] = agent;
+  const int w = threadIdx.x >> 5;
+  const int k = atomicAdd(&sm.n[w], 1);
+  sm.link_kind[w][k] = (uint32_t)link | (enter ? 0x80000000u : 0u);
+  sm.agent[w][k] = agent;
 }
 
 // Agent crosses to the next link of its route or arrives (agent.py:200-203, 107-116).  Returns true on arrival.
@@ -187,9 +188,10 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
   const AgentArrays& a = p.a;
   const int par = tick & 1;
   const int64_t tiles = (a.n + (int64_t)kAdvThreads * kAdvPerThread - 1) / ((int64_t)kAdvThreads * kAdvPerThread);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    if (threadIdx.x == 0) sm.n = 0;
-    __syncthreads();
+    if (lane == 0) sm.n[w] = 0;
+    __syncwarp();
     const int64_t i0 = (tile * kAdvThreads + threadIdx.x) * kAdvPerThread;
     if (i0 < a.n) {
       const uint32_t st4 = *reinterpret_cast<const uint32_t*>(a.state + i0);
@@ -237,23 +239,24 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
       }
       if (nst4 != st4) *reinterpret_cast<uint32_t*>(a.state + i0) = nst4;
     }
-    __syncthreads();
-    const int n = sm.n;
-    if (threadIdx.x == 0 && n) sm.base = atomicAdd(&p.ctr->n_events[par], n);
-    __syncthreads();
-    if (n) {
-      const int base = sm.base;
+    __syncwarp();
+    const int n = sm.n[w];
+    if (n) {  // one global atomic per warp that has events, spread over kEvSub counters
+      const int sub = (int)((tile * kAdvWarps + w) % kEvSub);
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&p.ctr->n_events[par][sub], n);
+      base = __shfl_sync(0xffffffffu, base, 0);
       if (base + n <= p.ev_cap) {
-        for (int k = threadIdx.x; k < n; k += blockDim.x) {
-          const uint32_t lkd = sm.link_kind[k];
-          emit_event(p.lk, p.events, base + k, (int32_t)(lkd & 0x7fffffffu), sm.agent[k], (lkd >> 31) ? 1 : -1,
-                     (uint32_t)tick);
+        for (int k = lane; k < n; k += 32) {
+          const uint32_t lkd = sm.link_kind[w][k];
+          emit_event(p.lk, p.events, sub * p.ev_cap + base + k, (int32_t)(lkd & 0x7fffffffu), sm.agent[w][k],
+                     (lkd >> 31) ? 1 : -1, (uint32_t)tick);
         }
-      } else if (threadIdx.x == 0) {
+      } else if (lane == 0) {
         atomicOr(&p.ctr->overflow, kOvfEvents);
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -267,9 +270,10 @@ __device__ __forceinline__ void start_on_route(const TickArgs& p, int32_t i, int
   a.route_idx[i] = 0;
   a.dist[i] = 0.0;
   a.cur_link[i] = link;
-  const int slot = atomicAdd(&p.ctr->n_events[tick & 1], 1);
+  const int sub = i % kEvSub;
+  const int slot = atomicAdd(&p.ctr->n_events[tick & 1][sub], 1);
   if (slot < p.ev_cap)
-    emit_event(p.lk, p.events, slot, link, a.base + (uint32_t)i, 1, (uint32_t)tick);
+    emit_event(p.lk, p.events, sub * p.ev_cap + slot, link, a.base + (uint32_t)i, 1, (uint32_t)tick);
   else
     atomicOr(&p.ctr->overflow, kOvfEvents);
 }
@@ -317,9 +321,9 @@ __device__ __forceinline__ void phase_inject(const TickArgs& p, int32_t tick, in
 // K3: ordered running count -> BPR factor -> entry speed (agent.py:154-160), and the end-of-tick
 // occupancy of every touched link.  Each event walks the list of its link.
 __device__ __forceinline__ void phase_resolve(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
-                                              const Event* __restrict__ events, int n_events, int32_t tick,
+                                              const Event* __restrict__ events, int e0, int n_events, int32_t tick,
                                               double kph_to_mps, const Rings& rg, const int32_t* __restrict__ arena) {
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_events; e += gridDim.x * blockDim.x) {
+  for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e0 + n_events; e += gridDim.x * blockDim.x) {
     const Event ev = events[e];
     const int first = (int)(lk.head[ev.link] & 0xffffffffu);
     int before = 0;  // sum of the deltas of events ordered before this one (agent-list order)
@@ -384,16 +388,40 @@ __global__ void k_link_events(LinkArrays lk, Event* __restrict__ events, int n_e
   }
 }
 
-// n_events < 0: take the local count of this tick from the counters.
+// n_events < 0: the local sub-buffers of this tick; otherwise `events` is one contiguous list.
 __global__ void k_resolve(const __grid_constant__ TickArgs p, const Event* __restrict__ events, int n_events, int32_t tick) {
   const int par = tick & 1;
-  if (n_events < 0) n_events = p.ctr->n_events[par];
-  phase_resolve(p.lk, p.a, p.ctr, events, n_events, tick, p.kph_to_mps, p.rg, p.arena);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {  // counters of the next tick
-    p.ctr->n_events[par ^ 1] = 0;
-    p.ctr->n_dep_req[par ^ 1] = 0;
-    p.ctr->n_pending = 0;
+  if (n_events < 0) {
+    for (int sub = 0; sub < kEvSub; ++sub)
+      phase_resolve(p.lk, p.a, p.ctr, events, sub * p.ev_cap, p.ctr->n_events[par][sub], tick, p.kph_to_mps, p.rg,
+                    p.arena);
+  } else {
+    phase_resolve(p.lk, p.a, p.ctr, events, 0, n_events, tick, p.kph_to_mps, p.rg, p.arena);
   }
+}
+
+// counters of the next tick (after k_resolve: nobody reads the other parity any more)
+__global__ void k_reset_counters(Counters* ctr, int32_t tick) {
+  const int par = tick & 1;
+  if (threadIdx.x < kEvSub) ctr->n_events[par ^ 1][threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    ctr->n_dep_req[par ^ 1] = 0;
+    ctr->n_pending = 0;
+  }
+}
+
+// Gather the local sub-buffers into one contiguous list (what the ranks exchange); total in *n_out.
+__global__ void k_compact_events(const Event* __restrict__ events, int32_t ev_cap, const Counters* ctr, int32_t tick,
+                                 Event* __restrict__ out, int32_t* __restrict__ n_out) {
+  const int par = tick & 1;
+  int off = 0;
+  for (int sub = 0; sub < kEvSub; ++sub) {
+    const int n = ctr->n_events[par][sub];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+      out[off + e] = events[(int64_t)sub * ev_cap + e];
+    off += n;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_out = off;
 }
 
 // ---- the persistent tick loop ---------------------------------------------------------------------
@@ -430,11 +458,10 @@ __global__ void __launch_bounds__(kAdvThreads, 4) k_tick_loop(const __grid_const
         t0 = t1;
       }
     }
-    phase_resolve(p.lk, p.a, ctr, p.events, ctr->n_events[par], tick, p.kph_to_mps, p.rg, p.arena);
-    if (lead) {
-      ctr->n_events[par ^ 1] = 0;
-      ctr->n_dep_req[par ^ 1] = 0;
-    }
+    for (int sub = 0; sub < kEvSub; ++sub)
+      phase_resolve(p.lk, p.a, ctr, p.events, sub * p.ev_cap, ctr->n_events[par][sub], tick, p.kph_to_mps, p.rg, p.arena);
+    if (blockIdx.x == 0 && threadIdx.x < kEvSub) ctr->n_events[par ^ 1][threadIdx.x] = 0;
+    if (lead) ctr->n_dep_req[par ^ 1] = 0;
     grid.sync();
     if (lead) {
       ctr->n_pending = 0;
