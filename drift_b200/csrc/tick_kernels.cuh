@@ -320,10 +320,50 @@ __device__ __forceinline__ void phase_inject(const TickArgs& p, int32_t tick, in
 // ---- phase C ------------------------------------------------------------------------------------
 // K3: ordered running count -> BPR factor -> entry speed (agent.py:154-160), and the end-of-tick
 // occupancy of every touched link.  Each event walks the list of its link.
+__device__ __forceinline__ void resolve_one(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
+                                            const Event* __restrict__ events, int e, int32_t tick, double kph_to_mps,
+                                            const Rings& rg, const int32_t* __restrict__ arena);
+
+// contiguous list [e0, e0 + n_events)
 __device__ __forceinline__ void phase_resolve(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
                                               const Event* __restrict__ events, int e0, int n_events, int32_t tick,
                                               double kph_to_mps, const Rings& rg, const int32_t* __restrict__ arena) {
-  for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e0 + n_events; e += gridDim.x * blockDim.x) {
+  for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e0 + n_events; e += gridDim.x * blockDim.x)
+    resolve_one(lk, a, ctr, events, e, tick, kph_to_mps, rg, arena);
+}
+
+// the kEvSub local sub-buffers of this tick, flattened into one index space
+__device__ __forceinline__ void phase_resolve_local(const TickArgs& p, int32_t tick) {
+  const int4* c4 = reinterpret_cast<const int4*>(&p.ctr->n_events[tick & 1][0]);
+  int cnt[kEvSub];
+#pragma unroll
+  for (int k = 0; k < kEvSub / 4; ++k) {
+    const int4 v = c4[k];
+    cnt[4 * k] = v.x;
+    cnt[4 * k + 1] = v.y;
+    cnt[4 * k + 2] = v.z;
+    cnt[4 * k + 3] = v.w;
+  }
+  int total = 0;
+#pragma unroll
+  for (int k = 0; k < kEvSub; ++k) total += cnt[k];
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+    int sub = 0, r = f;
+#pragma unroll
+    for (int k = 0; k < kEvSub - 1; ++k) {
+      if (sub == k && r >= cnt[k]) {
+        r -= cnt[k];
+        sub = k + 1;
+      }
+    }
+    resolve_one(p.lk, p.a, p.ctr, p.events, sub * p.ev_cap + r, tick, p.kph_to_mps, p.rg, p.arena);
+  }
+}
+
+__device__ __forceinline__ void resolve_one(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
+                                            const Event* __restrict__ events, int e, int32_t tick, double kph_to_mps,
+                                            const Rings& rg, const int32_t* __restrict__ arena) {
+  {
     const Event ev = events[e];
     const int first = (int)(lk.head[ev.link] & 0xffffffffu);
     int before = 0;  // sum of the deltas of events ordered before this one (agent-list order)
@@ -392,9 +432,7 @@ __global__ void k_link_events(LinkArrays lk, Event* __restrict__ events, int n_e
 __global__ void k_resolve(const __grid_constant__ TickArgs p, const Event* __restrict__ events, int n_events, int32_t tick) {
   const int par = tick & 1;
   if (n_events < 0) {
-    for (int sub = 0; sub < kEvSub; ++sub)
-      phase_resolve(p.lk, p.a, p.ctr, events, sub * p.ev_cap, p.ctr->n_events[par][sub], tick, p.kph_to_mps, p.rg,
-                    p.arena);
+    phase_resolve_local(p, tick);
   } else {
     phase_resolve(p.lk, p.a, p.ctr, events, 0, n_events, tick, p.kph_to_mps, p.rg, p.arena);
   }
@@ -458,8 +496,7 @@ __global__ void __launch_bounds__(kAdvThreads, 4) k_tick_loop(const __grid_const
         t0 = t1;
       }
     }
-    for (int sub = 0; sub < kEvSub; ++sub)
-      phase_resolve(p.lk, p.a, ctr, p.events, sub * p.ev_cap, ctr->n_events[par][sub], tick, p.kph_to_mps, p.rg, p.arena);
+    phase_resolve_local(p, tick);
     if (blockIdx.x == 0 && threadIdx.x < kEvSub) ctr->n_events[par ^ 1][threadIdx.x] = 0;
     if (lead) ctr->n_dep_req[par ^ 1] = 0;
     grid.sync();
