@@ -42,8 +42,11 @@ struct TickArgs {
   int32_t* arena;
   unsigned long long arena_cap;
   Counters* ctr;
-  Event* events;
-  int32_t ev_cap;      // capacity of one sub-buffer; sub-buffer b starts at events + b * ev_cap
+  Event* events;       // [n_regions * kRegionCap] per-warp regions, then the extra list
+  int32_t* warp_cnt;   // [n_regions] events in each region this tick (rewritten by every tick)
+  int32_t n_regions;
+  int32_t extra_base;  // first record of the extra list
+  int32_t extra_cap;
   const int32_t* pend_agent;
   const int64_t* pend_off;
   const int32_t* pend_len;
@@ -241,20 +244,12 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
     }
     __syncwarp();
     const int n = sm.n[w];
-    if (n) {  // one global atomic per warp that has events, spread over kEvSub counters
-      const int sub = (int)((tile * kAdvWarps + w) % kEvSub);
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&p.ctr->n_events[par][sub], n);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (base + n <= p.ev_cap) {
-        for (int k = lane; k < n; k += 32) {
-          const uint32_t lkd = sm.link_kind[w][k];
-          emit_event(p.lk, p.events, sub * p.ev_cap + base + k, (int32_t)(lkd & 0x7fffffffu), sm.agent[w][k],
-                     (lkd >> 31) ? 1 : -1, (uint32_t)tick);
-        }
-      } else if (lane == 0) {
-        atomicOr(&p.ctr->overflow, kOvfEvents);
-      }
+    const int region = (int)(tile * kAdvWarps + w);  // this warp's private slice of the event buffer
+    if (lane == 0) p.warp_cnt[region] = n;
+    for (int k = lane; k < n; k += 32) {
+      const uint32_t lkd = sm.link_kind[w][k];
+      emit_event(p.lk, p.events, region * kRegionCap + k, (int32_t)(lkd & 0x7fffffffu), sm.agent[w][k],
+                 (lkd >> 31) ? 1 : -1, (uint32_t)tick);
     }
     __syncwarp();
   }
@@ -270,10 +265,9 @@ __device__ __forceinline__ void start_on_route(const TickArgs& p, int32_t i, int
   a.route_idx[i] = 0;
   a.dist[i] = 0.0;
   a.cur_link[i] = link;
-  const int sub = i % kEvSub;
-  const int slot = atomicAdd(&p.ctr->n_events[tick & 1][sub], 1);
-  if (slot < p.ev_cap)
-    emit_event(p.lk, p.events, sub * p.ev_cap + slot, link, a.base + (uint32_t)i, 1, (uint32_t)tick);
+  const int slot = atomicAdd(&p.ctr->n_extra[tick & 1], 1);
+  if (slot < p.extra_cap)
+    emit_event(p.lk, p.events, p.extra_base + slot, link, a.base + (uint32_t)i, 1, (uint32_t)tick);
   else
     atomicOr(&p.ctr->overflow, kOvfEvents);
 }
@@ -332,32 +326,17 @@ __device__ __forceinline__ void phase_resolve(const LinkArrays& lk, const AgentA
     resolve_one(lk, a, ctr, events, e, tick, kph_to_mps, rg, arena);
 }
 
-// the kEvSub local sub-buffers of this tick, flattened into one index space
+// the local events of this tick: one warp per region, then the extra list
 __device__ __forceinline__ void phase_resolve_local(const TickArgs& p, int32_t tick) {
-  const int4* c4 = reinterpret_cast<const int4*>(&p.ctr->n_events[tick & 1][0]);
-  int cnt[kEvSub];
-#pragma unroll
-  for (int k = 0; k < kEvSub / 4; ++k) {
-    const int4 v = c4[k];
-    cnt[4 * k] = v.x;
-    cnt[4 * k + 1] = v.y;
-    cnt[4 * k + 2] = v.z;
-    cnt[4 * k + 3] = v.w;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int region = gwarp; region < p.n_regions; region += nwarps) {
+    const int n = p.warp_cnt[region];
+    for (int k = lane; k < n; k += 32)
+      resolve_one(p.lk, p.a, p.ctr, p.events, region * kRegionCap + k, tick, p.kph_to_mps, p.rg, p.arena);
   }
-  int total = 0;
-#pragma unroll
-  for (int k = 0; k < kEvSub; ++k) total += cnt[k];
-  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
-    int sub = 0, r = f;
-#pragma unroll
-    for (int k = 0; k < kEvSub - 1; ++k) {
-      if (sub == k && r >= cnt[k]) {
-        r -= cnt[k];
-        sub = k + 1;
-      }
-    }
-    resolve_one(p.lk, p.a, p.ctr, p.events, sub * p.ev_cap + r, tick, p.kph_to_mps, p.rg, p.arena);
-  }
+  phase_resolve(p.lk, p.a, p.ctr, p.events, p.extra_base, min(p.ctr->n_extra[tick & 1], p.extra_cap), tick, p.kph_to_mps,
+                p.rg, p.arena);
 }
 
 __device__ __forceinline__ void resolve_one(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
@@ -441,25 +420,30 @@ __global__ void k_resolve(const __grid_constant__ TickArgs p, const Event* __res
 // counters of the next tick (after k_resolve: nobody reads the other parity any more)
 __global__ void k_reset_counters(Counters* ctr, int32_t tick) {
   const int par = tick & 1;
-  if (threadIdx.x < kEvSub) ctr->n_events[par ^ 1][threadIdx.x] = 0;
   if (threadIdx.x == 0) {
+    ctr->n_extra[par ^ 1] = 0;
     ctr->n_dep_req[par ^ 1] = 0;
     ctr->n_pending = 0;
   }
 }
 
-// Gather the local sub-buffers into one contiguous list (what the ranks exchange); total in *n_out.
-__global__ void k_compact_events(const Event* __restrict__ events, int32_t ev_cap, const Counters* ctr, int32_t tick,
-                                 Event* __restrict__ out, int32_t* __restrict__ n_out) {
-  const int par = tick & 1;
-  int off = 0;
-  for (int sub = 0; sub < kEvSub; ++sub) {
-    const int n = ctr->n_events[par][sub];
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
-      out[off + e] = events[(int64_t)sub * ev_cap + e];
-    off += n;
+// Gather the local events into one contiguous list (what the ranks exchange); total in *n_out
+// (zeroed by the caller).  One atomic per non-empty region; the order of the list is irrelevant.
+__global__ void k_compact_events(const __grid_constant__ TickArgs p, int32_t tick, Event* __restrict__ out,
+                                 int32_t* __restrict__ n_out) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_extra = min(p.ctr->n_extra[tick & 1], p.extra_cap);
+  for (int region = gwarp; region <= p.n_regions; region += nwarps) {
+    const bool extra = region == p.n_regions;
+    const int n = extra ? n_extra : p.warp_cnt[region];
+    if (n == 0) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(n_out, n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const int64_t src = extra ? p.extra_base : (int64_t)region * kRegionCap;
+    for (int k = lane; k < n; k += 32) out[base + k] = p.events[src + k];
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *n_out = off;
 }
 
 // ---- the persistent tick loop ---------------------------------------------------------------------
@@ -497,8 +481,10 @@ __global__ void __launch_bounds__(kAdvThreads, 4) k_tick_loop(const __grid_const
       }
     }
     phase_resolve_local(p, tick);
-    if (blockIdx.x == 0 && threadIdx.x < kEvSub) ctr->n_events[par ^ 1][threadIdx.x] = 0;
-    if (lead) ctr->n_dep_req[par ^ 1] = 0;
+    if (lead) {
+      ctr->n_extra[par ^ 1] = 0;
+      ctr->n_dep_req[par ^ 1] = 0;
+    }
     grid.sync();
     if (lead) {
       ctr->n_pending = 0;
@@ -552,8 +538,12 @@ __global__ void k_refresh_weights(int32_t E, const double* __restrict__ tt, cons
   }
 }
 
-__global__ void k_stats(AgentArrays a, LinkArrays lk, Counters* ctr) {
+__global__ void k_stats(AgentArrays a, LinkArrays lk, Counters* ctr, const int32_t* __restrict__ warp_cnt,
+                        int32_t n_regions) {
   long long mv = 0, on = 0, lw = 0;
+  int evs = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_regions; r += gridDim.x * blockDim.x) evs += warp_cnt[r];
+  if (evs) atomicAdd(&ctr->n_events_sum, evs);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += stride) mv += a.state[i] == kMoving;
   for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < lk.L; l += stride) {

@@ -23,22 +23,24 @@ def measure(agents=16_000_000, ticks=40, grid=64, seed=0):
     rng = np.random.default_rng(seed)
     start = rng.integers(0, lg.V, size=agents).astype(np.int32)
     cand = rng.integers(0, lg.V, size=(agents, 2)).astype(np.int32)
-    hourly = np.full(24, 900.0)  # p = 900 * 4 / 3600 = 1 per one-second tick: everybody departs at tick 1
+    hourly = np.zeros(24)
+    hourly[6] = 900.0  # 06:00-07:00: p = 900 * 4 / 3600 = 1 per one-second tick: everybody departs at tick 1
     eng = Engine(lg, agents, route_arena_links=agents * 2 * 2 * grid)
     eng.set_demand(seed, hourly, start, chain_capacity=2, router=ROUTER_BATCHED)
     eng.set_option("route_window", 10 ** 6)
     eng.push_trips(cand)
     eng.run(3, 1.0, 0.0)  # plan + depart
+    eng.drain_departures()
     st = eng.stats()
     moving = st["moving_agents"]
     # persistent kernel phases
     eng.phase_times(reset=True)
-    eng.run(ticks, 1.0, 3.0)
+    eng.run(ticks, 1.0, 3600.0)  # 07:00: nobody departs any more
     ph = eng.phase_times(reset=True)
     ev = eng.stats()["events_last_tick"]
     # standalone kernel, CUDA events on the engine stream
     eng.set_profiling(True)
-    eng.run(ticks, 1.0, 3.0 + ticks)
+    eng.run(ticks, 1.0, 3600.0 + ticks)
     kt = eng.kernel_times()
     eng.set_profiling(False)
     st2 = eng.stats()
