@@ -118,7 +118,7 @@ struct drift_engine {
   int64_t f_heap_cap = 0;
   // persistent tick loop
   bool persistent = true;
-  int coop_blocks_per_sm = 2;
+  int coop_blocks_per_sm = 6;
   int num_sms = kSMs;
   // pending departures + staged route batch
   DevBuf<int32_t> pend_agent, pend_len;
@@ -703,10 +703,10 @@ int drift_add_agents(drift_engine* e, int64_t n_agents, int64_t agent_base, int6
   CU(e->pend_agent.alloc(n_agents));
   CU(e->pend_off.alloc(n_agents));
   CU(e->pend_len.alloc(n_agents));
-  e->arr_cap = std::max<int64_t>(n_agents, 4096);
+  e->arr_cap = n_agents + n_agents / 8 + 4096;
   CU(e->arr_agent.alloc(e->arr_cap));
   CU(e->arr_tick.alloc(e->arr_cap));
-  e->dl_cap = std::max<int64_t>(n_agents, 4096);
+  e->dl_cap = n_agents + n_agents / 8 + 4096;
   CU(e->dl_agent.alloc(e->dl_cap));
   CU(e->dl_tick.alloc(e->dl_cap));
   CU(e->dl_src.alloc(e->dl_cap));

@@ -275,7 +275,7 @@ __device__ __forceinline__ void start_on_route(const TickArgs& p, int32_t i, int
 // Agent.start_new_journey tail (agent.py:101-104) for host-committed departures, and the whole of
 // it (selector output = next ring entry, NetworkX-exact route, one thread per agent) for device
 // departures that had no prefetched route.
-__device__ __forceinline__ void phase_inject(const TickArgs& p, int32_t tick, int n_pending, int n_urgent) {
+__device__ __noinline__ void phase_inject(const TickArgs& p, int32_t tick, int n_pending, int n_urgent) {
   const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
   for (int64_t q = gtid; q < n_pending; q += gsz)
@@ -314,9 +314,9 @@ __device__ __forceinline__ void phase_inject(const TickArgs& p, int32_t tick, in
 // ---- phase C ------------------------------------------------------------------------------------
 // K3: ordered running count -> BPR factor -> entry speed (agent.py:154-160), and the end-of-tick
 // occupancy of every touched link.  Each event walks the list of its link.
-__device__ __forceinline__ void resolve_one(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
-                                            const Event* __restrict__ events, int e, int32_t tick, double kph_to_mps,
-                                            const Rings& rg, const int32_t* __restrict__ arena);
+__device__ __noinline__ void resolve_one(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
+                                         const Event* __restrict__ events, int e, int32_t tick, double kph_to_mps,
+                                         const Rings& rg, const int32_t* __restrict__ arena);
 
 // contiguous list [e0, e0 + n_events)
 __device__ __forceinline__ void phase_resolve(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
@@ -326,22 +326,44 @@ __device__ __forceinline__ void phase_resolve(const LinkArrays& lk, const AgentA
     resolve_one(lk, a, ctr, events, e, tick, kph_to_mps, rg, arena);
 }
 
-// the local events of this tick: one warp per region, then the extra list
+// The local events of this tick.  A warp takes 32 regions at a time, scans their counts and spreads
+// all their events over its lanes (most regions hold 0-3 events: one warp per region would leave
+// the lanes idle and serialise the long load chains of resolve_one); then the extra list.
 __device__ __forceinline__ void phase_resolve_local(const TickArgs& p, int32_t tick) {
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int region = gwarp; region < p.n_regions; region += nwarps) {
-    const int n = p.warp_cnt[region];
-    for (int k = lane; k < n; k += 32)
-      resolve_one(p.lk, p.a, p.ctr, p.events, region * kRegionCap + k, tick, p.kph_to_mps, p.rg, p.arena);
+  for (int r0 = gwarp * 32; r0 < p.n_regions; r0 += nwarps * 32) {
+    const int c = (r0 + lane < p.n_regions) ? p.warp_cnt[r0 + lane] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - c;
+    for (int fb = 0; fb < total; fb += 32) {
+      const int f = fb + lane;
+      // largest r with excl[r] <= f (5-step search over the lanes' prefixes)
+      int r = 0;
+#pragma unroll
+      for (int step = 16; step; step >>= 1) {
+        const int cand = r + step;
+        const int pv = __shfl_sync(0xffffffffu, excl, cand & 31);
+        if (cand < 32 && pv <= f) r = cand;
+      }
+      const int base = __shfl_sync(0xffffffffu, excl, r);
+      if (f < total)
+        resolve_one(p.lk, p.a, p.ctr, p.events, (r0 + r) * kRegionCap + (f - base), tick, p.kph_to_mps, p.rg, p.arena);
+    }
   }
   phase_resolve(p.lk, p.a, p.ctr, p.events, p.extra_base, min(p.ctr->n_extra[tick & 1], p.extra_cap), tick, p.kph_to_mps,
                 p.rg, p.arena);
 }
 
-__device__ __forceinline__ void resolve_one(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
-                                            const Event* __restrict__ events, int e, int32_t tick, double kph_to_mps,
-                                            const Rings& rg, const int32_t* __restrict__ arena) {
+__device__ __noinline__ void resolve_one(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
+                                         const Event* __restrict__ events, int e, int32_t tick, double kph_to_mps,
+                                         const Rings& rg, const int32_t* __restrict__ arena) {
   {
     const Event ev = events[e];
     const int first = (int)(lk.head[ev.link] & 0xffffffffu);
@@ -448,7 +470,7 @@ __global__ void k_compact_events(const __grid_constant__ TickArgs p, int32_t tic
 
 // ---- the persistent tick loop ---------------------------------------------------------------------
 // One cooperative launch runs `n_ticks` ticks: 2 grid barriers per tick (3 when phase A2 has work).
-__global__ void __launch_bounds__(kAdvThreads, 4) k_tick_loop(const __grid_constant__ TickArgs p, int32_t tick0, int32_t n_ticks, double p_dep) {
+__global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop(const __grid_constant__ TickArgs p, int32_t tick0, int32_t n_ticks, double p_dep) {
   __shared__ AdvSmem sm;
   cg::grid_group grid = cg::this_grid();
   Counters* ctr = p.ctr;

@@ -29,7 +29,7 @@ def measure(agents=16_000_000, ticks=40, grid=64, seed=0):
     eng.set_demand(seed, hourly, start, chain_capacity=2, router=ROUTER_BATCHED)
     eng.set_option("route_window", 10 ** 6)
     eng.push_trips(cand)
-    eng.run(3, 1.0, 0.0)  # plan + depart
+    eng.run(1, 1.0, 0.0)  # plan + depart
     eng.drain_departures()
     st = eng.stats()
     moving = st["moving_agents"]
