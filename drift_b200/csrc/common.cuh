@@ -28,15 +28,12 @@ struct HeapItem {  // (dist, push counter, node): nx:weighted.py heap entries
   int32_t node;
 };
 
-// Event buffer layout: every warp of phase A owns a fixed region of kRegionCap records (a warp
-// handles 128 agents, each emits <= 2 events), so reserving slots needs no atomics at all; the
-// rare events of phase A2 go to an "extra" list behind the regions.
-constexpr int kRegionCap = 256;
+// The event buffer is split into kEvSub sub-buffers with their own counters so that the warps of
+// phase A do not all hit one address when they reserve slots.
+constexpr int kEvSub = 16;
 
 struct Counters {
-  int32_t n_extra[2];     // [tick parity] events in the extra list
-  int32_t n_events_sum;   // filled by k_stats
-  int32_t pad1;
+  int32_t n_events[2][kEvSub];  // [tick parity][sub-buffer]: tick k resets the slots of tick k+1
   int32_t n_dep_req[2];   // departures of this tick that found no prefetched route
   int32_t n_pending;      // pending departures (committed routes) for the next tick
   int32_t overflow;       // bit flags, see kOvf*

@@ -105,10 +105,9 @@ struct drift_engine {
   DevBuf<int32_t> arena;
   int64_t arena_cap = 0;
   // events
-  DevBuf<Event> events, send;  // per-warp regions + extra list; contiguous copy for the rank exchange
-  int64_t ev_cap = 0, extra_cap = 0;
-  int32_t n_regions = 0;
-  DevBuf<int32_t> send_n, warp_cnt;
+  DevBuf<Event> events, send;  // kEvSub sub-buffers of ev_sub_cap records; contiguous copy for the rank exchange
+  int64_t ev_cap = 0, ev_sub_cap = 0;
+  DevBuf<int32_t> send_n;
   // in-tick fallback router scratch (device-driven demand)
   DevBuf<double> f_seen;
   DevBuf<int32_t> f_plink;
@@ -486,10 +485,7 @@ TickArgs make_tick_args(drift_engine* e, double delta, bool demand) {
   p.arena_cap = (unsigned long long)e->arena_cap;
   p.ctr = e->ctr.p;
   p.events = e->events.p;
-  p.warp_cnt = e->warp_cnt.p;
-  p.n_regions = e->n_regions;
-  p.extra_base = e->n_regions * kRegionCap;
-  p.extra_cap = (int32_t)e->extra_cap;
+  p.ev_cap = (int32_t)e->ev_sub_cap;
   p.pend_agent = e->pend_agent.p;
   p.pend_off = e->pend_off.p;
   p.pend_len = e->pend_len.p;
@@ -692,12 +688,12 @@ int drift_add_agents(drift_engine* e, int64_t n_agents, int64_t agent_base, int6
   if (route_arena_links <= 0) route_arena_links = std::max<int64_t>((int64_t)1 << 20, n_agents * 64);
   CU(e->arena.alloc(route_arena_links, false));
   e->arena_cap = route_arena_links;
-  e->n_regions = (int32_t)(Np / (32 * kAdvPerThread));
-  e->extra_cap = n_agents + 1024;  // phase A2 injects at most one event per agent
-  e->ev_cap = (int64_t)e->n_regions * kRegionCap + e->extra_cap;
+  // every sub-buffer can hold all events of a tick in the worst case only if the warps spread evenly;
+  // sized with a 4x margin over the even share and checked at run time (overflow flag)
+  e->ev_sub_cap = std::min<int64_t>(2 * n_agents + 1024, (2 * n_agents * 4) / kEvSub + 4096);
+  e->ev_cap = e->ev_sub_cap * kEvSub;
   if (e->ev_cap > 0x7fffffff) return fail(DRIFT_EINVAL, "too many agents for one engine");
   CU(e->events.alloc(e->ev_cap, false));
-  CU(e->warp_cnt.alloc(e->n_regions));
   CU(e->send_n.alloc(1));
   e->pend_cap = n_agents;
   CU(e->pend_agent.alloc(n_agents));
@@ -1022,9 +1018,8 @@ int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0) {
 // local events of the tick -> contiguous send buffer; returns their number
 static int compact_for_exchange(drift_engine* e, int64_t* n_events) {
   if (e->send.n < e->ev_cap) CU(e->send.alloc(e->ev_cap, false));
-  CU(cudaMemsetAsync(e->send_n.p, 0, sizeof(int32_t), e->stream));
-  const TickArgs p = make_tick_args(e, e->last_delta, e->have_demand);
-  k_compact_events<<<e->num_sms * 2, 256, 0, e->stream>>>(p, (int32_t)e->tick, e->send.p, e->send_n.p);
+  k_compact_events<<<e->num_sms, 256, 0, e->stream>>>(e->events.p, (int32_t)e->ev_sub_cap, e->ctr.p, (int32_t)e->tick,
+                                                     e->send.p, e->send_n.p);
   CU(cudaGetLastError());
   e->total_launches += 1;
   Counters c;
@@ -1032,8 +1027,8 @@ static int compact_for_exchange(drift_engine* e, int64_t* n_events) {
   if (rc) return rc;
   rc = check_overflow(e, c);
   if (rc) return rc;
-  int32_t tot = 0;
-  CU(cudaMemcpy(&tot, e->send_n.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  int64_t tot = 0;
+  for (int s = 0; s < kEvSub; ++s) tot += c.n_events[e->tick & 1][s];
   if (n_events) *n_events = tot;
   return DRIFT_OK;
 }
@@ -1211,9 +1206,8 @@ int drift_stats(drift_engine* e, drift_stats_out* out) {
   CU(cudaSetDevice(e->device));
   Counters* c = e->ctr.p;
   CU(cudaMemsetAsync(&c->moving, 0, 3 * sizeof(long long), e->stream));
-  CU(cudaMemsetAsync(&c->n_events_sum, 0, sizeof(int32_t), e->stream));
   if (e->N) {
-    k_stats<<<kSMs * 4, 256, 0, e->stream>>>(e->agents(), e->links(), c, e->warp_cnt.p, e->n_regions);
+    k_stats<<<kSMs * 4, 256, 0, e->stream>>>(e->agents(), e->links(), c);
     CU(cudaGetLastError());
   }
   Counters h;
@@ -1226,7 +1220,8 @@ int drift_stats(drift_engine* e, drift_stats_out* out) {
   out->arrivals_total = (int64_t)h.n_arrivals;
   out->departures_total = (int64_t)h.n_departures;
   out->route_arena_used = (int64_t)h.arena_cursor;
-  out->events_last_tick = (int64_t)h.n_events_sum + h.n_extra[e->tick & 1];
+  out->events_last_tick = 0;
+  for (int sb = 0; sb < kEvSub; ++sb) out->events_last_tick += h.n_events[e->tick & 1][sb];
   return check_overflow(e, h);
 }
 

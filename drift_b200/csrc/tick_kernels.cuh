@@ -42,11 +42,8 @@ struct TickArgs {
   int32_t* arena;
   unsigned long long arena_cap;
   Counters* ctr;
-  Event* events;       // [n_regions * kRegionCap] per-warp regions, then the extra list
-  int32_t* warp_cnt;   // [n_regions] events in each region this tick (rewritten by every tick)
-  int32_t n_regions;
-  int32_t extra_base;  // first record of the extra list
-  int32_t extra_cap;
+  Event* events;
+  int32_t ev_cap;      // capacity of one sub-buffer; sub-buffer b starts at events + b * ev_cap
   const int32_t* pend_agent;
   const int64_t* pend_off;
   const int32_t* pend_len;
@@ -108,8 +105,9 @@ __device__ __forceinline__ void emit_event(const LinkArrays& lk, Event* __restri
 constexpr int kAdvWarps = kAdvThreads / 32;
 constexpr int kStageCap = 2 * 32 * kAdvPerThread;  // every agent of a warp's slice emits <= 2 events
 
-struct AdvSmem {  // per-warp staging: no block-wide barrier in phase A
+struct AdvSmem {  // per-warp staging: warps do not wait for each other while they process agents
   int n[kAdvWarps];
+  int base;
   uint32_t link_kind[kAdvWarps][kStageCap];  // link | (enter ? 2^31 : 0)
   uint32_t agent[kAdvWarps][kStageCap];
 };
@@ -242,16 +240,30 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
       }
       if (nst4 != st4) *reinterpret_cast<uint32_t*>(a.state + i0) = nst4;
     }
-    __syncwarp();
-    const int n = sm.n[w];
-    const int region = (int)(tile * kAdvWarps + w);  // this warp's private slice of the event buffer
-    if (lane == 0) p.warp_cnt[region] = n;
-    for (int k = lane; k < n; k += 32) {
-      const uint32_t lkd = sm.link_kind[w][k];
-      emit_event(p.lk, p.events, region * kRegionCap + k, (int32_t)(lkd & 0x7fffffffu), sm.agent[w][k],
-                 (lkd >> 31) ? 1 : -1, (uint32_t)tick);
+    __syncthreads();  // all warps of the block have staged their events
+    int n_blk = 0, my_off = 0;
+#pragma unroll
+    for (int k = 0; k < kAdvWarps; ++k) {
+      if (k == w) my_off = n_blk;
+      n_blk += sm.n[k];
     }
-    __syncwarp();
+    if (n_blk) {  // one global atomic per block and tile, spread over kEvSub counters
+      const int sub = (int)(tile % kEvSub);
+      if (threadIdx.x == 0) sm.base = atomicAdd(&p.ctr->n_events[par][sub], n_blk);
+      __syncthreads();
+      const int base = sm.base + my_off;
+      const int n = sm.n[w];
+      if (sm.base + n_blk <= p.ev_cap) {
+        for (int k = lane; k < n; k += 32) {
+          const uint32_t lkd = sm.link_kind[w][k];
+          emit_event(p.lk, p.events, sub * p.ev_cap + base + k, (int32_t)(lkd & 0x7fffffffu), sm.agent[w][k],
+                     (lkd >> 31) ? 1 : -1, (uint32_t)tick);
+        }
+      } else if (threadIdx.x == 0) {
+        atomicOr(&p.ctr->overflow, kOvfEvents);
+      }
+    }
+    __syncthreads();  // staging and sm.base are reused by the next tile
   }
 }
 
@@ -265,9 +277,10 @@ __device__ __forceinline__ void start_on_route(const TickArgs& p, int32_t i, int
   a.route_idx[i] = 0;
   a.dist[i] = 0.0;
   a.cur_link[i] = link;
-  const int slot = atomicAdd(&p.ctr->n_extra[tick & 1], 1);
-  if (slot < p.extra_cap)
-    emit_event(p.lk, p.events, p.extra_base + slot, link, a.base + (uint32_t)i, 1, (uint32_t)tick);
+  const int sub = i % kEvSub;
+  const int slot = atomicAdd(&p.ctr->n_events[tick & 1][sub], 1);
+  if (slot < p.ev_cap)
+    emit_event(p.lk, p.events, sub * p.ev_cap + slot, link, a.base + (uint32_t)i, 1, (uint32_t)tick);
   else
     atomicOr(&p.ctr->overflow, kOvfEvents);
 }
@@ -314,9 +327,9 @@ __device__ __noinline__ void phase_inject(const TickArgs& p, int32_t tick, int n
 // ---- phase C ------------------------------------------------------------------------------------
 // K3: ordered running count -> BPR factor -> entry speed (agent.py:154-160), and the end-of-tick
 // occupancy of every touched link.  Each event walks the list of its link.
-__device__ __noinline__ void resolve_one(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
-                                         const Event* __restrict__ events, int e, int32_t tick, double kph_to_mps,
-                                         const Rings& rg, const int32_t* __restrict__ arena);
+__device__ __forceinline__ void resolve_one(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
+                                            const Event* __restrict__ events, int e, int32_t tick, double kph_to_mps,
+                                            const Rings& rg, const int32_t* __restrict__ arena);
 
 // contiguous list [e0, e0 + n_events)
 __device__ __forceinline__ void phase_resolve(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
@@ -326,44 +339,31 @@ __device__ __forceinline__ void phase_resolve(const LinkArrays& lk, const AgentA
     resolve_one(lk, a, ctr, events, e, tick, kph_to_mps, rg, arena);
 }
 
-// The local events of this tick.  A warp takes 32 regions at a time, scans their counts and spreads
-// all their events over its lanes (most regions hold 0-3 events: one warp per region would leave
-// the lanes idle and serialise the long load chains of resolve_one); then the extra list.
-__device__ __forceinline__ void phase_resolve_local(const TickArgs& p, int32_t tick) {
-  const int lane = threadIdx.x & 31;
-  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int r0 = gwarp * 32; r0 < p.n_regions; r0 += nwarps * 32) {
-    const int c = (r0 + lane < p.n_regions) ? p.warp_cnt[r0 + lane] : 0;
-    int incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
+// the kEvSub local sub-buffers of this tick, flattened into one index space; s_pref: kEvSub + 1 ints of
+// shared memory (exclusive prefix of the sub-buffer counts)
+__device__ __forceinline__ void phase_resolve_local(const TickArgs& p, int32_t tick, int* s_pref) {
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = 0; k < kEvSub; ++k) {
+      s_pref[k] = acc;
+      acc += min(p.ctr->n_events[tick & 1][k], p.ev_cap);
     }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    const int excl = incl - c;
-    for (int fb = 0; fb < total; fb += 32) {
-      const int f = fb + lane;
-      // largest r with excl[r] <= f (5-step search over the lanes' prefixes)
-      int r = 0;
-#pragma unroll
-      for (int step = 16; step; step >>= 1) {
-        const int cand = r + step;
-        const int pv = __shfl_sync(0xffffffffu, excl, cand & 31);
-        if (cand < 32 && pv <= f) r = cand;
-      }
-      const int base = __shfl_sync(0xffffffffu, excl, r);
-      if (f < total)
-        resolve_one(p.lk, p.a, p.ctr, p.events, (r0 + r) * kRegionCap + (f - base), tick, p.kph_to_mps, p.rg, p.arena);
-    }
+    s_pref[kEvSub] = acc;
   }
-  phase_resolve(p.lk, p.a, p.ctr, p.events, p.extra_base, min(p.ctr->n_extra[tick & 1], p.extra_cap), tick, p.kph_to_mps,
-                p.rg, p.arena);
+  __syncthreads();
+  const int total = s_pref[kEvSub];
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+    int sub = 0;
+#pragma unroll
+    for (int step = kEvSub / 2; step; step >>= 1)
+      if (s_pref[sub + step] <= f) sub += step;
+    resolve_one(p.lk, p.a, p.ctr, p.events, sub * p.ev_cap + (f - s_pref[sub]), tick, p.kph_to_mps, p.rg, p.arena);
+  }
 }
 
-__device__ __noinline__ void resolve_one(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
-                                         const Event* __restrict__ events, int e, int32_t tick, double kph_to_mps,
-                                         const Rings& rg, const int32_t* __restrict__ arena) {
+__device__ __forceinline__ void resolve_one(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
+                                            const Event* __restrict__ events, int e, int32_t tick, double kph_to_mps,
+                                            const Rings& rg, const int32_t* __restrict__ arena) {
   {
     const Event ev = events[e];
     const int first = (int)(lk.head[ev.link] & 0xffffffffu);
@@ -432,8 +432,9 @@ __global__ void k_link_events(LinkArrays lk, Event* __restrict__ events, int n_e
 // n_events < 0: the local sub-buffers of this tick; otherwise `events` is one contiguous list.
 __global__ void k_resolve(const __grid_constant__ TickArgs p, const Event* __restrict__ events, int n_events, int32_t tick) {
   const int par = tick & 1;
+  __shared__ int s_pref[kEvSub + 1];
   if (n_events < 0) {
-    phase_resolve_local(p, tick);
+    phase_resolve_local(p, tick, s_pref);
   } else {
     phase_resolve(p.lk, p.a, p.ctr, events, 0, n_events, tick, p.kph_to_mps, p.rg, p.arena);
   }
@@ -442,36 +443,32 @@ __global__ void k_resolve(const __grid_constant__ TickArgs p, const Event* __res
 // counters of the next tick (after k_resolve: nobody reads the other parity any more)
 __global__ void k_reset_counters(Counters* ctr, int32_t tick) {
   const int par = tick & 1;
+  if (threadIdx.x < kEvSub) ctr->n_events[par ^ 1][threadIdx.x] = 0;
   if (threadIdx.x == 0) {
-    ctr->n_extra[par ^ 1] = 0;
     ctr->n_dep_req[par ^ 1] = 0;
     ctr->n_pending = 0;
   }
 }
 
-// Gather the local events into one contiguous list (what the ranks exchange); total in *n_out
-// (zeroed by the caller).  One atomic per non-empty region; the order of the list is irrelevant.
-__global__ void k_compact_events(const __grid_constant__ TickArgs p, int32_t tick, Event* __restrict__ out,
-                                 int32_t* __restrict__ n_out) {
-  const int lane = threadIdx.x & 31;
-  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int n_extra = min(p.ctr->n_extra[tick & 1], p.extra_cap);
-  for (int region = gwarp; region <= p.n_regions; region += nwarps) {
-    const bool extra = region == p.n_regions;
-    const int n = extra ? n_extra : p.warp_cnt[region];
-    if (n == 0) continue;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(n_out, n);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    const int64_t src = extra ? p.extra_base : (int64_t)region * kRegionCap;
-    for (int k = lane; k < n; k += 32) out[base + k] = p.events[src + k];
+// Gather the local sub-buffers into one contiguous list (what the ranks exchange); total in *n_out.
+__global__ void k_compact_events(const Event* __restrict__ events, int32_t ev_cap, const Counters* ctr, int32_t tick,
+                                 Event* __restrict__ out, int32_t* __restrict__ n_out) {
+  const int par = tick & 1;
+  int off = 0;
+  for (int sub = 0; sub < kEvSub; ++sub) {
+    const int n = ctr->n_events[par][sub];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+      out[off + e] = events[(int64_t)sub * ev_cap + e];
+    off += n;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_out = off;
 }
 
 // ---- the persistent tick loop ---------------------------------------------------------------------
 // One cooperative launch runs `n_ticks` ticks: 2 grid barriers per tick (3 when phase A2 has work).
 __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop(const __grid_constant__ TickArgs p, int32_t tick0, int32_t n_ticks, double p_dep) {
   __shared__ AdvSmem sm;
+  __shared__ int s_pref[kEvSub + 1];
   cg::grid_group grid = cg::this_grid();
   Counters* ctr = p.ctr;
   const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
@@ -502,11 +499,9 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop(const __grid_const
         t0 = t1;
       }
     }
-    phase_resolve_local(p, tick);
-    if (lead) {
-      ctr->n_extra[par ^ 1] = 0;
-      ctr->n_dep_req[par ^ 1] = 0;
-    }
+    phase_resolve_local(p, tick, s_pref);
+    if (blockIdx.x == 0 && threadIdx.x < kEvSub) ctr->n_events[par ^ 1][threadIdx.x] = 0;
+    if (lead) ctr->n_dep_req[par ^ 1] = 0;
     grid.sync();
     if (lead) {
       ctr->n_pending = 0;
@@ -560,12 +555,8 @@ __global__ void k_refresh_weights(int32_t E, const double* __restrict__ tt, cons
   }
 }
 
-__global__ void k_stats(AgentArrays a, LinkArrays lk, Counters* ctr, const int32_t* __restrict__ warp_cnt,
-                        int32_t n_regions) {
+__global__ void k_stats(AgentArrays a, LinkArrays lk, Counters* ctr) {
   long long mv = 0, on = 0, lw = 0;
-  int evs = 0;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_regions; r += gridDim.x * blockDim.x) evs += warp_cnt[r];
-  if (evs) atomicAdd(&ctr->n_events_sum, evs);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += stride) mv += a.state[i] == kMoving;
   for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < lk.L; l += stride) {
