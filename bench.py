@@ -271,6 +271,7 @@ def run_b200(args):
     st0 = eng.stats()
     eng.set_option("time_plan", 1)
     eng.phase_times(reset=True)
+    eng.tree_stats(reset=True)
     with ClockSampler(local_rank) as clk:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -280,6 +281,7 @@ def run_b200(args):
         dt = time.perf_counter() - t0
     st1 = eng.stats()
     phases = eng.phase_times(reset=True)
+    trees = eng.tree_stats(reset=True)
     eng.set_option("time_plan", 0)
     launches = eng.kernel_times()["total_launches"] - launches0
     if dist is not None:
@@ -333,9 +335,39 @@ def run_b200(args):
     alg_bytes = waiting * 1.0 + moving * 33.0  # 1 B per waiting, 33 B per moving agent-step
     peak, peak_src = peaks()
     achieved = alg_bytes / (adv_ms * 1e-3) / 1e9 if adv_ms > 0 else 0.0
-    roof = dict(bound="hbm", kernel="k_advance", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                traffic=None, peak_source=peak_src, us_per_launch=adv_ms * 1e3, moving_agents=moving,
-                algorithmic_bytes_per_launch=alg_bytes)
+    roof_adv = dict(bound="hbm", kernel="k_advance (standalone launch, CUDA events on the engine stream)",
+                    achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                    peak_source=peak_src, us_per_launch=adv_ms * 1e3, moving_agents=moving,
+                    algorithmic_bytes_per_launch=alg_bytes,
+                    note="1 B per waiting + 33 B per moving agent-step (SURVEY.md 8d); at this size the kernel is "
+                         "latency-bound, see roofline_advance_saturated")
+    # the dominant kernel of the timed region: the batched tree builder when routing dominates
+    tick_ms = (phases["advance_us_per_tick"] + phases["inject_us_per_tick"] + phases["resolve_us_per_tick"]) * phases["ticks"] / 1e3
+    if trees["build_ms"] > tick_ms and trees["launches"] > 0:
+        tb = 20.0 * trees["edges_relaxed"] + 12.0 * trees["improved"] + 16.0 * trees["nodes_expanded"]
+        per_launch = tb / trees["launches"]
+        us = 1e3 * trees["build_ms"] / trees["launches"]
+        ach = per_launch / (us * 1e-6) / 1e9
+        roof = dict(bound="hbm", kernel="k_build_trees (batched reverse SSSP, CUDA events on the engine stream)",
+                    achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None, peak_source=peak_src,
+                    us_per_launch=us, algorithmic_bytes_per_launch=per_launch, launches=trees["launches"],
+                    trees=trees["trees"], edges_relaxed=trees["edges_relaxed"], improved=trees["improved"],
+                    nodes_expanded=trees["nodes_expanded"], share_of_step=trees["build_ms"] / (1e3 * dt),
+                    note="20 B per relaxed edge + 12 B per improving relaxation + 16 B per expanded node (SURVEY.md 8d)")
+    else:
+        roof = roof_adv
+    sat = None
+    if rank == 0 and world == 1 and args.saturated_agents > 0:
+        eng.close()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import advance_roofline
+
+        r = advance_roofline.measure(args.saturated_agents)
+        sat = dict(bound="hbm", kernel="advance phase of k_tick_loop / k_advance, all agents moving",
+                   agents=r["agents"], achieved=r["persistent_advance_gbs"], peak=peak, unit="GB/s",
+                   frac=r["persistent_advance_gbs"] / peak, us_per_tick=r["persistent_advance_us"],
+                   standalone_kernel_us=r["k_advance_us"], standalone_kernel_frac=r["k_advance_gbs"] / peak,
+                   algorithmic_bytes_per_launch=r["algorithmic_bytes"], peak_source=peak_src)
 
     line = None
     if rank == 0:
@@ -355,7 +387,8 @@ def run_b200(args):
             moving_fraction=float(moving / n_local),
             e2e=dict(value=e2e_value, unit="agent-steps/s", h2d_bytes_per_step=int(h2d),
                      d2h_bytes_per_step=int(d2h_total / K), ms_per_step=1e3 * dt_e2e / K),
-            gpu_launches=int(launches), roofline=roof, clocks=clk.summary(),
+            gpu_launches=int(launches), roofline=roof, roofline_advance=roof_adv, roofline_advance_saturated=sat,
+            clocks=clk.summary(),
             phases=dict(note="timed region: per-tick phase times of the persistent kernel (%globaltimer, barriers "
                              "included) and total ms in route-planning batches",
                         **{k: (round(v, 3) if isinstance(v, float) else v) for k, v in phases.items()}))
@@ -367,7 +400,8 @@ def run_b200(args):
                        "bidirectional Dijkstra), %d agents on a %d-node / %d-link road graph, %d ticks in %.1f s, %s demand"
                        % (cpu["agents"], cpu["nodes"], cpu["links"], cpu["ticks"], cpu["seconds"], model))
         print(json.dumps(line))
-    eng.close()
+    if sat is None:
+        eng.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -387,6 +421,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg (0 = skip)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
+    ap.add_argument("--saturated-agents", type=int, default=16_000_000,
+                    help="also time the advance kernel with this many agents all moving (0 = skip)")
     ap.add_argument("--coop-blocks", type=int, default=0, help="blocks per SM of the persistent tick kernel (0 = default)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -49,6 +49,10 @@ struct Counters {
   long long links_with_traffic;
   long long total_capacity;
   unsigned long long phase_ns[4];   // persistent kernel: accumulated %globaltimer time per phase
+  unsigned long long tree_relaxed;  // tree builder: edges relaxed / relaxations that improved / nodes expanded
+  unsigned long long tree_improved;
+  unsigned long long tree_expanded;
+  unsigned long long tree_jobs;
 };
 
 constexpr int kOvfEvents = 1;

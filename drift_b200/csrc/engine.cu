@@ -172,7 +172,8 @@ struct drift_engine {
   Counters* h_ctr = nullptr;  // pinned
   int64_t tick = 0;
   double last_delta = 1.0;
-  double plan_ms = 0;
+  double plan_ms = 0, tree_ms = 0;
+  int64_t tree_launches = 0;
   int64_t loop_ticks = 0;
   bool time_plan = false;
   int32_t ticks_since_plan = 0;
@@ -180,6 +181,7 @@ struct drift_engine {
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tree_timers;
   std::vector<std::pair<int, int>> adv_marks;  // (begin,end) event indices of advance launches
   int tick_ev0 = -1, tick_ev1 = -1;
   double adv_ms = 0, total_ms = 0;
@@ -406,8 +408,18 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     k_tree_hits<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, n_dev);
     k_tree_requests<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, e->ctr.p, n_dev);
     k_link_queries<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, n_dev);
+    cudaEvent_t tb0 = nullptr, tb1 = nullptr;
+    if (e->time_plan) {
+      cudaEventCreate(&tb0);
+      cudaEventCreate(&tb1);
+      cudaEventRecord(tb0, e->stream);
+    }
     k_build_trees<<<e->t_blocks, e->t_threads, 0, e->stream>>>(e->graph(), wb, wf, e->t_delta, tc, ts, qs, e->arena.p,
                                                                (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
+    if (tb0) {
+      cudaEventRecord(tb1, e->stream);
+      e->tree_timers.push_back({tb0, tb1});
+    }
     k_extract_paths<<<gq, 256, 0, e->stream>>>(e->graph(), Q, n_dev, qs, qd, tc, e->arena.p,
                                                 (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
     CU(cudaGetLastError());
@@ -1283,6 +1295,36 @@ int drift_kernel_times(drift_engine* e, double* advance_ms, int64_t* advance_lau
   if (advance_launches) *advance_launches = (int64_t)e->adv_marks.size();
   if (total_ms) *total_ms = 0;
   if (total_launches) *total_launches = e->total_launches;
+  return DRIFT_OK;
+}
+
+int drift_tree_stats(drift_engine* e, double* build_ms, int64_t* launches, int64_t* jobs, int64_t* relaxed,
+                     int64_t* improved, int64_t* expanded, int32_t reset) {
+  if (!e) return fail(DRIFT_EINVAL, "drift_tree_stats");
+  CU(cudaSetDevice(e->device));
+  Counters c;
+  int rc = fetch_counters(e, &c);
+  if (rc) return rc;
+  for (auto& t : e->tree_timers) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t.first, t.second);
+    e->tree_ms += ms;
+    e->tree_launches += 1;
+    cudaEventDestroy(t.first);
+    cudaEventDestroy(t.second);
+  }
+  e->tree_timers.clear();
+  if (build_ms) *build_ms = e->tree_ms;
+  if (launches) *launches = e->tree_launches;
+  if (jobs) *jobs = (int64_t)c.tree_jobs;
+  if (relaxed) *relaxed = (int64_t)c.tree_relaxed;
+  if (improved) *improved = (int64_t)c.tree_improved;
+  if (expanded) *expanded = (int64_t)c.tree_expanded;
+  if (reset) {
+    CU(cudaMemsetAsync(&e->ctr.p->tree_relaxed, 0, 4 * sizeof(unsigned long long), e->stream));
+    e->tree_ms = 0;
+    e->tree_launches = 0;
+  }
   return DRIFT_OK;
 }
 

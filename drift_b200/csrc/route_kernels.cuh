@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
   int32_t* farB = sc.lists + ((int64_t)blockIdx.x * 4 + 3) * V;
   uint32_t iter = sc.iter[blockIdx.x];
   const int n_jobs = *tc.n_jobs;
+  unsigned long long c_relaxed = 0, c_improved = 0, c_expanded = 0;  // per-thread work counters
   for (;;) {
     if (threadIdx.x == 0) s_job = atomicAdd(tc.job_cursor, 1);
     __syncthreads();
@@ -525,12 +526,15 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
         const int32_t v = nearA[i];
         const double dv = __longlong_as_double((long long)dist[v]);
         const int32_t e1 = g.bwd_rowptr[v + 1];
+        ++c_expanded;
+        c_relaxed += (unsigned long long)(e1 - g.bwd_rowptr[v]);
         for (int32_t e = g.bwd_rowptr[v]; e < e1; ++e) {
           const int32_t u = g.bwd_col[e];
           const double cand = __dadd_rn(dv, w_bwd[e]);
           const unsigned long long cb = (unsigned long long)__double_as_longlong(cand);
           const unsigned long long old = atomicMin(&dist[u], cb);
           if (cb < old) {
+            ++c_improved;
             if (cand <= T) {
               if (atomicExch(&stamp[u], iter) != iter) nearB[atomicAdd(&s_next_n, 1)] = u;
             } else if (atomicExch(&infar[u], 1u) == 0u) {
@@ -637,6 +641,17 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
     __syncthreads();
   }
   if (threadIdx.x == 0) sc.iter[blockIdx.x] = iter;
+  for (int o = 16; o; o >>= 1) {
+    c_relaxed += __shfl_down_sync(0xffffffffu, c_relaxed, o);
+    c_improved += __shfl_down_sync(0xffffffffu, c_improved, o);
+    c_expanded += __shfl_down_sync(0xffffffffu, c_expanded, o);
+  }
+  if ((threadIdx.x & 31) == 0 && c_expanded) {
+    atomicAdd(&ctr->tree_relaxed, c_relaxed);
+    atomicAdd(&ctr->tree_improved, c_improved);
+    atomicAdd(&ctr->tree_expanded, c_expanded);
+  }
+  if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&ctr->tree_jobs, (unsigned long long)n_jobs);
 }
 
 // Pointer walk over the cached trees: route of every query into the arena.

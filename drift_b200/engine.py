@@ -282,6 +282,13 @@ class Engine:
         return dict(ticks=n.value, advance_us_per_tick=a.value / t / 1e3, inject_us_per_tick=i.value / t / 1e3,
                     resolve_us_per_tick=r.value / t / 1e3, plan_ms=pl.value)
 
+    def tree_stats(self, reset=True):
+        ms = C.c_double(0)
+        v = [C.c_int64(0) for _ in range(5)]
+        _capi.check(self._lib.drift_tree_stats(self._h, C.byref(ms), *[C.byref(x) for x in v], int(bool(reset))))
+        return dict(build_ms=ms.value, launches=v[0].value, trees=v[1].value, edges_relaxed=v[2].value,
+                    improved=v[3].value, nodes_expanded=v[4].value)
+
     def set_option(self, name, value):
         _capi.check(self._lib.drift_set_option(self._h, name.encode(), float(value)))
 

@@ -207,6 +207,10 @@ int drift_set_profiling(drift_engine* e, int32_t on);
  * route-planning batches (CUDA events; needs option "time_plan" = 1). */
 int drift_phase_times(drift_engine* e, double* advance_ns, double* inject_ns, double* resolve_ns, double* plan_ms,
                       int64_t* ticks, int32_t reset);
+/* Work and time of the batched tree builder since the last reset (needs option "time_plan" = 1 for
+ * the CUDA-event time): trees built, edges relaxed, relaxations that improved a label, nodes expanded. */
+int drift_tree_stats(drift_engine* e, double* build_ms, int64_t* launches, int64_t* jobs, int64_t* relaxed,
+                     int64_t* improved, int64_t* expanded, int32_t reset);
 /* Tunables: "tree_cache_bytes" (HBM budget of the destination-tree cache, before first use),
  * "tree_delta_scale" (multiplies the near-far bucket width). */
 int drift_set_option(drift_engine* e, const char* name, double value);
