@@ -61,6 +61,7 @@ SIGNATURES = {
     "drift_run": (C.c_int, [ENGINE, C.c_int32, C.c_double, C.c_double]),
     "drift_update_travel_times": (C.c_int, [ENGINE]),
     "drift_reroute_moving": (C.c_int, [ENGINE, C.c_int32, c_i64p]),
+    "drift_invalidate_prefetch": (C.c_int, [ENGINE, C.c_double, C.c_double, C.c_int32]),
     "drift_read_occupancy": (C.c_int, [ENGINE, c_i32p]),
     "drift_recount_occupancy": (C.c_int, [ENGINE, c_i32p]),
     "drift_read_travel_times": (C.c_int, [ENGINE, c_f64p]),

@@ -176,8 +176,9 @@ struct drift_engine {
   int64_t tree_launches = 0;
   int64_t loop_ticks = 0;
   bool time_plan = false;
+  bool use_congested = false;
   int32_t ticks_since_plan = 0;
-  int64_t routes_planned = 0;
+  int64_t routes_planned = 0, reroutes_total = 0;
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -200,6 +201,7 @@ struct drift_engine {
     a.route_off = route_off.p;
     a.trip_count = trip_count.p;
     a.cur_node = cur_node.p;
+    a.dest_node = cur_node.p;
     a.chain_dst = chain_dst.p;
     a.chain_head = chain_head.p;
     a.chain_cnt = chain_cnt.p;
@@ -490,9 +492,9 @@ TickArgs make_tick_args(drift_engine* e, double delta, bool demand) {
     p.fsc.heap_cap = e->f_heap_cap;
     p.fsc.workers = e->f_workers;
   }
-  p.w_fwd = e->fwd_w.p;
-  p.w_bwd = e->bwd_w.p;
-  p.link_cost = e->link_t0.p;
+  p.w_fwd = e->use_congested ? e->fwd_wc.p : e->fwd_w.p;
+  p.w_bwd = e->use_congested ? e->bwd_wc.p : e->bwd_w.p;
+  p.link_cost = e->use_congested ? e->link_tt.p : e->link_t0.p;
   p.arena = e->arena.p;
   p.arena_cap = (unsigned long long)e->arena_cap;
   p.ctr = e->ctr.p;
@@ -948,7 +950,7 @@ static int plan_window(drift_engine* e) {
   }
   for (int64_t q0 = 0; q0 < Q; q0 += chunk) {
     const int64_t n = std::min(chunk, Q - q0);
-    rc = launch_router(e, e->demand_router, n, 0, nullptr, q0);
+    rc = launch_router(e, e->demand_router, n, e->use_congested ? 1 : 0, nullptr, q0);
     if (rc) return rc;
   }
   if (Q > 0) {
@@ -1061,13 +1063,64 @@ int drift_update_travel_times(drift_engine* e) {
   k_refresh_weights<<<grid_for(e->Ef, 256, kSMs * 8), 256, 0, e->stream>>>(e->Ef, e->link_tt.p, e->fwd_link.p,
                                                                            e->bwd_link.p, e->fwd_wc.p, e->bwd_wc.p);
   CU(cudaGetLastError());
+  e->use_congested = true;  // from now on departures and the in-tick fallback route on tt
   return invalidate_trees(e);  // cached trees were built on the old weights
 }
 
 int drift_reroute_moving(drift_engine* e, int32_t router, int64_t* n_rerouted) {
-  (void)router;
+  if (!e || !e->N) return fail(DRIFT_EINVAL, "drift_reroute_moving");
+  CU(cudaSetDevice(e->device));
   if (n_rerouted) *n_rerouted = 0;
-  return fail(DRIFT_ESTATE, "drift_reroute_moving: not implemented yet");
+  int rc = ensure_qcap(e, e->N);
+  if (rc) return rc;
+  Counters* c = e->ctr.p;
+  CU(cudaMemsetAsync(&c->n_plan, 0, sizeof(int32_t), e->stream));
+  k_reroute_requests<<<grid_for(e->N, 256, kSMs * 8), 256, 0, e->stream>>>(e->agents(), e->link_v.p, c, e->q_src.p,
+                                                                            e->q_dst.p, e->q_agent.p, (int32_t)e->q_cap);
+  CU(cudaGetLastError());
+  Counters hc;
+  rc = fetch_counters(e, &hc);
+  if (rc) return rc;
+  const int64_t Q = std::min<int64_t>(hc.n_plan, e->q_cap);
+  int64_t chunk = std::max<int64_t>(Q, 1);
+  if (router == DRIFT_ROUTER_BATCHED) {
+    rc = ensure_trees(e);
+    if (rc) return rc;
+    chunk = std::max<int64_t>(1, e->t_max_slots);
+  }
+  for (int64_t q0 = 0; q0 < Q; q0 += chunk) {
+    rc = launch_router(e, router, std::min(chunk, Q - q0), 1, nullptr, q0);
+    if (rc) return rc;
+  }
+  if (Q > 0) {
+    k_apply_reroutes<<<grid_for(Q, 128, kSMs * 8), 128, 0, e->stream>>>(Q, e->q_agent.p, e->q_off.p, e->q_len.p,
+                                                                       e->q_status.p, e->agents(), e->arena.p,
+                                                                       (unsigned long long)e->arena_cap, c);
+    CU(cudaGetLastError());
+  }
+  e->total_launches += 2;
+  e->reroutes_total += Q;
+  if (n_rerouted) *n_rerouted = Q;
+  return DRIFT_OK;
+}
+
+int drift_invalidate_prefetch(drift_engine* e, double t0, double delta, int32_t n_ticks) {
+  if (!e || !e->have_demand || n_ticks <= 0) return fail(DRIFT_EINVAL, "drift_invalidate_prefetch");
+  CU(cudaSetDevice(e->device));
+  std::vector<double> p(n_ticks);
+  double t = t0;
+  for (int32_t k = 0; k < n_ticks; ++k) {
+    t += delta;
+    p[k] = departure_probability(e, t, delta);
+  }
+  DevBuf<double> dp;
+  CU(dp.upload(p.data(), n_ticks));
+  k_invalidate_prefetch<<<grid_for(e->N, 256, kSMs * 8), 256, 0, e->stream>>>(e->agents(), e->seed,
+                                                                               (int32_t)e->tick + 1, n_ticks, dp.p);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(e->stream));  // dp is freed on return
+  e->ticks_since_plan = 0;              // plan again before the next tick
+  return DRIFT_OK;
 }
 
 int drift_read_occupancy(drift_engine* e, int32_t* occ_out) {

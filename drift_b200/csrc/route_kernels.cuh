@@ -280,6 +280,65 @@ __global__ void k_plan_requests(AgentArrays a, Counters* ctr, int32_t* __restric
   }
 }
 
+// Extension (congestion-aware rerouting, SURVEY.md 8c last row): every moving agent asks for a new
+// route from the head of its current link to its destination.
+__global__ void k_reroute_requests(AgentArrays a, const int32_t* __restrict__ link_v, Counters* ctr,
+                                   int32_t* __restrict__ q_src, int32_t* __restrict__ q_dst,
+                                   int32_t* __restrict__ q_agent, int32_t q_cap) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (a.state[i] != kMoving) continue;
+    const int32_t l = a.cur_link[i];
+    if (l < 0 || a.next_link[i] < 0) continue;  // on its last link: nothing to re-plan
+    const int32_t t = a.dest_node[i];
+    const int r = atomicAdd(&ctr->n_plan, 1);
+    if (r < q_cap) {
+      q_src[r] = link_v[l];
+      q_dst[r] = t;
+      q_agent[r] = (int32_t)i;
+    }
+  }
+}
+
+// New route = current link + new path; the agent stays where it is on the current link.
+__global__ void k_apply_reroutes(int64_t Q, const int32_t* __restrict__ q_agent, const int64_t* __restrict__ q_off,
+                                 const int32_t* __restrict__ q_len, const int32_t* __restrict__ q_status,
+                                 AgentArrays a, int32_t* __restrict__ arena, unsigned long long arena_cap,
+                                 Counters* ctr) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
+    if (q_status[q] != DRIFT_ROUTE_OK || q_len[q] <= 0) continue;
+    const int32_t i = q_agent[q];
+    const int32_t n = q_len[q] + 1;
+    const unsigned long long off = atomicAdd(&ctr->arena_cursor, (unsigned long long)n);
+    if (off + n > arena_cap) {
+      atomicOr(&ctr->overflow, kOvfArena);
+      continue;
+    }
+    arena[off] = a.cur_link[i];
+    for (int k = 1; k < n; ++k) arena[off + k] = arena[q_off[q] + k - 1];
+    a.route_off[i] = (int64_t)off;
+    a.route_len[i] = n;
+    a.route_idx[i] = 0;
+    a.next_link[i] = arena[off + 1];
+  }
+}
+
+// Waiting agents that will depart within the next n_ticks ticks (same Philox draws as the tick
+// kernel) drop their prefetched routes so that the next planning batch recomputes them on the
+// current travel times.
+__global__ void k_invalidate_prefetch(AgentArrays a, uint64_t seed, int32_t tick0, int32_t n_ticks,
+                                      const double* __restrict__ p_dep) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (a.state[i] != kWaiting || a.chain_cnt[i] == 0 || a.next_status[i] == 0) continue;
+    for (int k = 0; k < n_ticks; ++k) {
+      if (philox_uniform53(seed, a.base + (uint32_t)i, (uint32_t)(tick0 + k)) < p_dep[k]) {
+        a.next_status[i] = 0;
+        a.next_status[a.npad + i] = 0;
+        break;
+      }
+    }
+  }
+}
+
 __global__ void k_store_prefetch(int64_t Q, const int32_t* __restrict__ q_agent, const int64_t* __restrict__ q_off,
                                  const int32_t* __restrict__ q_len, const int32_t* __restrict__ q_status,
                                  AgentArrays a) {

@@ -173,6 +173,16 @@ class Engine:
     def update_travel_times(self):
         _capi.check(self._lib.drift_update_travel_times(self._h))
 
+    def reroute_moving(self, router=ROUTER_NX_EXACT):
+        """Extension: re-plan every en-route agent from the head of its current link on the congested
+        travel times (call ``update_travel_times`` first).  Returns the number of agents rerouted."""
+        n = C.c_int64(0)
+        _capi.check(self._lib.drift_reroute_moving(self._h, int(router), C.byref(n)))
+        return n.value
+
+    def invalidate_prefetch(self, t0, delta, n_ticks):
+        _capi.check(self._lib.drift_invalidate_prefetch(self._h, float(t0), float(delta), int(n_ticks)))
+
     def tick_begin(self, delta):
         n = C.c_int64(0)
         _capi.check(self._lib.drift_tick_begin(self._h, float(delta), C.byref(n)))

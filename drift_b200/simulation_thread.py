@@ -79,6 +79,7 @@ class AgentView:
         self.target = initial_node
         self.current_trip_data = None
         self._departures = 0  # routed departures so far (decides whether 'speed' exists yet)
+        self._pidx_base = 0   # path_index of device route index 0 (changes when the agent is re-planned)
 
     # -- device-backed attributes -------------------------------------------------------------
     def _dev(self, name):
@@ -86,7 +87,9 @@ class AgentView:
 
     @property
     def path_index(self):
-        return int(self._dev("route_idx")) if hasattr(self, "path") and self.path is not None else 0
+        if not hasattr(self, "path") or self.path is None:
+            return 0
+        return self._pidx_base + int(self._dev("route_idx"))
 
     @property
     def speed(self):
@@ -160,6 +163,13 @@ class SimulationThread(QThread):
         self.lowered: LoweredGraph | None = lowered
         self.engine: Engine | None = None
         self.guard_reference_crashes = True  # see finish_simulation
+        # Extension, off by default (the reference never updates travel_time): every `reroute_period`
+        # simulated seconds link travel times become t0 / BPR factor(volume), en-route agents are
+        # re-planned from the head of their current link and later departures route on those times.
+        self.reroute_period = None
+        self._last_reroute = 0.0
+        self._congested = False
+        self.reroutes = 0
         self._waiting = []
         self._open = None
         self._snap = None
@@ -291,12 +301,13 @@ class SimulationThread(QThread):
             index = lg.node_index
             src = [index.get(agents[i].source, -1) for i in departing]
             dst = [index.get(agents[i].target, -1) for i in departing]
-            status, n_links, links = eng.route(src, dst, router=ROUTER_NX_EXACT)
+            status, n_links, links = eng.route(src, dst, router=ROUTER_NX_EXACT, congested=self._congested)
             nodes = lg.nodes
             for i, s, st, ln in zip(departing, src, status, links):
                 a = agents[i]
                 if st == ROUTE_OK:
                     a.path = [nodes[k] for k in lg.links_to_nodes(s, ln)]
+                    a._pidx_base = 0
                     a.state = "moving"
                     a._departures += 1
                     started.append(i)
@@ -332,6 +343,8 @@ class SimulationThread(QThread):
             if arrived:
                 self._waiting = sorted(self._waiting + arrived)
             self._moving_count += len(started) - len(arrived)
+        if self.reroute_period and t - self._last_reroute >= self.reroute_period:
+            self._reroute(t)
         if self.step % self.update_frequency == 0:
             with QMutexLocker(self.update_mutex):
                 data = self._prepare_agent_data()
@@ -344,6 +357,27 @@ class SimulationThread(QThread):
         if self.simulation_time - self.last_report_time >= 1800:
             self._emit_progress_report()
         return True
+
+    def _reroute(self, t):
+        """Extension step: congested travel times, re-plan en-route agents, keep the host paths in sync.
+        The device restarts a re-planned route at index 0 (route = current link + new path), the host
+        keeps the reference's convention path = path[:path_index + 1] + new_path."""
+        eng, lg = self.engine, self.lowered
+        before = eng.agents(fields=("route_idx",))["route_idx"]
+        eng.update_travel_times()
+        self._congested = True
+        self.reroutes += eng.reroute_moving(ROUTER_NX_EXACT)
+        self._last_reroute = t
+        self._snap = None
+        after = self._snapshot()["route_idx"]
+        nodes = lg.nodes
+        for a in self.agents:
+            if a.state != "moving" or int(after[a.index]) != 0:
+                continue
+            pidx = a._pidx_base + int(before[a.index])
+            links = eng.agent_route(a.index)
+            a.path = a.path[:pidx] + [nodes[k] for k in lg.links_to_nodes(lg.link_u[links[0]], links)]
+            a._pidx_base = pidx
 
     def _start_new_journey(self, a):
         """Agent.start_new_journey up to the routing call (lib/agent.py:46-91)."""
@@ -457,7 +491,7 @@ class SimulationThread(QThread):
             rec.speed = float(snap["speed"][a.index]) if a._departures else 0
             rec.source, rec.target = a.source, a.target
             rec.path = getattr(a, "path", [])
-            rec.path_index = int(snap["route_idx"][a.index]) if a._departures else 0
+            rec.path_index = a._pidx_base + int(snap["route_idx"][a.index]) if a._departures else 0
             rec.current_node = rec.target_node = None
             rec.progress = 0.0
             out.append(rec)
@@ -501,7 +535,7 @@ class SimulationThread(QThread):
         snap = self._snapshot()
         for a in self.agents:
             if self._open[a.index]:
-                upto = int(snap["route_idx"][a.index]) if a.state == "moving" else (
+                upto = a._pidx_base + int(snap["route_idx"][a.index]) if a.state == "moving" else (
                     len(a.path) - 2 if getattr(a, "path", None) else -1)
                 self._end_trip(a, self.simulation_time, upto)
         csv_file = self.data_logger.save_to_csv()

@@ -167,6 +167,10 @@ int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0);
  * per link) and rerouting of en-route agents from the head of their current link. */
 int drift_update_travel_times(drift_engine* e);
 int drift_reroute_moving(drift_engine* e, int32_t router, int64_t* n_rerouted);
+/* Device-driven demand + extension: waiting agents that will depart during the next n_ticks ticks
+ * (clock t0, tick length delta) drop their prefetched routes; the next drift_run replans them on the
+ * current travel times. */
+int drift_invalidate_prefetch(drift_engine* e, double t0, double delta, int32_t n_ticks);
 
 /* Readback.  Any output pointer may be NULL. */
 int drift_read_occupancy(drift_engine* e, int32_t* occ_out /* [L] */);

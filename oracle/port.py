@@ -356,6 +356,39 @@ class PortSim:
                     a.trip["route"].append(node)
         return True
 
+    # ---- extension: congestion-aware rerouting (no reference behaviour; SURVEY.md 8c last row) -----
+    # Composed from reference pieces: the BPR factor of traffic_manager.py:92-107 turned into a link
+    # travel time tt = t0 / factor(occupancy), NetworkX-order bidirectional Dijkstra on those
+    # weights, new route spliced after the current link.  A (u, v) pair keeps the link chosen on
+    # free-flow travel times (differs from a literal NetworkX composition only on graphs with
+    # parallel edges).
+    def update_travel_times(self):
+        pg = self.pg
+        tt = [float(pg.link_tt[l]) / bpr_factor(self.occ[l], int(pg.link_cap[l]), self.alpha, self.beta)
+              for l in range(pg.L)]
+        self.tt = tt
+        succ = [[(v, tt[lid], lid, lmin) for v, _w, lid, lmin in row] for row in pg.succ]
+        pair = [{v: w for v, w, _l, _m in row} for row in succ]
+        pred = [[(u, pair[u][v]) for u, _w in row] for v, row in enumerate(pg.pred)]
+
+        class _G:
+            pass
+
+        g = _G()
+        g.succ, g.pred = succ, pred
+        self.route_fn = lambda s, t, _g=g: bidirectional_route(_g, s, t)
+
+    def reroute_moving(self):
+        n = 0
+        for a in self.agents:
+            if a.state != 1 or a.pidx >= len(a.path) - 2:
+                continue  # not moving, or already on its last link
+            new = self.route_fn(a.path[a.pidx + 1], a.target)
+            n += 1
+            if new is not None and len(new) > 1:
+                a.path = a.path[:a.pidx + 1] + new
+        return n
+
     def finish(self):
         """simulation_thread.py:483-489"""
         for a in self.agents:
