@@ -75,7 +75,6 @@ struct AgentArrays {
   int64_t* route_off;   // [Npad] start of the route in the arena
   int32_t* trip_count;  // [Npad]
   int32_t* cur_node;    // [Npad] Agent.target: where the next trip starts
-  int32_t* dest_node;   // [Npad] alias of cur_node (the destination of the current trip)
   // host-generated trip chain: a small ring of upcoming destinations per agent, topped up by
   // drift_push_trips; entry k of agent i is chain_dst[i * chain_cap + (chain_head[i] + k) % chain_cap]
   int32_t* chain_dst;    // [N][chain_cap]

@@ -201,7 +201,6 @@ struct drift_engine {
     a.route_off = route_off.p;
     a.trip_count = trip_count.p;
     a.cur_node = cur_node.p;
-    a.dest_node = cur_node.p;
     a.chain_dst = chain_dst.p;
     a.chain_head = chain_head.p;
     a.chain_cnt = chain_cnt.p;
@@ -1075,8 +1074,9 @@ int drift_reroute_moving(drift_engine* e, int32_t router, int64_t* n_rerouted) {
   if (rc) return rc;
   Counters* c = e->ctr.p;
   CU(cudaMemsetAsync(&c->n_plan, 0, sizeof(int32_t), e->stream));
-  k_reroute_requests<<<grid_for(e->N, 256, kSMs * 8), 256, 0, e->stream>>>(e->agents(), e->link_v.p, c, e->q_src.p,
-                                                                            e->q_dst.p, e->q_agent.p, (int32_t)e->q_cap);
+  k_reroute_requests<<<grid_for(e->N, 256, kSMs * 8), 256, 0, e->stream>>>(e->agents(), e->link_v.p, e->arena.p, c,
+                                                                            e->q_src.p, e->q_dst.p, e->q_agent.p,
+                                                                            (int32_t)e->q_cap);
   CU(cudaGetLastError());
   Counters hc;
   rc = fetch_counters(e, &hc);

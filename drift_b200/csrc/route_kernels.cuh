@@ -282,14 +282,15 @@ __global__ void k_plan_requests(AgentArrays a, Counters* ctr, int32_t* __restric
 
 // Extension (congestion-aware rerouting, SURVEY.md 8c last row): every moving agent asks for a new
 // route from the head of its current link to its destination.
-__global__ void k_reroute_requests(AgentArrays a, const int32_t* __restrict__ link_v, Counters* ctr,
+__global__ void k_reroute_requests(AgentArrays a, const int32_t* __restrict__ link_v,
+                                   const int32_t* __restrict__ arena, Counters* ctr,
                                    int32_t* __restrict__ q_src, int32_t* __restrict__ q_dst,
                                    int32_t* __restrict__ q_agent, int32_t q_cap) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
     if (a.state[i] != kMoving) continue;
     const int32_t l = a.cur_link[i];
     if (l < 0 || a.next_link[i] < 0) continue;  // on its last link: nothing to re-plan
-    const int32_t t = a.dest_node[i];
+    const int32_t t = link_v[arena[a.route_off[i] + a.route_len[i] - 1]];  // head of the route's last link
     const int r = atomicAdd(&ctr->n_plan, 1);
     if (r < q_cap) {
       q_src[r] = link_v[l];
