@@ -37,8 +37,9 @@ WORKLOADS = {
     # name: (graph nodes, agents per GPU, demand model, description)
     "regional1m": dict(nodes=400_000, agents=1_000_000, model="activity",
                        desc="configs[2]: regional road graph ~1.16M links, activity-structured demand, 1M agents/GPU"),
-    "brussels100k": dict(nodes=50_000, agents=100_000, model="gravity",
-                         desc="configs[1]: city road graph ~53k nodes, gravity-structured demand, 100k agents/GPU"),
+    "brussels100k": dict(nodes=50_000, agents=100_000, model="gravity", reroute=True,
+                         desc="configs[1]: city road graph ~53k nodes, gravity-structured demand, 100k agents/GPU, "
+                              "congestion-aware reroute of en-route agents every step (5 simulated minutes; extension)"),
     "bundled": dict(nodes=100, agents=300, model="random",
                     desc="configs[0]-sized: 100-node graph, random demand, 300 agents"),
 }
@@ -252,11 +253,18 @@ def run_b200(args):
     t_sim = T_START
     launches0 = 0
 
+    reroute = bool(w.get("reroute")) and not args.no_reroute and sharded is None
+    n_reroutes = [0]
+
     def run_block(resident=True):
         nonlocal t_sim
         if resident:
             eng.refill_from_pool(step_no[0])
             step_no[0] += 1
+        if reroute and eng.tick > 0:  # K4 + reroute of en-route agents + fresh routes for this step's departures
+            eng.update_travel_times()
+            n_reroutes[0] += eng.reroute_moving(ROUTER_BATCHED)
+            eng.invalidate_prefetch(t_sim, delta, TPS)
         if sharded is not None:
             t_sim = sharded.run(TPS, delta, t_sim)
         else:
@@ -269,6 +277,7 @@ def run_b200(args):
     barrier()
     launches0 = eng.kernel_times()["total_launches"]
     st0 = eng.stats()
+    n_reroutes[0] = 0
     eng.set_option("time_plan", 1)
     eng.phase_times(reset=True)
     eng.tree_stats(reset=True)
@@ -291,6 +300,7 @@ def run_b200(args):
     total_agents = n_local * world
     value = total_agents * TPS * K / dt
     routes = st1["departures_total"] - st0["departures_total"]
+    reroutes_timed = n_reroutes[0]
 
     # ---- e2e pass: per step H2D of the step's chains (pinned) + D2H of arrivals/departures/volumes
     _, dst_s = make_chains(model, rng, lg, start, trips_per_step * (K + 1))
@@ -384,6 +394,7 @@ def run_b200(args):
                         multi_gpu=("agents sharded by id block, graph replicated, per-tick all-gather of link events "
                                    "(NCCL), every rank resolves the global event set") if world > 1 else "n/a"),
             routes_per_s=routes / dt, routes_in_timed_region=int(routes),
+            reroutes_per_s=(reroutes_timed / dt) if reroute else None, reroutes_in_timed_region=int(reroutes_timed),
             moving_fraction=float(moving / n_local),
             e2e=dict(value=e2e_value, unit="agent-steps/s", h2d_bytes_per_step=int(h2d),
                      d2h_bytes_per_step=int(d2h_total / K), ms_per_step=1e3 * dt_e2e / K),
@@ -421,6 +432,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg (0 = skip)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
+    ap.add_argument("--no-reroute", action="store_true", help="switch the periodic reroute extension off")
     ap.add_argument("--saturated-agents", type=int, default=16_000_000,
                     help="also time the advance kernel with this many agents all moving (0 = skip)")
     ap.add_argument("--coop-blocks", type=int, default=0, help="blocks per SM of the persistent tick kernel (0 = default)")

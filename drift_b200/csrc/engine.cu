@@ -391,7 +391,9 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     tc.job_qhead = e->t_job_qhead.p;
     tc.job_cnt = e->t_job_cnt.p;
     tc.q_next = e->t_q_next.p;  // indexed by the query number inside this call
-    tc.bounded_max = e->t_bounded_max >= 0 ? e->t_bounded_max : (e->t_max_slots >= e->V ? 0 : kMaxBounded);
+    // automatic: full trees only pay off when they can all stay cached and the weights do not change
+    tc.bounded_max = e->t_bounded_max >= 0 ? e->t_bounded_max
+                                           : ((e->t_max_slots >= e->V && !use_congested) ? 0 : kMaxBounded);
     CU(cudaMemsetAsync(out.status, 0xff, sizeof(int32_t) * Q, e->stream));  // -1 = not answered yet
     tc.n_jobs = e->t_ctl.p + 1;
     tc.job_cursor = e->t_ctl.p + 2;
