@@ -125,7 +125,7 @@ def pinned(arr):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (sequential Python restatement of the reference's step, oracle/port.py)
 # ------------------------------------------------------------------------------------------------
-def cpu_port_rate(model, seed, budget_s=20.0, agents=10_000, nodes=20_000, ticks=300):
+def cpu_port_rate(model, seed, budget_s=20.0, agents=10_000, nodes=20_000, ticks=300, reroute=False):
     """Times the oracle port on a bounded sample of the same kind of workload.  1 thread: the
     reference is single-threaded Python (one QThread under the GIL)."""
     import random
@@ -146,12 +146,21 @@ def cpu_port_rate(model, seed, budget_s=20.0, agents=10_000, nodes=20_000, ticks
     sim.t = T_START
     t0 = time.perf_counter()
     done = 0
+    n_rer = 0
+    if reroute:  # the step starts with the extension's travel-time update + reroute, like the B200 arm
+        warm = 0
+        while warm < 100:  # put some agents on the road first (not timed)
+            sim.tick()
+            warm += 1
+        t0 = time.perf_counter()
+        sim.update_travel_times()
+        n_rer = sim.reroute_moving()
     while done < ticks and time.perf_counter() - t0 < budget_s:
         sim.tick()
         done += 1
     dt = time.perf_counter() - t0
-    return dict(agent_steps_per_s=agents * done / dt, routes_per_s=sim.routes_computed / dt, seconds=dt, ticks=done,
-                agents=agents, nodes=lg.V, links=lg.L, routes=sim.routes_computed)
+    return dict(agent_steps_per_s=agents * done / dt, routes_per_s=(sim.routes_computed + n_rer) / dt, seconds=dt,
+                ticks=done, agents=agents, nodes=lg.V, links=lg.L, routes=sim.routes_computed, reroutes=n_rer)
 
 
 def run_reference_arm(args):
@@ -166,7 +175,7 @@ def run_reference_arm(args):
     t_all = time.perf_counter()
     for k in range(args.steps):
         r = cpu_port_rate(w["model"], args.seed + k, budget_s=max(5.0, 120.0 / max(args.steps, 1)), agents=10_000,
-                          nodes=20_000, ticks=args.ticks_per_step)
+                          nodes=20_000, ticks=args.ticks_per_step, reroute=bool(w.get("reroute")) and not args.no_reroute)
         vals.append(r["agent_steps_per_s"])
     wall = time.perf_counter() - t_all
     v = float(np.mean(vals))
@@ -381,7 +390,8 @@ def run_b200(args):
 
     line = None
     if rank == 0:
-        cpu = cpu_port_rate(model, args.seed, budget_s=args.cpu_seconds, ticks=TPS) if args.cpu_seconds > 0 else None
+        cpu = cpu_port_rate(model, args.seed, budget_s=args.cpu_seconds, ticks=TPS, reroute=reroute) \
+            if args.cpu_seconds > 0 else None
         line = dict(
             metric="agent-steps/s", value=value, unit="agent-steps/s", n_gpus=world, steps=K, warmup=W,
             ms_per_step=1e3 * dt / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
