@@ -77,6 +77,10 @@ SIGNATURES = {
     "drift_tick_begin_demand": (C.c_int, [ENGINE, C.c_double, C.c_double, c_i64p]),
     "drift_events_ptr": (C.c_int, [ENGINE, C.POINTER(C.c_void_p), c_i64p]),
     "drift_tick_finish": (C.c_int, [ENGINE, C.c_void_p, C.c_int64]),
+    "drift_set_stream": (C.c_int, [ENGINE, C.c_void_p]),
+    "drift_tick_begin_async": (C.c_int, [ENGINE, C.c_double, C.c_double, C.c_void_p, C.c_int32]),
+    "drift_tick_finish_gathered": (C.c_int, [ENGINE, C.c_void_p, C.c_int32, C.c_int32]),
+    "drift_max_events": (C.c_int, [ENGINE, c_i64p, C.c_int32]),
     "drift_kernel_times": (C.c_int, [ENGINE, c_f64p, c_i64p, c_f64p, c_i64p]),
     "drift_set_profiling": (C.c_int, [ENGINE, C.c_int32]),
     "drift_phase_times": (C.c_int, [ENGINE, c_f64p, c_f64p, c_f64p, c_f64p, c_i64p, C.c_int32]),

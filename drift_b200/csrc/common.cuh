@@ -38,6 +38,7 @@ struct Counters {
   int32_t n_pending;      // pending departures (committed routes) for the next tick
   int32_t overflow;       // bit flags, see kOvf*
   int32_t n_plan;         // route requests of the current planning batch
+  int32_t max_events;     // largest per-tick event count of this rank since the last reset (exchange sizing)
   int32_t pad0;
   unsigned long long n_arrivals;    // total appended to the arrival ring
   unsigned long long n_departures;  // total appended to the departure log ring
@@ -62,6 +63,7 @@ constexpr int kOvfHeap = 8;
 constexpr int kOvfDepLog = 16;
 constexpr int kOvfEntries = 32;
 constexpr int kOvfStage = 64;
+constexpr int kOvfExchange = 128;
 
 struct AgentArrays {
   uint8_t* state;       // [Npad] kWaiting / kMoving

@@ -79,6 +79,7 @@ inline int grid_for(int64_t n, int threads, int max_blocks) {
 struct drift_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   // graph
   int32_t V = 0, L = 0, Ef = 0, Eb = 0;
   DevBuf<int32_t> fwd_rowptr, fwd_col, fwd_link, bwd_rowptr, bwd_col, bwd_link, link_cap, link_u, link_v, link_cls;
@@ -276,6 +277,7 @@ int check_overflow(drift_engine* e, const Counters& c) {
   if (c.overflow & kOvfDepLog) what += " departure-log";
   if (c.overflow & kOvfEntries) what += " entry-trace";
   if (c.overflow & kOvfStage) what += " tree-cache";
+  if (c.overflow & kOvfExchange) what += " event-exchange (raise the exchange capacity)";
   return fail(DRIFT_EOVERFLOW, "device buffer overflow:%s", what.c_str());
 }
 
@@ -649,7 +651,7 @@ int drift_destroy(drift_engine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   if (e->h_ctr) cudaFreeHost(e->h_ctr);
-  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->stream && e->own_stream) cudaStreamDestroy(e->stream);
   delete e;
   return DRIFT_OK;
 }
@@ -1320,6 +1322,54 @@ int drift_tick_finish(drift_engine* e, const void* events_dev, int64_t n_events)
   if (n_events > 0x7fffffff) return fail(DRIFT_EINVAL, "drift_tick_finish: too many events");
   CU(cudaSetDevice(e->device));
   return tick_finish(e, (Event*)events_dev, n_events, true, e->last_delta);
+}
+
+int drift_set_stream(drift_engine* e, void* cuda_stream) {
+  if (!e) return fail(DRIFT_EINVAL, "drift_set_stream");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  if (e->own_stream) cudaStreamDestroy(e->stream);
+  e->stream = (cudaStream_t)cuda_stream;
+  e->own_stream = false;
+  return DRIFT_OK;
+}
+
+int drift_tick_begin_async(drift_engine* e, double delta, double t, void* send_dev, int32_t cap) {
+  if (!e || !e->N || !e->have_bpr || !send_dev || cap <= 0) return fail(DRIFT_EINVAL, "drift_tick_begin_async");
+  CU(cudaSetDevice(e->device));
+  int rc = e->have_demand ? demand_tick_begin(e, delta, t) : tick_begin(e, delta, false, 0.0);
+  if (rc) return rc;
+  e->last_delta = delta;
+  k_pack_events<<<e->num_sms, 256, 0, e->stream>>>(e->events.p, (int32_t)e->ev_sub_cap, e->ctr.p, (int32_t)e->tick,
+                                                  (Event*)send_dev, cap);
+  CU(cudaGetLastError());
+  e->total_launches += 1;
+  return DRIFT_OK;
+}
+
+int drift_tick_finish_gathered(drift_engine* e, void* recv_dev, int32_t world, int32_t cap) {
+  if (!e || !recv_dev || world <= 0 || world > 16 || cap <= 0) return fail(DRIFT_EINVAL, "drift_tick_finish_gathered");
+  CU(cudaSetDevice(e->device));
+  const TickArgs p = make_tick_args(e, e->last_delta, e->have_demand);
+  const int32_t tick = (int32_t)e->tick;
+  const int g = e->num_sms * 4;
+  k_link_gathered<<<g, 256, 0, e->stream>>>(e->links(), (Event*)recv_dev, world, cap, tick);
+  k_resolve_gathered<<<g, 256, 0, e->stream>>>(p, (const Event*)recv_dev, world, cap, tick);
+  k_reset_counters<<<1, 32, 0, e->stream>>>(e->ctr.p, tick);
+  CU(cudaGetLastError());
+  e->total_launches += 3;
+  return DRIFT_OK;
+}
+
+int drift_max_events(drift_engine* e, int64_t* max_events, int32_t reset) {
+  if (!e || !max_events) return fail(DRIFT_EINVAL, "drift_max_events");
+  CU(cudaSetDevice(e->device));
+  Counters c;
+  int rc = fetch_counters(e, &c);
+  if (rc) return rc;
+  *max_events = c.max_events;
+  if (reset) CU(cudaMemsetAsync(&e->ctr.p->max_events, 0, sizeof(int32_t), e->stream));
+  return check_overflow(e, c);
 }
 
 int drift_set_profiling(drift_engine* e, int32_t on) {

@@ -464,6 +464,73 @@ __global__ void k_compact_events(const Event* __restrict__ events, int32_t ev_ca
   if (blockIdx.x == 0 && threadIdx.x == 0) *n_out = off;
 }
 
+// ---- multi-rank exchange without host round trips -------------------------------------------------
+// Send buffer of one rank: row 0 = header (link field = number of events), rows 1..cap = events.
+__global__ void k_pack_events(const Event* __restrict__ events, int32_t ev_cap, Counters* ctr, int32_t tick,
+                              Event* __restrict__ out, int32_t cap) {
+  const int par = tick & 1;
+  int off = 0;
+  for (int sub = 0; sub < kEvSub; ++sub) {
+    const int n = min(ctr->n_events[par][sub], ev_cap);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+      if (off + e < cap) out[1 + off + e] = events[(int64_t)sub * ev_cap + e];
+    off += n;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    Event h;
+    h.link = min(off, cap);
+    h.agent = 0;
+    h.kind = 0;
+    h.aux = off;
+    out[0] = h;
+    if (off > cap) atomicOr(&ctr->overflow, kOvfExchange);
+    atomicMax(&ctr->max_events, off);
+  }
+}
+
+// Gathered buffers of all ranks: [world][cap + 1] records.  Flattened index -> (rank, event).
+__device__ __forceinline__ int gathered_index(const Event* __restrict__ recv, int world, int cap, int f, int* s_pref) {
+  int r = 0;
+  while (r + 1 < world && s_pref[r + 1] <= f) ++r;
+  return r * (cap + 1) + 1 + (f - s_pref[r]);
+}
+
+__global__ void k_link_gathered(LinkArrays lk, Event* __restrict__ recv, int world, int cap, int32_t tick) {
+  __shared__ int s_pref[17];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int r = 0; r < world; ++r) {
+      s_pref[r] = acc;
+      acc += recv[(int64_t)r * (cap + 1)].link;
+    }
+    s_pref[world] = acc;
+  }
+  __syncthreads();
+  const int total = s_pref[world];
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+    const int e = gathered_index(recv, world, cap, f, s_pref);
+    const Event ev = recv[e];
+    emit_event(lk, recv, e, ev.link, ev.agent, ev.kind, (uint32_t)tick | 0x80000000u);
+  }
+}
+
+__global__ void k_resolve_gathered(const __grid_constant__ TickArgs p, const Event* __restrict__ recv, int world,
+                                   int cap, int32_t tick) {
+  __shared__ int s_pref[17];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int r = 0; r < world; ++r) {
+      s_pref[r] = acc;
+      acc += recv[(int64_t)r * (cap + 1)].link;
+    }
+    s_pref[world] = acc;
+  }
+  __syncthreads();
+  const int total = s_pref[world];
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x)
+    resolve_one(p.lk, p.a, p.ctr, recv, gathered_index(recv, world, cap, f, s_pref), tick, p.kph_to_mps, p.rg, p.arena);
+}
+
 // ---- the persistent tick loop ---------------------------------------------------------------------
 // One cooperative launch runs `n_ticks` ticks: 2 grid barriers per tick (3 when phase A2 has work).
 __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop(const __grid_constant__ TickArgs p, int32_t tick0, int32_t n_ticks, double p_dep) {

@@ -56,9 +56,15 @@ def exchange_events(local: torch.Tensor, n_local: int, group=None):
 
 
 class ShardedEngine:
-    """One rank of a sharded run: wraps a local ``Engine`` and performs the per-tick exchange."""
+    """One rank of a sharded run: wraps a local ``Engine`` and performs the per-tick exchange.
 
-    def __init__(self, lg, n_total, alpha=0.15, beta=4.0, device=0, route_arena_links=0, group=None):
+    The engine runs on torch's current CUDA stream; a tick is: advance + pack (engine kernels) ->
+    ``all_gather_into_tensor`` of fixed-size send buffers (NCCL, same stream) -> link + resolve
+    (engine kernels).  Nothing waits on the host; the buffer capacity follows the largest event
+    count seen in the previous block of ticks with a 3x margin (an overflow raises)."""
+
+    def __init__(self, lg, n_total, alpha=0.15, beta=4.0, device=0, route_arena_links=0, group=None,
+                 exchange_capacity=0):
         from .engine import Engine
 
         self.group = group
@@ -66,29 +72,49 @@ class ShardedEngine:
         self.world = dist.get_world_size(group)
         self.lo, self.hi = shard_bounds(n_total, self.rank, self.world)
         self.n_total = n_total
+        self.device = torch.device("cuda", device)
         self.engine = Engine(lg, self.hi - self.lo, alpha=alpha, beta=beta, device=device, agent_base=self.lo,
                              route_arena_links=route_arena_links)
-        ptr, cap = self.engine.events_ptr()
-        self._events = torch.as_tensor(_DevPtr(ptr, cap * EVENT_WORDS), device="cuda:%d" % device).view(cap, EVENT_WORDS)
-        self._keep = None
+        self.engine.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self.cap = 0
+        self._fixed_cap = exchange_capacity > 0
+        self._set_cap(exchange_capacity if exchange_capacity > 0 else max(4096, (self.hi - self.lo) // 4))
 
-    def _finish(self, n_local):
-        events, counts = exchange_events(self._events, n_local, self.group)
-        self._keep = events  # alive until the next tick's kernels are done with it
-        torch.cuda.current_stream().synchronize()
-        self.engine.tick_finish(events.data_ptr() if events.numel() else self._events.data_ptr(), int(sum(counts)))
-        return counts
+    def _set_cap(self, cap):
+        cap = int(cap)
+        if cap == self.cap:
+            return
+        self.cap = cap
+        self._send = torch.zeros((cap + 1, EVENT_WORDS), dtype=torch.int32, device=self.device)
+        self._recv = torch.zeros((self.world, cap + 1, EVENT_WORDS), dtype=torch.int32, device=self.device)
+
+    def _tick(self, delta, t):
+        self.engine.tick_begin_async(delta, t, self._send.data_ptr(), self.cap)
+        dist.all_gather_into_tensor(self._recv.view(-1), self._send.view(-1), group=self.group)
+        self.engine.tick_finish_gathered(self._recv.data_ptr(), self.world, self.cap)
+
+    def _after_block(self):
+        """One host sync per block of ticks: overflow check and capacity for the next block."""
+        m = self.engine.max_events(reset=True)  # raises on overflow
+        if not self._fixed_cap:
+            mt = torch.tensor([m], dtype=torch.int64, device=self.device)
+            dist.all_reduce(mt, op=dist.ReduceOp.MAX, group=self.group)
+            want = max(4096, 3 * int(mt.item()))
+            if want > self.cap or want < self.cap // 4:
+                self._set_cap(want)
 
     def step(self, delta):
         """Trace / host-driven mode: pending departures were submitted to the local engine."""
-        return self._finish(self.engine.tick_begin(delta))
+        self._tick(delta, 0.0)
+        self._after_block()
 
     def run(self, n_ticks, delta, t0):
         """Device-driven demand, ``n_ticks`` ticks starting at clock ``t0``."""
         t = t0
         for _ in range(n_ticks):
             t += delta
-            self._finish(self.engine.tick_begin_demand(delta, t))
+            self._tick(delta, t)
+        self._after_block()
         return t
 
     def close(self):

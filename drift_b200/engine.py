@@ -193,6 +193,20 @@ class Engine:
         _capi.check(self._lib.drift_tick_begin_demand(self._h, float(delta), float(t), C.byref(n)))
         return n.value
 
+    def set_stream(self, cuda_stream_handle):
+        _capi.check(self._lib.drift_set_stream(self._h, C.c_void_p(cuda_stream_handle)))
+
+    def tick_begin_async(self, delta, t, send_ptr, cap):
+        _capi.check(self._lib.drift_tick_begin_async(self._h, float(delta), float(t), C.c_void_p(send_ptr), int(cap)))
+
+    def tick_finish_gathered(self, recv_ptr, world, cap):
+        _capi.check(self._lib.drift_tick_finish_gathered(self._h, C.c_void_p(recv_ptr), int(world), int(cap)))
+
+    def max_events(self, reset=True):
+        n = C.c_int64(0)
+        _capi.check(self._lib.drift_max_events(self._h, C.byref(n), int(bool(reset))))
+        return n.value
+
     def events_ptr(self):
         p, cap = C.c_void_p(), C.c_int64(0)
         _capi.check(self._lib.drift_events_ptr(self._h, C.byref(p), C.byref(cap)))

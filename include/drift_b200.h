@@ -201,6 +201,17 @@ int drift_tick_begin_demand(drift_engine* e, double delta, double t, int64_t* n_
 int drift_events_ptr(drift_engine* e, void** dev_ptr, int64_t* capacity);
 int drift_tick_finish(drift_engine* e, const void* events_dev, int64_t n_events);
 
+/* The same exchange without host round trips (what drift_b200/dist.py uses): the engine runs on the
+ * caller's CUDA stream (drift_set_stream, e.g. torch's current stream), drift_tick_begin_async
+ * leaves [header, events...] in `send_dev` (cap + 1 records of 16 B, header.link = count), the caller
+ * all-gathers the send buffers of all ranks into `recv_dev` ([world][cap + 1] records) on that stream,
+ * and drift_tick_finish_gathered resolves them.  `t` is the clock after the tick (device-driven
+ * demand only).  drift_max_events reports the largest per-tick count seen, for sizing `cap`. */
+int drift_set_stream(drift_engine* e, void* cuda_stream);
+int drift_tick_begin_async(drift_engine* e, double delta, double t, void* send_dev, int32_t cap);
+int drift_tick_finish_gathered(drift_engine* e, void* recv_dev, int32_t world, int32_t cap);
+int drift_max_events(drift_engine* e, int64_t* max_events, int32_t reset);
+
 /* Timing of the kernels launched by the last drift_step/drift_run (CUDA events on the engine
  * stream): total milliseconds spent in the advance kernel and number of advance launches. */
 int drift_kernel_times(drift_engine* e, double* advance_ms, int64_t* advance_launches, double* total_ms,
