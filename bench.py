@@ -309,6 +309,10 @@ def run_b200(args):
     total_agents = n_local * world
     value = total_agents * TPS * K / dt
     routes = st1["departures_total"] - st0["departures_total"]
+    if dist is not None:  # whole-job count
+        rt = torch.tensor([routes], device="cuda", dtype=torch.int64)
+        dist.all_reduce(rt)
+        routes = int(rt.item())
     reroutes_timed = n_reroutes[0]
 
     # ---- e2e pass: per step H2D of the step's chains (pinned) + D2H of arrivals/departures/volumes
