@@ -67,6 +67,7 @@ SIGNATURES = {
     "drift_read_travel_times": (C.c_int, [ENGINE, c_f64p]),
     "drift_read_agents": (C.c_int, [ENGINE, c_u8p, c_f64p, c_f64p, c_f64p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p]),
     "drift_read_agent_route": (C.c_int, [ENGINE, C.c_int64, c_i32p, C.c_int64, c_i64p]),
+    "drift_export_routes": (C.c_int, [ENGINE, C.c_int64, c_i32p, c_i32p, c_f64p, c_i32p, C.c_int64]),
     "drift_drain_arrivals": (C.c_int, [ENGINE, c_i32p, c_i32p, C.c_int64, c_i64p]),
     "drift_drain_departures": (C.c_int, [ENGINE, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int64, c_i64p]),
     "drift_enable_entry_trace": (C.c_int, [ENGINE, C.c_int64]),

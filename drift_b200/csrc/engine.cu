@@ -1212,6 +1212,47 @@ static int drain_ring(drift_engine* e, unsigned long long total, unsigned long l
   return DRIFT_OK;
 }
 
+int drift_export_routes(drift_engine* e, int64_t n, const int32_t* agents, int32_t* n_links, double* metres,
+                        int32_t* links_out, int64_t cap) {
+  if (!e || n < 0 || (n && !agents)) return fail(DRIFT_EINVAL, "drift_export_routes");
+  CU(cudaSetDevice(e->device));
+  if (n == 0) return DRIFT_OK;
+  for (int64_t r = 0; r < n; ++r)
+    if (agents[r] < 0 || agents[r] >= e->N) return fail(DRIFT_EINVAL, "drift_export_routes: agent out of range");
+  DevBuf<int32_t> d_agents, d_len, d_links;
+  DevBuf<int64_t> d_off;
+  DevBuf<double> d_m;
+  CU(d_agents.upload(agents, n));
+  CU(d_len.alloc(n));
+  CU(d_m.alloc(n));
+  CU(cudaStreamSynchronize(e->stream));
+  // pass 1: lengths (and metres)
+  k_gather_routes<<<grid_for(n, 128, kSMs * 8), 128, 0, e->stream>>>(n, d_agents.p, e->agents(), e->arena.p,
+                                                                     e->link_len.p, nullptr, nullptr, d_m.p, d_len.p);
+  CU(cudaGetLastError());
+  std::vector<int32_t> len(n);
+  CU(cudaMemcpyAsync(len.data(), d_len.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+  if (metres) CU(cudaMemcpyAsync(metres, d_m.p, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  if (n_links) memcpy(n_links, len.data(), sizeof(int32_t) * n);
+  if (links_out) {
+    std::vector<int64_t> off(n + 1, 0);
+    for (int64_t r = 0; r < n; ++r) off[r + 1] = off[r] + len[r];
+    if (off[n] > cap) return fail(DRIFT_EINVAL, "drift_export_routes: output buffer too small (%lld needed)", (long long)off[n]);
+    if (off[n] > 0) {
+      CU(d_off.upload(off.data(), n + 1));
+      CU(d_links.alloc(off[n], false));
+      k_gather_routes<<<grid_for(n, 128, kSMs * 8), 128, 0, e->stream>>>(n, d_agents.p, e->agents(), e->arena.p,
+                                                                         e->link_len.p, d_off.p, d_links.p, d_m.p,
+                                                                         nullptr);
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(links_out, d_links.p, sizeof(int32_t) * off[n], cudaMemcpyDeviceToHost, e->stream));
+      CU(cudaStreamSynchronize(e->stream));
+    }
+  }
+  return DRIFT_OK;
+}
+
 int drift_drain_arrivals(drift_engine* e, int32_t* agent, int32_t* tick, int64_t cap, int64_t* n) {
   if (!e || !n || cap < 0) return fail(DRIFT_EINVAL, "drift_drain_arrivals");
   CU(cudaSetDevice(e->device));

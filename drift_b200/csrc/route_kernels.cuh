@@ -323,6 +323,27 @@ __global__ void k_apply_reroutes(int64_t Q, const int32_t* __restrict__ q_agent,
   }
 }
 
+// Trip-record export: length (metres, left-to-right fp64 sum) and, optionally, the links of the
+// current route of each listed agent.
+__global__ void k_gather_routes(int64_t n, const int32_t* __restrict__ agents, AgentArrays a,
+                                const int32_t* __restrict__ arena, const double* __restrict__ link_len,
+                                const int64_t* __restrict__ out_off, int32_t* __restrict__ out_links,
+                                double* __restrict__ out_metres, int32_t* __restrict__ out_len) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t i = agents[r];
+    const int64_t off = a.route_off[i];
+    const int32_t len = a.route_len[i];
+    double m = 0.0;
+    for (int32_t k = 0; k < len; ++k) {
+      const int32_t l = arena[off + k];
+      m = __dadd_rn(m, link_len[l]);
+      if (out_links) out_links[out_off[r] + k] = l;
+    }
+    out_metres[r] = m;
+    if (out_len) out_len[r] = len;
+  }
+}
+
 // Waiting agents that will depart within the next n_ticks ticks (same Philox draws as the tick
 // kernel) drop their prefetched routes so that the next planning batch recomputes them on the
 // current travel times.

@@ -256,6 +256,24 @@ class Engine:
             _capi.check(self._lib.drift_read_agent_route(self._h, int(agent), _p(out, C.c_int32), n.value, C.byref(n)))
         return out[:n.value]
 
+    def export_routes(self, agents, with_links=False):
+        """(n_links int32[], metres float64[], links list-of-arrays | None) of the agents' current routes."""
+        a = _i32(agents)
+        n = len(a)
+        nl = np.zeros(max(n, 1), dtype=np.int32)
+        m = np.zeros(max(n, 1))
+        if n == 0:
+            return nl[:0], m[:0], ([] if with_links else None)
+        _capi.check(self._lib.drift_export_routes(self._h, n, _p(a, C.c_int32), _p(nl, C.c_int32), _p(m, C.c_double), None, 0))
+        links = None
+        if with_links:
+            total = int(nl[:n].sum())
+            flat = np.zeros(max(total, 1), dtype=np.int32)
+            _capi.check(self._lib.drift_export_routes(self._h, n, _p(a, C.c_int32), _p(nl, C.c_int32), _p(m, C.c_double),
+                                                      _p(flat, C.c_int32), total))
+            links = np.split(flat[:total], np.cumsum(nl[:n])[:-1])
+        return nl[:n], m[:n], links
+
     def _drain(self, fn, specs, chunk=1 << 16):
         cols = [[] for _ in specs]
         while True:

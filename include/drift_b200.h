@@ -180,6 +180,10 @@ int drift_read_agents(drift_engine* e, uint8_t* state, double* dist_on_link, dou
                       int32_t* cur_link, int32_t* route_idx, int32_t* route_len, int32_t* trip_count,
                       int32_t* cur_node);
 int drift_read_agent_route(drift_engine* e, int64_t agent, int32_t* links_out, int64_t cap, int64_t* n);
+/* Trip-record export (lib/data_logger.py:55-120): hops, length in metres (sum of link lengths) and,
+ * when links_out != NULL, the link ids (concatenated) of the current route of each listed agent. */
+int drift_export_routes(drift_engine* e, int64_t n, const int32_t* agents, int32_t* n_links, double* metres,
+                        int32_t* links_out, int64_t cap);
 int drift_drain_arrivals(drift_engine* e, int32_t* agent, int32_t* tick, int64_t cap, int64_t* n);
 int drift_drain_departures(drift_engine* e, int32_t* agent, int32_t* tick, int32_t* src, int32_t* dst,
                            int32_t* status, int64_t cap, int64_t* n);

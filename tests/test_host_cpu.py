@@ -98,3 +98,25 @@ def test_capi_fails_loudly_without_gpu():
     with pytest.raises(_capi.DriftError) as ei:
         Engine(grid_graph(3, 3, seed=0), 8)
     assert "no CPU path" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_graph_cache_round_trip(tmp_path):
+    from drift_b200 import graph_cache
+    from drift_b200.graph import lower_graph
+
+    case = golden.GoldenCase("multi_random_s0")
+    G = case.nx_graph()
+    lg = lower_graph(G)
+    a = graph_cache.lower_cached(G, cache_dir=str(tmp_path))
+    assert len(os.listdir(tmp_path)) == 1
+    b = graph_cache.lower_cached(G, cache_dir=str(tmp_path))  # served from disk
+    for x in (a, b):
+        assert x.nodes == lg.nodes and x.link_key == lg.link_key
+        for f in graph_cache._ARRAYS:
+            assert np.array_equal(getattr(x, f), getattr(lg, f)), f
+    G2 = case.nx_graph()
+    G2[G2.nodes.__iter__().__next__()]  # same graph object content -> same digest
+    assert graph_cache.graph_digest(G2) == graph_cache.graph_digest(G)
+    u, v, k = next(iter(G2.edges(keys=True)))
+    G2[u][v][k]["length"] += 1.0
+    assert graph_cache.graph_digest(G2) != graph_cache.graph_digest(G)
