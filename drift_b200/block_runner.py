@@ -94,8 +94,8 @@ class BlockSimulation:
         ev.sort()
         ok_idx = np.nonzero(ok)[0]
         metres = links = None
+        last = {}
         if ok.any():
-            last = {}
             for k in ok_idx.tolist():
                 last[int(d_agent[k])] = k  # the route still held by the agent is the one of its last departure
             ags = np.fromiter(last.keys(), dtype=np.int32, count=len(last))
@@ -115,10 +115,11 @@ class BlockSimulation:
                     self._open_src[agent] = d_src[kk]
                     self._open_dst[agent] = d_dst[kk]
                     self._open[agent] = True
-                self._open_m[agent] = metres.get(agent, 0.0) if metres else 0.0
-                if self.record_routes and links is not None and agent in links:
+                # the exported route is the one of the agent's last departure in this block
+                is_last = last.get(agent) == kk
+                self._open_m[agent] = metres.get(agent, 0.0) if (metres and is_last) else 0.0
+                if self.record_routes and links is not None and is_last:
                     self._routes[agent] = self.lg.links_to_nodes(int(d_src[kk]), links[agent])
-                self._cur_dst = None
             else:
                 if self._open[agent]:
                     rows.append(self._close(agent, t))
