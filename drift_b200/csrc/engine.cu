@@ -103,8 +103,9 @@ struct drift_engine {
   DevBuf<int32_t> trip_stage, trip_pool;
   int64_t pool_blocks = 0, pool_k = 0;
   DevBuf<int64_t> route_off;
-  DevBuf<int32_t> arena;
+  DevBuf<int32_t> arena, arena2;  // live arena + spare used by the compaction
   int64_t arena_cap = 0;
+  int64_t compactions = 0;
   // events
   DevBuf<Event> events, send;  // kEvSub sub-buffers of ev_sub_cap records; contiguous copy for the rank exchange
   int64_t ev_cap = 0, ev_sub_cap = 0;
@@ -285,6 +286,24 @@ int fetch_counters(drift_engine* e, Counters* out) {
   CU(cudaMemcpyAsync(e->h_ctr, e->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   *out = *e->h_ctr;
+  return DRIFT_OK;
+}
+
+// Copy the live routes into the spare arena when more than half of the arena is used.  Pending
+// (committed, not yet injected) departures and a staged drift_route_od batch must not exist: called at
+// the start of a routing batch only.
+int maybe_compact_arena(drift_engine* e, unsigned long long cursor) {
+  if (cursor * 2 < (unsigned long long)e->arena_cap) return DRIFT_OK;
+  if (!e->arena2.p) CU(e->arena2.alloc(e->arena_cap, false));
+  Counters* c = e->ctr.p;
+  CU(cudaMemsetAsync(&c->arena_cursor, 0, sizeof(unsigned long long), e->stream));
+  k_compact_routes<<<grid_for(e->N, 128, kSMs * 16), 128, 0, e->stream>>>(
+      e->agents(), e->arena.p, e->arena2.p, &c->arena_cursor, (unsigned long long)e->arena_cap, c);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(e->stream));
+  std::swap(e->arena.p, e->arena2.p);
+  e->compactions += 1;
+  e->last_Q = 0;  // offsets of a staged batch are stale now
   return DRIFT_OK;
 }
 
@@ -746,6 +765,15 @@ int drift_route_od(drift_engine* e, int32_t router, int64_t Q, const int32_t* sr
   Counters c0;
   rc = fetch_counters(e, &c0);
   if (rc) return rc;
+  if (c0.n_pending == 0) {
+    rc = maybe_compact_arena(e, c0.arena_cursor);
+    if (rc) return rc;
+    if (e->compactions && c0.arena_cursor * 2 >= (unsigned long long)e->arena_cap) {
+      rc = fetch_counters(e, &c0);
+      if (rc) return rc;
+    }
+  }
+  e->last_Q = Q;
   e->last_arena_begin = c0.arena_cursor;
   rc = launch_router(e, router, Q, use_congested);
   if (rc) return rc;
@@ -945,6 +973,8 @@ static int plan_window(drift_engine* e) {
   if (rc) return rc;
   const int64_t Q = std::min<int64_t>(hc.n_plan, e->q_cap);
   e->routes_planned += Q;
+  rc = maybe_compact_arena(e, hc.arena_cursor);
+  if (rc) return rc;
   int64_t chunk = Q;
   if (e->demand_router == DRIFT_ROUTER_BATCHED) {
     rc = ensure_trees(e);
@@ -1330,6 +1360,7 @@ int drift_stats(drift_engine* e, drift_stats_out* out) {
   out->arrivals_total = (int64_t)h.n_arrivals;
   out->departures_total = (int64_t)h.n_departures;
   out->route_arena_used = (int64_t)h.arena_cursor;
+  out->arena_compactions = e->compactions;
   out->events_last_tick = 0;
   for (int sb = 0; sb < kEvSub; ++sb) out->events_last_tick += h.n_events[e->tick & 1][sb];
   return check_overflow(e, h);

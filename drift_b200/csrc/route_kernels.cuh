@@ -323,6 +323,41 @@ __global__ void k_apply_reroutes(int64_t Q, const int32_t* __restrict__ q_agent,
   }
 }
 
+// Route arena compaction: copy the live routes (the route of every moving agent and the prefetched
+// routes) into a fresh arena and repoint the agents.
+__global__ void k_compact_routes(AgentArrays a, const int32_t* __restrict__ src, int32_t* __restrict__ dst,
+                                 unsigned long long* __restrict__ cursor, unsigned long long cap, Counters* ctr) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (a.state[i] == kMoving) {
+      const int32_t len = a.route_len[i];
+      const unsigned long long off = atomicAdd(cursor, (unsigned long long)len);
+      if (off + len <= cap) {
+        const int64_t o = a.route_off[i];
+        for (int32_t k = 0; k < len; ++k) dst[off + k] = src[o + k];
+        a.route_off[i] = (int64_t)off;
+      } else {
+        atomicOr(&ctr->overflow, kOvfArena);
+      }
+    } else {
+      a.route_len[i] = 0;  // the finished route is dropped
+      a.route_off[i] = 0;
+    }
+    for (int k = 0; k < 2; ++k) {
+      const int64_t idx = (int64_t)k * a.npad + i;
+      if (a.next_status[idx] != 1 + DRIFT_ROUTE_OK) continue;
+      const int32_t len = a.next_len[idx];
+      const unsigned long long off = atomicAdd(cursor, (unsigned long long)len);
+      if (off + len <= cap) {
+        const int64_t o = a.next_off[idx];
+        for (int32_t j = 0; j < len; ++j) dst[off + j] = src[o + j];
+        a.next_off[idx] = (int64_t)off;
+      } else {
+        atomicOr(&ctr->overflow, kOvfArena);
+      }
+    }
+  }
+}
+
 // Trip-record export: length (metres, left-to-right fp64 sum) and, optionally, the links of the
 // current route of each listed agent.
 __global__ void k_gather_routes(int64_t n, const int32_t* __restrict__ agents, AgentArrays a,

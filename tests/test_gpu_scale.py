@@ -97,3 +97,37 @@ def test_run_to_run_determinism():
             assert np.array_equal(a1[k], a2[k]), k  # bit-identical fp64 state
         assert sorted(zip(*[x.tolist() for x in d1])) == sorted(zip(*[x.tolist() for x in d2]))
         assert sorted(zip(*[x.tolist() for x in r1])) == sorted(zip(*[x.tolist() for x in r2]))
+
+
+def test_route_arena_compaction_is_transparent():
+    """A tiny arena forces several compactions; results equal a run with a large arena."""
+    from drift_b200 import demand
+    from drift_b200.engine import Engine, ROUTER_BATCHED
+    from drift_b200.synth import road_graph
+
+    lg = road_graph(4000, seed=9)
+    N = 6000
+    outs = []
+    for arena in (1 << 24, 300_000):
+        rng = np.random.default_rng(2)
+        start = rng.integers(0, lg.V, size=N).astype(np.int32)
+        eng = Engine(lg, N, route_arena_links=arena)
+        eng.set_demand(5, np.full(24, 0.9), start, chain_capacity=4, router=ROUTER_BATCHED)
+        eng.set_option("route_window", 40)
+        t = 0.0
+        snap = []
+        for b in range(12):
+            _, cand = demand.random_chains(rng, lg.V, start, 2)
+            eng.push_trips(cand.reshape(N, 2))
+            eng.run(40, 1.0, t)
+            t += 40
+            snap.append((eng.occupancy().copy(), eng.agents(fields=("state", "dist", "speed", "route_idx"))))
+            eng.drain_departures(), eng.drain_arrivals()
+        st = eng.stats()
+        eng.close()
+        outs.append((snap, st))
+    assert outs[0][1]["arena_compactions"] == 0 and outs[1][1]["arena_compactions"] >= 2
+    for (o1, a1), (o2, a2) in zip(outs[0][0], outs[1][0]):
+        assert np.array_equal(o1, o2)
+        for k in a1:
+            assert np.array_equal(a1[k], a2[k])
