@@ -108,7 +108,7 @@ def test_route_arena_compaction_is_transparent():
     lg = road_graph(4000, seed=9)
     N = 6000
     outs = []
-    for arena in (1 << 24, 300_000):
+    for arena in (1 << 24, 1_200_000):
         rng = np.random.default_rng(2)
         start = rng.integers(0, lg.V, size=N).astype(np.int32)
         eng = Engine(lg, N, route_arena_links=arena)
