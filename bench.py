@@ -242,6 +242,8 @@ def run_b200(args):
     for kv in args.opt:
         k, v = kv.split("=")
         eng.set_option(k, float(v))
+    if args.landmarks > 0:
+        eng.set_landmarks(args.landmarks)
     eng.set_demand(args.seed, HOURLY, start, chain_capacity=4, router=ROUTER_BATCHED)
     eng.set_option("route_window", TPS)
     if args.coop_blocks:
@@ -446,6 +448,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg (0 = skip)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
+    ap.add_argument("--landmarks", type=int, default=8, help="ALT landmarks for goal-directed bounded searches (0 = off)")
     ap.add_argument("--no-reroute", action="store_true", help="switch the periodic reroute extension off")
     ap.add_argument("--saturated-agents", type=int, default=16_000_000,
                     help="also time the advance kernel with this many agents all moving (0 = skip)")

@@ -149,6 +149,8 @@ struct drift_engine {
   int64_t tree_scratch_bytes = (int64_t)24 << 30;
   uint32_t t_batch = 0;
   DevBuf<int32_t> t_lists;
+  DevBuf<double> lm_from, lm_to;
+  int32_t lm_K = 0;
   int32_t t_max_slots = 0, t_blocks = 0;
   double t_delta = 1.0;
   int64_t tree_budget_bytes = (int64_t)48 << 30;
@@ -345,7 +347,7 @@ int ensure_trees(drift_engine* e) {
   int64_t slots = std::min<int64_t>(V, e->tree_budget_bytes / (4 * V));
   slots = std::max<int64_t>(slots, 1);
   // resident builder blocks: 32 B of scratch per node each
-  int64_t blocks = std::min<int64_t>((int64_t)e->num_sms * (2048 / e->t_threads), e->tree_scratch_bytes / (32 * V));
+  int64_t blocks = std::min<int64_t>((int64_t)e->num_sms * (2048 / e->t_threads), e->tree_scratch_bytes / (36 * V));
   blocks = std::max<int64_t>(blocks, 1);
   CU(e->t_slot_of.alloc(V, false));
   CU(cudaMemset(e->t_slot_of.p, 0xff, sizeof(int32_t) * V));
@@ -361,10 +363,12 @@ int ensure_trees(drift_engine* e) {
   CU(e->t_job_slot.alloc(slots));
   CU(e->t_ctl.alloc(4));
   CU(e->t_dist.alloc(blocks * V, false));
+  k_fill_u64<<<kSMs * 8, 256, 0, e->stream>>>(e->t_dist.p, blocks * V, kInfBits);  // jobs keep it at +inf
+  CU(cudaGetLastError());
   CU(e->t_stamp.alloc(blocks * V, true));
   CU(e->t_infar.alloc(blocks * V, true));
   CU(e->t_iter.alloc(blocks, true));
-  CU(e->t_lists.alloc(blocks * 4 * V, false));
+  CU(e->t_lists.alloc(blocks * 5 * V, false));
   e->t_max_slots = (int32_t)slots;
   e->t_blocks = (int32_t)blocks;
   return DRIFT_OK;
@@ -431,6 +435,10 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     const int gq = grid_for(Q, 256, kSMs * 4);
     k_tree_hits<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, n_dev);
     k_tree_requests<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, e->ctr.p, n_dev);
+    Landmarks lm;
+    lm.from = e->lm_from.p;
+    lm.to = e->lm_to.p;
+    lm.K = use_congested ? 0 : e->lm_K;  // the landmark distances are free-flow distances
     k_link_queries<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, n_dev);
     cudaEvent_t tb0 = nullptr, tb1 = nullptr;
     if (e->time_plan) {
@@ -439,7 +447,7 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
       cudaEventRecord(tb0, e->stream);
     }
     k_build_trees<<<e->t_blocks, e->t_threads, 0, e->stream>>>(e->graph(), wb, wf, e->t_delta, tc, ts, qs, e->arena.p,
-                                                               (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
+                                                               (unsigned long long)e->arena_cap, e->ctr.p, out, lc, lm);
     if (tb0) {
       cudaEventRecord(tb1, e->stream);
       e->tree_timers.push_back({tb0, tb1});
@@ -1522,6 +1530,18 @@ int drift_phase_times(drift_engine* e, double* advance_ns, double* inject_ns, do
     e->plan_ms = 0;
     e->loop_ticks = 0;
   }
+  return DRIFT_OK;
+}
+
+int drift_set_landmarks(drift_engine* e, int32_t K, const double* dist_from, const double* dist_to) {
+  if (!e || K < 0 || (K && (!dist_from || !dist_to))) return fail(DRIFT_EINVAL, "drift_set_landmarks");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  e->lm_K = 0;
+  if (K == 0) return DRIFT_OK;
+  CU(e->lm_from.upload(dist_from, (int64_t)K * e->V));
+  CU(e->lm_to.upload(dist_to, (int64_t)K * e->V));
+  e->lm_K = K;
   return DRIFT_OK;
 }
 

@@ -408,6 +408,10 @@ __global__ void k_store_prefetch(int64_t Q, const int32_t* __restrict__ q_agent,
   }
 }
 
+__global__ void k_fill_u64(unsigned long long* __restrict__ p, int64_t n, unsigned long long v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 // =====================================================================================
 // K5b: batched multi-source SSSP -- one reverse shortest-path tree per destination.
 //
@@ -425,8 +429,16 @@ struct TreeScratch {   // per resident block
   unsigned long long* dist;  // [blocks][V] fp64 bit patterns (non-negative doubles order like u64)
   uint32_t* stamp;           // [blocks][V] near-list dedupe stamp
   uint32_t* infar;           // [blocks][V] node is queued in the far list
-  int32_t* lists;            // [blocks][4][V] nearA, nearB, farA, farB
+  int32_t* lists;            // [blocks][5][V] nearA, nearB, farA, farB, touched
   uint32_t* iter;            // [blocks] running stamp
+};
+
+// Landmark lower bounds for goal-directed bounded searches (ALT: A*, landmarks, triangle inequality;
+// Goldberg & Harrelson 2005).  d(s,v) >= from[k][v] - from[k][s] and >= to[k][s] - to[k][v].
+struct Landmarks {
+  const double* from;  // [K][V] distance landmark -> node
+  const double* to;    // [K][V] distance node -> landmark
+  int32_t K;
 };
 
 struct TreeCache {
@@ -537,18 +549,20 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
                                                               const int32_t* __restrict__ q_src,
                                                               int32_t* __restrict__ arena, unsigned long long arena_cap,
                                                               Counters* ctr, RouteOut out,
-                                                              const double* __restrict__ link_cost) {
-  __shared__ int s_job, s_near_n, s_next_n, s_far_n, s_far2_n, s_done;
+                                                              const double* __restrict__ link_cost, Landmarks lm) {
+  __shared__ int s_job, s_near_n, s_next_n, s_far_n, s_far2_n, s_done, s_touched, s_lmk[2], s_lmdir[2];
+  __shared__ double s_lmref[2];
   __shared__ int s_bsrc[kMaxBounded], s_bq[kMaxBounded];
   __shared__ unsigned long long s_min;
   const int64_t V = g.V;
   unsigned long long* dist = sc.dist + (int64_t)blockIdx.x * V;
   uint32_t* stamp = sc.stamp + (int64_t)blockIdx.x * V;
   uint32_t* infar = sc.infar + (int64_t)blockIdx.x * V;
-  int32_t* nearA = sc.lists + ((int64_t)blockIdx.x * 4 + 0) * V;
-  int32_t* nearB = sc.lists + ((int64_t)blockIdx.x * 4 + 1) * V;
-  int32_t* farA = sc.lists + ((int64_t)blockIdx.x * 4 + 2) * V;
-  int32_t* farB = sc.lists + ((int64_t)blockIdx.x * 4 + 3) * V;
+  int32_t* nearA = sc.lists + ((int64_t)blockIdx.x * 5 + 0) * V;
+  int32_t* nearB = sc.lists + ((int64_t)blockIdx.x * 5 + 1) * V;
+  int32_t* farA = sc.lists + ((int64_t)blockIdx.x * 5 + 2) * V;
+  int32_t* farB = sc.lists + ((int64_t)blockIdx.x * 5 + 3) * V;
+  int32_t* touched = sc.lists + ((int64_t)blockIdx.x * 5 + 4) * V;
   uint32_t iter = sc.iter[blockIdx.x];
   const int n_jobs = *tc.n_jobs;
   unsigned long long c_relaxed = 0, c_improved = 0, c_expanded = 0;  // per-thread work counters
@@ -569,20 +583,64 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
         s_bsrc[k] = q_src[q];
       }
     }
-    for (int64_t v = threadIdx.x; v < V; v += blockDim.x) {
-      dist[v] = kInfBits;
-      infar[v] = 0;
-    }
+    // dist[] is +inf and infar[] 0 for every node here: each job resets what it touched when it ends
     if (threadIdx.x == 0) {
       s_near_n = 1;
       s_next_n = 0;
       s_far_n = 0;
       s_far2_n = 0;
+      s_touched = 1;
       nearA[0] = dest;
+      touched[0] = dest;
+      dist[dest] = 0ULL;
+      // goal direction for a single-source bounded job: the two landmarks with the best bound on d(s, dest)
+      s_lmk[0] = s_lmk[1] = -1;
+      if (bounded && nb == 1 && lm.K > 0) {
+        const int32_t sn = s_bsrc[0];
+        double best[2] = {0.0, 0.0};
+        if (sn >= 0 && sn < V) {
+          for (int k = 0; k < lm.K; ++k) {
+            for (int dir = 0; dir < 2; ++dir) {
+              const double* arr = (dir == 0 ? lm.from : lm.to) + (int64_t)k * V;
+              const double b = dir == 0 ? arr[dest] - arr[sn] : arr[sn] - arr[dest];
+              if (!(b > 0.0) || b > 1e300) continue;  // useless or undefined (unreachable landmark)
+              const int slot = b > best[0] ? 0 : (b > best[1] ? 1 : -1);
+              if (slot < 0) continue;
+              if (slot == 0) {
+                best[1] = best[0];
+                s_lmk[1] = s_lmk[0];
+                s_lmdir[1] = s_lmdir[0];
+                s_lmref[1] = s_lmref[0];
+              }
+              best[slot] = b;
+              s_lmk[slot] = k;
+              s_lmdir[slot] = dir;
+              s_lmref[slot] = arr[sn];
+            }
+          }
+        }
+      }
     }
     __syncthreads();
-    if (threadIdx.x == 0) dist[dest] = 0ULL;
-    double T_old = -1.0, T = delta;
+    const int lk0 = s_lmk[0], lk1 = s_lmk[1];
+    const double* lma0 = lk0 >= 0 ? (s_lmdir[0] == 0 ? lm.from : lm.to) + (int64_t)lk0 * V : nullptr;
+    const double* lma1 = lk1 >= 0 ? (s_lmdir[1] == 0 ? lm.from : lm.to) + (int64_t)lk1 * V : nullptr;
+    const double lmr0 = s_lmref[0], lmr1 = s_lmref[1];
+    const int lmd0 = s_lmdir[0], lmd1 = s_lmdir[1];
+    // feasible potential: lower bound on the remaining distance d(source, v); 0 without landmarks
+    auto pot = [&](int32_t v) -> double {
+      double h = 0.0;
+      if (lma0) {
+        const double b = lmd0 == 0 ? lma0[v] - lmr0 : lmr0 - lma0[v];
+        if (b > h && b < 1e300) h = b;
+      }
+      if (lma1) {
+        const double b = lmd1 == 0 ? lma1[v] - lmr1 : lmr1 - lma1[v];
+        if (b > h && b < 1e300) h = b;
+      }
+      return h;
+    };
+    double T_old = -1.0, T = pot(dest) + delta;
     __syncthreads();
     for (;;) {
       const int n = s_near_n;
@@ -608,15 +666,17 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
         __syncthreads();
         unsigned long long m = kInfBits;
         for (int i = threadIdx.x; i < nf; i += blockDim.x) {
-          const unsigned long long d = dist[farA[i]];
-          m = d < m ? d : m;
+          const int32_t u = farA[i];
+          const double key = __dadd_rn(__longlong_as_double((long long)dist[u]), pot(u));
+          const unsigned long long kb = (unsigned long long)__double_as_longlong(key);
+          m = kb < m ? kb : m;
         }
         const double minfar = __longlong_as_double((long long)block_min_u64(m, &s_min));
         T_old = T;
         T = (minfar > T ? minfar : T) + delta;
         for (int i = threadIdx.x; i < nf; i += blockDim.x) {
           const int32_t u = farA[i];
-          const double d = __longlong_as_double((long long)dist[u]);
+          const double d = __dadd_rn(__longlong_as_double((long long)dist[u]), pot(u));
           if (d <= T_old) {
             infar[u] = 0;  // already expanded as a near node
           } else if (d <= T) {
@@ -651,7 +711,8 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
           const unsigned long long old = atomicMin(&dist[u], cb);
           if (cb < old) {
             ++c_improved;
-            if (cand <= T) {
+            if (old == kInfBits) touched[atomicAdd(&s_touched, 1)] = u;  // exactly one thread sees the first label
+            if (__dadd_rn(cand, pot(u)) <= T) {
               if (atomicExch(&stamp[u], iter) != iter) nearB[atomicAdd(&s_next_n, 1)] = u;
             } else if (atomicExch(&infar[u], 1u) == 0u) {
               farA[atomicAdd(&s_far_n, 1)] = u;  // at most one far entry per node: <= V entries
@@ -734,6 +795,11 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
         tc.slot_owner[tc.job_slot[job]] = -1;
       }
       __syncthreads();
+      for (int i = threadIdx.x; i < s_touched; i += blockDim.x) {  // leave the scratch clean for the next job
+        dist[touched[i]] = kInfBits;
+        infar[touched[i]] = 0;
+      }
+      __syncthreads();
       continue;
     }
     // first link of the shortest path u -> dest: first forward entry (CSR order) that attains dist[u]
@@ -753,6 +819,11 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
         }
       }
       next_link[u] = nl;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < s_touched; i += blockDim.x) {
+      dist[touched[i]] = kInfBits;
+      infar[touched[i]] = 0;
     }
     __syncthreads();
   }

@@ -231,6 +231,10 @@ int drift_phase_times(drift_engine* e, double* advance_ns, double* inject_ns, do
  * the CUDA-event time): trees built, edges relaxed, relaxations that improved a label, nodes expanded. */
 int drift_tree_stats(drift_engine* e, double* build_ms, int64_t* launches, int64_t* jobs, int64_t* relaxed,
                      int64_t* improved, int64_t* expanded, int32_t reset);
+/* Landmark distances for goal-directed bounded searches in the batched router (ALT): K landmarks,
+ * dist_from[K][V] = free-flow travel time landmark -> node, dist_to[K][V] = node -> landmark (+inf where
+ * unreachable).  Only used while routing on the static travel times.  K = 0 switches it off. */
+int drift_set_landmarks(drift_engine* e, int32_t K, const double* dist_from, const double* dist_to);
 /* Tunables: "tree_cache_bytes" (HBM budget of the destination-tree cache, before first use),
  * "tree_delta_scale" (multiplies the near-far bucket width). */
 int drift_set_option(drift_engine* e, const char* name, double value);

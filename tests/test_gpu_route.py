@@ -222,8 +222,8 @@ def test_tree_cache_eviction():
             eng.route(list(range(20, 40)), list(range(100, 120)), router=ROUTER_BATCHED)
 
 
-@pytest.mark.parametrize("bounded_max", [8, 0])
-def test_batched_router_cold_destinations(bounded_max):
+@pytest.mark.parametrize("bounded_max,landmarks", [(8, 0), (0, 0), (8, 6), (1, 3)])
+def test_batched_router_cold_destinations(bounded_max, landmarks):
     """Random (s, t) pairs: most destinations are wanted by a handful of queries, so the builder
     stops as soon as their sources are settled and writes the routes itself (bounded search)."""
     import networkx as nx
@@ -240,6 +240,8 @@ def test_batched_router_cold_destinations(bounded_max):
     pairs += [(7, 7), (len(nodes) - 4, 3), (3, len(nodes) - 4)]  # trivial, and the unreachable / dead-end extras
     with Engine(lg, 8, route_arena_links=1 << 22) as eng:
         eng.set_option("bounded_max", bounded_max)
+        if landmarks:
+            assert len(eng.set_landmarks(landmarks)) == landmarks  # goal-directed (ALT) bounded searches
         for rnd in range(2):
             st, nl, links = eng.route([p[0] for p in pairs], [p[1] for p in pairs], router=ROUTER_BATCHED)
             costs = eng.route_costs(len(pairs))
