@@ -347,7 +347,7 @@ int ensure_trees(drift_engine* e) {
   int64_t slots = std::min<int64_t>(V, e->tree_budget_bytes / (4 * V));
   slots = std::max<int64_t>(slots, 1);
   // resident builder blocks: 32 B of scratch per node each
-  int64_t blocks = std::min<int64_t>((int64_t)e->num_sms * (2048 / e->t_threads), e->tree_scratch_bytes / (36 * V));
+  int64_t blocks = std::min<int64_t>((int64_t)e->num_sms * std::min(32, 2048 / e->t_threads), e->tree_scratch_bytes / (36 * V));
   blocks = std::max<int64_t>(blocks, 1);
   CU(e->t_slot_of.alloc(V, false));
   CU(cudaMemset(e->t_slot_of.p, 0xff, sizeof(int32_t) * V));
@@ -1568,7 +1568,7 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
   } else if (s == "tree_threads") {
     if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_threads must be set before the first batched route");
     const int v = (int)value;
-    if (v != 128 && v != 256 && v != 512 && v != 1024) return fail(DRIFT_EINVAL, "tree_threads: 128/256/512/1024");
+    if (v != 64 && v != 128 && v != 256 && v != 512 && v != 1024) return fail(DRIFT_EINVAL, "tree_threads: 64..1024");
     e->t_threads = v;
   } else if (s == "bounded_max") {
     e->t_bounded_max = std::max(0, std::min((int)value, kMaxBounded));

@@ -640,7 +640,9 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
       }
       return h;
     };
-    double T_old = -1.0, T = pot(dest) + delta;
+    // goal-directed keys cluster just below d(source, dest): finer buckets keep the search inside the corridor
+    const double jdelta = (lma0 != nullptr) ? delta * 0.25 : delta;
+    double T_old = -1.0, T = pot(dest) + jdelta;
     __syncthreads();
     for (;;) {
       const int n = s_near_n;
@@ -673,7 +675,7 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
         }
         const double minfar = __longlong_as_double((long long)block_min_u64(m, &s_min));
         T_old = T;
-        T = (minfar > T ? minfar : T) + delta;
+        T = (minfar > T ? minfar : T) + jdelta;
         for (int i = threadIdx.x; i < nf; i += blockDim.x) {
           const int32_t u = farA[i];
           const double d = __dadd_rn(__longlong_as_double((long long)dist[u]), pot(u));
