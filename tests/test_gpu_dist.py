@@ -92,3 +92,80 @@ def test_two_rank_replay_matches_reference(name):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def _worker_demand(rank, world, port, out):
+    """Device-driven demand sharded over 2 ranks == the same run on one engine (bit for bit)."""
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from drift_b200.dist import ShardedEngine
+        from drift_b200.engine import Engine, ROUTER_BATCHED
+        from drift_b200.synth import road_graph
+
+        lg = road_graph(5000, seed=4)
+        N, blocks, ticks = 40_000, 4, 60
+        rng = np.random.default_rng(3)
+        start = rng.integers(0, lg.V, size=N).astype(np.int32)
+        cands = rng.integers(0, lg.V, size=(blocks, N, 2)).astype(np.int32)
+        first = rng.integers(0, lg.V, size=(N, 4)).astype(np.int32)
+        hourly = np.full(24, 0.9)
+
+        def drive(eng_like, eng, lo, hi):
+            eng.set_demand(77, hourly, start[lo:hi], chain_capacity=4, router=ROUTER_BATCHED)
+            eng.set_option("route_window", ticks)
+            eng.push_trips(first[lo:hi])
+            t, occs = 0.0, []
+            for b in range(blocks):
+                eng.push_trips(cands[b, lo:hi])
+                if eng_like is eng:
+                    eng.run(ticks, 1.0, t)
+                    t += ticks
+                else:
+                    t = eng_like.run(ticks, 1.0, t)
+                occs.append(eng.occupancy().copy())
+            return occs, eng.agents(fields=("state", "dist", "speed", "route_idx", "trip_count"))
+
+        se = ShardedEngine(lg, N, device=rank, route_arena_links=N * 300)
+        occ_s, ag_s = drive(se, se.engine, se.lo, se.hi)
+        se.close()
+        if rank == 0:
+            eng = Engine(lg, N, device=0, route_arena_links=N * 300)
+            occ_1, ag_1 = drive(eng, eng, 0, N)
+            eng.close()
+            for a, b in zip(occ_s, occ_1):
+                assert np.array_equal(a, b), "sharded volumes differ from the single-engine run"
+            assert occ_1[-1].sum() > 1000
+            for k in ag_s:
+                assert np.array_equal(ag_s[k], ag_1[k][se.lo:se.hi]), k
+        dist.barrier()
+        out.put((rank, "ok"))
+    except Exception:
+        import traceback
+
+        out.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_device_demand_equals_single_engine():
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_demand, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
