@@ -405,8 +405,10 @@ def run_b200(args):
             config=dict(workload=args.workload, description=w["desc"], agents_per_gpu=n_local, total_agents=total_agents,
                         nodes=lg.V, links=lg.L, demand=model, ticks_per_step=TPS, tick_seconds=delta,
                         router="batched reverse-tree SSSP + destination cache", clock="08:00 peak",
-                        l2="agent state (%.0f MB) and link arrays exceed L2 only for >= 4M agents; the tick loop touches "
-                           "all of it every tick, no flush" % (n_local * 45 / 1e6),
+                        l2="no explicit flush: every step's route planning streams the tree-builder scratch, tree cache "
+                           "and route arena (GBs, >> 126 MB L2) between tick blocks; the per-tick agent state (%.0f MB "
+                           "hot) can stay L2-resident at this size, which is why roofline_advance_saturated uses 16 M "
+                           "agents (400 MB of hot state)" % (n_local * 25 / 1e6),
                         multi_gpu=("agents sharded by id block, graph replicated, per-tick all-gather of link events "
                                    "(NCCL), every rank resolves the global event set") if world > 1 else "n/a"),
             routes_per_s=routes / dt, routes_in_timed_region=int(routes),

@@ -39,7 +39,7 @@ class Engine:
     """
 
     def __init__(self, lg: LoweredGraph, num_agents: int, alpha: float = 0.15, beta: float = 4.0, device: int = 0,
-                 agent_base: int = 0, route_arena_links: int = 0, total_agents: int | None = None):
+                 agent_base: int = 0, route_arena_links: int = 0):
         self._lib = _capi.load()
         self.lg = lg
         self.N = int(num_agents)
