@@ -103,7 +103,7 @@ def build_workload(name, agents, seed, rank, nodes=None):
     from drift_b200.synth import road_graph
 
     w = WORKLOADS[name]
-    lg = road_graph(nodes or w["nodes"], seed=seed)
+    lg = road_graph(nodes or w["nodes"], seed=seed, morton=os.environ.get("DRIFT_NO_MORTON") is None)
     rng = np.random.default_rng(seed * 1000 + 17 + rank)
     start = rng.integers(0, lg.V, size=agents).astype(np.int32)
     return lg, start, w["model"], rng
@@ -377,7 +377,8 @@ def run_b200(args):
                     achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None, peak_source=peak_src,
                     us_per_launch=us, algorithmic_bytes_per_launch=per_launch, launches=trees["launches"],
                     trees=trees["trees"], edges_relaxed=trees["edges_relaxed"], improved=trees["improved"],
-                    nodes_expanded=trees["nodes_expanded"], share_of_step=trees["build_ms"] / (1e3 * dt),
+                    nodes_expanded=trees["nodes_expanded"], waves=trees["waves"], far_visits=trees["far_visits"],
+                    share_of_step=trees["build_ms"] / (1e3 * dt),
                     note="20 B per relaxed edge + 12 B per improving relaxation + 16 B per expanded node (SURVEY.md 8d)")
     else:
         roof = roof_adv

@@ -54,6 +54,8 @@ struct Counters {
   unsigned long long tree_improved;
   unsigned long long tree_expanded;
   unsigned long long tree_jobs;
+  unsigned long long tree_iters;      // near-list waves (block barriers) over all jobs
+  unsigned long long tree_far_visits; // far-list entries scanned by threshold advances
 };
 
 constexpr int kOvfEvents = 1;

@@ -140,8 +140,8 @@ struct drift_engine {
   int64_t r_heap_cap = 0;
   // tree cache + tree builder scratch (batched router)
   DevBuf<int32_t> t_slot_of, t_next, t_job_dst, t_job_slot, t_ctl;  // t_ctl: n_slots, n_jobs, job_cursor
-  DevBuf<unsigned long long> t_dist;
-  DevBuf<uint32_t> t_stamp, t_infar, t_iter, t_slot_stamp;
+  DevBuf<NodeRec> t_rec;
+  DevBuf<uint32_t> t_iter, t_slot_stamp;
   DevBuf<int32_t> t_slot_owner, t_slot_job, t_job_qhead, t_job_cnt, t_q_next;
   DevBuf<uint32_t> t_slot_job_batch;
   int32_t t_bounded_max = -1;  // -1 = automatic: bounded search only when the cache cannot hold every destination
@@ -362,11 +362,9 @@ int ensure_trees(drift_engine* e) {
   CU(e->t_job_dst.alloc(slots));
   CU(e->t_job_slot.alloc(slots));
   CU(e->t_ctl.alloc(4));
-  CU(e->t_dist.alloc(blocks * V, false));
-  k_fill_u64<<<kSMs * 8, 256, 0, e->stream>>>(e->t_dist.p, blocks * V, kInfBits);  // jobs keep it at +inf
+  CU(e->t_rec.alloc(blocks * V, false));
+  k_init_noderecs<<<kSMs * 8, 256, 0, e->stream>>>(e->t_rec.p, blocks * V);  // jobs leave it at +inf / 0
   CU(cudaGetLastError());
-  CU(e->t_stamp.alloc(blocks * V, true));
-  CU(e->t_infar.alloc(blocks * V, true));
   CU(e->t_iter.alloc(blocks, true));
   CU(e->t_lists.alloc(blocks * 5 * V, false));
   e->t_max_slots = (int32_t)slots;
@@ -426,9 +424,7 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     tc.job_dst = e->t_job_dst.p;
     tc.job_slot = e->t_job_slot.p;
     TreeScratch ts;
-    ts.dist = e->t_dist.p;
-    ts.stamp = e->t_stamp.p;
-    ts.infar = e->t_infar.p;
+    ts.rec = e->t_rec.p;
     ts.lists = e->t_lists.p;
     ts.iter = e->t_iter.p;
     CU(cudaMemsetAsync(e->t_ctl.p + 1, 0, 2 * sizeof(int32_t), e->stream));
@@ -1484,7 +1480,7 @@ int drift_kernel_times(drift_engine* e, double* advance_ms, int64_t* advance_lau
 }
 
 int drift_tree_stats(drift_engine* e, double* build_ms, int64_t* launches, int64_t* jobs, int64_t* relaxed,
-                     int64_t* improved, int64_t* expanded, int32_t reset) {
+                     int64_t* improved, int64_t* expanded, int64_t* iters, int64_t* far_visits, int32_t reset) {
   if (!e) return fail(DRIFT_EINVAL, "drift_tree_stats");
   CU(cudaSetDevice(e->device));
   Counters c;
@@ -1505,8 +1501,10 @@ int drift_tree_stats(drift_engine* e, double* build_ms, int64_t* launches, int64
   if (relaxed) *relaxed = (int64_t)c.tree_relaxed;
   if (improved) *improved = (int64_t)c.tree_improved;
   if (expanded) *expanded = (int64_t)c.tree_expanded;
+  if (iters) *iters = (int64_t)c.tree_iters;
+  if (far_visits) *far_visits = (int64_t)c.tree_far_visits;
   if (reset) {
-    CU(cudaMemsetAsync(&e->ctr.p->tree_relaxed, 0, 4 * sizeof(unsigned long long), e->stream));
+    CU(cudaMemsetAsync(&e->ctr.p->tree_relaxed, 0, 6 * sizeof(unsigned long long), e->stream));
     e->tree_ms = 0;
     e->tree_launches = 0;
   }

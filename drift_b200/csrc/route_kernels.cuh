@@ -408,9 +408,8 @@ __global__ void k_store_prefetch(int64_t Q, const int32_t* __restrict__ q_agent,
   }
 }
 
-__global__ void k_fill_u64(unsigned long long* __restrict__ p, int64_t n, unsigned long long v) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
-}
+struct NodeRec;
+__global__ void k_init_noderecs(NodeRec* __restrict__ p, int64_t n);
 
 // =====================================================================================
 // K5b: batched multi-source SSSP -- one reverse shortest-path tree per destination.
@@ -425,10 +424,14 @@ __global__ void k_fill_u64(unsigned long long* __restrict__ p, int64_t n, unsign
 // path equals NetworkX's wherever the shortest path is unique; cost parity 1e-9 relative.
 // =====================================================================================
 
+struct __align__(16) NodeRec {
+  unsigned long long dist;  // fp64 bit pattern (non-negative doubles order like u64)
+  uint32_t stamp;           // near-list dedupe stamp
+  uint32_t infar;           // node is queued in the far list
+};
+
 struct TreeScratch {   // per resident block
-  unsigned long long* dist;  // [blocks][V] fp64 bit patterns (non-negative doubles order like u64)
-  uint32_t* stamp;           // [blocks][V] near-list dedupe stamp
-  uint32_t* infar;           // [blocks][V] node is queued in the far list
+  NodeRec* rec;              // [blocks][V]
   int32_t* lists;            // [blocks][5][V] nearA, nearB, farA, farB, touched
   uint32_t* iter;            // [blocks] running stamp
 };
@@ -555,9 +558,8 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
   __shared__ int s_bsrc[kMaxBounded], s_bq[kMaxBounded];
   __shared__ unsigned long long s_min;
   const int64_t V = g.V;
-  unsigned long long* dist = sc.dist + (int64_t)blockIdx.x * V;
-  uint32_t* stamp = sc.stamp + (int64_t)blockIdx.x * V;
-  uint32_t* infar = sc.infar + (int64_t)blockIdx.x * V;
+  // per-node scratch packed into one 16-byte record: a relaxation touches one sector, not three
+  NodeRec* rec = sc.rec + (int64_t)blockIdx.x * V;
   int32_t* nearA = sc.lists + ((int64_t)blockIdx.x * 5 + 0) * V;
   int32_t* nearB = sc.lists + ((int64_t)blockIdx.x * 5 + 1) * V;
   int32_t* farA = sc.lists + ((int64_t)blockIdx.x * 5 + 2) * V;
@@ -566,6 +568,7 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
   uint32_t iter = sc.iter[blockIdx.x];
   const int n_jobs = *tc.n_jobs;
   unsigned long long c_relaxed = 0, c_improved = 0, c_expanded = 0;  // per-thread work counters
+  unsigned long long c_iters = 0, c_far = 0;
   for (;;) {
     if (threadIdx.x == 0) s_job = atomicAdd(tc.job_cursor, 1);
     __syncthreads();
@@ -592,7 +595,7 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
       s_touched = 1;
       nearA[0] = dest;
       touched[0] = dest;
-      dist[dest] = 0ULL;
+      rec[dest].dist = 0ULL;
       // goal direction for a single-source bounded job: the two landmarks with the best bound on d(s, dest)
       s_lmk[0] = s_lmk[1] = -1;
       if (bounded && nb == 1 && lm.K > 0) {
@@ -654,7 +657,7 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
             int done = 1;
             for (int k = 0; k < nb; ++k) {
               const int32_t sn = s_bsrc[k];
-              if (sn >= 0 && sn < V && __longlong_as_double((long long)dist[sn]) > T) done = 0;
+              if (sn >= 0 && sn < V && __longlong_as_double((long long)rec[sn].dist) > T) done = 0;
             }
             s_done = done;
           }
@@ -669,20 +672,21 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
         unsigned long long m = kInfBits;
         for (int i = threadIdx.x; i < nf; i += blockDim.x) {
           const int32_t u = farA[i];
-          const double key = __dadd_rn(__longlong_as_double((long long)dist[u]), pot(u));
+          const double key = __dadd_rn(__longlong_as_double((long long)rec[u].dist), pot(u));
           const unsigned long long kb = (unsigned long long)__double_as_longlong(key);
           m = kb < m ? kb : m;
         }
         const double minfar = __longlong_as_double((long long)block_min_u64(m, &s_min));
+        if (threadIdx.x == 0) c_far += (unsigned long long)nf;
         T_old = T;
         T = (minfar > T ? minfar : T) + jdelta;
         for (int i = threadIdx.x; i < nf; i += blockDim.x) {
           const int32_t u = farA[i];
-          const double d = __dadd_rn(__longlong_as_double((long long)dist[u]), pot(u));
+          const double d = __dadd_rn(__longlong_as_double((long long)rec[u].dist), pot(u));
           if (d <= T_old) {
-            infar[u] = 0;  // already expanded as a near node
+            rec[u].infar = 0;  // already expanded as a near node
           } else if (d <= T) {
-            infar[u] = 0;
+            rec[u].infar = 0;
             nearA[atomicAdd(&s_near_n, 1)] = u;
           } else {
             farB[atomicAdd(&s_far2_n, 1)] = u;
@@ -700,9 +704,10 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
         continue;
       }
       ++iter;
+      if (threadIdx.x == 0) ++c_iters;
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int32_t v = nearA[i];
-        const double dv = __longlong_as_double((long long)dist[v]);
+        const double dv = __longlong_as_double((long long)rec[v].dist);
         const int32_t e1 = g.bwd_rowptr[v + 1];
         ++c_expanded;
         c_relaxed += (unsigned long long)(e1 - g.bwd_rowptr[v]);
@@ -710,13 +715,13 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
           const int32_t u = g.bwd_col[e];
           const double cand = __dadd_rn(dv, w_bwd[e]);
           const unsigned long long cb = (unsigned long long)__double_as_longlong(cand);
-          const unsigned long long old = atomicMin(&dist[u], cb);
+          const unsigned long long old = atomicMin(&rec[u].dist, cb);
           if (cb < old) {
             ++c_improved;
             if (old == kInfBits) touched[atomicAdd(&s_touched, 1)] = u;  // exactly one thread sees the first label
             if (__dadd_rn(cand, pot(u)) <= T) {
-              if (atomicExch(&stamp[u], iter) != iter) nearB[atomicAdd(&s_next_n, 1)] = u;
-            } else if (atomicExch(&infar[u], 1u) == 0u) {
+              if (atomicExch(&rec[u].stamp, iter) != iter) nearB[atomicAdd(&s_next_n, 1)] = u;
+            } else if (atomicExch(&rec[u].infar, 1u) == 0u) {
               farA[atomicAdd(&s_far_n, 1)] = u;  // at most one far entry per node: <= V entries
             }
           }
@@ -734,7 +739,7 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
     }
     if (bounded) {
       // routes of the few sources, straight from dist[]: at x follow the first forward entry (CSR
-      // order) with dist[head] + w == dist[x]; every node on the way is already final
+      // order) with rec[head].dist + w == rec[x].dist; every node on the way is already final
       if (threadIdx.x < nb) {
         const int32_t q = s_bq[threadIdx.x];
         const int32_t sn = s_bsrc[threadIdx.x];
@@ -743,16 +748,16 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
         double cost = 0.0;
         if (sn == dest) {
           status = DRIFT_ROUTE_TRIVIAL;
-        } else if (sn >= 0 && sn < V && dist[sn] != kInfBits) {
+        } else if (sn >= 0 && sn < V && rec[sn].dist != kInfBits) {
           for (int pass = 0; pass < 2; ++pass) {
             int32_t x = sn;
             int k = 0;
             while (x != dest) {
-              const unsigned long long dx = dist[x];
+              const unsigned long long dx = rec[x].dist;
               int32_t nl = -1, nx = -1;
               const int32_t e1 = g.fwd_rowptr[x + 1];
               for (int32_t e = g.fwd_rowptr[x]; e < e1; ++e) {
-                const unsigned long long dvb = dist[g.fwd_col[e]];
+                const unsigned long long dvb = rec[g.fwd_col[e]].dist;
                 if (dvb == kInfBits) continue;
                 const double c = __dadd_rn(__longlong_as_double((long long)dvb), w_fwd[e]);
                 if ((unsigned long long)__double_as_longlong(c) == dx) {
@@ -798,20 +803,20 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
       }
       __syncthreads();
       for (int i = threadIdx.x; i < s_touched; i += blockDim.x) {  // leave the scratch clean for the next job
-        dist[touched[i]] = kInfBits;
-        infar[touched[i]] = 0;
+        rec[touched[i]].dist = kInfBits;
+        rec[touched[i]].infar = 0;
       }
       __syncthreads();
       continue;
     }
-    // first link of the shortest path u -> dest: first forward entry (CSR order) that attains dist[u]
+    // first link of the shortest path u -> dest: first forward entry (CSR order) that attains rec[u].dist
     for (int64_t u = threadIdx.x; u < V; u += blockDim.x) {
       int32_t nl = -1;
-      const unsigned long long du = dist[u];
+      const unsigned long long du = rec[u].dist;
       if (u != dest && du != kInfBits) {
         const int32_t e1 = g.fwd_rowptr[u + 1];
         for (int32_t e = g.fwd_rowptr[u]; e < e1; ++e) {
-          const unsigned long long dvb = dist[g.fwd_col[e]];
+          const unsigned long long dvb = rec[g.fwd_col[e]].dist;
           if (dvb == kInfBits) continue;
           const double c = __dadd_rn(__longlong_as_double((long long)dvb), w_fwd[e]);
           if ((unsigned long long)__double_as_longlong(c) == du) {
@@ -824,8 +829,8 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
     }
     __syncthreads();
     for (int i = threadIdx.x; i < s_touched; i += blockDim.x) {
-      dist[touched[i]] = kInfBits;
-      infar[touched[i]] = 0;
+      rec[touched[i]].dist = kInfBits;
+      rec[touched[i]].infar = 0;
     }
     __syncthreads();
   }
@@ -841,6 +846,20 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
     atomicAdd(&ctr->tree_expanded, c_expanded);
   }
   if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&ctr->tree_jobs, (unsigned long long)n_jobs);
+  if (threadIdx.x == 0 && c_iters) {
+    atomicAdd(&ctr->tree_iters, c_iters);
+    atomicAdd(&ctr->tree_far_visits, c_far);
+  }
+}
+
+__global__ void k_init_noderecs(NodeRec* __restrict__ p, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    NodeRec r;
+    r.dist = kInfBits;
+    r.stamp = 0;
+    r.infar = 0;
+    p[i] = r;
+  }
 }
 
 // Pointer walk over the cached trees: route of every query into the arena.

@@ -326,10 +326,10 @@ class Engine:
 
     def tree_stats(self, reset=True):
         ms = C.c_double(0)
-        v = [C.c_int64(0) for _ in range(5)]
+        v = [C.c_int64(0) for _ in range(7)]
         _capi.check(self._lib.drift_tree_stats(self._h, C.byref(ms), *[C.byref(x) for x in v], int(bool(reset))))
         return dict(build_ms=ms.value, launches=v[0].value, trees=v[1].value, edges_relaxed=v[2].value,
-                    improved=v[3].value, nodes_expanded=v[4].value)
+                    improved=v[3].value, nodes_expanded=v[4].value, waves=v[5].value, far_visits=v[6].value)
 
     def set_landmarks(self, K=8, seed=0):
         """Pick K far-apart landmarks and upload their free-flow distance arrays (host: scipy Dijkstra, a

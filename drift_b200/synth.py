@@ -37,7 +37,20 @@ def grid_graph(nx_cols, ny_rows, seed=0, len_lo=50.0, len_hi=300.0, speed_kph=50
     return from_links(V, u, v, length, np.full(L, float(speed_kph)), np.full(L, float(lanes)), pos=pos)
 
 
-def road_graph(num_nodes, seed=0, mean_degree=2.6) -> LoweredGraph:
+def _morton(x, y):
+    """Z-order code of 16-bit lattice coordinates: neighbouring nodes get nearby numbers, so the
+    per-node arrays the router and the tick kernels gather from are touched a sector at a time."""
+    def spread(v):
+        v = v.astype(np.uint64) & np.uint64(0xFFFF)
+        v = (v | (v << np.uint64(8))) & np.uint64(0x00FF00FF)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x0F0F0F0F)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x33333333)
+        v = (v | (v << np.uint64(1))) & np.uint64(0x55555555)
+        return v
+    return spread(x) | (spread(y) << np.uint64(1))
+
+
+def road_graph(num_nodes, seed=0, mean_degree=2.6, morton=True) -> LoweredGraph:
     """Planar random road network (configs 2/3): nodes on a jittered lattice, lattice edges kept at
     random to reach the requested mean out-degree, both directions, largest connected component
     kept.  Lengths LogNormal(ln 90 m, 0.6) clipped to [10, 2000] (continuous => unique shortest
@@ -61,7 +74,14 @@ def road_graph(num_nodes, seed=0, mean_degree=2.6) -> LoweredGraph:
     _, lab = connected_components(adj, directed=False)
     big = np.argmax(np.bincount(lab))
     keep = lab == big
-    new_id = np.cumsum(keep) - 1
+    if morton:  # number the kept nodes along a Z-order curve instead of row by row
+        kept = np.nonzero(keep)[0]
+        rank = np.empty(len(kept), dtype=np.int64)
+        rank[np.argsort(_morton(col[kept], row[kept]), kind="stable")] = np.arange(len(kept))
+        new_id = np.full(V0, -1, dtype=np.int64)
+        new_id[kept] = rank
+    else:
+        new_id = np.cumsum(keep) - 1
     und = und[keep[und[:, 0]] & keep[und[:, 1]]]
     und = np.stack([new_id[und[:, 0]], new_id[und[:, 1]]], axis=1)
     V = int(keep.sum())
@@ -73,5 +93,8 @@ def road_graph(num_nodes, seed=0, mean_degree=2.6) -> LoweredGraph:
     length = np.clip(rng.lognormal(np.log(90.0), 0.6, size=L), 10.0, 2000.0)
     speed = rng.choice([30.0, 50.0, 70.0, 90.0], size=L, p=[0.5, 0.3, 0.15, 0.05])
     lanes = rng.choice([1.0, 2.0, 3.0], size=L, p=[0.6, 0.3, 0.1])
-    pos = np.stack([col[keep] + rng.uniform(-0.3, 0.3, V), row[keep] + rng.uniform(-0.3, 0.3, V)], axis=1)
+    pos = np.empty((V, 2))
+    kept = np.nonzero(keep)[0]
+    pos[new_id[kept], 0] = col[kept] + rng.uniform(-0.3, 0.3, V)
+    pos[new_id[kept], 1] = row[kept] + rng.uniform(-0.3, 0.3, V)
     return from_links(V, u, v, length, speed, lanes, pos=pos)

@@ -230,7 +230,7 @@ int drift_phase_times(drift_engine* e, double* advance_ns, double* inject_ns, do
 /* Work and time of the batched tree builder since the last reset (needs option "time_plan" = 1 for
  * the CUDA-event time): trees built, edges relaxed, relaxations that improved a label, nodes expanded. */
 int drift_tree_stats(drift_engine* e, double* build_ms, int64_t* launches, int64_t* jobs, int64_t* relaxed,
-                     int64_t* improved, int64_t* expanded, int32_t reset);
+                     int64_t* improved, int64_t* expanded, int64_t* iters, int64_t* far_visits, int32_t reset);
 /* Landmark distances for goal-directed bounded searches in the batched router (ALT): K landmarks,
  * dist_from[K][V] = free-flow travel time landmark -> node, dist_to[K][V] = node -> landmark (+inf where
  * unreachable).  Only used while routing on the static travel times.  K = 0 switches it off. */
