@@ -555,6 +555,8 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
                                                               const double* __restrict__ link_cost, Landmarks lm) {
   __shared__ int s_job, s_near_n, s_next_n, s_far_n, s_far2_n, s_done, s_touched, s_lmk[2], s_lmdir[2];
   __shared__ double s_lmref[2];
+  __shared__ int s_e0[kTreeThreadsMax], s_off[kTreeThreadsMax], s_wsum[32];
+  __shared__ double s_dv[kTreeThreadsMax];
   __shared__ int s_bsrc[kMaxBounded], s_bq[kMaxBounded];
   __shared__ unsigned long long s_min;
   const int64_t V = g.V;
@@ -705,15 +707,55 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
       }
       ++iter;
       if (threadIdx.x == 0) ++c_iters;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int32_t v = nearA[i];
-        const double dv = __longlong_as_double((long long)rec[v].dist);
-        const int32_t e1 = g.bwd_rowptr[v + 1];
-        ++c_expanded;
-        c_relaxed += (unsigned long long)(e1 - g.bwd_rowptr[v]);
-        for (int32_t e = g.bwd_rowptr[v]; e < e1; ++e) {
+      // Edge-parallel expansion: the block loads a chunk of frontier nodes, scans their degrees and
+      // then every thread relaxes ONE edge, so the dependent-load chain of a wave does not grow with
+      // the degree (a wave of a road network holds few nodes: latency, not bandwidth, is the cost).
+      for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        int deg = 0;
+        if (i < n) {
+          const int32_t v = nearA[i];
+          const int32_t e0 = g.bwd_rowptr[v];
+          deg = g.bwd_rowptr[v + 1] - e0;
+          s_e0[threadIdx.x] = e0;
+          s_dv[threadIdx.x] = __longlong_as_double((long long)rec[v].dist);
+          ++c_expanded;
+          c_relaxed += (unsigned long long)deg;
+        }
+        // block-wide exclusive scan of the degrees
+        int incl = deg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int x = __shfl_up_sync(0xffffffffu, incl, o);
+          if ((threadIdx.x & 31) >= o) incl += x;
+        }
+        if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+          const int nw = (blockDim.x + 31) >> 5;
+          int wv = threadIdx.x < nw ? s_wsum[threadIdx.x] : 0;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, wv, o);
+            if (threadIdx.x >= o) wv += x;
+          }
+          s_wsum[threadIdx.x] = wv;  // inclusive warp totals
+        }
+        __syncthreads();
+        const int wbase = (threadIdx.x >> 5) ? s_wsum[(threadIdx.x >> 5) - 1] : 0;
+        s_off[threadIdx.x] = wbase + incl - deg;
+        const int total = s_wsum[((blockDim.x + 31) >> 5) - 1];
+        const int cnt = min((int)blockDim.x, n - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < total; k += blockDim.x) {
+          int lo = 0, hi = cnt - 1;  // owner j: largest j with s_off[j] <= k
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_off[mid] <= k) lo = mid; else hi = mid - 1;
+          }
+          const int32_t e = s_e0[lo] + (k - s_off[lo]);
           const int32_t u = g.bwd_col[e];
-          const double cand = __dadd_rn(dv, w_bwd[e]);
+          const double cand = __dadd_rn(s_dv[lo], w_bwd[e]);
           const unsigned long long cb = (unsigned long long)__double_as_longlong(cand);
           const unsigned long long old = atomicMin(&rec[u].dist, cb);
           if (cb < old) {
@@ -726,6 +768,7 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
             }
           }
         }
+        __syncthreads();  // s_e0 / s_dv / s_off are reused by the next chunk
       }
       __syncthreads();
       if (threadIdx.x == 0) {
