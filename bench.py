@@ -361,7 +361,10 @@ def run_b200(args):
     peak, peak_src = peaks()
     achieved = alg_bytes / (adv_ms * 1e-3) / 1e9 if adv_ms > 0 else 0.0
     roof_adv = dict(bound="hbm", kernel="k_advance (standalone launch, CUDA events on the engine stream)",
-                    achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                    achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                    traffic=43.5e6 if (args.workload == "regional1m" and not args.agents) else None,
+                    traffic_source="dram__bytes_read+write per launch, ncu --set full capture of this kernel on this "
+                                   "workload at 43 % moving (profiles/r1_k_advance_set_full_raw.csv)",
                     peak_source=peak_src, us_per_launch=adv_ms * 1e3, moving_agents=moving,
                     algorithmic_bytes_per_launch=alg_bytes,
                     note="1 B per waiting + 33 B per moving agent-step (SURVEY.md 8d); at this size the kernel is "
