@@ -235,6 +235,10 @@ def run_b200(args):
         eng = sharded.engine
     else:
         eng = Engine(lg, n_local, device=local_rank, agent_base=0, route_arena_links=max(1 << 24, n_local * 1536))
+        bench_stream = torch.cuda.Stream(device=local_rank)  # the engine launches here, so torch events see its kernels
+        eng.set_stream(bench_stream.cuda_stream)
+    if sharded is not None:
+        bench_stream = torch.cuda.current_stream(local_rank)
     # HBM-resident pass: candidate destinations of all warm-up + timed steps uploaded once
     total_steps = W + K
     _, dst_all = make_chains(model, rng, lg, start, 4 + trips_per_step * total_steps)
@@ -294,11 +298,12 @@ def run_b200(args):
     eng.tree_stats(reset=True)
     with ClockSampler(local_rank) as clk:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
+        ev0.record(bench_stream)
         for _ in range(K):
             run_block()
+        ev1.record(bench_stream)
         barrier()
-        dt = time.perf_counter() - t0
+        dt = ev0.elapsed_time(ev1) * 1e-3  # device time on the engine's stream, host planning gaps included
     st1 = eng.stats()
     phases = eng.phase_times(reset=True)
     trees = eng.tree_stats(reset=True)
@@ -327,7 +332,7 @@ def run_b200(args):
     run_block(False)  # warm the per-step path
     eng.drain_arrivals(), eng.drain_departures(), eng.occupancy()
     barrier()
-    t0 = time.perf_counter()
+    ev0.record(bench_stream)
     for b in range(K):
         eng.push_trips(blocks_p[b])
         run_block(False)
@@ -335,8 +340,9 @@ def run_b200(args):
         d = eng.drain_departures()
         occ = eng.occupancy()
         d2h_total += sum(x.nbytes for x in a) + sum(x.nbytes for x in d) + occ.nbytes
+    ev1.record(bench_stream)
     barrier()
-    dt_e2e = time.perf_counter() - t0
+    dt_e2e = ev0.elapsed_time(ev1) * 1e-3
     if dist is not None:
         tt = torch.tensor([dt_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -420,7 +426,8 @@ def run_b200(args):
             moving_fraction=float(moving / n_local),
             e2e=dict(value=e2e_value, unit="agent-steps/s", h2d_bytes_per_step=int(h2d),
                      d2h_bytes_per_step=int(d2h_total / K), ms_per_step=1e3 * dt_e2e / K),
-            gpu_launches=int(launches), roofline=roof, roofline_advance=roof_adv, roofline_advance_saturated=sat,
+            gpu_launches=int(launches), router_stats={k: (round(v, 3) if isinstance(v, float) else v) for k, v in trees.items()},
+            roofline=roof, roofline_advance=roof_adv, roofline_advance_saturated=sat,
             clocks=clk.summary(),
             phases=dict(note="timed region: per-tick phase times of the persistent kernel (%globaltimer, barriers "
                              "included) and total ms in route-planning batches",

@@ -144,7 +144,10 @@ struct drift_engine {
   DevBuf<int32_t> tw_lists;
   DevBuf<uint32_t> tw_iter;
   int32_t tw_jobs = 0;             // concurrent warp searches
-  bool warp_search = true;
+  bool warp_search = false;  // measured slower than one block per search (profiles/r1_summary.md)
+  int32_t t_sides = 2;       // 2 = trees out of hot sources as well as into hot destinations
+  DevBuf<int32_t> t_cnt;
+  DevBuf<uint8_t> t_q_side;
   int64_t warp_scratch_bytes = (int64_t)40 << 30;
   DevBuf<uint32_t> t_iter, t_slot_stamp;
   DevBuf<int32_t> t_slot_owner, t_slot_job, t_job_qhead, t_job_cnt, t_q_next;
@@ -349,13 +352,14 @@ int ensure_qcap(drift_engine* e, int64_t Q) {
 int ensure_trees(drift_engine* e) {
   if (e->t_max_slots) return DRIFT_OK;
   const int64_t V = e->V;
-  int64_t slots = std::min<int64_t>(V, e->tree_budget_bytes / (4 * V));
+  int64_t slots = std::min<int64_t>(e->t_sides * V, e->tree_budget_bytes / (4 * V));
   slots = std::max<int64_t>(slots, 1);
   // resident builder blocks: 32 B of scratch per node each
   int64_t blocks = std::min<int64_t>((int64_t)e->num_sms * std::min(32, 2048 / e->t_threads), e->tree_scratch_bytes / (36 * V));
   blocks = std::max<int64_t>(blocks, 1);
-  CU(e->t_slot_of.alloc(V, false));
-  CU(cudaMemset(e->t_slot_of.p, 0xff, sizeof(int32_t) * V));
+  CU(e->t_slot_of.alloc(2 * V, false));  // keys: destination t, or V + source s
+  CU(cudaMemset(e->t_slot_of.p, 0xff, sizeof(int32_t) * 2 * V));
+  CU(e->t_cnt.alloc(2 * V, true));
   CU(e->t_next.alloc(slots * V, false));
   CU(e->t_slot_owner.alloc(slots, false));
   CU(cudaMemset(e->t_slot_owner.p, 0xff, sizeof(int32_t) * slots));
@@ -389,7 +393,7 @@ int ensure_trees(drift_engine* e) {
 
 int invalidate_trees(drift_engine* e) {
   if (!e->t_max_slots) return DRIFT_OK;
-  CU(cudaMemsetAsync(e->t_slot_of.p, 0xff, sizeof(int32_t) * e->V, e->stream));
+  CU(cudaMemsetAsync(e->t_slot_of.p, 0xff, sizeof(int32_t) * 2 * e->V, e->stream));
   CU(cudaMemsetAsync(e->t_slot_owner.p, 0xff, sizeof(int32_t) * e->t_max_slots, e->stream));
   CU(cudaMemsetAsync(e->t_ctl.p, 0, 4 * sizeof(int32_t), e->stream));
   return DRIFT_OK;
@@ -423,7 +427,11 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     if (e->t_q_next.n < Q + q0) {
       CU(cudaStreamSynchronize(e->stream));
       CU(e->t_q_next.alloc(std::max<int64_t>(e->q_cap, Q + q0), false));
+      CU(e->t_q_side.alloc(std::max<int64_t>(e->q_cap, Q + q0), false));
     }
+    tc.cnt = e->t_cnt.p;
+    tc.q_side = e->t_q_side.p;
+    tc.V = e->V;
     tc.slot_job = e->t_slot_job.p;
     tc.slot_job_batch = e->t_slot_job_batch.p;
     tc.job_qhead = e->t_job_qhead.p;
@@ -432,6 +440,8 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     // automatic: full trees only pay off when they can all stay cached and the weights do not change
     tc.bounded_max = e->t_bounded_max >= 0 ? e->t_bounded_max
                                            : ((e->t_max_slots >= e->V && !use_congested) ? 0 : kMaxBounded);
+    // with full trees only, every key of a batch needs a slot: source-side keys only if all 2V fit
+    tc.sides = (tc.bounded_max == 0 && e->t_max_slots < 2 * e->V) ? 1 : e->t_sides;
     CU(cudaMemsetAsync(out.status, 0xff, sizeof(int32_t) * Q, e->stream));  // -1 = not answered yet
     tc.n_jobs = e->t_ctl.p + 1;
     tc.job_cursor = e->t_ctl.p + 2;
@@ -444,13 +454,14 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     ts.iter = e->t_iter.p;
     CU(cudaMemsetAsync(e->t_ctl.p + 1, 0, 3 * sizeof(int32_t), e->stream));
     const int gq = grid_for(Q, 256, kSMs * 4);
-    k_tree_hits<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, n_dev);
-    k_tree_requests<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, e->ctr.p, n_dev);
+    k_tree_count<<<gq, 256, 0, e->stream>>>(Q, qs, qd, tc, n_dev);
+    k_tree_hits<<<gq, 256, 0, e->stream>>>(Q, qs, qd, tc, n_dev);
+    k_tree_requests<<<gq, 256, 0, e->stream>>>(Q, qs, qd, tc, e->ctr.p, n_dev);
     Landmarks lm;
     lm.from = e->lm_from.p;
     lm.to = e->lm_to.p;
     lm.K = use_congested ? 0 : e->lm_K;  // the landmark distances are free-flow distances
-    k_link_queries<<<gq, 256, 0, e->stream>>>(Q, qd, e->V, tc, n_dev);
+    k_link_queries<<<gq, 256, 0, e->stream>>>(Q, qs, qd, tc, n_dev);
     cudaEvent_t tb0 = nullptr, tb1 = nullptr;
     if (e->time_plan) {
       cudaEventCreate(&tb0);
@@ -477,7 +488,7 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     k_extract_paths<<<gq, 256, 0, e->stream>>>(e->graph(), Q, n_dev, qs, qd, tc, e->arena.p,
                                                 (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
     CU(cudaGetLastError());
-    e->total_launches += use_warp ? 6 : 5;
+    e->total_launches += use_warp ? 7 : 6;
     return DRIFT_OK;
   }
   int rc = ensure_router(e, Q);
@@ -1586,6 +1597,9 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
     e->route_window = (int32_t)value;
   } else if (s == "replan") {
     e->ticks_since_plan = 0;
+  } else if (s == "tree_sides") {
+    if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_sides must be set before the first batched route");
+    e->t_sides = value >= 2 ? 2 : 1;
   } else if (s == "warp_search") {
     if (e->t_max_slots) return fail(DRIFT_ESTATE, "warp_search must be set before the first batched route");
     e->warp_search = value != 0;

@@ -463,6 +463,13 @@ struct TreeCache {
   int32_t* job_cnt;         // [max_slots] queries on that list
   int32_t* q_next;          // [Q]
   int32_t bounded_max;      // jobs with <= this many queries search only until their sources are settled (0 = off)
+  // Trees hang off either end of a trip: key t in [0, V) = reverse tree towards destination t, key
+  // V + s = forward tree out of source s (return legs to scattered targets leave from few places:
+  // depots, hubs, activity pools -- lib/st_selection.py).  cnt[key] = queries of this batch per key.
+  int32_t* cnt;             // [2V], zero between batches
+  uint8_t* q_side;          // [Q] 0 = answered from the destination's tree, 1 = from the source's
+  int32_t V;
+  int32_t sides;            // 1 = destination trees only, 2 = both
 };
 
 constexpr int kMaxBounded = 8;
@@ -470,26 +477,56 @@ constexpr int kMaxBounded = 8;
 constexpr unsigned long long kInfBits = 0x7FF0000000000000ULL;
 constexpr int kTreeThreadsMax = 1024;
 
-// Pass 1: destinations already cached pin their slot for this batch.
-__global__ void k_tree_hits(int64_t Q, const int32_t* __restrict__ dst, int32_t V, TreeCache tc,
-                            const int32_t* __restrict__ n_dev) {
+__device__ __forceinline__ bool tree_query_ok(int32_t s, int32_t t, int32_t V) {
+  return s >= 0 && t >= 0 && s < V && t < V && s != t;
+}
+
+// Pass 0: how many queries of this batch share each destination / each source.
+__global__ void k_tree_count(int64_t Q, const int32_t* __restrict__ src, const int32_t* __restrict__ dst, TreeCache tc,
+                             const int32_t* __restrict__ n_dev) {
   const int64_t n = n_dev ? (int64_t)*n_dev : Q;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
-    const int32_t t = dst[q];
-    if (t < 0 || t >= V) continue;
-    const int32_t s = tc.slot_of[t];
-    if (s >= 0) tc.slot_stamp[s] = tc.batch;
+    const int32_t s = src[q], t = dst[q];
+    if (!tree_query_ok(s, t, tc.V)) continue;
+    atomicAdd(&tc.cnt[t], 1);
+    if (tc.sides > 1) atomicAdd(&tc.cnt[tc.V + s], 1);
   }
 }
 
-// Pass 2: every other destination gets a slot from the FIFO ring (evicting the oldest tree that is
-// not used by this batch) and becomes a build job.
-__global__ void k_tree_requests(int64_t Q, const int32_t* __restrict__ dst, int32_t V, TreeCache tc, Counters* ctr,
-                                const int32_t* __restrict__ n_dev) {
+// Pass 1: choose the end of the trip whose tree answers the query -- a cached tree first (it pins its
+// slot for this batch), else the end shared by more queries of the batch.
+__global__ void k_tree_hits(int64_t Q, const int32_t* __restrict__ src, const int32_t* __restrict__ dst, TreeCache tc,
+                            const int32_t* __restrict__ n_dev) {
   const int64_t n = n_dev ? (int64_t)*n_dev : Q;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
-    const int32_t t = dst[q];
-    if (t < 0 || t >= V) continue;
+    const int32_t s = src[q], t = dst[q];
+    tc.q_side[q] = 0;
+    if (!tree_query_ok(s, t, tc.V)) continue;
+    int32_t slot = tc.slot_of[t];
+    if (slot >= 0) {
+      tc.slot_stamp[slot] = tc.batch;
+      continue;
+    }
+    if (tc.sides < 2) continue;
+    slot = tc.slot_of[tc.V + s];
+    if (slot >= 0) {
+      tc.slot_stamp[slot] = tc.batch;
+      tc.q_side[q] = 1;
+      continue;
+    }
+    const int32_t cs = tc.cnt[tc.V + s], cd = tc.cnt[t];
+    if (cs > cd && cs > tc.bounded_max) tc.q_side[q] = 1;
+  }
+}
+
+// Pass 2: every other key gets a slot from the FIFO ring (evicting the oldest tree that is not used
+// by this batch) and becomes a build job.
+__global__ void k_tree_requests(int64_t Q, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                TreeCache tc, Counters* ctr, const int32_t* __restrict__ n_dev) {
+  const int64_t n = n_dev ? (int64_t)*n_dev : Q;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    if (!tree_query_ok(src[q], dst[q], tc.V)) continue;
+    const int32_t t = tc.q_side[q] ? tc.V + src[q] : dst[q];
     if (atomicCAS(&tc.slot_of[t], -1, -2) != -1) continue;  // cached, or another thread is allocating it
     int32_t s = -1;
     for (int tries = 0; tries < tc.max_slots; ++tries) {
@@ -499,13 +536,13 @@ __global__ void k_tree_requests(int64_t Q, const int32_t* __restrict__ dst, int3
         break;
       }
     }
-    if (s < 0) {  // more distinct destinations in one batch than slots
+    if (s < 0) {  // more distinct keys in one batch than slots
       tc.slot_of[t] = -1;
       atomicOr(&ctr->overflow, kOvfStage);
       continue;
     }
     const int32_t old = tc.slot_owner[s];
-    if (old >= 0) tc.slot_of[old] = -1;  // evicted (old != any destination of this batch: its slot is stamped)
+    if (old >= 0) tc.slot_of[old] = -1;  // evicted (old != any key of this batch: its slot is stamped)
     tc.slot_owner[s] = t;
     const int32_t j = atomicAdd(tc.n_jobs, 1);
     tc.job_dst[j] = t;
@@ -518,13 +555,16 @@ __global__ void k_tree_requests(int64_t Q, const int32_t* __restrict__ dst, int3
   }
 }
 
-// Pass 3: hang every query whose destination is being built in this batch on that job's list.
-__global__ void k_link_queries(int64_t Q, const int32_t* __restrict__ dst, int32_t V, TreeCache tc,
-                               const int32_t* __restrict__ n_dev) {
+// Pass 3: hang every query whose tree is being built in this batch on that job's list; leave cnt[]
+// zero for the next batch.
+__global__ void k_link_queries(int64_t Q, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                               TreeCache tc, const int32_t* __restrict__ n_dev) {
   const int64_t n = n_dev ? (int64_t)*n_dev : Q;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
-    const int32_t t = dst[q];
-    if (t < 0 || t >= V) continue;
+    if (!tree_query_ok(src[q], dst[q], tc.V)) continue;
+    tc.cnt[dst[q]] = 0;
+    if (tc.sides > 1) tc.cnt[tc.V + src[q]] = 0;
+    const int32_t t = tc.q_side[q] ? tc.V + src[q] : dst[q];
     const int32_t s = tc.slot_of[t];
     if (s < 0 || tc.slot_job_batch[s] != tc.batch) continue;
     const int32_t j = tc.slot_job[s];
@@ -578,10 +618,15 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
     const int job = s_job;
     __syncthreads();
     if (job >= n_jobs) break;
-    const int32_t dest = tc.job_dst[job];
+    const int32_t key = tc.job_dst[job];
+    const bool out_tree = key >= g.V;  // forward tree out of a source: expand along forward entries
+    const int32_t dest = out_tree ? key - g.V : key;
+    const int32_t* __restrict__ x_rowptr = out_tree ? g.fwd_rowptr : g.bwd_rowptr;
+    const int32_t* __restrict__ x_col = out_tree ? g.fwd_col : g.bwd_col;
+    const double* __restrict__ x_w = out_tree ? w_fwd : w_bwd;
     int32_t* next_link = tc.next_link + (int64_t)tc.job_slot[job] * V;
     const int nb = tc.job_cnt[job];
-    const bool bounded = nb > 0 && nb <= tc.bounded_max;
+    const bool bounded = !out_tree && nb > 0 && nb <= tc.bounded_max;
     if (bounded && skip_bounded) continue;  // k_search_warp takes it
     if (threadIdx.x == 0) ++c_jobs;
     if (bounded && threadIdx.x == 0) {
@@ -718,8 +763,8 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
         int deg = 0;
         if (i < n) {
           const int32_t v = nearA[i];
-          const int32_t e0 = g.bwd_rowptr[v];
-          deg = g.bwd_rowptr[v + 1] - e0;
+          const int32_t e0 = x_rowptr[v];
+          deg = x_rowptr[v + 1] - e0;
           s_e0[threadIdx.x] = e0;
           s_dv[threadIdx.x] = __longlong_as_double((long long)rec[v].dist);
           ++c_expanded;
@@ -757,8 +802,8 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
             if (s_off[mid] <= k) lo = mid; else hi = mid - 1;
           }
           const int32_t e = s_e0[lo] + (k - s_off[lo]);
-          const int32_t u = g.bwd_col[e];
-          const double cand = __dadd_rn(s_dv[lo], w_bwd[e]);
+          const int32_t u = x_col[e];
+          const double cand = __dadd_rn(s_dv[lo], x_w[e]);
           const unsigned long long cb = (unsigned long long)__double_as_longlong(cand);
           const unsigned long long old = atomicMin(&rec[u].dist, cb);
           if (cb < old) {
@@ -855,23 +900,30 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
       __syncthreads();
       continue;
     }
-    // first link of the shortest path u -> dest: first forward entry (CSR order) that attains rec[u].dist
-    for (int64_t u = threadIdx.x; u < V; u += blockDim.x) {
-      int32_t nl = -1;
-      const unsigned long long du = rec[u].dist;
-      if (u != dest && du != kInfBits) {
-        const int32_t e1 = g.fwd_rowptr[u + 1];
-        for (int32_t e = g.fwd_rowptr[u]; e < e1; ++e) {
-          const unsigned long long dvb = rec[g.fwd_col[e]].dist;
-          if (dvb == kInfBits) continue;
-          const double c = __dadd_rn(__longlong_as_double((long long)dvb), w_fwd[e]);
-          if ((unsigned long long)__double_as_longlong(c) == du) {
-            nl = g.fwd_link[e];
-            break;
+    // reverse tree: first link of the shortest path u -> dest = first forward entry (CSR order) that
+    // attains rec[u].dist; forward tree: last link of the shortest path dest -> u = first backward entry
+    {
+      const int32_t* __restrict__ y_rowptr = out_tree ? g.bwd_rowptr : g.fwd_rowptr;
+      const int32_t* __restrict__ y_col = out_tree ? g.bwd_col : g.fwd_col;
+      const double* __restrict__ y_w = out_tree ? w_bwd : w_fwd;
+      const int32_t* __restrict__ y_link = out_tree ? g.bwd_link : g.fwd_link;
+      for (int64_t u = threadIdx.x; u < V; u += blockDim.x) {
+        int32_t nl = -1;
+        const unsigned long long du = rec[u].dist;
+        if (u != dest && du != kInfBits) {
+          const int32_t e1 = y_rowptr[u + 1];
+          for (int32_t e = y_rowptr[u]; e < e1; ++e) {
+            const unsigned long long dvb = rec[y_col[e]].dist;
+            if (dvb == kInfBits) continue;
+            const double c = __dadd_rn(__longlong_as_double((long long)dvb), y_w[e]);
+            if ((unsigned long long)__double_as_longlong(c) == du) {
+              nl = y_link[e];
+              break;
+            }
           }
         }
+        next_link[u] = nl;
       }
-      next_link[u] = nl;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < s_touched; i += blockDim.x) {
@@ -949,7 +1001,7 @@ __global__ void __launch_bounds__(kWarpSearchThreads) k_search_warp(
     job = __shfl_sync(0xffffffffu, job, 0);
     if (job >= n_jobs) break;
     const int nb = tc.job_cnt[job];
-    if (!(nb > 0 && nb <= tc.bounded_max)) continue;  // keeps a tree: k_build_trees
+    if (!(nb > 0 && nb <= tc.bounded_max) || tc.job_dst[job] >= g.V) continue;  // keeps a tree: k_build_trees
     ++c_jobs;
     const int32_t dest = tc.job_dst[job];
     // lane k < nb holds query k of the job
@@ -1226,7 +1278,9 @@ __global__ void __launch_bounds__(kWarpSearchThreads) k_search_warp(
   }
 }
 
-// Pointer walk over the cached trees: route of every query into the arena.
+// Pointer walk over the cached trees: route of every query into the arena.  A reverse tree is walked
+// from the source (links come out in travel order), a forward tree from the destination back to the
+// source (links are written back to front); the cost is always summed in travel order.
 __global__ void k_extract_paths(GraphArrays g, int64_t Q, const int32_t* __restrict__ n_dev,
                                 const int32_t* __restrict__ src, const int32_t* __restrict__ dst, TreeCache tc,
                                 int32_t* __restrict__ arena, unsigned long long arena_cap, Counters* ctr,
@@ -1246,22 +1300,25 @@ __global__ void k_extract_paths(GraphArrays g, int64_t Q, const int32_t* __restr
       out.status[q] = DRIFT_ROUTE_TRIVIAL;
       continue;
     }
-    const int32_t slot = tc.slot_of[t];
+    const bool out_tree = tc.q_side[q] != 0;
+    const int32_t slot = tc.slot_of[out_tree ? g.V + s : t];
     if (slot < 0) {
       out.status[q] = DRIFT_ROUTE_NOPATH;
       continue;
     }
     const int32_t* next_link = tc.next_link + (int64_t)slot * g.V;
+    const int32_t* step_to = out_tree ? g.link_u : g.link_v;
+    const int32_t from = out_tree ? t : s, to = out_tree ? s : t;
     int hops = 0;
-    int32_t x = s;
-    while (x != t) {
+    int32_t x = from;
+    while (x != to) {
       const int32_t l = next_link[x];
       if (l < 0 || hops > g.V) {
         hops = -1;
         break;
       }
       ++hops;
-      x = g.link_v[l];
+      x = step_to[l];
     }
     if (hops < 0) {
       out.status[q] = DRIFT_ROUTE_NOPATH;
@@ -1274,12 +1331,21 @@ __global__ void k_extract_paths(GraphArrays g, int64_t Q, const int32_t* __restr
       continue;
     }
     double c = 0.0;
-    x = s;
-    for (int k = 0; k < hops; ++k) {
-      const int32_t l = next_link[x];
-      arena[off + k] = l;
-      c = __dadd_rn(c, link_cost[l]);
-      x = g.link_v[l];
+    x = from;
+    if (!out_tree) {
+      for (int k = 0; k < hops; ++k) {
+        const int32_t l = next_link[x];
+        arena[off + k] = l;
+        c = __dadd_rn(c, link_cost[l]);
+        x = g.link_v[l];
+      }
+    } else {
+      for (int k = hops - 1; k >= 0; --k) {
+        const int32_t l = next_link[x];
+        arena[off + k] = l;
+        x = g.link_u[l];
+      }
+      for (int k = 0; k < hops; ++k) c = __dadd_rn(c, link_cost[arena[off + k]]);
     }
     out.status[q] = DRIFT_ROUTE_OK;
     out.n_links[q] = hops;

@@ -260,3 +260,47 @@ def test_batched_router_cold_destinations(bounded_max, landmarks):
                 for l in links[q]:
                     c += lg.link_t0[l]
                 assert costs[q] == c
+
+
+@pytest.mark.parametrize("sides", [1, 2])
+def test_batched_router_hot_sources(sides):
+    """Return legs leave a few places (depots, hubs) for scattered targets: the batched router then
+    builds a forward tree out of the source and walks it back from each destination.  Same routes
+    as NetworkX on a unique-path graph, incl. mixed batches and the cache hits of a second batch."""
+    import networkx as nx
+    from drift_b200.engine import Engine, ROUTE_OK, ROUTE_TRIVIAL, ROUTE_NOPATH, ROUTER_BATCHED
+    from drift_b200.graph import lower_graph
+
+    G = _unique_path_graph(31, n=500, m=1400)
+    lg = lower_graph(G)
+    nodes = list(G.nodes)
+    rng = random.Random(5)
+    depots = [3, 77, 402]
+    pools = [10, 11, 250]
+    pairs = [(rng.choice(depots), rng.randrange(500)) for _ in range(900)]       # hot source, cold target
+    pairs += [(rng.randrange(500), rng.choice(pools)) for _ in range(900)]       # cold source, hot target
+    pairs += [(rng.choice(depots), rng.choice(pools)) for _ in range(100)]       # both hot
+    pairs += [(rng.randrange(500), rng.randrange(500)) for _ in range(300)]      # both cold
+    pairs += [(3, 3), (len(nodes) - 4, 3), (3, len(nodes) - 4)]
+    rng.shuffle(pairs)
+    with Engine(lg, 8, route_arena_links=1 << 23) as eng:
+        eng.set_option("tree_sides", sides)
+        eng.set_option("bounded_max", 8)
+        for rnd in range(2):
+            st, nl, links = eng.route([p[0] for p in pairs], [p[1] for p in pairs], router=ROUTER_BATCHED)
+            costs = eng.route_costs(len(pairs))
+            for q, ((s, t), stt) in enumerate(zip(pairs, st)):
+                if s == t:
+                    assert stt == ROUTE_TRIVIAL
+                    continue
+                try:
+                    want = nx.shortest_path(G, nodes[s], nodes[t], weight="travel_time")
+                except nx.NetworkXNoPath:
+                    assert stt == ROUTE_NOPATH, (q, s, t)
+                    continue
+                assert stt == ROUTE_OK, (q, s, t)
+                assert [nodes[i] for i in lg.links_to_nodes(s, links[q])] == want
+                c = 0.0
+                for l in links[q]:
+                    c += lg.link_t0[l]
+                assert costs[q] == c
