@@ -233,6 +233,8 @@ def run_b200(args):
 
         sharded = ShardedEngine(lg, n_local * world, device=local_rank, route_arena_links=max(1 << 24, n_local * 1536))
         eng = sharded.engine
+        if args.exchange == "p2p":
+            sharded.enable_p2p()
     else:
         eng = Engine(lg, n_local, device=local_rank, agent_base=0, route_arena_links=max(1 << 24, n_local * 1536))
         bench_stream = torch.cuda.Stream(device=local_rank)  # the engine launches here, so torch events see its kernels
@@ -330,7 +332,7 @@ def run_b200(args):
     d2h_total = 0
     eng.push_trips(blocks_p[K])
     run_block(False)  # warm the per-step path
-    eng.drain_arrivals(), eng.drain_departures(), eng.occupancy()
+    eng.drain_arrivals(), eng.drain_departures(), (sharded.occupancy() if sharded is not None else eng.occupancy())
     barrier()
     ev0.record(bench_stream)
     for b in range(K):
@@ -338,7 +340,7 @@ def run_b200(args):
         run_block(False)
         a = eng.drain_arrivals()
         d = eng.drain_departures()
-        occ = eng.occupancy()
+        occ = sharded.occupancy() if sharded is not None else eng.occupancy()
         d2h_total += sum(x.nbytes for x in a) + sum(x.nbytes for x in d) + occ.nbytes
     ev1.record(bench_stream)
     barrier()
@@ -419,8 +421,12 @@ def run_b200(args):
                            "and route arena (GBs, >> 126 MB L2) between tick blocks; the per-tick agent state (%.0f MB "
                            "hot) can stay L2-resident at this size, which is why roofline_advance_saturated uses 16 M "
                            "agents (400 MB of hot state)" % (n_local * 25 / 1e6),
-                        multi_gpu=("agents sharded by id block, graph replicated, per-tick all-gather of link events "
-                                   "(NCCL), every rank resolves the global event set") if world > 1 else "n/a"),
+                        multi_gpu=(("agents sharded by id block, graph replicated, links owned round-robin: events stored "
+                                    "into the owner's inbox and entry speeds into the home rank's arrays over NVLink peer "
+                                    "memory inside the persistent tick kernel (k_tick_loop_p2p), no collective call"
+                                    if args.exchange == "p2p" else
+                                    "agents sharded by id block, graph replicated, per-tick all-gather of link events "
+                                    "(NCCL), every rank resolves the global event set")) if world > 1 else "n/a"),
             routes_per_s=routes / dt, routes_in_timed_region=int(routes),
             reroutes_per_s=(reroutes_timed / dt) if reroute else None, reroutes_in_timed_region=int(reroutes_timed),
             moving_fraction=float(moving / n_local),
@@ -465,6 +471,8 @@ def main():
     ap.add_argument("--no-reroute", action="store_true", help="switch the periodic reroute extension off")
     ap.add_argument("--saturated-agents", type=int, default=16_000_000,
                     help="also time the advance kernel with this many agents all moving (0 = skip)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"],
+                    help="multi-GPU: link events over NVLink peer memory inside the tick kernel, or per-tick NCCL all-gather")
     ap.add_argument("--coop-blocks", type=int, default=0, help="blocks per SM of the persistent tick kernel (0 = default)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -82,6 +82,8 @@ SIGNATURES = {
     "drift_tick_begin_async": (C.c_int, [ENGINE, C.c_double, C.c_double, C.c_void_p, C.c_int32]),
     "drift_tick_finish_gathered": (C.c_int, [ENGINE, C.c_void_p, C.c_int32, C.c_int32]),
     "drift_max_events": (C.c_int, [ENGINE, c_i64p, C.c_int32]),
+    "drift_p2p_export": (C.c_int, [ENGINE, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+    "drift_p2p_connect": (C.c_int, [ENGINE, C.c_void_p]),
     "drift_kernel_times": (C.c_int, [ENGINE, c_f64p, c_i64p, c_f64p, c_i64p]),
     "drift_set_profiling": (C.c_int, [ENGINE, C.c_int32]),
     "drift_phase_times": (C.c_int, [ENGINE, c_f64p, c_f64p, c_f64p, c_f64p, c_i64p, C.c_int32]),

@@ -179,6 +179,13 @@ struct drift_engine {
   double hourly[24];
   DevBuf<int32_t> dep_req;
   int32_t demand_router = DRIFT_ROUTER_NX_EXACT;
+  // peer-memory exchange (k_tick_loop_p2p)
+  bool p2p_on = false;
+  P2PArgs p2p;
+  DevBuf<Event> p2p_inbox;
+  DevBuf<unsigned long long> p2p_flags;
+  DevBuf<int32_t> p2p_out_cnt;
+  std::vector<void*> p2p_opened;
   // counters
   DevBuf<Counters> ctr;
   Counters* h_ctr = nullptr;  // pinned
@@ -623,6 +630,22 @@ int run_tick_loop(drift_engine* e, int32_t n_ticks, double delta, bool demand, d
   const int64_t tiles = (e->N + (int64_t)kAdvThreads * kAdvPerThread - 1) / ((int64_t)kAdvThreads * kAdvPerThread);
   int blocks = e->num_sms * std::min(max_per_sm, e->coop_blocks_per_sm);
   if (tiles < blocks) blocks = (int)std::max<int64_t>(tiles, 1);
+  if (e->p2p_on) {
+    static int max_p2p = 0;
+    if (!max_p2p) {
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_p2p, k_tick_loop_p2p, kAdvThreads, 0));
+      if (max_p2p < 1) return fail(DRIFT_ECUDA, "k_tick_loop_p2p does not fit on an SM");
+    }
+    blocks = e->num_sms * std::min(max_p2p, e->coop_blocks_per_sm);
+    if (tiles < blocks) blocks = (int)std::max<int64_t>(tiles, 1);
+    void* xargs[] = {(void*)&p, (void*)&e->p2p, (void*)&tick0, (void*)&n_ticks, (void*)&p_dep};
+    CU(cudaLaunchCooperativeKernel((void*)k_tick_loop_p2p, dim3(blocks), dim3(kAdvThreads), xargs, 0, e->stream));
+    e->tick += n_ticks;
+    e->loop_ticks += n_ticks;
+    e->total_launches += 1;
+    e->adv_launches += n_ticks;
+    return DRIFT_OK;
+  }
   void* args[] = {(void*)&p, (void*)&tick0, (void*)&n_ticks, (void*)&p_dep};
   CU(cudaLaunchCooperativeKernel((void*)k_tick_loop, dim3(blocks), dim3(kAdvThreads), args, 0, e->stream));
   e->tick += n_ticks;
@@ -709,6 +732,8 @@ int drift_destroy(drift_engine* e) {
   if (!e) return DRIFT_OK;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  for (void* q : e->p2p_opened) cudaIpcCloseMemHandle(q);
+  e->p2p_opened.clear();
   for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   if (e->h_ctr) cudaFreeHost(e->h_ctr);
   if (e->stream && e->own_stream) cudaStreamDestroy(e->stream);
@@ -1067,7 +1092,7 @@ int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0) {
   if (!e->have_bpr) return fail(DRIFT_ESTATE, "drift_run: call drift_set_bpr first");
   CU(cudaSetDevice(e->device));
   double t = t0;
-  if (e->persistent && !e->profiling) {
+  if ((e->persistent && !e->profiling) || e->p2p_on) {
     // split into runs of ticks that share the departure probability and do not cross a planning boundary
     int32_t k = 0;
     while (k < n_ticks) {
@@ -1471,6 +1496,57 @@ int drift_tick_finish_gathered(drift_engine* e, void* recv_dev, int32_t world, i
   k_reset_counters<<<1, 32, 0, e->stream>>>(e->ctr.p, tick);
   CU(cudaGetLastError());
   e->total_launches += 3;
+  return DRIFT_OK;
+}
+
+int drift_p2p_export(drift_engine* e, int32_t rank, int32_t world, int64_t n_total, int32_t cap, void* handles_out) {
+  if (!e || !handles_out || world < 1 || world > kMaxRanks || rank < 0 || rank >= world || cap <= 0 || !e->N)
+    return fail(DRIFT_EINVAL, "drift_p2p_export: bad arguments (call drift_add_agents first; world <= %d)", kMaxRanks);
+  if (e->tick != 0) return fail(DRIFT_ESTATE, "drift_p2p_export: the exchange mode is fixed before the first tick");
+  CU(cudaSetDevice(e->device));
+  const int64_t base = n_total / world, rem = n_total % world;
+  if (e->N != base + (rank < rem ? 1 : 0) || (int64_t)e->agent_base != rank * base + std::min<int64_t>(rank, rem))
+    return fail(DRIFT_EINVAL, "drift_p2p_export: this engine does not hold rank %d's contiguous block of %lld agents",
+                rank, (long long)n_total);
+  CU(e->p2p_inbox.alloc((int64_t)world * cap, true));
+  CU(e->p2p_flags.alloc(std::max<int64_t>(2 * kMaxRanks, (2 << 20) / 8), true));
+  CU(e->p2p_out_cnt.alloc(kMaxRanks, true));
+  memset(&e->p2p, 0, sizeof(e->p2p));
+  e->p2p.rank = rank;
+  e->p2p.world = world;
+  e->p2p.cap = cap;
+  e->p2p.shard_base = (uint32_t)base;
+  e->p2p.shard_rem = (uint32_t)rem;
+  e->p2p.out_cnt = e->p2p_out_cnt.p;
+  e->p2p.inbox[rank] = e->p2p_inbox.p;
+  e->p2p.flags[rank] = e->p2p_flags.p;
+  e->p2p.speed[rank] = e->speed.p;
+  e->p2p.elen[rank] = e->elen.p;
+  cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)handles_out;
+  CU(cudaIpcGetMemHandle(&h[0], e->p2p_inbox.p));
+  CU(cudaIpcGetMemHandle(&h[1], e->p2p_flags.p));
+  CU(cudaIpcGetMemHandle(&h[2], e->speed.p));
+  CU(cudaIpcGetMemHandle(&h[3], e->elen.p));
+  return DRIFT_OK;
+}
+
+int drift_p2p_connect(drift_engine* e, const void* all_handles) {
+  if (!e || !all_handles || e->p2p.world < 1 || !e->p2p_inbox.p) return fail(DRIFT_ESTATE, "drift_p2p_connect: export first");
+  CU(cudaSetDevice(e->device));
+  const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)all_handles;
+  for (int r = 0; r < e->p2p.world; ++r) {
+    if (r == e->p2p.rank) continue;
+    void* ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 4; ++k) {
+      CU(cudaIpcOpenMemHandle(&ptr[k], h[r * 4 + k], cudaIpcMemLazyEnablePeerAccess));
+      e->p2p_opened.push_back(ptr[k]);
+    }
+    e->p2p.inbox[r] = (Event*)ptr[0];
+    e->p2p.flags[r] = (unsigned long long*)ptr[1];
+    e->p2p.speed[r] = (double*)ptr[2];
+    e->p2p.elen[r] = (double*)ptr[3];
+  }
+  e->p2p_on = true;
   return DRIFT_OK;
 }
 

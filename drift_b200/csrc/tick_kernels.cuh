@@ -112,6 +112,30 @@ struct AdvSmem {  // per-warp staging: warps do not wait for each other while th
   uint32_t agent[kAdvWarps][kStageCap];
 };
 
+// ---- multi-GPU over NVLink peer memory (k_tick_loop_p2p) -------------------------------------------
+// Links are owned round-robin (owner = link % world).  A rank writes every event of its agents straight
+// into the owner's inbox (peer store), the owner orders the events of its links and writes the entry
+// speed straight into the home rank's agent arrays: the exchange is part of the tick kernel, the work
+// per rank does not grow with the number of ranks, occupancy is held by the owner only.
+constexpr int kMaxRanks = 16;
+
+struct P2PArgs {
+  int32_t rank, world;
+  int32_t cap;                            // events one rank may send to one owner per tick
+  uint32_t shard_base, shard_rem;         // agents per rank: n_total / world (+1 for the first n_total % world ranks)
+  Event* inbox[kMaxRanks];                // inbox of every rank (peer-mapped): [world][cap], region r written by rank r
+  unsigned long long* flags[kMaxRanks];   // of every rank: [2][kMaxRanks]; row 0: tick << 32 | events sent by rank r,
+                                          // row 1: tick << 32 once rank r has resolved its links
+  double* speed[kMaxRanks];               // agent arrays of every rank
+  double* elen[kMaxRanks];
+  int32_t* out_cnt;                       // local [kMaxRanks]: events written to each owner in this tick
+};
+
+struct P2PSmem {
+  int ocnt[kMaxRanks], obase[kMaxRanks];
+  uint16_t idx[kAdvWarps][kStageCap];
+};
+
 __device__ __forceinline__ void stage_event(AdvSmem& sm, int32_t link, uint32_t agent, bool enter) {
   const int w = threadIdx.x >> 5;
   const int k = atomicAdd(&sm.n[w], 1);
@@ -120,13 +144,16 @@ __device__ __forceinline__ void stage_event(AdvSmem& sm, int32_t link, uint32_t 
 }
 
 // Agent crosses to the next link of its route or arrives (agent.py:200-203, 107-116).  Returns true on arrival.
-__device__ __noinline__ bool cross_agent(const TickArgs& p, int64_t i, int32_t tick, AdvSmem& sm) {
+__device__ __noinline__ bool cross_agent(const TickArgs& p, int64_t i, int32_t tick, AdvSmem& sm, bool own_next) {
   const AgentArrays& a = p.a;
   const int32_t old_link = a.cur_link[i], nl = a.next_link[i];
-  a.route_idx[i] += 1;
+  const int32_t ri = a.route_idx[i] + 1;
+  a.route_idx[i] = ri;
   stage_event(sm, old_link, a.base + (uint32_t)i, false);
-  if (nl >= 0) {  // next_link is refreshed in phase C when the enter event is resolved
+  if (nl >= 0) {  // next_link is refreshed in phase C when the enter event is resolved ...
     a.cur_link[i] = nl;
+    // ... unless the link is resolved on another GPU (k_tick_loop_p2p): then the home rank does it here
+    if (own_next) a.next_link[i] = ri + 1 < a.route_len[i] ? p.arena[a.route_off[i] + ri + 1] : -1;
     stage_event(sm, nl, a.base + (uint32_t)i, true);
     return false;
   }
@@ -142,7 +169,7 @@ __device__ __noinline__ bool cross_agent(const TickArgs& p, int64_t i, int32_t t
 }
 
 // Agent.start_new_journey (agent.py:46-104) with the prefetched route.  Returns true if the agent is now moving.
-__device__ __noinline__ bool depart_agent(const TickArgs& p, int64_t i, int cnt, int32_t tick, AdvSmem& sm) {
+__device__ __noinline__ bool depart_agent(const TickArgs& p, int64_t i, int cnt, int32_t tick, AdvSmem& sm, bool own_next) {
   const AgentArrays& a = p.a;
   Counters* ctr = p.ctr;
   const int32_t ns = a.next_status[i];
@@ -180,18 +207,21 @@ __device__ __noinline__ bool depart_agent(const TickArgs& p, int64_t i, int cnt,
   a.route_idx[i] = 0;
   a.dist[i] = 0.0;
   a.cur_link[i] = fl;
+  if (own_next) a.next_link[i] = nlen > 1 ? p.arena[noff + 1] : -1;
   stage_event(sm, fl, a.base + (uint32_t)i, true);
   return true;
 }
 
-template <bool DEMAND>
-__device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, double p_dep, AdvSmem& sm) {
+template <bool DEMAND, bool P2P = false>
+__device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, double p_dep, AdvSmem& sm,
+                                              const P2PArgs* x = nullptr, P2PSmem* xs = nullptr) {
   const AgentArrays& a = p.a;
   const int par = tick & 1;
   const int64_t tiles = (a.n + (int64_t)kAdvThreads * kAdvPerThread - 1) / ((int64_t)kAdvThreads * kAdvPerThread);
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     if (lane == 0) sm.n[w] = 0;
+    if (P2P && threadIdx.x < kMaxRanks) xs->ocnt[threadIdx.x] = 0;
     __syncwarp();
     const int64_t i0 = (tile * kAdvThreads + threadIdx.x) * kAdvPerThread;
     if (i0 < a.n) {
@@ -202,10 +232,15 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
       if (st4) {  // at least one of the four agents is moving
         const double2 d01 = *reinterpret_cast<const double2*>(a.dist + i0);
         const double2 d23 = *reinterpret_cast<const double2*>(a.dist + i0 + 2);
-        const double2 s01 = *reinterpret_cast<const double2*>(a.speed + i0);
-        const double2 s23 = *reinterpret_cast<const double2*>(a.speed + i0 + 2);
-        const double2 e01 = *reinterpret_cast<const double2*>(a.elen + i0);
-        const double2 e23 = *reinterpret_cast<const double2*>(a.elen + i0 + 2);
+        // speed / elen may have been written by another GPU: read them past the (non-coherent) L1
+        const double2 s01 = P2P ? __ldcg(reinterpret_cast<const double2*>(a.speed + i0))
+                                : *reinterpret_cast<const double2*>(a.speed + i0);
+        const double2 s23 = P2P ? __ldcg(reinterpret_cast<const double2*>(a.speed + i0 + 2))
+                                : *reinterpret_cast<const double2*>(a.speed + i0 + 2);
+        const double2 e01 = P2P ? __ldcg(reinterpret_cast<const double2*>(a.elen + i0))
+                                : *reinterpret_cast<const double2*>(a.elen + i0);
+        const double2 e23 = P2P ? __ldcg(reinterpret_cast<const double2*>(a.elen + i0 + 2))
+                                : *reinterpret_cast<const double2*>(a.elen + i0 + 2);
         double d[4] = {d01.x, d01.y, d23.x, d23.y};
         const double sp[4] = {s01.x, s01.y, s23.x, s23.y};
         const double el[4] = {e01.x, e01.y, e23.x, e23.y};
@@ -225,7 +260,7 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
         while (cross) {
           const int j = __ffs(cross) - 1;
           cross &= cross - 1;
-          if (cross_agent(p, i0 + j, tick, sm)) nst4 &= ~(0xffu << (8 * j));  // arrived: waiting again
+          if (cross_agent(p, i0 + j, tick, sm, P2P)) nst4 &= ~(0xffu << (8 * j));  // arrived: waiting again
         }
       }
       if (DEMAND) {
@@ -235,7 +270,7 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
           const int cnt = (cn4 >> (8 * j)) & 0xffu;
           if (((st4 >> (8 * j)) & 0xffu) != kWaiting || cnt == 0 || i0 + j >= a.n) continue;
           const double u = philox_uniform53(p.dm.seed, a.base + (uint32_t)(i0 + j), (uint32_t)tick);
-          if (u < p_dep && depart_agent(p, i0 + j, cnt, tick, sm)) nst4 |= (uint32_t)kMoving << (8 * j);  // agent.py:180
+          if (u < p_dep && depart_agent(p, i0 + j, cnt, tick, sm, P2P)) nst4 |= (uint32_t)kMoving << (8 * j);  // agent.py:180
         }
       }
       if (nst4 != st4) *reinterpret_cast<uint32_t*>(a.state + i0) = nst4;
@@ -247,7 +282,33 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
       if (k == w) my_off = n_blk;
       n_blk += sm.n[k];
     }
-    if (n_blk) {  // one global atomic per block and tile, spread over kEvSub counters
+    if (P2P) {
+      if (n_blk) {  // bucket the staged events by owner: one local atomic per block, tile and owner
+        const int n = sm.n[w];
+        for (int k = lane; k < n; k += 32)
+          xs->idx[w][k] = (uint16_t)atomicAdd(&xs->ocnt[(sm.link_kind[w][k] & 0x7fffffffu) % (uint32_t)x->world], 1);
+        __syncthreads();
+        if (threadIdx.x < x->world && xs->ocnt[threadIdx.x])
+          xs->obase[threadIdx.x] = atomicAdd(&x->out_cnt[threadIdx.x], xs->ocnt[threadIdx.x]);
+        __syncthreads();
+        for (int k = lane; k < n; k += 32) {
+          const uint32_t lkd = sm.link_kind[w][k];
+          const int32_t link = (int32_t)(lkd & 0x7fffffffu);
+          const int o = (int)((uint32_t)link % (uint32_t)x->world);
+          const int pos = xs->obase[o] + xs->idx[w][k];
+          if (pos < x->cap) {
+            Event e;
+            e.link = link;
+            e.agent = sm.agent[w][k];
+            e.kind = (lkd >> 31) ? 1 : -1;
+            e.aux = 0;
+            *reinterpret_cast<int4*>(x->inbox[o] + (int64_t)x->rank * x->cap + pos) = *reinterpret_cast<const int4*>(&e);
+          } else {
+            atomicOr(&p.ctr->overflow, kOvfExchange);
+          }
+        }
+      }
+    } else if (n_blk) {  // one global atomic per block and tile, spread over kEvSub counters
       const int sub = (int)(tile % kEvSub);
       if (threadIdx.x == 0) sm.base = atomicAdd(&p.ctr->n_events[par][sub], n_blk);
       __syncthreads();
@@ -576,6 +637,235 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop(const __grid_const
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       ctr->phase_ns[2] += t1 - t0;
     }
+  }
+}
+
+// ---- the persistent tick loop over NVLink peer memory ---------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Every block waits until all ranks have published `tick` in this row of the local flags; the low
+// words (event counts) go to s_val.  A rank that never shows up (crashed peer) traps after 60 s
+// instead of hanging the GPU.
+__device__ __forceinline__ void p2p_wait(const unsigned long long* row, int world, uint32_t tick, int* s_val) {
+  if (threadIdx.x < world) {
+    const unsigned long long t0 = global_ns();
+    unsigned long long v;
+    for (;;) {
+      v = ld_acquire_sys(row + threadIdx.x);
+      if ((uint32_t)(v >> 32) >= tick) break;
+      if (global_ns() - t0 > 60000000000ULL) {
+        printf("drift_b200: rank flag %d did not reach tick %u within 60 s\n", (int)threadIdx.x, tick);
+        __trap();
+      }
+      __nanosleep(64);
+    }
+    if (s_val) s_val[threadIdx.x] = (int)(uint32_t)(v & 0xffffffffu);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void p2p_home(const P2PArgs& x, uint32_t agent, int& home, uint32_t& local) {
+  const uint32_t big = (x.shard_base + 1u) * x.shard_rem;  // agents held by the ranks with one extra agent
+  if (agent < big) {
+    home = (int)(agent / (x.shard_base + 1u));
+    local = agent - (uint32_t)home * (x.shard_base + 1u);
+  } else {
+    const uint32_t r = agent - big;
+    const uint32_t q = r / x.shard_base;
+    home = (int)(x.shard_rem + q);
+    local = r - q * x.shard_base;
+  }
+}
+
+__device__ __forceinline__ void p2p_send_one(const TickArgs& p, const P2PArgs& x, int32_t link, uint32_t agent,
+                                             int32_t kind) {
+  const int o = (int)((uint32_t)link % (uint32_t)x.world);
+  const int pos = atomicAdd(&x.out_cnt[o], 1);
+  if (pos < x.cap) {
+    Event e;
+    e.link = link;
+    e.agent = agent;
+    e.kind = kind;
+    e.aux = 0;
+    *reinterpret_cast<int4*>(x.inbox[o] + (int64_t)x.rank * x.cap + pos) = *reinterpret_cast<const int4*>(&e);
+  } else {
+    atomicOr(&p.ctr->overflow, kOvfExchange);
+  }
+}
+
+// phase A2 with peer delivery (host-committed departures and in-tick fallback routes)
+__device__ __noinline__ void phase_inject_p2p(const TickArgs& p, const P2PArgs& x, int32_t tick, int n_pending,
+                                              int n_urgent) {
+  const AgentArrays& a = p.a;
+  auto start = [&](int32_t i, int64_t off, int32_t len) {
+    const int32_t link = p.arena[off];
+    a.state[i] = kMoving;
+    a.route_off[i] = off;
+    a.route_len[i] = len;
+    a.route_idx[i] = 0;
+    a.dist[i] = 0.0;
+    a.cur_link[i] = link;
+    a.next_link[i] = len > 1 ? p.arena[off + 1] : -1;
+    p2p_send_one(p, x, link, a.base + (uint32_t)i, 1);
+  };
+  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = gtid; q < n_pending; q += gsz)
+    if (p.pend_len[q] > 0) start(p.pend_agent[q], p.pend_off[q], p.pend_len[q]);
+  if (n_urgent > 0 && gtid < p.fsc.workers) {
+    uint32_t epoch = p.fsc.epoch[gtid];
+    for (int r = (int)gtid; r < n_urgent; r += p.fsc.workers) {
+      const int32_t i = p.dm.dep_req[r];
+      const int head = a.chain_head[i];
+      const int32_t s = a.cur_node[i];
+      const int32_t t = a.chain_dst[(int64_t)i * a.chain_cap + head];
+      a.chain_head[i] = (uint8_t)((head + 1) % a.chain_cap);
+      a.chain_cnt[i] -= 1;
+      a.trip_count[i] += 1;
+      a.cur_node[i] = t;
+      const RouteResult rr = route_nx_one(p.g, p.w_fwd, p.w_bwd, s, t, p.fsc, (int)gtid, epoch, p.arena, p.arena_cap,
+                                          p.ctr, p.link_cost);
+      const unsigned long long slot = atomicAdd(&p.ctr->n_departures, 1ULL);
+      if (slot - p.dm.log_drained < p.dm.log_cap) {
+        const unsigned long long k = slot % p.dm.log_cap;
+        p.dm.log_agent[k] = i;
+        p.dm.log_tick[k] = tick;
+        p.dm.log_src[k] = s;
+        p.dm.log_dst[k] = t;
+        p.dm.log_status[k] = rr.status;
+      } else {
+        atomicOr(&p.ctr->overflow, kOvfDepLog);
+      }
+      if (rr.status == DRIFT_ROUTE_OK) start(i, rr.off, rr.n_links);
+    }
+    p.fsc.epoch[gtid] = epoch;
+  }
+}
+
+// Owner side of phase C: ordered count on an owned link -> entry speed, written into the home
+// rank's agent arrays (peer store); the list head writes the end-of-tick occupancy of the link.
+__device__ __forceinline__ void resolve_one_p2p(const TickArgs& p, const P2PArgs& x, const Event* __restrict__ events,
+                                                int e) {
+  const LinkArrays& lk = p.lk;
+  const Event ev = events[e];
+  const int first = (int)(lk.head[ev.link] & 0xffffffffu);
+  int before = 0, net = 0, occ0 = 0;
+  int j = first;
+  for (;;) {
+    const Event o = events[j];
+    net += o.kind;
+    if (o.agent < ev.agent) before += o.kind;
+    if (o.aux < 0) {
+      occ0 = -o.aux - 1;
+      break;
+    }
+    j = o.aux;
+  }
+  if (first == e) lk.occ[ev.link] = occ0 + net;
+  if (ev.kind > 0) {
+    int home;
+    uint32_t li;
+    p2p_home(x, ev.agent, home, li);
+    const int32_t count = occ0 + before + 1;  // includes the entering agent itself
+    const double f = bpr_factor_lookup(lk, ev.link, count);
+    x.speed[home][li] = __dmul_rn(__dmul_rn(lk.v0[ev.link], f), p.kph_to_mps);
+    x.elen[home][li] = lk.len[ev.link];
+  }
+}
+
+// One cooperative launch per rank runs `n_ticks` ticks; the ranks meet twice per tick through flags
+// in peer memory (events delivered / links resolved), never through the host.
+__global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_constant__ TickArgs p,
+                                                                  const __grid_constant__ P2PArgs x, int32_t tick0,
+                                                                  int32_t n_ticks, double p_dep) {
+  __shared__ AdvSmem sm;
+  __shared__ P2PSmem xs;
+  __shared__ int s_in[kMaxRanks], s_pref[kMaxRanks + 1];
+  cg::grid_group grid = cg::this_grid();
+  Counters* ctr = p.ctr;
+  const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+  Event* inbox = x.inbox[x.rank];
+  unsigned long long* my_flags = x.flags[x.rank];
+  unsigned long long t0 = 0;
+  for (int32_t k = 0; k < n_ticks; ++k) {
+    const int32_t tick = tick0 + k;
+    const int par = tick & 1;
+    if (lead) t0 = global_ns();
+    if (p.demand)
+      phase_advance<true, true>(p, tick, p_dep, sm, &x, &xs);
+    else
+      phase_advance<false, true>(p, tick, p_dep, sm, &x, &xs);
+    __threadfence_system();  // the peer stores of this thread are visible before the count is published
+    grid.sync();
+    const int n_pending = ctr->n_pending, n_urgent = ctr->n_dep_req[par];
+    if (n_pending | n_urgent) {  // uniform across the grid
+      phase_inject_p2p(p, x, tick, n_pending, n_urgent);
+      __threadfence_system();
+      grid.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x < x.world) {  // publish: this rank's events are in owner o's inbox
+      const int o = threadIdx.x;
+      int cnt = x.out_cnt[o];
+      x.out_cnt[o] = 0;
+      atomicMax(&ctr->max_events, cnt);
+      if (cnt > x.cap) cnt = x.cap;  // overflow already flagged by the writers
+      st_release_sys(x.flags[o] + x.rank, ((unsigned long long)(uint32_t)tick << 32) | (uint32_t)cnt);
+    }
+    if (lead) {
+      ctr->n_dep_req[par ^ 1] = 0;
+      const unsigned long long t1 = global_ns();
+      ctr->phase_ns[0] += t1 - t0;
+      t0 = t1;
+    }
+    p2p_wait(my_flags, x.world, (uint32_t)tick, s_in);
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      for (int r = 0; r < x.world; ++r) {
+        s_pref[r] = acc;
+        acc += s_in[r];
+      }
+      s_pref[x.world] = acc;
+    }
+    __syncthreads();
+    const int total = s_pref[x.world];
+    // link the events of the owned links (all ranks' regions of the inbox)
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+      int r = 0;
+      while (r + 1 < x.world && s_pref[r + 1] <= f) ++r;
+      const int e = r * x.cap + (f - s_pref[r]);
+      const int4 raw = __ldcg(reinterpret_cast<const int4*>(inbox + e));  // written by a peer: bypass L1
+      emit_event(p.lk, inbox, e, raw.x, (uint32_t)raw.y, raw.z, (uint32_t)tick);
+    }
+    grid.sync();
+    if (lead) {
+      ctr->n_pending = 0;
+      const unsigned long long t1 = global_ns();
+      ctr->phase_ns[1] += t1 - t0;  // exchange wait + list building
+      t0 = t1;
+    }
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+      int r = 0;
+      while (r + 1 < x.world && s_pref[r + 1] <= f) ++r;
+      resolve_one_p2p(p, x, inbox, r * x.cap + (f - s_pref[r]));
+    }
+    __threadfence_system();  // entry speeds are in the home ranks' arrays before "done" is published
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x < x.world)
+      st_release_sys(x.flags[threadIdx.x] + kMaxRanks + x.rank, (unsigned long long)(uint32_t)tick << 32);
+    p2p_wait(my_flags + kMaxRanks, x.world, (uint32_t)tick, nullptr);
+    if (lead) ctr->phase_ns[2] += global_ns() - t0;
   }
 }
 

@@ -77,8 +77,35 @@ class ShardedEngine:
                              route_arena_links=route_arena_links)
         self.engine.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self.cap = 0
+        self.p2p = False
         self._fixed_cap = exchange_capacity > 0
         self._set_cap(exchange_capacity if exchange_capacity > 0 else max(4096, (self.hi - self.lo) // 4))
+
+    def enable_p2p(self, cap=0):
+        """Move the exchange into the tick kernel (NVLink peer memory, ``k_tick_loop_p2p``): links are
+        owned round-robin, events go straight into the owner's inbox, entry speeds straight back into
+        the home rank's agent arrays.  One process per GPU on one node; call on all ranks before the
+        first tick.  ``cap`` = events one rank may send to one owner per tick."""
+        n_local = self.hi - self.lo
+        cap = int(cap) if cap > 0 else max(8192, 2 * n_local // self.world + 4096)
+        mine = self.engine.p2p_export(self.rank, self.world, self.n_total, cap)
+        send = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(self.device)
+        recv = torch.empty(self.world * len(mine), dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        self.engine.p2p_connect(recv.cpu().numpy().tobytes())
+        dist.barrier(group=self.group)
+        self.p2p = True
+        self.p2p_cap = cap
+
+    def occupancy(self):
+        """Link volumes, identical on every rank.  With the peer-memory exchange a link's volume lives
+        on its owner only (0 elsewhere): sum over ranks."""
+        occ = self.engine.occupancy()
+        if not self.p2p:
+            return occ
+        t = torch.from_numpy(occ).to(self.device)
+        dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
 
     def _set_cap(self, cap):
         cap = int(cap)
@@ -111,6 +138,12 @@ class ShardedEngine:
     def run(self, n_ticks, delta, t0):
         """Device-driven demand, ``n_ticks`` ticks starting at clock ``t0``."""
         t = t0
+        if self.p2p:  # the whole block is a few cooperative launches per rank, no collective call
+            self.engine.run(n_ticks, delta, t0)
+            for _ in range(n_ticks):
+                t += delta
+            self.engine.max_events(reset=True)  # raises on overflow
+            return t
         for _ in range(n_ticks):
             t += delta
             self._tick(delta, t)
@@ -118,4 +151,7 @@ class ShardedEngine:
         return t
 
     def close(self):
+        if self.p2p:
+            self.engine.sync()
+            dist.barrier(group=self.group)  # nobody unmaps a buffer a peer's kernel may still write
         self.engine.close()

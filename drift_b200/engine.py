@@ -202,6 +202,17 @@ class Engine:
     def tick_finish_gathered(self, recv_ptr, world, cap):
         _capi.check(self._lib.drift_tick_finish_gathered(self._h, C.c_void_p(recv_ptr), int(world), int(cap)))
 
+    def p2p_export(self, rank, world, n_total, cap):
+        """Allocate the peer-memory inbox / flags of this rank; returns its 4 CUDA IPC handles (256 bytes)."""
+        buf = (C.c_ubyte * 256)()
+        _capi.check(self._lib.drift_p2p_export(self._h, int(rank), int(world), int(n_total), int(cap), buf))
+        return bytes(buf)
+
+    def p2p_connect(self, all_handles):
+        """``all_handles``: the handles of all ranks in rank order (world x 256 bytes)."""
+        buf = (C.c_ubyte * len(all_handles)).from_buffer_copy(all_handles)
+        _capi.check(self._lib.drift_p2p_connect(self._h, buf))
+
     def max_events(self, reset=True):
         n = C.c_int64(0)
         _capi.check(self._lib.drift_max_events(self._h, C.byref(n), int(bool(reset))))

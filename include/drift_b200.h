@@ -217,6 +217,21 @@ int drift_tick_begin_async(drift_engine* e, double delta, double t, void* send_d
 int drift_tick_finish_gathered(drift_engine* e, void* recv_dev, int32_t world, int32_t cap);
 int drift_max_events(drift_engine* e, int64_t* max_events, int32_t reset);
 
+/* The exchange inside the tick kernel, over NVLink peer memory (one process per GPU on one node; what
+ * drift_b200/dist.py uses for device-driven demand).  Links are owned round-robin (link % world): every
+ * rank stores the events of its agents straight into the owner's inbox, the owner orders the events of
+ * its links (lib/agent.py:106-160 + lib/managers/traffic_manager.py:63-107 for those links) and stores
+ * the entry speed straight into the home rank's agent arrays; the ranks meet twice per tick through
+ * flags in peer memory.  Work per rank does not grow with `world`; the link volumes are held by the
+ * owner only (drift_read_occupancy returns 0 for links owned elsewhere: sum over ranks).
+ *   drift_p2p_export   allocates inbox / flags and writes 4 CUDA IPC handles (4 x 64 bytes) to
+ *                      handles_out; `cap` = events one rank may send to one owner per tick
+ *   drift_p2p_connect  all_handles = the world x 4 handles of all ranks in rank order (exchanged by
+ *                      the caller, e.g. torch.distributed.all_gather); from then on drift_run launches
+ *                      k_tick_loop_p2p.  All ranks must call drift_run with the same arguments. */
+int drift_p2p_export(drift_engine* e, int32_t rank, int32_t world, int64_t n_total, int32_t cap, void* handles_out);
+int drift_p2p_connect(drift_engine* e, const void* all_handles);
+
 /* Timing of the kernels launched by the last drift_step/drift_run (CUDA events on the engine
  * stream): total milliseconds spent in the advance kernel and number of advance launches. */
 int drift_kernel_times(drift_engine* e, double* advance_ms, int64_t* advance_launches, double* total_ms,

@@ -94,7 +94,7 @@ def test_two_rank_replay_matches_reference(name):
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
 
 
-def _worker_demand(rank, world, port, out):
+def _worker_demand(rank, world, port, out, p2p=False):
     """Device-driven demand sharded over 2 ranks == the same run on one engine (bit for bit)."""
     import torch
     import torch.distributed as dist
@@ -128,10 +128,12 @@ def _worker_demand(rank, world, port, out):
                     t += ticks
                 else:
                     t = eng_like.run(ticks, 1.0, t)
-                occs.append(eng.occupancy().copy())
+                occs.append((eng if eng_like is eng else eng_like).occupancy().copy())
             return occs, eng.agents(fields=("state", "dist", "speed", "route_idx", "trip_count"))
 
         se = ShardedEngine(lg, N, device=rank, route_arena_links=N * 300)
+        if p2p:
+            se.enable_p2p()
         occ_s, ag_s = drive(se, se.engine, se.lo, se.hi)
         se.close()
         if rank == 0:
@@ -153,7 +155,10 @@ def _worker_demand(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_two_rank_device_demand_equals_single_engine():
+@pytest.mark.parametrize("p2p", [False, True])
+def test_two_rank_device_demand_equals_single_engine(p2p):
+    """p2p=False: per-tick all-gather of the link events (NCCL); p2p=True: the exchange inside the
+    persistent tick kernel over NVLink peer memory (k_tick_loop_p2p, link-owner resolution)."""
     import torch
     import torch.multiprocessing as mp
 
@@ -162,7 +167,7 @@ def test_two_rank_device_demand_equals_single_engine():
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker_demand, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker_demand, args=(r, 2, port, out, p2p)) for r in range(2)]
     for p in procs:
         p.start()
     res = [out.get(timeout=600) for _ in procs]
