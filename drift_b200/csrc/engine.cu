@@ -106,6 +106,7 @@ struct drift_engine {
   DevBuf<int32_t> arena, arena2;  // live arena + spare used by the compaction
   int64_t arena_cap = 0;
   int64_t compactions = 0;
+  double arena_compact_frac = 0.75;  // live routes are compacted once this fraction of the arena is used
   // events
   DevBuf<Event> events, send;  // kEvSub sub-buffers of ev_sub_cap records; contiguous copy for the rank exchange
   int64_t ev_cap = 0, ev_sub_cap = 0;
@@ -306,15 +307,15 @@ int fetch_counters(drift_engine* e, Counters* out) {
   return DRIFT_OK;
 }
 
-// Copy the live routes into the spare arena when more than half of the arena is used.  Pending
+// Copy the live routes into the spare arena when more than three quarters of the arena are used.  Pending
 // (committed, not yet injected) departures and a staged drift_route_od batch must not exist: called at
 // the start of a routing batch only.
 int maybe_compact_arena(drift_engine* e, unsigned long long cursor) {
-  if (cursor * 2 < (unsigned long long)e->arena_cap) return DRIFT_OK;
+  if ((double)cursor < e->arena_compact_frac * (double)e->arena_cap) return DRIFT_OK;
   if (!e->arena2.p) CU(e->arena2.alloc(e->arena_cap, false));
   Counters* c = e->ctr.p;
   CU(cudaMemsetAsync(&c->arena_cursor, 0, sizeof(unsigned long long), e->stream));
-  k_compact_routes<<<grid_for(e->N, 128, kSMs * 16), 128, 0, e->stream>>>(
+  k_compact_routes<<<grid_for(e->N * 32, 256, kSMs * 8), 256, 0, e->stream>>>(
       e->agents(), e->arena.p, e->arena2.p, &c->arena_cursor, (unsigned long long)e->arena_cap, c);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(e->stream));
@@ -406,6 +407,14 @@ int invalidate_trees(drift_engine* e) {
   return DRIFT_OK;
 }
 
+// Largest batch the tree cache can take in one go: every hot key needs a slot, and a key is hot only
+// if more than bounded_max queries of the batch share it.
+int64_t router_chunk(drift_engine* e, int64_t Q, bool congested) {
+  const int32_t bm = e->t_bounded_max >= 0 ? e->t_bounded_max : ((e->t_max_slots >= e->V && !congested) ? 0 : kMaxBounded);
+  if (bm > 0) return std::max<int64_t>(1, (int64_t)e->t_max_slots * (bm + 1));
+  return e->t_max_slots >= (int64_t)e->t_sides * e->V ? std::max<int64_t>(Q, 1) : std::max<int64_t>(1, e->t_max_slots);
+}
+
 // launches the router over the staged q_src/q_dst (device).  Q is the host-known batch size or an
 // upper bound; when n_dev != nullptr the kernels read the actual size from device memory.
 int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_congested, const int32_t* n_dev = nullptr,
@@ -433,8 +442,14 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     tc.batch = ++e->t_batch;
     if (e->t_q_next.n < Q + q0) {
       CU(cudaStreamSynchronize(e->stream));
-      CU(e->t_q_next.alloc(std::max<int64_t>(e->q_cap, Q + q0), false));
-      CU(e->t_q_side.alloc(std::max<int64_t>(e->q_cap, Q + q0), false));
+      const int64_t need = std::max<int64_t>(e->q_cap, Q + q0);
+      CU(e->t_q_next.alloc(need, false));
+      CU(e->t_q_side.alloc(need, false));
+      // per-batch job table: at most one job per query (bounded searches take no cache slot)
+      CU(e->t_job_qhead.alloc(need + e->t_max_slots));
+      CU(e->t_job_cnt.alloc(need + e->t_max_slots));
+      CU(e->t_job_dst.alloc(need + e->t_max_slots));
+      CU(e->t_job_slot.alloc(need + e->t_max_slots));
     }
     tc.cnt = e->t_cnt.p;
     tc.q_side = e->t_q_side.p;
@@ -834,7 +849,7 @@ int drift_route_od(drift_engine* e, int32_t router, int64_t Q, const int32_t* sr
   if (c0.n_pending == 0) {
     rc = maybe_compact_arena(e, c0.arena_cursor);
     if (rc) return rc;
-    if (e->compactions && c0.arena_cursor * 2 >= (unsigned long long)e->arena_cap) {
+    if (e->compactions && (double)c0.arena_cursor >= e->arena_compact_frac * (double)e->arena_cap) {
       rc = fetch_counters(e, &c0);
       if (rc) return rc;
     }
@@ -1045,7 +1060,7 @@ static int plan_window(drift_engine* e) {
   if (e->demand_router == DRIFT_ROUTER_BATCHED) {
     rc = ensure_trees(e);
     if (rc) return rc;
-    chunk = std::max<int64_t>(1, e->t_max_slots);  // a chunk never needs more distinct trees than slots
+    chunk = router_chunk(e, Q, e->use_congested);
   }
   for (int64_t q0 = 0; q0 < Q; q0 += chunk) {
     const int64_t n = std::min(chunk, Q - q0);
@@ -1186,7 +1201,7 @@ int drift_reroute_moving(drift_engine* e, int32_t router, int64_t* n_rerouted) {
   if (router == DRIFT_ROUTER_BATCHED) {
     rc = ensure_trees(e);
     if (rc) return rc;
-    chunk = std::max<int64_t>(1, e->t_max_slots);
+    chunk = router_chunk(e, Q, true);
   }
   for (int64_t q0 = 0; q0 < Q; q0 += chunk) {
     rc = launch_router(e, router, std::min(chunk, Q - q0), 1, nullptr, q0);
@@ -1673,6 +1688,8 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
     e->route_window = (int32_t)value;
   } else if (s == "replan") {
     e->ticks_since_plan = 0;
+  } else if (s == "arena_compact_frac") {
+    e->arena_compact_frac = std::min(0.95, std::max(0.05, value));
   } else if (s == "tree_sides") {
     if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_sides must be set before the first batched route");
     e->t_sides = value >= 2 ? 2 : 1;

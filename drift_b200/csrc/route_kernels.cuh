@@ -324,36 +324,44 @@ __global__ void k_apply_reroutes(int64_t Q, const int32_t* __restrict__ q_agent,
 }
 
 // Route arena compaction: copy the live routes (the route of every moving agent and the prefetched
-// routes) into a fresh arena and repoint the agents.
+// routes) into a fresh arena and repoint the agents.  One warp per agent: one reservation for its
+// (up to three) routes, coalesced copies.
 __global__ void k_compact_routes(AgentArrays a, const int32_t* __restrict__ src, int32_t* __restrict__ dst,
                                  unsigned long long* __restrict__ cursor, unsigned long long cap, Counters* ctr) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; i < a.n; i += warps) {
+    int32_t len[3] = {0, 0, 0};
+    int64_t off[3] = {0, 0, 0};
     if (a.state[i] == kMoving) {
-      const int32_t len = a.route_len[i];
-      const unsigned long long off = atomicAdd(cursor, (unsigned long long)len);
-      if (off + len <= cap) {
-        const int64_t o = a.route_off[i];
-        for (int32_t k = 0; k < len; ++k) dst[off + k] = src[o + k];
-        a.route_off[i] = (int64_t)off;
-      } else {
-        atomicOr(&ctr->overflow, kOvfArena);
-      }
-    } else {
-      a.route_len[i] = 0;  // the finished route is dropped
-      a.route_off[i] = 0;
+      len[0] = a.route_len[i];
+      off[0] = a.route_off[i];
     }
     for (int k = 0; k < 2; ++k) {
       const int64_t idx = (int64_t)k * a.npad + i;
       if (a.next_status[idx] != 1 + DRIFT_ROUTE_OK) continue;
-      const int32_t len = a.next_len[idx];
-      const unsigned long long off = atomicAdd(cursor, (unsigned long long)len);
-      if (off + len <= cap) {
-        const int64_t o = a.next_off[idx];
-        for (int32_t j = 0; j < len; ++j) dst[off + j] = src[o + j];
-        a.next_off[idx] = (int64_t)off;
-      } else {
-        atomicOr(&ctr->overflow, kOvfArena);
+      len[1 + k] = a.next_len[idx];
+      off[1 + k] = a.next_off[idx];
+    }
+    const unsigned long long total = (unsigned long long)len[0] + len[1] + len[2];
+    unsigned long long base = 0;
+    if (lane == 0 && total) base = atomicAdd(cursor, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const bool fits = base + total <= cap;
+    if (!fits && lane == 0) atomicOr(&ctr->overflow, kOvfArena);
+    unsigned long long o = base;
+    for (int r = 0; r < 3; ++r) {
+      if (fits)
+        for (int32_t k = lane; k < len[r]; k += 32) dst[o + k] = src[off[r] + k];
+      if (lane == 0) {
+        if (r == 0) {
+          a.route_off[i] = len[0] && fits ? (int64_t)o : 0;
+          if (!len[0]) a.route_len[i] = 0;  // the finished route is dropped
+        } else if (len[r] && fits) {
+          a.next_off[(int64_t)(r - 1) * a.npad + i] = (int64_t)o;
+        }
       }
+      o += (unsigned long long)len[r];
     }
   }
 }
@@ -528,6 +536,17 @@ __global__ void k_tree_requests(int64_t Q, const int32_t* __restrict__ src, cons
     if (!tree_query_ok(src[q], dst[q], tc.V)) continue;
     const int32_t t = tc.q_side[q] ? tc.V + src[q] : dst[q];
     if (atomicCAS(&tc.slot_of[t], -1, -2) != -1) continue;  // cached, or another thread is allocating it
+    if (t < tc.V && tc.bounded_max > 0 && tc.cnt[t] <= tc.bounded_max) {
+      // cold destination: a bounded search answers its few queries and keeps no tree -> no slot;
+      // slot_of[t] = -(job + 3) until the job is done
+      const int32_t j = atomicAdd(tc.n_jobs, 1);
+      tc.job_dst[j] = t;
+      tc.job_slot[j] = -1;
+      tc.job_qhead[j] = -1;
+      tc.job_cnt[j] = 0;
+      tc.slot_of[t] = -(j + 3);
+      continue;
+    }
     int32_t s = -1;
     for (int tries = 0; tries < tc.max_slots; ++tries) {
       const int32_t c = (int32_t)((uint32_t)atomicAdd(tc.ring_cursor, 1) % (uint32_t)tc.max_slots);
@@ -536,7 +555,7 @@ __global__ void k_tree_requests(int64_t Q, const int32_t* __restrict__ src, cons
         break;
       }
     }
-    if (s < 0) {  // more distinct keys in one batch than slots
+    if (s < 0) {  // more distinct hot keys in one batch than slots
       tc.slot_of[t] = -1;
       atomicOr(&ctr->overflow, kOvfStage);
       continue;
@@ -566,8 +585,13 @@ __global__ void k_link_queries(int64_t Q, const int32_t* __restrict__ src, const
     if (tc.sides > 1) tc.cnt[tc.V + src[q]] = 0;
     const int32_t t = tc.q_side[q] ? tc.V + src[q] : dst[q];
     const int32_t s = tc.slot_of[t];
-    if (s < 0 || tc.slot_job_batch[s] != tc.batch) continue;
-    const int32_t j = tc.slot_job[s];
+    int32_t j;
+    if (s <= -3)
+      j = -(s + 3);  // bounded job of this batch
+    else if (s >= 0 && tc.slot_job_batch[s] == tc.batch)
+      j = tc.slot_job[s];
+    else
+      continue;
     tc.q_next[q] = atomicExch(&tc.job_qhead[j], (int32_t)q);
     atomicAdd(&tc.job_cnt[j], 1);
   }
@@ -624,9 +648,10 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
     const int32_t* __restrict__ x_rowptr = out_tree ? g.fwd_rowptr : g.bwd_rowptr;
     const int32_t* __restrict__ x_col = out_tree ? g.fwd_col : g.bwd_col;
     const double* __restrict__ x_w = out_tree ? w_fwd : w_bwd;
-    int32_t* next_link = tc.next_link + (int64_t)tc.job_slot[job] * V;
-    const int nb = tc.job_cnt[job];
-    const bool bounded = !out_tree && nb > 0 && nb <= tc.bounded_max;
+    const int32_t slot = tc.job_slot[job];
+    int32_t* next_link = tc.next_link + (int64_t)(slot < 0 ? 0 : slot) * V;
+    const int nb = min(tc.job_cnt[job], kMaxBounded);
+    const bool bounded = slot < 0;  // decided when the job was created (k_tree_requests)
     if (bounded && skip_bounded) continue;  // k_search_warp takes it
     if (threadIdx.x == 0) ++c_jobs;
     if (bounded && threadIdx.x == 0) {
@@ -888,10 +913,7 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
         out.off[q] = status == DRIFT_ROUTE_OK ? off : 0;
         out.cost[q] = cost;
       }
-      if (threadIdx.x == 0) {  // no tree was kept
-        tc.slot_of[dest] = -1;
-        tc.slot_owner[tc.job_slot[job]] = -1;
-      }
+      if (threadIdx.x == 0) tc.slot_of[dest] = -1;  // no tree was kept
       __syncthreads();
       for (int i = threadIdx.x; i < s_touched; i += blockDim.x) {  // leave the scratch clean for the next job
         rec[touched[i]].dist = kInfBits;
@@ -1000,8 +1022,8 @@ __global__ void __launch_bounds__(kWarpSearchThreads) k_search_warp(
     if (lane == 0) job = atomicAdd(job_cursor, 1);
     job = __shfl_sync(0xffffffffu, job, 0);
     if (job >= n_jobs) break;
-    const int nb = tc.job_cnt[job];
-    if (!(nb > 0 && nb <= tc.bounded_max) || tc.job_dst[job] >= g.V) continue;  // keeps a tree: k_build_trees
+    const int nb = min(tc.job_cnt[job], kMaxBounded);
+    if (tc.job_slot[job] >= 0) continue;  // keeps a tree: k_build_trees
     ++c_jobs;
     const int32_t dest = tc.job_dst[job];
     // lane k < nb holds query k of the job
@@ -1247,10 +1269,7 @@ __global__ void __launch_bounds__(kWarpSearchThreads) k_search_warp(
       out.off[my_q] = status == DRIFT_ROUTE_OK ? off : 0;
       out.cost[my_q] = cost;
     }
-    if (lane == 0) {  // no tree was kept
-      tc.slot_of[dest] = -1;
-      tc.slot_owner[tc.job_slot[job]] = -1;
-    }
+    if (lane == 0) tc.slot_of[dest] = -1;  // no tree was kept
     __syncwarp();
     for (int i = lane; i < touched_n; i += 32) {  // leave the scratch clean for the next job
       rec[touched[i]].dist = kInfBits;

@@ -218,6 +218,7 @@ def test_tree_cache_eviction():
                 want = nx.shortest_path(G, nodes[s], nodes[t], weight="travel_time")
                 assert stt == ROUTE_OK and [nodes[i] for i in lg.links_to_nodes(s, ln)] == want
         from drift_b200._capi import DriftError
+        eng.set_option("bounded_max", 0)  # full trees only: every destination of a batch needs a slot
         with pytest.raises(DriftError):  # 20 distinct destinations cannot fit 8 slots in one batch
             eng.route(list(range(20, 40)), list(range(100, 120)), router=ROUTER_BATCHED)
 

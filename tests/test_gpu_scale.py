@@ -114,6 +114,7 @@ def test_route_arena_compaction_is_transparent():
         eng = Engine(lg, N, route_arena_links=arena)
         eng.set_demand(5, np.full(24, 0.9), start, chain_capacity=4, router=ROUTER_BATCHED)
         eng.set_option("route_window", 40)
+        eng.set_option("arena_compact_frac", 0.5)
         t = 0.0
         snap = []
         for b in range(12):
