@@ -149,10 +149,10 @@ __device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_
   c3 = n3;
 }
 
-// uniform double in [0,1) with 53 random bits, same construction as MT19937 genrand_res53
-// (what Python's random.random() returns): (a>>5, b>>6) -> (a*2^26+b)/2^53.
-__device__ __forceinline__ double philox_uniform53(uint64_t seed, uint32_t agent, uint32_t tick) {
-  uint32_t c0 = agent, c1 = tick, c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
+// One Philox4x32-10 block = 128 random bits = the draws of TWO agents: the counter is
+// (agent >> 1, tick), the even agent takes words 0-1, the odd one words 2-3.
+__device__ __forceinline__ void philox4x32_10(uint64_t seed, uint32_t pair, uint32_t tick, uint32_t out[4]) {
+  uint32_t c0 = pair, c1 = tick, c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -160,8 +160,34 @@ __device__ __forceinline__ double philox_uniform53(uint64_t seed, uint32_t agent
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
-  uint32_t a = c0 >> 5, b = c1 >> 6;
-  return __dmul_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 1.0 / 9007199254740992.0);
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
+// 53 random bits the way MT19937's genrand_res53 (Python's random.random()) builds them:
+// (a >> 5, b >> 6) -> a * 2^26 + b; the uniform double is that integer * 2^-53.
+__device__ __forceinline__ unsigned long long bits53(uint32_t a, uint32_t b) {
+  return ((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6);
+}
+
+// u < p for u = x * 2^-53  <=>  x < ceil(p * 2^53) (scaling by 2^53 is exact): the per-tick
+// Bernoulli test (lib/agent.py:180) as one integer compare.
+__device__ __forceinline__ unsigned long long departure_threshold(double p) {
+  if (!(p > 0.0)) return 0ULL;
+  const double s = ceil(__dmul_rn(p, 9007199254740992.0));
+  return s >= 18446744073709551615.0 ? ~0ULL : (unsigned long long)s;
+}
+
+__device__ __forceinline__ unsigned long long philox_bits53(uint64_t seed, uint32_t agent, uint32_t tick) {
+  uint32_t o[4];
+  philox4x32_10(seed, agent >> 1, tick, o);
+  return (agent & 1u) ? bits53(o[2], o[3]) : bits53(o[0], o[1]);
+}
+
+__device__ __forceinline__ double philox_uniform53(uint64_t seed, uint32_t agent, uint32_t tick) {
+  return __dmul_rn((double)philox_bits53(seed, agent, tick), 1.0 / 9007199254740992.0);
 }
 
 }  // namespace drift

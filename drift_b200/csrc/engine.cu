@@ -181,6 +181,7 @@ struct drift_engine {
   DevBuf<int32_t> dep_req;
   int32_t demand_router = DRIFT_ROUTER_NX_EXACT;
   // peer-memory exchange (k_tick_loop_p2p)
+  int32_t debug_mask = 0;
   bool p2p_on = false;
   P2PArgs p2p;
   DevBuf<Event> p2p_inbox;
@@ -591,6 +592,7 @@ TickArgs make_tick_args(drift_engine* e, double delta, bool demand) {
   p.delta = delta;
   p.kph_to_mps = kKphToMps;
   p.demand = demand ? 1 : 0;
+  p.debug = e->debug_mask;
   return p;
 }
 
@@ -1690,6 +1692,8 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
     e->ticks_since_plan = 0;
   } else if (s == "arena_compact_frac") {
     e->arena_compact_frac = std::min(0.95, std::max(0.05, value));
+  } else if (s == "debug_mask") {
+    e->debug_mask = (int32_t)value;
   } else if (s == "tree_sides") {
     if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_sides must be set before the first batched route");
     e->t_sides = value >= 2 ? 2 : 1;

@@ -50,6 +50,7 @@ struct TickArgs {
   double delta;
   double kph_to_mps;
   int32_t demand;           // device-driven departures on/off
+  int32_t debug;            // timing probes only (tools/tick_probe.py): 1 = no departure draws, 2 = crossers stay, 4 = events not emitted
 };
 
 // Block-level slot allocation: every thread asks for `n` consecutive slots of a global
@@ -169,27 +170,41 @@ __device__ __noinline__ bool cross_agent(const TickArgs& p, int64_t i, int32_t t
 }
 
 // Agent.start_new_journey (agent.py:46-104) with the prefetched route.  Returns true if the agent is now moving.
+// Rare (about one agent in a thousand per tick) but on the critical path of its block: all loads are
+// issued up front in two dependent levels, then the stores -- written naively (load, store, load ...)
+// the ~20 accesses serialise and the block reaches the grid barrier ~10 us late.
 __device__ __noinline__ bool depart_agent(const TickArgs& p, int64_t i, int cnt, int32_t tick, AdvSmem& sm, bool own_next) {
   const AgentArrays& a = p.a;
   Counters* ctr = p.ctr;
+  // level 1
   const int32_t ns = a.next_status[i];
+  const int head = a.chain_head[i];
+  const int32_t src = a.cur_node[i];
+  const int64_t noff = a.next_off[i];
+  const int32_t nlen = a.next_len[i];
+  const int32_t ns2 = a.next_status[a.npad + i];
+  const int64_t noff2 = a.next_off[a.npad + i];
+  const int32_t nlen2 = a.next_len[a.npad + i];
+  const int32_t trips = a.trip_count[i];
   if (ns == 0) {  // no prefetched route: routed in phase A2 of this tick (rare)
     p.dm.dep_req[atomicAdd(&ctr->n_dep_req[tick & 1], 1)] = (int32_t)i;
     return false;
   }
-  const int head = a.chain_head[i];
-  const int32_t src = a.cur_node[i], dst = a.chain_dst[i * a.chain_cap + head];
+  // level 2
+  const bool go = ns == 1 + DRIFT_ROUTE_OK;
+  const int32_t dst = a.chain_dst[i * a.chain_cap + head];
+  const int32_t fl = go ? p.arena[noff] : -1;
+  const int32_t nl = (go && own_next && nlen > 1) ? p.arena[noff + 1] : -1;
+  const unsigned long long slot = atomicAdd(&ctr->n_departures, 1ULL);
+  // stores
   a.chain_head[i] = (uint8_t)((head + 1) % a.chain_cap);
   a.chain_cnt[i] = (uint8_t)(cnt - 1);
-  a.trip_count[i] += 1;
+  a.trip_count[i] = trips + 1;
   a.cur_node[i] = dst;
-  const int64_t noff = a.next_off[i];
-  const int32_t nlen = a.next_len[i];
-  a.next_status[i] = a.next_status[a.npad + i];  // shift the second prefetched route up
-  a.next_off[i] = a.next_off[a.npad + i];
-  a.next_len[i] = a.next_len[a.npad + i];
+  a.next_status[i] = ns2;  // shift the second prefetched route up
+  a.next_off[i] = noff2;
+  a.next_len[i] = nlen2;
   a.next_status[a.npad + i] = 0;
-  const unsigned long long slot = atomicAdd(&ctr->n_departures, 1ULL);
   if (slot - p.dm.log_drained < p.dm.log_cap) {
     const unsigned long long k = slot % p.dm.log_cap;
     p.dm.log_agent[k] = (int32_t)i;
@@ -200,14 +215,13 @@ __device__ __noinline__ bool depart_agent(const TickArgs& p, int64_t i, int cnt,
   } else {
     atomicOr(&ctr->overflow, kOvfDepLog);
   }
-  if (ns != 1 + DRIFT_ROUTE_OK) return false;
-  const int32_t fl = p.arena[noff];
+  if (!go) return false;
   a.route_off[i] = noff;
   a.route_len[i] = nlen;
   a.route_idx[i] = 0;
   a.dist[i] = 0.0;
   a.cur_link[i] = fl;
-  if (own_next) a.next_link[i] = nlen > 1 ? p.arena[noff + 1] : -1;
+  if (own_next) a.next_link[i] = nl;
   stage_event(sm, fl, a.base + (uint32_t)i, true);
   return true;
 }
@@ -217,6 +231,7 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
                                               const P2PArgs* x = nullptr, P2PSmem* xs = nullptr) {
   const AgentArrays& a = p.a;
   const int par = tick & 1;
+  const unsigned long long dep_thresh = DEMAND ? departure_threshold(p_dep) : 0ULL;
   const int64_t tiles = (a.n + (int64_t)kAdvThreads * kAdvPerThread - 1) / ((int64_t)kAdvThreads * kAdvPerThread);
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -257,6 +272,7 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
         }
         *reinterpret_cast<double2*>(a.dist + i0) = make_double2(d[0], d[1]);
         *reinterpret_cast<double2*>(a.dist + i0 + 2) = make_double2(d[2], d[3]);
+        if (p.debug & 2) cross = 0;
         while (cross) {
           const int j = __ffs(cross) - 1;
           cross &= cross - 1;
@@ -264,13 +280,39 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
         }
       }
       if (DEMAND) {
+        // agents that draw this tick: waiting at tick start (an agent arriving this tick draws from
+        // the next tick on) with a trip in their ring
+        uint32_t want = 0;
 #pragma unroll
         for (int j = 0; j < kAdvPerThread; ++j) {
-          // an agent arriving this tick draws from the next tick on: test the state at tick start
           const int cnt = (cn4 >> (8 * j)) & 0xffu;
-          if (((st4 >> (8 * j)) & 0xffu) != kWaiting || cnt == 0 || i0 + j >= a.n) continue;
-          const double u = philox_uniform53(p.dm.seed, a.base + (uint32_t)(i0 + j), (uint32_t)tick);
-          if (u < p_dep && depart_agent(p, i0 + j, cnt, tick, sm, P2P)) nst4 |= (uint32_t)kMoving << (8 * j);  // agent.py:180
+          if (((st4 >> (8 * j)) & 0xffu) == kWaiting && cnt != 0 && i0 + j < a.n) want |= 1u << j;
+        }
+        if (p.debug & 1) want = 0;
+        uint32_t dep = 0;
+        if (want) {
+          const uint32_t gid0 = a.base + (uint32_t)i0;
+          if ((gid0 & 1u) == 0) {  // one Philox block serves the two agents of a pair
+#pragma unroll
+            for (int h = 0; h < kAdvPerThread / 2; ++h) {
+              if (!(want & (3u << (2 * h)))) continue;
+              uint32_t o[4];
+              philox4x32_10(p.dm.seed, (gid0 >> 1) + (uint32_t)h, (uint32_t)tick, o);
+              if (bits53(o[0], o[1]) < dep_thresh) dep |= 1u << (2 * h);
+              if (bits53(o[2], o[3]) < dep_thresh) dep |= 2u << (2 * h);
+            }
+            dep &= want;
+          } else {
+#pragma unroll
+            for (int j = 0; j < kAdvPerThread; ++j)
+              if (((want >> j) & 1u) && philox_bits53(p.dm.seed, gid0 + (uint32_t)j, (uint32_t)tick) < dep_thresh)
+                dep |= 1u << j;
+          }
+        }
+        while (dep) {  // agent.py:180
+          const int j = __ffs(dep) - 1;
+          dep &= dep - 1;
+          if (depart_agent(p, i0 + j, (cn4 >> (8 * j)) & 0xffu, tick, sm, P2P)) nst4 |= (uint32_t)kMoving << (8 * j);
         }
       }
       if (nst4 != st4) *reinterpret_cast<uint32_t*>(a.state + i0) = nst4;
@@ -308,7 +350,7 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
           }
         }
       }
-    } else if (n_blk) {  // one global atomic per block and tile, spread over kEvSub counters
+    } else if (n_blk && !(p.debug & 4)) {  // one global atomic per block and tile, spread over kEvSub counters
       const int sub = (int)(tile % kEvSub);
       if (threadIdx.x == 0) sm.base = atomicAdd(&p.ctr->n_events[par][sub], n_blk);
       __syncthreads();
@@ -425,46 +467,61 @@ __device__ __forceinline__ void phase_resolve_local(const TickArgs& p, int32_t t
 __device__ __forceinline__ void resolve_one(const LinkArrays& lk, const AgentArrays& a, Counters* ctr,
                                             const Event* __restrict__ events, int e, int32_t tick, double kph_to_mps,
                                             const Rings& rg, const int32_t* __restrict__ arena) {
-  {
-    const Event ev = events[e];
-    const int first = (int)(lk.head[ev.link] & 0xffffffffu);
-    int before = 0;  // sum of the deltas of events ordered before this one (agent-list order)
-    int net = 0;
-    int occ0 = 0;
-    int j = first;
-    for (;;) {
-      const Event o = events[j];
-      net += o.kind;
-      if (o.agent < ev.agent) before += o.kind;
-      if (o.aux < 0) {
-        occ0 = -o.aux - 1;
-        break;
-      }
-      j = o.aux;
+  const Event ev = events[e];
+  // Everything that depends only on the event itself is loaded before the list walk, so that the walk
+  // (a chain of dependent event loads) overlaps with the link / route lookups instead of preceding them.
+  const int first = (int)(lk.head[ev.link] & 0xffffffffu);
+  const uint32_t li = ev.agent - a.base;
+  const bool mine = ev.kind > 0 && ev.agent >= a.base && (int64_t)li < a.n;  // entry of a local agent
+  double v0 = 0.0, len = 0.0;
+  int64_t f_lo = 0, f_hi = 1;
+  int32_t next = -1;
+  if (mine) {
+    const int32_t c = lk.cls[ev.link];
+    v0 = lk.v0[ev.link];
+    len = lk.len[ev.link];
+    const int32_t ri = a.route_idx[li] + 1;
+    const int32_t rlen = a.route_len[li];
+    const int64_t roff = a.route_off[li];
+    f_lo = lk.cls_off[c];
+    f_hi = lk.cls_off[c + 1];
+    if (ri < rlen) next = arena[roff + ri];
+  }
+  int before = 0;  // sum of the deltas of events ordered before this one (agent-list order)
+  int net = 0;
+  int occ0 = 0;
+  int j = first;
+  for (;;) {
+    const Event o = events[j];
+    net += o.kind;
+    if (o.agent < ev.agent) before += o.kind;
+    if (o.aux < 0) {
+      occ0 = -o.aux - 1;
+      break;
     }
-    if (first == e) lk.occ[ev.link] = occ0 + net;
-    if (ev.kind > 0) {
-      const uint32_t li = ev.agent - a.base;
-      if (ev.agent >= a.base && (int64_t)li < a.n) {
-        const int32_t count = occ0 + before + 1;  // includes the entering agent itself
-        const double f = bpr_factor_lookup(lk, ev.link, count);
-        const double sp = __dmul_rn(__dmul_rn(lk.v0[ev.link], f), kph_to_mps);
-        a.speed[li] = sp;
-        a.elen[li] = lk.len[ev.link];
-        const int32_t ri = a.route_idx[li] + 1;
-        a.next_link[li] = ri < a.route_len[li] ? arena[a.route_off[li] + ri] : -1;
-        if (rg.ent_cap) {
-          const unsigned long long slot = atomicAdd(&ctr->n_entries, 1ULL);
-          if (slot - rg.ent_drained < rg.ent_cap) {
-            const unsigned long long k = slot % rg.ent_cap;
-            rg.ent_tick[k] = tick;
-            rg.ent_agent[k] = (int32_t)li;
-            rg.ent_link[k] = ev.link;
-            rg.ent_speed[k] = sp;
-          } else {
-            atomicOr(&ctr->overflow, kOvfEntries);
-          }
-        }
+    j = o.aux;
+  }
+  if (first == e) lk.occ[ev.link] = occ0 + net;
+  if (mine) {
+    const int32_t count = occ0 + before + 1;  // includes the entering agent itself
+    // host-tabulated max(0.1, 1/(1+alpha*(count/cap)**beta)) (traffic_manager.py:88-107), saturated at the floor
+    int64_t idx = f_lo + (int64_t)count;
+    if (idx >= f_hi) idx = f_hi - 1;
+    const double f = lk.factor[idx];
+    const double sp = __dmul_rn(__dmul_rn(v0, f), kph_to_mps);
+    a.speed[li] = sp;
+    a.elen[li] = len;
+    a.next_link[li] = next;
+    if (rg.ent_cap) {
+      const unsigned long long slot = atomicAdd(&ctr->n_entries, 1ULL);
+      if (slot - rg.ent_drained < rg.ent_cap) {
+        const unsigned long long k = slot % rg.ent_cap;
+        rg.ent_tick[k] = tick;
+        rg.ent_agent[k] = (int32_t)li;
+        rg.ent_link[k] = ev.link;
+        rg.ent_speed[k] = sp;
+      } else {
+        atomicOr(&ctr->overflow, kOvfEntries);
       }
     }
   }
@@ -761,6 +818,15 @@ __device__ __forceinline__ void resolve_one_p2p(const TickArgs& p, const P2PArgs
   const LinkArrays& lk = p.lk;
   const Event ev = events[e];
   const int first = (int)(lk.head[ev.link] & 0xffffffffu);
+  double v0 = 0.0, len = 0.0;
+  int64_t f_lo = 0, f_hi = 1;
+  if (ev.kind > 0) {  // loaded before the list walk: independent of it
+    const int32_t c = lk.cls[ev.link];
+    v0 = lk.v0[ev.link];
+    len = lk.len[ev.link];
+    f_lo = lk.cls_off[c];
+    f_hi = lk.cls_off[c + 1];
+  }
   int before = 0, net = 0, occ0 = 0;
   int j = first;
   for (;;) {
@@ -779,9 +845,10 @@ __device__ __forceinline__ void resolve_one_p2p(const TickArgs& p, const P2PArgs
     uint32_t li;
     p2p_home(x, ev.agent, home, li);
     const int32_t count = occ0 + before + 1;  // includes the entering agent itself
-    const double f = bpr_factor_lookup(lk, ev.link, count);
-    x.speed[home][li] = __dmul_rn(__dmul_rn(lk.v0[ev.link], f), p.kph_to_mps);
-    x.elen[home][li] = lk.len[ev.link];
+    int64_t idx = f_lo + (int64_t)count;
+    if (idx >= f_hi) idx = f_hi - 1;
+    x.speed[home][li] = __dmul_rn(__dmul_rn(v0, lk.factor[idx]), p.kph_to_mps);
+    x.elen[home][li] = len;
   }
 }
 

@@ -2,8 +2,10 @@
 
 The reference draws ``random.random()`` (MT19937) per waiting agent per tick (lib/agent.py:180); a
 sequential stream cannot be consumed in parallel, so the device-driven demand mode uses
-Philox4x32-10 (Salmon et al., SC'11) keyed (seed, global agent id, tick) and builds the double the
-same way MT's genrand_res53 does.  This file pins that generator independently of the CUDA code.
+Philox4x32-10 (Salmon et al., SC'11): one block = 128 bits = the draws of two agents, counter
+(global agent id >> 1, tick), key = seed; the even agent takes words 0-1, the odd one words 2-3,
+and the double is built the way MT's genrand_res53 does.  This file pins that generator
+independently of the CUDA code.
 """
 import numpy as np
 
@@ -15,7 +17,8 @@ MASK = np.uint64(0xFFFFFFFF)
 def uniform53(seed, agent, tick):
     """Vectorised over ``agent`` (uint32 array); ``tick`` scalar.  float64 in [0, 1)."""
     agent = np.asarray(agent, dtype=np.uint64)
-    c0 = agent & MASK
+    odd = (agent & np.uint64(1)).astype(bool)
+    c0 = (agent >> np.uint64(1)) & MASK
     c1 = np.full_like(c0, np.uint64(tick))
     c2 = np.full_like(c0, np.uint64(0x9E3779B9))
     c3 = np.full_like(c0, np.uint64(0xBB67AE85))
@@ -31,6 +34,6 @@ def uniform53(seed, agent, tick):
         c0, c1, c2, c3 = n0, lo1, n2, lo0
         k0 = (k0 + W0) & 0xFFFFFFFF
         k1 = (k1 + W1) & 0xFFFFFFFF
-    a = (c0 >> np.uint64(5)).astype(np.float64)
-    b = (c1 >> np.uint64(6)).astype(np.float64)
+    a = (np.where(odd, c2, c0) >> np.uint64(5)).astype(np.float64)
+    b = (np.where(odd, c3, c1) >> np.uint64(6)).astype(np.float64)
     return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0)
