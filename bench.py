@@ -42,6 +42,14 @@ WORKLOADS = {
                               "congestion-aware reroute of en-route agents every step (5 simulated minutes; extension)"),
     "bundled": dict(nodes=100, agents=300, model="random",
                     desc="configs[0]-sized: 100-node graph, random demand, 300 agents"),
+    # cold demand (every trip has its own source and destination): routing is one bounded search per trip
+    "grid_zone": dict(graph="grid", nodes=1_000_000, agents=1_000_000, model="zone", lookahead=True, arena_per_agent=768,
+                      desc="configs[3] at half linear scale (--nodes 4000000 --agents 10000000 = full size): 4-neighbour "
+                           "grid, lengths U[50,300] m, 50 km/h, zone-structured demand, lookahead route planning"),
+    "rgg_hub": dict(graph="rgg", nodes=200_000, agents=200_000, model="hub", reroute=True, lookahead=True, tps=30,
+                    arena_per_agent=768,
+                    desc="configs[4] scaled down: random geometric graph (mean degree 6), hub-and-spoke demand, "
+                         "congestion-aware reroute of every en-route agent at every step (30 ticks; extension)"),
 }
 T_START = 2 * 3600.0  # 08:00 in simulation clock terms (06:00 + 2 h): the morning peak (p = 0.35 * 4 / 3600 per s)
 
@@ -100,10 +108,17 @@ class ClockSampler:
 
 
 def build_workload(name, agents, seed, rank, nodes=None):
-    from drift_b200.synth import road_graph
+    from drift_b200.synth import grid_graph, rgg_graph, road_graph
 
     w = WORKLOADS[name]
-    lg = road_graph(nodes or w["nodes"], seed=seed, morton=os.environ.get("DRIFT_NO_MORTON") is None)
+    kind = w.get("graph", "road")
+    if kind == "grid":
+        side = int(round((nodes or w["nodes"]) ** 0.5))
+        lg = grid_graph(side, side, seed=seed, morton=True)
+    elif kind == "rgg":
+        lg = rgg_graph(nodes or w["nodes"], seed=seed)
+    else:
+        lg = road_graph(nodes or w["nodes"], seed=seed, morton=os.environ.get("DRIFT_NO_MORTON") is None)
     rng = np.random.default_rng(seed * 1000 + 17 + rank)
     start = rng.integers(0, lg.V, size=agents).astype(np.int32)
     return lg, start, w["model"], rng
@@ -168,6 +183,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     w = WORKLOADS[args.workload]
+    args.ticks_per_step = args.ticks_per_step or w.get("tps", 300)
     vals = []
     r = None
     for _ in range(args.warmup):
@@ -224,19 +240,20 @@ def run_b200(args):
     w = WORKLOADS[args.workload]
     n_local = args.agents or w["agents"]
     lg, start, model, rng = build_workload(args.workload, n_local, args.seed, rank, nodes=args.nodes)
-    K, W, TPS = args.steps, args.warmup, args.ticks_per_step
+    K, W, TPS = args.steps, args.warmup, args.ticks_per_step or w.get("tps", 300)
+    arena_links = max(1 << 24, n_local * w.get("arena_per_agent", 1536))
     trips_per_step = 2
     delta = 1.0
     sharded = None
     if world > 1:
         from drift_b200.dist import ShardedEngine
 
-        sharded = ShardedEngine(lg, n_local * world, device=local_rank, route_arena_links=max(1 << 24, n_local * 1536))
+        sharded = ShardedEngine(lg, n_local * world, device=local_rank, route_arena_links=arena_links)
         eng = sharded.engine
         if args.exchange == "p2p":
             sharded.enable_p2p()
     else:
-        eng = Engine(lg, n_local, device=local_rank, agent_base=0, route_arena_links=max(1 << 24, n_local * 1536))
+        eng = Engine(lg, n_local, device=local_rank, agent_base=0, route_arena_links=arena_links)
         bench_stream = torch.cuda.Stream(device=local_rank)  # the engine launches here, so torch events see its kernels
         eng.set_stream(bench_stream.cuda_stream)
     if sharded is not None:
@@ -245,6 +262,8 @@ def run_b200(args):
     total_steps = W + K
     _, dst_all = make_chains(model, rng, lg, start, 4 + trips_per_step * total_steps)
     dst_all = dst_all.reshape(n_local, -1)
+    if w.get("lookahead"):
+        eng.set_option("plan_lookahead", 1)
     for kv in args.opt:
         k, v = kv.split("=")
         eng.set_option(k, float(v))
@@ -428,6 +447,7 @@ def run_b200(args):
                                     "agents sharded by id block, graph replicated, per-tick all-gather of link events "
                                     "(NCCL), every rank resolves the global event set")) if world > 1 else "n/a"),
             routes_per_s=routes / dt, routes_in_timed_region=int(routes),
+            fallback_routes_in_timed_region=int(st1["fallback_routes"] - st0["fallback_routes"]),
             reroutes_per_s=(reroutes_timed / dt) if reroute else None, reroutes_in_timed_region=int(reroutes_timed),
             moving_fraction=float(moving / n_local),
             e2e=dict(value=e2e_value, unit="agent-steps/s", h2d_bytes_per_step=int(h2d),
@@ -463,7 +483,7 @@ def main():
     ap.add_argument("--workload", default="regional1m", choices=sorted(WORKLOADS))
     ap.add_argument("--agents", type=int, default=0, help="agents per GPU (default: the workload's)")
     ap.add_argument("--nodes", type=int, default=0, help="graph nodes (default: the workload's)")
-    ap.add_argument("--ticks-per-step", type=int, default=300)
+    ap.add_argument("--ticks-per-step", type=int, default=0, help="ticks per step (default: the workload's, 300)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg (0 = skip)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")

@@ -35,7 +35,7 @@ class GraphDesc(C.Structure):
 class StatsOut(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "moving_agents", "total_agents_on_roads", "total_capacity", "links_with_traffic",
-        "arrivals_total", "departures_total", "route_arena_used", "events_last_tick", "arena_compactions")]
+        "arrivals_total", "departures_total", "route_arena_used", "events_last_tick", "arena_compactions", "fallback_routes")]
 
 
 # name -> (restype, argtypes); must list every symbol of include/drift_b200.h

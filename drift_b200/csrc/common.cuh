@@ -56,6 +56,7 @@ struct Counters {
   unsigned long long tree_jobs;
   unsigned long long tree_iters;      // near-list waves (block barriers) over all jobs
   unsigned long long tree_far_visits; // far-list entries scanned by threshold advances
+  unsigned long long n_fallback;      // departures routed inside the tick because no planned route was ready
 };
 
 constexpr int kOvfEvents = 1;

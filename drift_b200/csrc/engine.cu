@@ -100,6 +100,10 @@ struct drift_engine {
   DevBuf<int64_t> next_off;
   int32_t chain_cap = 4;
   int32_t route_window = 300;
+  int32_t plan_lookahead = 0;   // 1 = plan routes only for departures that can happen in the coming window
+  int32_t plan_arrival_hops = -1;  // moving agents with at most this many links left may arrive in the window (-1 = from vmax / min length)
+  double vmax_kph = 0.0, min_len = 0.0;
+  DevBuf<unsigned long long> plan_thresh;
   DevBuf<int32_t> trip_stage, trip_pool;
   int64_t pool_blocks = 0, pool_k = 0;
   DevBuf<int64_t> route_off;
@@ -714,6 +718,10 @@ int drift_create(drift_engine** out, int device, const drift_graph_desc* g) {
   CUX(e->bwd_link.upload(g->bwd_link, g->Eb));
   CUX(e->link_len.upload(g->link_len, g->L));
   CUX(e->link_v0.upload(g->link_v0, g->L));
+  for (int32_t l = 0; l < g->L; ++l) {
+    e->vmax_kph = std::max(e->vmax_kph, g->link_v0[l]);
+    e->min_len = l == 0 ? g->link_len[l] : std::min(e->min_len, g->link_len[l]);
+  }
   CUX(e->link_t0.upload(g->link_t0, g->L));
   CUX(e->link_tt.upload(g->link_t0, g->L));
   CUX(e->link_cap.upload(g->link_cap, g->L));
@@ -1038,7 +1046,10 @@ int drift_refill_from_pool(drift_engine* e, int32_t block) {
 
 // Window planning: route, as one large batch, every missing prefetched route (next two trips of
 // every agent).  One host sync per window to learn the batch size.
-static int plan_window(drift_engine* e) {
+static double departure_probability(drift_engine* e, double t, double delta);
+
+// t_first = clock of the first tick of the window (lookahead planning evaluates the window's draws)
+static int plan_window(drift_engine* e, double t_first, double delta) {
   Counters* c = e->ctr.p;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (e->time_plan) {
@@ -1047,8 +1058,31 @@ static int plan_window(drift_engine* e) {
     cudaEventRecord(ev0, e->stream);
   }
   CU(cudaMemsetAsync(&c->n_plan, 0, sizeof(int32_t), e->stream));
-  k_plan_requests<<<grid_for(e->N, 256, kSMs * 8), 256, 0, e->stream>>>(e->agents(), c, e->q_src.p, e->q_dst.p,
-                                                                         e->q_agent.p, (int32_t)e->q_cap);
+  if (e->plan_lookahead) {
+    const int32_t W = e->route_window;
+    std::vector<unsigned long long> th(W);
+    double t = t_first;
+    for (int32_t k = 0; k < W; ++k) {  // same thresholds as the tick kernel's departure_threshold()
+      const double pk = departure_probability(e, t, delta);
+      const double sc = std::ceil(pk * 9007199254740992.0);
+      th[k] = !(pk > 0.0) ? 0ULL : (sc >= 18446744073709551615.0 ? ~0ULL : (unsigned long long)sc);
+      t += delta;
+    }
+    if (e->plan_thresh.n < W) CU(e->plan_thresh.alloc(W, false));
+    CU(cudaMemcpyAsync(e->plan_thresh.p, th.data(), sizeof(unsigned long long) * W, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));  // th is a stack-lifetime buffer
+    int32_t hops = e->plan_arrival_hops;
+    if (hops < 0) {
+      const double reach = (double)W * delta * e->vmax_kph * kKphToMps;  // metres an agent can cover in the window
+      hops = (int32_t)std::min(2.0e9, std::ceil(reach / std::max(e->min_len, 1e-3)) + 1.0);
+    }
+    k_plan_lookahead<<<grid_for((e->N + 1) / 2, 256, kSMs * 8), 256, 0, e->stream>>>(
+        e->agents(), c, e->q_src.p, e->q_dst.p, e->q_agent.p, (int32_t)e->q_cap, e->seed, (int32_t)e->tick + 1, W,
+        e->plan_thresh.p, hops);
+  } else {
+    k_plan_requests<<<grid_for(e->N, 256, kSMs * 8), 256, 0, e->stream>>>(e->agents(), c, e->q_src.p, e->q_dst.p,
+                                                                           e->q_agent.p, (int32_t)e->q_cap);
+  }
   CU(cudaGetLastError());
   e->total_launches += 1;
   Counters hc;
@@ -1095,7 +1129,7 @@ static double departure_probability(drift_engine* e, double t, double delta) {
 // one tick of device-driven demand up to (not including) the event resolution
 static int demand_tick_begin(drift_engine* e, double delta, double t) {
   if (e->ticks_since_plan <= 0) {
-    int rc = plan_window(e);
+    int rc = plan_window(e, t, delta);
     if (rc) return rc;
     e->ticks_since_plan = e->route_window;
   }
@@ -1114,7 +1148,7 @@ int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0) {
     int32_t k = 0;
     while (k < n_ticks) {
       if (e->ticks_since_plan <= 0) {
-        int rc = plan_window(e);
+        int rc = plan_window(e, t + delta, delta);
         if (rc) return rc;
         e->ticks_since_plan = e->route_window;
       }
@@ -1444,6 +1478,7 @@ int drift_stats(drift_engine* e, drift_stats_out* out) {
   out->departures_total = (int64_t)h.n_departures;
   out->route_arena_used = (int64_t)h.arena_cursor;
   out->arena_compactions = e->compactions;
+  out->fallback_routes = (int64_t)h.n_fallback;
   out->events_last_tick = 0;
   for (int sb = 0; sb < kEvSub; ++sb) out->events_last_tick += h.n_events[e->tick & 1][sb];
   return check_overflow(e, h);
@@ -1685,6 +1720,10 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
     e->persistent = value != 0;
   } else if (s == "coop_blocks_per_sm") {
     e->coop_blocks_per_sm = std::max(1, (int)value);
+  } else if (s == "plan_lookahead") {
+    e->plan_lookahead = value != 0;
+  } else if (s == "plan_arrival_hops") {
+    e->plan_arrival_hops = (int32_t)value;
   } else if (s == "route_window") {
     if (value < 1) return fail(DRIFT_EINVAL, "route_window must be >= 1");
     e->route_window = (int32_t)value;

@@ -280,6 +280,62 @@ __global__ void k_plan_requests(AgentArrays a, Counters* ctr, int32_t* __restric
   }
 }
 
+// Lookahead planning: the departure draws are counter-based (seed, agent, tick), so the planner can
+// evaluate the coming window's draws and ask for routes only where departures can happen in it:
+// agents with one hit need the route of their next trip, agents with two or more hits also the one
+// after it (a short first trip can end inside the window).  Moving agents count only if they may
+// arrive within the window (at most `max_hops_left` links to go).  A third departure inside one
+// window falls back to the in-tick router.  One thread per agent pair (the two agents of a pair share
+// a Philox block, common.cuh).
+__global__ void k_plan_lookahead(AgentArrays a, Counters* ctr, int32_t* __restrict__ q_src, int32_t* __restrict__ q_dst,
+                                 int32_t* __restrict__ q_agent, int32_t q_cap, uint64_t seed, int32_t tick0,
+                                 int32_t n_ticks, const unsigned long long* __restrict__ thresh,
+                                 int32_t max_hops_left) {
+  const int64_t pairs = (a.n + 1) / 2;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < pairs; t += (int64_t)gridDim.x * blockDim.x) {
+    bool want[2] = {false, false};
+    for (int h = 0; h < 2; ++h) {
+      const int64_t i = 2 * t + h;
+      if (i >= a.n || a.chain_cnt[i] == 0) continue;
+      if (a.next_status[i] != 0 && (a.chain_cnt[i] < 2 || a.next_status[a.npad + i] != 0)) continue;  // nothing missing
+      want[h] = a.state[i] != kMoving || (a.route_len[i] - a.route_idx[i] - 1 <= max_hops_left);
+    }
+    if (!want[0] && !want[1]) continue;
+    const uint32_t gid0 = a.base + (uint32_t)(2 * t);
+    int hits[2] = {0, 0};
+    for (int k = 0; k < n_ticks; ++k) {
+      const unsigned long long th = thresh[k];
+      if ((gid0 & 1u) == 0) {
+        uint32_t o[4];
+        philox4x32_10(seed, gid0 >> 1, (uint32_t)(tick0 + k), o);
+        hits[0] += bits53(o[0], o[1]) < th;
+        hits[1] += bits53(o[2], o[3]) < th;
+      } else {
+        if (want[0]) hits[0] += philox_bits53(seed, gid0, (uint32_t)(tick0 + k)) < th;
+        if (want[1]) hits[1] += philox_bits53(seed, gid0 + 1u, (uint32_t)(tick0 + k)) < th;
+      }
+      if ((hits[0] >= 2 || !want[0]) && (hits[1] >= 2 || !want[1])) break;
+    }
+    for (int h = 0; h < 2; ++h) {
+      if (!want[h] || hits[h] == 0) continue;
+      const int64_t i = 2 * t + h;
+      const int head = a.chain_head[i];
+      const int32_t* ring = a.chain_dst + i * a.chain_cap;
+      for (int k = 0; k < 2; ++k) {
+        if (k == 1 && (hits[h] < 2 || a.chain_cnt[i] < 2)) break;
+        if (a.next_status[(int64_t)k * a.npad + i] != 0) continue;
+        const int r = atomicAdd(&ctr->n_plan, 1);
+        if (r < q_cap) {
+          // trip k starts where trip k-1 ends; trip 0 at the agent's position / current target
+          q_src[r] = k == 0 ? a.cur_node[i] : ring[head];
+          q_dst[r] = ring[(head + k) % a.chain_cap];
+          q_agent[r] = (int32_t)i * 2 + k;
+        }
+      }
+    }
+  }
+}
+
 // Extension (congestion-aware rerouting, SURVEY.md 8c last row): every moving agent asks for a new
 // route from the head of its current link to its destination.
 __global__ void k_reroute_requests(AgentArrays a, const int32_t* __restrict__ link_v,

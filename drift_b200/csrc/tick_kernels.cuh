@@ -396,6 +396,7 @@ __device__ __noinline__ void phase_inject(const TickArgs& p, int32_t tick, int n
   const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
   for (int64_t q = gtid; q < n_pending; q += gsz)
     if (p.pend_len[q] > 0) start_on_route(p, p.pend_agent[q], p.pend_off[q], p.pend_len[q], tick);
+  if (n_urgent > 0 && gtid == 0) p.ctr->n_fallback += (unsigned long long)n_urgent;
   if (n_urgent > 0 && gtid < p.fsc.workers) {
     const AgentArrays& a = p.a;
     uint32_t epoch = p.fsc.epoch[gtid];
@@ -781,6 +782,7 @@ __device__ __noinline__ void phase_inject_p2p(const TickArgs& p, const P2PArgs& 
   const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
   for (int64_t q = gtid; q < n_pending; q += gsz)
     if (p.pend_len[q] > 0) start(p.pend_agent[q], p.pend_off[q], p.pend_len[q]);
+  if (n_urgent > 0 && gtid == 0) p.ctr->n_fallback += (unsigned long long)n_urgent;
   if (n_urgent > 0 && gtid < p.fsc.workers) {
     uint32_t epoch = p.fsc.epoch[gtid];
     for (int r = (int)gtid; r < n_urgent; r += p.fsc.workers) {

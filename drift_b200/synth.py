@@ -13,8 +13,11 @@ import numpy as np
 from .graph import LoweredGraph, from_links
 
 
-def grid_graph(nx_cols, ny_rows, seed=0, len_lo=50.0, len_hi=300.0, speed_kph=50.0, lanes=1.0) -> LoweredGraph:
-    """4-neighbour grid, both directions (config 4: 2000 x 2000 -> 4 M nodes / 15.992 M links)."""
+def grid_graph(nx_cols, ny_rows, seed=0, len_lo=50.0, len_hi=300.0, speed_kph=50.0, lanes=1.0,
+               morton=False) -> LoweredGraph:
+    """4-neighbour grid, both directions (config 4: 2000 x 2000 -> 4 M nodes / 15.992 M links).
+    ``morton``: number the nodes along a Z-order curve instead of row by row (same graph, better
+    locality of the per-node arrays)."""
     rng = np.random.default_rng(seed)
     W, H = int(nx_cols), int(ny_rows)
     V = W * H
@@ -34,6 +37,15 @@ def grid_graph(nx_cols, ny_rows, seed=0, len_lo=50.0, len_hi=300.0, speed_kph=50
     L = len(u)
     length = rng.uniform(len_lo, len_hi, size=L)
     pos = np.stack([col, row], axis=1).astype(np.float64)
+    if morton:
+        rank = np.empty(V, dtype=np.int64)
+        rank[np.argsort(_morton(col, row), kind="stable")] = np.arange(V)
+        u, v = rank[u], rank[v]
+        order = np.lexsort((v, u))
+        u, v, length = u[order], v[order], length[order]
+        p2 = np.empty_like(pos)
+        p2[rank] = pos
+        pos = p2
     return from_links(V, u, v, length, np.full(L, float(speed_kph)), np.full(L, float(lanes)), pos=pos)
 
 
@@ -98,3 +110,43 @@ def road_graph(num_nodes, seed=0, mean_degree=2.6, morton=True) -> LoweredGraph:
     pos[new_id[kept], 0] = col[kept] + rng.uniform(-0.3, 0.3, V)
     pos[new_id[kept], 1] = row[kept] + rng.uniform(-0.3, 0.3, V)
     return from_links(V, u, v, length, speed, lanes, pos=pos)
+
+
+def rgg_graph(num_nodes, seed=0, mean_degree=6.0, mean_length_m=120.0, speed_kph=50.0, morton=True) -> LoweredGraph:
+    """Random geometric graph (config 5): points uniform in the unit square, an edge in both
+    directions between points closer than the radius that gives ``mean_degree`` neighbours, largest
+    connected component kept, length = Euclidean distance scaled to ``mean_length_m`` on average
+    (continuous => unique shortest paths), one lane at ``speed_kph``."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from scipy.spatial import cKDTree
+
+    rng = np.random.default_rng(seed)
+    n0 = int(num_nodes * 1.03)
+    pts = rng.random((n0, 2))
+    r = np.sqrt(mean_degree / (np.pi * n0))
+    pairs = cKDTree(pts).query_pairs(r, output_type="ndarray")
+    adj = coo_matrix((np.ones(len(pairs), dtype=np.int8), (pairs[:, 0], pairs[:, 1])), shape=(n0, n0))
+    _, lab = connected_components(adj, directed=False)
+    keep = lab == np.argmax(np.bincount(lab))
+    kept = np.nonzero(keep)[0]
+    V = len(kept)
+    new_id = np.full(n0, -1, dtype=np.int64)
+    if morton:
+        q = np.minimum((pts[kept] * 65535.0).astype(np.int64), 65535)
+        new_id[kept[np.argsort(_morton(q[:, 0], q[:, 1]), kind="stable")]] = np.arange(V)
+    else:
+        new_id[kept] = np.arange(V)
+    pairs = pairs[keep[pairs[:, 0]] & keep[pairs[:, 1]]]
+    a, b = new_id[pairs[:, 0]], new_id[pairs[:, 1]]
+    d = np.hypot(*(pts[pairs[:, 0]] - pts[pairs[:, 1]]).T)
+    u = np.concatenate([a, b])
+    v = np.concatenate([b, a])
+    length = np.concatenate([d, d])
+    order = np.lexsort((v, u))
+    u, v, length = u[order], v[order], length[order]
+    length = np.maximum(length * (mean_length_m / length.mean()), 1.0)
+    L = len(u)
+    pos = np.empty((V, 2))
+    pos[new_id[kept]] = pts[kept]
+    return from_links(V, u, v, length, np.full(L, float(speed_kph)), np.ones(L), pos=pos)

@@ -87,6 +87,7 @@ typedef struct drift_stats_out {
   int64_t route_arena_used;      /* link ids currently held in the route arena */
   int64_t events_last_tick;
   int64_t arena_compactions;     /* times the live routes were copied into the spare arena */
+  int64_t fallback_routes;       /* departures routed inside a tick because no planned route was ready */
 } drift_stats_out;
 
 const char* drift_last_error(void);

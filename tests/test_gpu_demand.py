@@ -14,10 +14,12 @@ from oracle.port import DEFAULT_HOURLY, PortSim, travel_probability
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,router,window,persistent", [
-    ("g40_congested", 0, 25, 1), ("g100_random_s0", 0, 300, 1), ("multi_random_s0", 0, 7, 1), ("g40_congested", 0, 1, 1),
-    ("g40_congested", 0, 25, 0), ("multi_random_s0", 0, 300, 0)])
-def test_device_demand_matches_port(name, router, window, persistent):
+@pytest.mark.parametrize("name,router,window,persistent,lookahead", [
+    ("g40_congested", 0, 25, 1, 0), ("g100_random_s0", 0, 300, 1, 0), ("multi_random_s0", 0, 7, 1, 0),
+    ("g40_congested", 0, 1, 1, 0), ("g40_congested", 0, 25, 0, 0), ("multi_random_s0", 0, 300, 0, 0),
+    # lookahead planning: routes only for the departures the coming window's draws allow
+    ("g40_congested", 0, 25, 1, 1), ("g100_random_s0", 0, 50, 1, 1), ("multi_random_s0", 0, 7, 0, 1)])
+def test_device_demand_matches_port(name, router, window, persistent, lookahead):
     from drift_b200.engine import Engine
     from drift_b200.graph import lower_graph
 
@@ -36,6 +38,7 @@ def test_device_demand_matches_port(name, router, window, persistent):
         eng.set_demand(seed, h24, start, chain_capacity=per_agent, router=router)
         eng.set_option("route_window", window)
         eng.set_option("persistent", persistent)
+        eng.set_option("plan_lookahead", lookahead)
         eng.push_trips(cands)
         occs, t = [], 0.0
         dep_log = []
