@@ -159,7 +159,8 @@ struct drift_engine {
   DevBuf<uint32_t> t_slot_job_batch;
   int32_t t_bounded_max = -1;  // -1 = automatic: bounded search only when the cache cannot hold every destination
   int32_t t_threads = 256;
-  int64_t tree_scratch_bytes = (int64_t)24 << 30;
+  int64_t tree_scratch_bytes = (int64_t)64 << 30;
+  bool tree_budget_set = false, tree_scratch_set = false;
   uint32_t t_batch = 0;
   DevBuf<int32_t> t_lists;
   DevBuf<double> lm_from, lm_to;
@@ -365,6 +366,12 @@ int ensure_qcap(drift_engine* e, int64_t Q) {
 int ensure_trees(drift_engine* e) {
   if (e->t_max_slots) return DRIFT_OK;
   const int64_t V = e->V;
+  {  // budgets follow the free HBM unless set by option: up to 48 GB of cached trees, 64 GB of search scratch
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    if (!e->tree_budget_set) e->tree_budget_bytes = std::min<int64_t>((int64_t)48 << 30, (int64_t)(free_b * 0.30));
+    if (!e->tree_scratch_set) e->tree_scratch_bytes = std::min<int64_t>((int64_t)64 << 30, (int64_t)(free_b * 0.40));
+  }
   int64_t slots = std::min<int64_t>(e->t_sides * V, e->tree_budget_bytes / (4 * V));
   slots = std::max<int64_t>(slots, 1);
   // resident builder blocks: 32 B of scratch per node each
@@ -814,6 +821,9 @@ int drift_add_agents(drift_engine* e, int64_t n_agents, int64_t agent_base, int6
   CU(e->next_status.alloc(2 * Np));
   if (route_arena_links <= 0) route_arena_links = std::max<int64_t>((int64_t)1 << 20, n_agents * 64);
   CU(e->arena.alloc(route_arena_links, false));
+  // the spare arena of the compaction is allocated up front: a first cudaMalloc of several GB inside a
+  // planning window costs ~100 ms (observed as a one-off spike of the step time)
+  if (route_arena_links >= ((int64_t)1 << 26)) CU(e->arena2.alloc(route_arena_links, false));
   e->arena_cap = route_arena_links;
   // every sub-buffer can hold all events of a tick in the worst case only if the warps spread evenly;
   // sized with a 4x margin over the even share and checked at run time (overflow flag)
@@ -1714,6 +1724,7 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
   if (s == "tree_cache_bytes") {
     if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_cache_bytes must be set before the first batched route");
     e->tree_budget_bytes = (int64_t)value;
+    e->tree_budget_set = true;
   } else if (s == "time_plan") {
     e->time_plan = value != 0;
   } else if (s == "persistent") {
@@ -1745,10 +1756,11 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
   } else if (s == "tree_scratch_bytes") {
     if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_scratch_bytes must be set before the first batched route");
     e->tree_scratch_bytes = (int64_t)value;
+    e->tree_scratch_set = true;
   } else if (s == "tree_threads") {
     if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_threads must be set before the first batched route");
     const int v = (int)value;
-    if (v != 64 && v != 128 && v != 256 && v != 512 && v != 1024) return fail(DRIFT_EINVAL, "tree_threads: 64..1024");
+    if (v != 64 && v != 128 && v != 256) return fail(DRIFT_EINVAL, "tree_threads: 64, 128 or 256");
     e->t_threads = v;
   } else if (s == "bounded_max") {
     e->t_bounded_max = std::max(0, std::min((int)value, kMaxBounded));

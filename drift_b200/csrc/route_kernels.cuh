@@ -539,7 +539,8 @@ struct TreeCache {
 constexpr int kMaxBounded = 8;
 
 constexpr unsigned long long kInfBits = 0x7FF0000000000000ULL;
-constexpr int kTreeThreadsMax = 1024;
+constexpr int kTreeThreadsMax = 256;
+constexpr int kTreeBlocksPerSM = 8;  // 32 registers per thread: searches are latency-bound, residency is what pays
 
 __device__ __forceinline__ bool tree_query_ok(int32_t s, int32_t t, int32_t V) {
   return s >= 0 && t >= 0 && s < V && t < V && s != t;
@@ -663,10 +664,109 @@ __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v
   return *s_min;
 }
 
+// First entry e of [e0, e1) (CSR order) whose hop is tight: rec[col[e]].dist + w[e] == du.  The loads of
+// four entries are issued together (col/w, then the four labels), so a hop of the walk below costs
+// three dependent memory levels instead of two per entry.  Returns the entry, its label in *d_next.
+__device__ __forceinline__ int32_t find_tight_entry(int32_t e0, int32_t e1, unsigned long long du,
+                                                    const NodeRec* __restrict__ rec, const int32_t* __restrict__ col,
+                                                    const double* __restrict__ w, unsigned long long* d_next) {
+  for (int32_t eb = e0; eb < e1; eb += 4) {
+    int32_t c[4];
+    double ww[4];
+    unsigned long long d[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int32_t e = eb + k < e1 ? eb + k : e1 - 1;
+      c[k] = col[e];
+      ww[k] = w[e];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d[k] = rec[c[k]].dist;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (eb + k >= e1 || d[k] == kInfBits) continue;
+      const double s = __dadd_rn(__longlong_as_double((long long)d[k]), ww[k]);
+      if ((unsigned long long)__double_as_longlong(s) == du) {
+        *d_next = d[k];
+        return eb + k;
+      }
+    }
+  }
+  return -1;
+}
+
+// Route of one query of a bounded search, straight from dist[]: at x follow the first forward entry
+// (CSR order) that is tight; every node on the way is already final.  One pass: the links go to `tmp`
+// (scratch of the finished search) and are copied into the arena once their number is known; routes
+// longer than `tmp_cap` are walked a second time instead.
+__device__ __forceinline__ void route_from_labels(const GraphArrays& g, const double* __restrict__ w_fwd,
+                                                  const NodeRec* __restrict__ rec, int32_t sn, int32_t dest,
+                                                  int32_t* __restrict__ tmp, int32_t tmp_cap,
+                                                  int32_t* __restrict__ arena, unsigned long long arena_cap,
+                                                  Counters* ctr, const double* __restrict__ link_cost, int32_t q,
+                                                  const RouteOut& out) {
+  const int64_t V = g.V;
+  int32_t status = DRIFT_ROUTE_NOPATH, hops = 0;
+  int64_t off = 0;
+  double cost = 0.0;
+  if (sn == dest) {
+    status = DRIFT_ROUTE_TRIVIAL;
+  } else if (sn >= 0 && sn < V && rec[sn].dist != kInfBits) {
+    int k = 0;
+    int32_t x = sn;
+    unsigned long long dx = rec[sn].dist;
+    while (x != dest) {
+      unsigned long long dn = 0;
+      const int32_t e = find_tight_entry(g.fwd_rowptr[x], g.fwd_rowptr[x + 1], dx, rec, g.fwd_col, w_fwd, &dn);
+      if (e < 0 || k > V) {
+        k = -1;
+        break;
+      }
+      if (k < tmp_cap) tmp[k] = g.fwd_link[e];
+      ++k;
+      x = g.fwd_col[e];
+      dx = dn;
+    }
+    if (k > 0) {
+      hops = k;
+      const unsigned long long o = atomicAdd(&ctr->arena_cursor, (unsigned long long)hops);
+      if (o + hops > arena_cap) {
+        atomicOr(&ctr->overflow, kOvfArena);
+      } else {
+        off = (int64_t)o;
+        if (hops <= tmp_cap) {
+          for (int j = 0; j < hops; ++j) {
+            const int32_t l = tmp[j];
+            arena[off + j] = l;
+            cost = __dadd_rn(cost, link_cost[l]);
+          }
+        } else {  // longer than the scratch: walk again
+          x = sn;
+          dx = rec[sn].dist;
+          for (int j = 0; j < hops; ++j) {
+            unsigned long long dn = 0;
+            const int32_t e = find_tight_entry(g.fwd_rowptr[x], g.fwd_rowptr[x + 1], dx, rec, g.fwd_col, w_fwd, &dn);
+            const int32_t l = g.fwd_link[e];
+            arena[off + j] = l;
+            cost = __dadd_rn(cost, link_cost[l]);
+            x = g.fwd_col[e];
+            dx = dn;
+          }
+        }
+        status = DRIFT_ROUTE_OK;
+      }
+    }
+  }
+  out.status[q] = status;
+  out.n_links[q] = status == DRIFT_ROUTE_OK ? hops : 0;
+  out.off[q] = status == DRIFT_ROUTE_OK ? off : 0;
+  out.cost[q] = cost;
+}
+
 // Jobs whose destination is wanted by at most tc.bounded_max queries of the batch ("cold"
 // destinations) stop as soon as all their sources are settled, write those routes themselves
 // (walking dist[] from the source) and do not keep a tree; the others build and cache the tree.
-__global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, const double* __restrict__ w_bwd,
+__global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_trees(GraphArrays g, const double* __restrict__ w_bwd,
                                                               const double* __restrict__ w_fwd, double delta,
                                                               TreeCache tc, TreeScratch sc,
                                                               const int32_t* __restrict__ q_src,
@@ -886,11 +986,12 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
           const int32_t u = x_col[e];
           const double cand = __dadd_rn(s_dv[lo], x_w[e]);
           const unsigned long long cb = (unsigned long long)__double_as_longlong(cand);
+          const double pu = pot(u);  // issued before the atomic: one dependent memory level less per wave
           const unsigned long long old = atomicMin(&rec[u].dist, cb);
           if (cb < old) {
             ++c_improved;
             if (old == kInfBits) touched[atomicAdd(&s_touched, 1)] = u;  // exactly one thread sees the first label
-            if (__dadd_rn(cand, pot(u)) <= T) {
+            if (__dadd_rn(cand, pu) <= T) {
               if (atomicExch(&rec[u].stamp, iter) != iter) nearB[atomicAdd(&s_next_n, 1)] = u;
             } else if (atomicExch(&rec[u].infar, 1u) == 0u) {
               farA[atomicAdd(&s_far_n, 1)] = u;  // at most one far entry per node: <= V entries
@@ -910,64 +1011,12 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
       __syncthreads();
     }
     if (bounded) {
-      // routes of the few sources, straight from dist[]: at x follow the first forward entry (CSR
-      // order) with rec[head].dist + w == rec[x].dist; every node on the way is already final
+      // routes of the few sources, straight from dist[] (route_from_labels); the far list of the finished
+      // search is the scratch the links are collected in
       if (threadIdx.x < nb) {
-        const int32_t q = s_bq[threadIdx.x];
-        const int32_t sn = s_bsrc[threadIdx.x];
-        int32_t status = DRIFT_ROUTE_NOPATH, hops = 0;
-        int64_t off = 0;
-        double cost = 0.0;
-        if (sn == dest) {
-          status = DRIFT_ROUTE_TRIVIAL;
-        } else if (sn >= 0 && sn < V && rec[sn].dist != kInfBits) {
-          for (int pass = 0; pass < 2; ++pass) {
-            int32_t x = sn;
-            int k = 0;
-            while (x != dest) {
-              const unsigned long long dx = rec[x].dist;
-              int32_t nl = -1, nx = -1;
-              const int32_t e1 = g.fwd_rowptr[x + 1];
-              for (int32_t e = g.fwd_rowptr[x]; e < e1; ++e) {
-                const unsigned long long dvb = rec[g.fwd_col[e]].dist;
-                if (dvb == kInfBits) continue;
-                const double c = __dadd_rn(__longlong_as_double((long long)dvb), w_fwd[e]);
-                if ((unsigned long long)__double_as_longlong(c) == dx) {
-                  nl = g.fwd_link[e];
-                  nx = g.fwd_col[e];
-                  break;
-                }
-              }
-              if (nl < 0 || k > V) {
-                k = -1;
-                break;
-              }
-              if (pass) {
-                arena[off + k] = nl;
-                cost = __dadd_rn(cost, link_cost[nl]);
-              }
-              ++k;
-              x = nx;
-            }
-            if (k < 0) break;
-            if (!pass) {
-              hops = k;
-              const unsigned long long o = atomicAdd(&ctr->arena_cursor, (unsigned long long)hops);
-              if (o + hops > arena_cap) {
-                atomicOr(&ctr->overflow, kOvfArena);
-                hops = 0;
-                break;
-              }
-              off = (int64_t)o;
-            } else {
-              status = DRIFT_ROUTE_OK;
-            }
-          }
-        }
-        out.status[q] = status;
-        out.n_links[q] = status == DRIFT_ROUTE_OK ? hops : 0;
-        out.off[q] = status == DRIFT_ROUTE_OK ? off : 0;
-        out.cost[q] = cost;
+        const int32_t tcap = (int32_t)(V / kMaxBounded);
+        route_from_labels(g, w_fwd, rec, s_bsrc[threadIdx.x], dest, farB + (int64_t)threadIdx.x * tcap, tcap, arena,
+                          arena_cap, ctr, link_cost, s_bq[threadIdx.x], out);
       }
       if (threadIdx.x == 0) tc.slot_of[dest] = -1;  // no tree was kept
       __syncthreads();
@@ -989,16 +1038,9 @@ __global__ void __launch_bounds__(kTreeThreadsMax) k_build_trees(GraphArrays g, 
         int32_t nl = -1;
         const unsigned long long du = rec[u].dist;
         if (u != dest && du != kInfBits) {
-          const int32_t e1 = y_rowptr[u + 1];
-          for (int32_t e = y_rowptr[u]; e < e1; ++e) {
-            const unsigned long long dvb = rec[y_col[e]].dist;
-            if (dvb == kInfBits) continue;
-            const double c = __dadd_rn(__longlong_as_double((long long)dvb), y_w[e]);
-            if ((unsigned long long)__double_as_longlong(c) == du) {
-              nl = y_link[e];
-              break;
-            }
-          }
+          unsigned long long dn = 0;
+          const int32_t e = find_tight_entry(y_rowptr[u], y_rowptr[u + 1], du, rec, y_col, y_w, &dn);
+          if (e >= 0) nl = y_link[e];
         }
         next_link[u] = nl;
       }
@@ -1270,60 +1312,9 @@ __global__ void __launch_bounds__(kWarpSearchThreads) k_search_warp(
     }
     // routes of the sources, straight from dist[] (as in k_build_trees)
     if (my_q >= 0) {
-      const int32_t sn = my_src;
-      int32_t status = DRIFT_ROUTE_NOPATH, hops = 0;
-      int64_t off = 0;
-      double cost = 0.0;
-      if (sn == dest) {
-        status = DRIFT_ROUTE_TRIVIAL;
-      } else if (sn >= 0 && sn < V && rec[sn].dist != kInfBits) {
-        for (int pass = 0; pass < 2; ++pass) {
-          int32_t x = sn;
-          int k = 0;
-          while (x != dest) {
-            const unsigned long long dx = rec[x].dist;
-            int32_t nl = -1, nx = -1;
-            const int32_t e1 = g.fwd_rowptr[x + 1];
-            for (int32_t e = g.fwd_rowptr[x]; e < e1; ++e) {
-              const unsigned long long dvb = rec[g.fwd_col[e]].dist;
-              if (dvb == kInfBits) continue;
-              const double c = __dadd_rn(__longlong_as_double((long long)dvb), w_fwd[e]);
-              if ((unsigned long long)__double_as_longlong(c) == dx) {
-                nl = g.fwd_link[e];
-                nx = g.fwd_col[e];
-                break;
-              }
-            }
-            if (nl < 0 || k > V) {
-              k = -1;
-              break;
-            }
-            if (pass) {
-              arena[off + k] = nl;
-              cost = __dadd_rn(cost, link_cost[nl]);
-            }
-            ++k;
-            x = nx;
-          }
-          if (k < 0) break;
-          if (!pass) {
-            hops = k;
-            const unsigned long long o = atomicAdd(&ctr->arena_cursor, (unsigned long long)hops);
-            if (o + hops > arena_cap) {
-              atomicOr(&ctr->overflow, kOvfArena);
-              hops = 0;
-              break;
-            }
-            off = (int64_t)o;
-          } else {
-            status = DRIFT_ROUTE_OK;
-          }
-        }
-      }
-      out.status[my_q] = status;
-      out.n_links[my_q] = status == DRIFT_ROUTE_OK ? hops : 0;
-      out.off[my_q] = status == DRIFT_ROUTE_OK ? off : 0;
-      out.cost[my_q] = cost;
+      const int32_t tcap = (int32_t)(V / kMaxBounded);
+      route_from_labels(g, w_fwd, rec, my_src, dest, farB + (int64_t)lane * tcap, tcap, arena, arena_cap, ctr, link_cost,
+                        my_q, out);
     }
     if (lane == 0) tc.slot_of[dest] = -1;  // no tree was kept
     __syncwarp();

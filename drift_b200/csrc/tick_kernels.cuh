@@ -349,6 +349,7 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
             atomicOr(&p.ctr->overflow, kOvfExchange);
           }
         }
+        if (n) __threadfence_system();  // this warp's peer stores are visible before the block reaches the grid barrier
       }
     } else if (n_blk && !(p.debug & 4)) {  // one global atomic per block and tile, spread over kEvSub counters
       const int sub = (int)(tile % kEvSub);
@@ -758,6 +759,7 @@ __device__ __forceinline__ void p2p_send_one(const TickArgs& p, const P2PArgs& x
     e.kind = kind;
     e.aux = 0;
     *reinterpret_cast<int4*>(x.inbox[o] + (int64_t)x.rank * x.cap + pos) = *reinterpret_cast<const int4*>(&e);
+    __threadfence_system();
   } else {
     atomicOr(&p.ctr->overflow, kOvfExchange);
   }
@@ -815,7 +817,7 @@ __device__ __noinline__ void phase_inject_p2p(const TickArgs& p, const P2PArgs& 
 
 // Owner side of phase C: ordered count on an owned link -> entry speed, written into the home
 // rank's agent arrays (peer store); the list head writes the end-of-tick occupancy of the link.
-__device__ __forceinline__ void resolve_one_p2p(const TickArgs& p, const P2PArgs& x, const Event* __restrict__ events,
+__device__ __forceinline__ bool resolve_one_p2p(const TickArgs& p, const P2PArgs& x, const Event* __restrict__ events,
                                                 int e) {
   const LinkArrays& lk = p.lk;
   const Event ev = events[e];
@@ -851,7 +853,9 @@ __device__ __forceinline__ void resolve_one_p2p(const TickArgs& p, const P2PArgs
     if (idx >= f_hi) idx = f_hi - 1;
     x.speed[home][li] = __dmul_rn(__dmul_rn(v0, lk.factor[idx]), p.kph_to_mps);
     x.elen[home][li] = len;
+    return home != x.rank;
   }
+  return false;
 }
 
 // One cooperative launch per rank runs `n_ticks` ticks; the ranks meet twice per tick through flags
@@ -876,12 +880,10 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
       phase_advance<true, true>(p, tick, p_dep, sm, &x, &xs);
     else
       phase_advance<false, true>(p, tick, p_dep, sm, &x, &xs);
-    __threadfence_system();  // the peer stores of this thread are visible before the count is published
-    grid.sync();
+    grid.sync();  // writers fenced their peer stores (system scope) before arriving here
     const int n_pending = ctr->n_pending, n_urgent = ctr->n_dep_req[par];
     if (n_pending | n_urgent) {  // uniform across the grid
       phase_inject_p2p(p, x, tick, n_pending, n_urgent);
-      __threadfence_system();
       grid.sync();
     }
     if (blockIdx.x == 0 && threadIdx.x < x.world) {  // publish: this rank's events are in owner o's inbox
@@ -927,9 +929,9 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
       int r = 0;
       while (r + 1 < x.world && s_pref[r + 1] <= f) ++r;
-      resolve_one_p2p(p, x, inbox, r * x.cap + (f - s_pref[r]));
+      if (resolve_one_p2p(p, x, inbox, r * x.cap + (f - s_pref[r])))
+        __threadfence_system();  // the entry speed is in the home rank's arrays before "done" is published
     }
-    __threadfence_system();  // entry speeds are in the home ranks' arrays before "done" is published
     grid.sync();
     if (blockIdx.x == 0 && threadIdx.x < x.world)
       st_release_sys(x.flags[threadIdx.x] + kMaxRanks + x.rank, (unsigned long long)(uint32_t)tick << 32);
