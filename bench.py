@@ -79,7 +79,7 @@ class ClockSampler:
                 self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -241,7 +241,7 @@ def run_b200(args):
     n_local = args.agents or w["agents"]
     lg, start, model, rng = build_workload(args.workload, n_local, args.seed, rank, nodes=args.nodes)
     K, W, TPS = args.steps, args.warmup, args.ticks_per_step or w.get("tps", 300)
-    arena_links = max(1 << 24, n_local * w.get("arena_per_agent", 1536))
+    arena_links = max(1 << 24, n_local * w.get("arena_per_agent", 2560))
     trips_per_step = 2
     delta = 1.0
     sharded = None
@@ -260,8 +260,12 @@ def run_b200(args):
         bench_stream = torch.cuda.current_stream(local_rank)
     # HBM-resident pass: candidate destinations of all warm-up + timed steps uploaded once
     total_steps = W + K
-    _, dst_all = make_chains(model, rng, lg, start, 4 + trips_per_step * total_steps)
+    # one chain per agent covers both passes (resident + e2e), so that both draw from the same activity
+    # pools / hubs and the e2e pass does not pay for trees of a second, unrelated demand pattern
+    _, dst_all = make_chains(model, rng, lg, start, 4 + trips_per_step * (total_steps + K + 1))
     dst_all = dst_all.reshape(n_local, -1)
+    dst_e2e = dst_all[:, 4 + trips_per_step * total_steps:]
+    dst_all = dst_all[:, :4 + trips_per_step * total_steps]
     if w.get("lookahead"):
         eng.set_option("plan_lookahead", 1)
     for kv in args.opt:
@@ -297,6 +301,7 @@ def run_b200(args):
         if resident:
             eng.refill_from_pool(step_no[0])
             step_no[0] += 1
+            eng.discard_logs()  # nothing is read back in the resident pass: free the rings (no copy)
         if reroute and eng.tick > 0:  # K4 + reroute of en-route agents + fresh routes for this step's departures
             eng.update_travel_times()
             n_reroutes[0] += eng.reroute_moving(ROUTER_BATCHED)
@@ -344,8 +349,7 @@ def run_b200(args):
     reroutes_timed = n_reroutes[0]
 
     # ---- e2e pass: per step H2D of the step's chains (pinned) + D2H of arrivals/departures/volumes
-    _, dst_s = make_chains(model, rng, lg, start, trips_per_step * (K + 1))
-    dst_s = dst_s.reshape(n_local, K + 1, trips_per_step)
+    dst_s = np.ascontiguousarray(dst_e2e).reshape(n_local, K + 1, trips_per_step)
     keep_t, blocks_p = zip(*[pinned(dst_s[:, b, :]) for b in range(K + 1)])
     h2d = blocks_p[0].nbytes
     d2h_total = 0
@@ -353,6 +357,10 @@ def run_b200(args):
     run_block(False)  # warm the per-step path
     eng.drain_arrivals(), eng.drain_departures(), (sharded.occupancy() if sharded is not None else eng.occupancy())
     barrier()
+    st_e0 = eng.stats()
+    eng.phase_times(reset=True)
+    eng.tree_stats(reset=True)
+    eng.set_option("time_plan", 1)
     ev0.record(bench_stream)
     for b in range(K):
         eng.push_trips(blocks_p[b])
@@ -364,6 +372,10 @@ def run_b200(args):
     ev1.record(bench_stream)
     barrier()
     dt_e2e = ev0.elapsed_time(ev1) * 1e-3
+    e2e_phases = eng.phase_times(reset=True)
+    e2e_trees = eng.tree_stats(reset=True)
+    eng.set_option("time_plan", 0)
+    e2e_fallbacks = eng.stats()["fallback_routes"] - st_e0["fallback_routes"]
     if dist is not None:
         tt = torch.tensor([dt_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -451,7 +463,10 @@ def run_b200(args):
             reroutes_per_s=(reroutes_timed / dt) if reroute else None, reroutes_in_timed_region=int(reroutes_timed),
             moving_fraction=float(moving / n_local),
             e2e=dict(value=e2e_value, unit="agent-steps/s", h2d_bytes_per_step=int(h2d),
-                     d2h_bytes_per_step=int(d2h_total / K), ms_per_step=1e3 * dt_e2e / K),
+                     d2h_bytes_per_step=int(d2h_total / K), ms_per_step=1e3 * dt_e2e / K,
+                     fallback_routes=int(e2e_fallbacks), arena_compactions=int(eng.stats()["arena_compactions"]),
+                     router_stats={k: (round(v, 3) if isinstance(v, float) else v) for k, v in e2e_trees.items()},
+                     phases={k: (round(v, 3) if isinstance(v, float) else v) for k, v in e2e_phases.items()}),
             gpu_launches=int(launches), router_stats={k: (round(v, 3) if isinstance(v, float) else v) for k, v in trees.items()},
             roofline=roof, roofline_advance=roof_adv, roofline_advance_saturated=sat,
             clocks=clk.summary(),
@@ -477,7 +492,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="regional1m", choices=sorted(WORKLOADS))

@@ -961,14 +961,16 @@ __global__ void k_travel_times(LinkArrays lk) {
   }
 }
 
-// Top up every agent's chain ring from a block of host-generated candidate destinations
-// (k per agent, row-major); candidates that do not fit are dropped.
+// Top up every agent's chain ring from a block of host-generated candidate destinations (k per agent,
+// row-major).  The k candidates of an agent are one unit (e.g. an out leg and its return leg): they are
+// taken together when the ring has room for all of them, else the whole row is dropped -- a partial
+// take would splice chains (out, out, ...) that no s-t model produces.
 __global__ void k_refill_chains(AgentArrays a, const int32_t* __restrict__ cand, int32_t k) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
     int cnt = a.chain_cnt[i];
+    if (cnt + k > a.chain_cap) continue;
     const int head = a.chain_head[i];
-    for (int j = 0; j < k && cnt < a.chain_cap; ++j, ++cnt)
-      a.chain_dst[i * a.chain_cap + (head + cnt) % a.chain_cap] = cand[i * k + j];
+    for (int j = 0; j < k; ++j, ++cnt) a.chain_dst[i * a.chain_cap + (head + cnt) % a.chain_cap] = cand[i * k + j];
     a.chain_cnt[i] = (uint8_t)cnt;
   }
 }

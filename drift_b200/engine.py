@@ -285,7 +285,7 @@ class Engine:
             links = np.split(flat[:total], np.cumsum(nl[:n])[:-1])
         return nl[:n], m[:n], links
 
-    def _drain(self, fn, specs, chunk=1 << 16):
+    def _drain(self, fn, specs, chunk=1 << 18):
         cols = [[] for _ in specs]
         while True:
             bufs = [np.zeros(chunk, dtype=dt) for dt, _ in specs]
@@ -306,6 +306,14 @@ class Engine:
         """(agent, tick, src, dst, status) of device-driven departures since the last drain."""
         i32 = (np.int32, C.c_int32)
         return self._drain(self._lib.drift_drain_departures, [i32] * 5)
+
+    def discard_logs(self):
+        """Advance the arrival / departure rings past everything logged so far without copying it out
+        (null output pointers): for runs that never read the logs but must not overflow them."""
+        n = C.c_int64(0)
+        big = 1 << 40
+        _capi.check(self._lib.drift_drain_arrivals(self._h, None, None, big, C.byref(n)))
+        _capi.check(self._lib.drift_drain_departures(self._h, None, None, None, None, None, big, C.byref(n)))
 
     def enable_entry_trace(self, cap=1 << 20):
         _capi.check(self._lib.drift_enable_entry_trace(self._h, int(cap)))

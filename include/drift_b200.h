@@ -155,8 +155,9 @@ int drift_step(drift_engine* e, int32_t n_ticks, double delta);
 int drift_set_demand(drift_engine* e, uint64_t seed, const double hourly24[24], const int32_t* start_node,
                      int32_t chain_capacity, int32_t router);
 /* Top up every agent's ring from `k` candidate destinations per agent (row-major [N][k] host
- * buffer, copied asynchronously: keep it alive until the next synchronising call).  Candidates
- * that do not fit are dropped. */
+ * buffer, copied asynchronously: keep it alive until the next synchronising call).  The k
+ * candidates of an agent are one unit (e.g. an out leg and its return leg): taken together when the
+ * ring has room for all k, otherwise the row is dropped. */
 int drift_push_trips(drift_engine* e, const int32_t* candidates, int32_t k);
 /* Same, from a pool kept in HBM: n_blocks blocks of [N][k] candidates uploaded once. */
 int drift_store_trip_pool(drift_engine* e, const int32_t* candidates, int32_t n_blocks, int32_t k);
