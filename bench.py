@@ -375,7 +375,8 @@ def run_b200(args):
     e2e_phases = eng.phase_times(reset=True)
     e2e_trees = eng.tree_stats(reset=True)
     eng.set_option("time_plan", 0)
-    e2e_fallbacks = eng.stats()["fallback_routes"] - st_e0["fallback_routes"]
+    st_e1 = eng.stats()
+    e2e_fallbacks = st_e1["fallback_routes"] - st_e0["fallback_routes"]
     if dist is not None:
         tt = torch.tensor([dt_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -464,7 +465,7 @@ def run_b200(args):
             moving_fraction=float(moving / n_local),
             e2e=dict(value=e2e_value, unit="agent-steps/s", h2d_bytes_per_step=int(h2d),
                      d2h_bytes_per_step=int(d2h_total / K), ms_per_step=1e3 * dt_e2e / K,
-                     fallback_routes=int(e2e_fallbacks), arena_compactions=int(eng.stats()["arena_compactions"]),
+                     fallback_routes=int(e2e_fallbacks), arena_compactions=int(st_e1["arena_compactions"]),
                      router_stats={k: (round(v, 3) if isinstance(v, float) else v) for k, v in e2e_trees.items()},
                      phases={k: (round(v, 3) if isinstance(v, float) else v) for k, v in e2e_phases.items()}),
             gpu_launches=int(launches), router_stats={k: (round(v, 3) if isinstance(v, float) else v) for k, v in trees.items()},
