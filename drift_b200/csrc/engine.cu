@@ -1570,8 +1570,8 @@ int drift_p2p_export(drift_engine* e, int32_t rank, int32_t world, int64_t n_tot
   if (e->N != base + (rank < rem ? 1 : 0) || (int64_t)e->agent_base != rank * base + std::min<int64_t>(rank, rem))
     return fail(DRIFT_EINVAL, "drift_p2p_export: this engine does not hold rank %d's contiguous block of %lld agents",
                 rank, (long long)n_total);
-  CU(e->p2p_inbox.alloc((int64_t)world * cap, true));
-  CU(e->p2p_flags.alloc(std::max<int64_t>(2 * kMaxRanks, (2 << 20) / 8), true));
+  CU(e->p2p_inbox.alloc((int64_t)2 * world * cap, true));  // double-buffered by tick parity
+  CU(e->p2p_flags.alloc(std::max<int64_t>(3 * kMaxRanks, (2 << 20) / 8), true));
   CU(e->p2p_out_cnt.alloc(kMaxRanks, true));
   memset(&e->p2p, 0, sizeof(e->p2p));
   e->p2p.rank = rank;

@@ -119,14 +119,18 @@ struct AdvSmem {  // per-warp staging: warps do not wait for each other while th
 // speed straight into the home rank's agent arrays: the exchange is part of the tick kernel, the work
 // per rank does not grow with the number of ranks, occupancy is held by the owner only.
 constexpr int kMaxRanks = 16;
+// Entry speed not yet delivered by the link's owner: the home rank writes this when it emits the enter
+// event and the next advance of that agent waits for a real (positive) speed -- per-agent hand-over
+// instead of a second all-rank barrier per tick.
+constexpr double kSpeedPending = -1.0;
 
 struct P2PArgs {
   int32_t rank, world;
   int32_t cap;                            // events one rank may send to one owner per tick
   uint32_t shard_base, shard_rem;         // agents per rank: n_total / world (+1 for the first n_total % world ranks)
-  Event* inbox[kMaxRanks];                // inbox of every rank (peer-mapped): [world][cap], region r written by rank r
-  unsigned long long* flags[kMaxRanks];   // of every rank: [2][kMaxRanks]; row 0: tick << 32 | events sent by rank r,
-                                          // row 1: tick << 32 once rank r has resolved its links
+  Event* inbox[kMaxRanks];                // inbox of every rank (peer-mapped): [2 tick parities][world][cap], region r written by rank r
+  unsigned long long* flags[kMaxRanks];   // of every rank: [3][kMaxRanks]; rows 0-1 (tick parity): tick << 32 | events
+                                          // sent by rank r, row 2: last tick << 32 once rank r has finished a launch
   double* speed[kMaxRanks];               // agent arrays of every rank
   double* elen[kMaxRanks];
   int32_t* out_cnt;                       // local [kMaxRanks]: events written to each owner in this tick
@@ -136,6 +140,24 @@ struct P2PSmem {
   int ocnt[kMaxRanks], obase[kMaxRanks];
   uint16_t idx[kAdvWarps][kStageCap];
 };
+
+__device__ __noinline__ double p2p_wait_speed(const double* p) {
+  unsigned long long t0 = 0;
+  for (;;) {
+    unsigned long long bits;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(bits) : "l"(p) : "memory");
+    const double v = __longlong_as_double((long long)bits);
+    if (v >= 0.0) return v;
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (!t0) t0 = now;
+    if (now - t0 > 60000000000ULL) {
+      printf("drift_b200: an entry speed was not delivered within 60 s\n");
+      __trap();
+    }
+    __nanosleep(32);
+  }
+}
 
 __device__ __forceinline__ void stage_event(AdvSmem& sm, int32_t link, uint32_t agent, bool enter) {
   const int w = threadIdx.x >> 5;
@@ -154,7 +176,11 @@ __device__ __noinline__ bool cross_agent(const TickArgs& p, int64_t i, int32_t t
   if (nl >= 0) {  // next_link is refreshed in phase C when the enter event is resolved ...
     a.cur_link[i] = nl;
     // ... unless the link is resolved on another GPU (k_tick_loop_p2p): then the home rank does it here
-    if (own_next) a.next_link[i] = ri + 1 < a.route_len[i] ? p.arena[a.route_off[i] + ri + 1] : -1;
+    if (own_next) {
+      a.next_link[i] = ri + 1 < a.route_len[i] ? p.arena[a.route_off[i] + ri + 1] : -1;
+      a.elen[i] = p.lk.len[nl];  // link tables are replicated: only the speed has to come from the owner
+      a.speed[i] = kSpeedPending;
+    }
     stage_event(sm, nl, a.base + (uint32_t)i, true);
     return false;
   }
@@ -221,7 +247,11 @@ __device__ __noinline__ bool depart_agent(const TickArgs& p, int64_t i, int cnt,
   a.route_idx[i] = 0;
   a.dist[i] = 0.0;
   a.cur_link[i] = fl;
-  if (own_next) a.next_link[i] = nl;
+  if (own_next) {
+    a.next_link[i] = nl;
+    a.elen[i] = p.lk.len[fl];
+    a.speed[i] = kSpeedPending;
+  }
   stage_event(sm, fl, a.base + (uint32_t)i, true);
   return true;
 }
@@ -257,8 +287,13 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
         const double2 e23 = P2P ? __ldcg(reinterpret_cast<const double2*>(a.elen + i0 + 2))
                                 : *reinterpret_cast<const double2*>(a.elen + i0 + 2);
         double d[4] = {d01.x, d01.y, d23.x, d23.y};
-        const double sp[4] = {s01.x, s01.y, s23.x, s23.y};
+        double sp[4] = {s01.x, s01.y, s23.x, s23.y};
         const double el[4] = {e01.x, e01.y, e23.x, e23.y};
+        if (P2P) {  // entered a link last tick and the owner's speed has not landed yet: wait for it
+#pragma unroll
+          for (int j = 0; j < kAdvPerThread; ++j)
+            if (((st4 >> (8 * j)) & 0xffu) && sp[j] < 0.0) sp[j] = p2p_wait_speed(a.speed + i0 + j);
+        }
         uint32_t cross = 0;
 #pragma unroll
         for (int j = 0; j < kAdvPerThread; ++j) {
@@ -344,7 +379,8 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
             e.agent = sm.agent[w][k];
             e.kind = (lkd >> 31) ? 1 : -1;
             e.aux = 0;
-            *reinterpret_cast<int4*>(x->inbox[o] + (int64_t)x->rank * x->cap + pos) = *reinterpret_cast<const int4*>(&e);
+            *reinterpret_cast<int4*>(x->inbox[o] + ((int64_t)par * x->world + x->rank) * x->cap + pos) =
+              *reinterpret_cast<const int4*>(&e);
           } else {
             atomicOr(&p.ctr->overflow, kOvfExchange);
           }
@@ -748,7 +784,7 @@ __device__ __forceinline__ void p2p_home(const P2PArgs& x, uint32_t agent, int& 
   }
 }
 
-__device__ __forceinline__ void p2p_send_one(const TickArgs& p, const P2PArgs& x, int32_t link, uint32_t agent,
+__device__ __forceinline__ void p2p_send_one(const TickArgs& p, const P2PArgs& x, int par, int32_t link, uint32_t agent,
                                              int32_t kind) {
   const int o = (int)((uint32_t)link % (uint32_t)x.world);
   const int pos = atomicAdd(&x.out_cnt[o], 1);
@@ -758,7 +794,7 @@ __device__ __forceinline__ void p2p_send_one(const TickArgs& p, const P2PArgs& x
     e.agent = agent;
     e.kind = kind;
     e.aux = 0;
-    *reinterpret_cast<int4*>(x.inbox[o] + (int64_t)x.rank * x.cap + pos) = *reinterpret_cast<const int4*>(&e);
+    *reinterpret_cast<int4*>(x.inbox[o] + ((int64_t)par * x.world + x.rank) * x.cap + pos) = *reinterpret_cast<const int4*>(&e);
     __threadfence_system();
   } else {
     atomicOr(&p.ctr->overflow, kOvfExchange);
@@ -778,7 +814,9 @@ __device__ __noinline__ void phase_inject_p2p(const TickArgs& p, const P2PArgs& 
     a.dist[i] = 0.0;
     a.cur_link[i] = link;
     a.next_link[i] = len > 1 ? p.arena[off + 1] : -1;
-    p2p_send_one(p, x, link, a.base + (uint32_t)i, 1);
+    a.elen[i] = p.lk.len[link];
+    a.speed[i] = kSpeedPending;
+    p2p_send_one(p, x, tick & 1, link, a.base + (uint32_t)i, 1);
   };
   const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
@@ -822,12 +860,11 @@ __device__ __forceinline__ bool resolve_one_p2p(const TickArgs& p, const P2PArgs
   const LinkArrays& lk = p.lk;
   const Event ev = events[e];
   const int first = (int)(lk.head[ev.link] & 0xffffffffu);
-  double v0 = 0.0, len = 0.0;
+  double v0 = 0.0;
   int64_t f_lo = 0, f_hi = 1;
   if (ev.kind > 0) {  // loaded before the list walk: independent of it
     const int32_t c = lk.cls[ev.link];
     v0 = lk.v0[ev.link];
-    len = lk.len[ev.link];
     f_lo = lk.cls_off[c];
     f_hi = lk.cls_off[c + 1];
   }
@@ -851,8 +888,7 @@ __device__ __forceinline__ bool resolve_one_p2p(const TickArgs& p, const P2PArgs
     const int32_t count = occ0 + before + 1;  // includes the entering agent itself
     int64_t idx = f_lo + (int64_t)count;
     if (idx >= f_hi) idx = f_hi - 1;
-    x.speed[home][li] = __dmul_rn(__dmul_rn(v0, lk.factor[idx]), p.kph_to_mps);
-    x.elen[home][li] = len;
+    x.speed[home][li] = __dmul_rn(__dmul_rn(v0, lk.factor[idx]), p.kph_to_mps);  // the home rank waits for it per agent
     return home != x.rank;
   }
   return false;
@@ -892,7 +928,7 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
       x.out_cnt[o] = 0;
       atomicMax(&ctr->max_events, cnt);
       if (cnt > x.cap) cnt = x.cap;  // overflow already flagged by the writers
-      st_release_sys(x.flags[o] + x.rank, ((unsigned long long)(uint32_t)tick << 32) | (uint32_t)cnt);
+      st_release_sys(x.flags[o] + par * kMaxRanks + x.rank, ((unsigned long long)(uint32_t)tick << 32) | (uint32_t)cnt);
     }
     if (lead) {
       ctr->n_dep_req[par ^ 1] = 0;
@@ -900,7 +936,7 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
       ctr->phase_ns[0] += t1 - t0;
       t0 = t1;
     }
-    p2p_wait(my_flags, x.world, (uint32_t)tick, s_in);
+    p2p_wait(my_flags + par * kMaxRanks, x.world, (uint32_t)tick, s_in);
     if (threadIdx.x == 0) {
       int acc = 0;
       for (int r = 0; r < x.world; ++r) {
@@ -915,7 +951,7 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
       int r = 0;
       while (r + 1 < x.world && s_pref[r + 1] <= f) ++r;
-      const int e = r * x.cap + (f - s_pref[r]);
+      const int e = (par * x.world + r) * x.cap + (f - s_pref[r]);
       const int4 raw = __ldcg(reinterpret_cast<const int4*>(inbox + e));  // written by a peer: bypass L1
       emit_event(p.lk, inbox, e, raw.x, (uint32_t)raw.y, raw.z, (uint32_t)tick);
     }
@@ -929,15 +965,20 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
       int r = 0;
       while (r + 1 < x.world && s_pref[r + 1] <= f) ++r;
-      if (resolve_one_p2p(p, x, inbox, r * x.cap + (f - s_pref[r])))
-        __threadfence_system();  // the entry speed is in the home rank's arrays before "done" is published
+      const bool remote = resolve_one_p2p(p, x, inbox, (par * x.world + r) * x.cap + (f - s_pref[r]));
+      if (remote && k == n_ticks - 1) __threadfence_system();  // landed before the launch-end barrier below
     }
-    grid.sync();
-    if (blockIdx.x == 0 && threadIdx.x < x.world)
-      st_release_sys(x.flags[threadIdx.x] + kMaxRanks + x.rank, (unsigned long long)(uint32_t)tick << 32);
-    p2p_wait(my_flags + kMaxRanks, x.world, (uint32_t)tick, nullptr);
     if (lead) ctr->phase_ns[2] += global_ns() - t0;
+    // No all-rank barrier here: the next advance waits per agent for a pending entry speed, the inbox and
+    // the event flags are double-buffered by tick parity, and a rank cannot run two ticks ahead of a peer
+    // (it needs that peer's events of the next tick first).
   }
+  // launch end: every rank has delivered the entry speeds of the last tick before any rank returns to its host
+  grid.sync();
+  const uint32_t last = (uint32_t)(tick0 + n_ticks - 1);
+  if (blockIdx.x == 0 && threadIdx.x < x.world)
+    st_release_sys(x.flags[threadIdx.x] + 2 * kMaxRanks + x.rank, (unsigned long long)last << 32);
+  p2p_wait(my_flags + 2 * kMaxRanks, x.world, last, nullptr);
 }
 
 // ---- auxiliary passes -------------------------------------------------------------------------------
