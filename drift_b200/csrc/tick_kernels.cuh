@@ -256,6 +256,22 @@ __device__ __noinline__ bool depart_agent(const TickArgs& p, int64_t i, int cnt,
   return true;
 }
 
+// Peer exchange: an agent that entered a link in the previous tick is advanced after everything else of
+// its tile, when the owner of that link has had the time of a whole tile to deliver the entry speed.
+__device__ __noinline__ bool advance_late(const TickArgs& p, int64_t i, int32_t tick, AdvSmem& sm) {
+  const AgentArrays& a = p.a;
+  const double d = a.dist[i];
+  const double el = __ldcg(a.elen + i);
+  const double sp = p2p_wait_speed(a.speed + i);
+  const double nd = __dadd_rn(d, __dmul_rn(sp, p.delta));  // agent.py:197-198
+  if (nd >= el) {
+    a.dist[i] = 0.0;
+    return cross_agent(p, i, tick, sm, true);
+  }
+  a.dist[i] = nd;
+  return false;
+}
+
 template <bool DEMAND, bool P2P = false>
 __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, double p_dep, AdvSmem& sm,
                                               const P2PArgs* x = nullptr, P2PSmem* xs = nullptr) {
@@ -274,6 +290,7 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
       uint32_t cn4 = 0;
       if (DEMAND) cn4 = *reinterpret_cast<const uint32_t*>(a.chain_cnt + i0);  // independent of the state load
       uint32_t nst4 = st4;
+      uint32_t pend = 0;  // P2P: agents waiting for their entry speed
       if (st4) {  // at least one of the four agents is moving
         const double2 d01 = *reinterpret_cast<const double2*>(a.dist + i0);
         const double2 d23 = *reinterpret_cast<const double2*>(a.dist + i0 + 2);
@@ -289,15 +306,15 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
         double d[4] = {d01.x, d01.y, d23.x, d23.y};
         double sp[4] = {s01.x, s01.y, s23.x, s23.y};
         const double el[4] = {e01.x, e01.y, e23.x, e23.y};
-        if (P2P) {  // entered a link last tick and the owner's speed has not landed yet: wait for it
+        if (P2P) {  // entered a link last tick and the owner's speed has not landed yet: advanced last (below)
 #pragma unroll
           for (int j = 0; j < kAdvPerThread; ++j)
-            if (((st4 >> (8 * j)) & 0xffu) && sp[j] < 0.0) sp[j] = p2p_wait_speed(a.speed + i0 + j);
+            if (((st4 >> (8 * j)) & 0xffu) && sp[j] < 0.0) pend |= 1u << j;
         }
         uint32_t cross = 0;
 #pragma unroll
         for (int j = 0; j < kAdvPerThread; ++j) {
-          if ((st4 >> (8 * j)) & 0xffu) {
+          if (((st4 >> (8 * j)) & 0xffu) && !((pend >> j) & 1u)) {
             // two roundings, never contracted to an FMA (agent.py:197-198)
             const double nd = __dadd_rn(d[j], __dmul_rn(sp[j], p.delta));
             const bool c = nd >= el[j];  // agent.py:200-203: at most one link per tick, overshoot dropped
@@ -348,6 +365,13 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
           const int j = __ffs(dep) - 1;
           dep &= dep - 1;
           if (depart_agent(p, i0 + j, (cn4 >> (8 * j)) & 0xffu, tick, sm, P2P)) nst4 |= (uint32_t)kMoving << (8 * j);
+        }
+      }
+      if (P2P) {  // by now the owner has usually delivered: the wait overlaps with the rest of the tile
+        while (pend) {
+          const int j = __ffs(pend) - 1;
+          pend &= pend - 1;
+          if (advance_late(p, i0 + j, tick, sm)) nst4 &= ~(0xffu << (8 * j));
         }
       }
       if (nst4 != st4) *reinterpret_cast<uint32_t*>(a.state + i0) = nst4;
