@@ -424,7 +424,26 @@ def run_b200(args):
                     share_of_step=trees["build_ms"] / (1e3 * dt),
                     note="20 B per relaxed edge + 12 B per improving relaxation + 16 B per expanded node (SURVEY.md 8d)")
     else:
-        roof = roof_adv
+        # the tick kernel dominates: roofline of the persistent kernel itself, from its own phase clocks
+        # (%globaltimer, grid barriers included) over the timed region
+        tick_us = phases["advance_us_per_tick"] + phases["inject_us_per_tick"] + phases["resolve_us_per_tick"]
+        ev_tick = float(st1["events_last_tick"])
+        mv_t = 0.5 * (st0["moving_agents"] + st1["moving_agents"])
+        alg_tick = (n_local - mv_t) * 1.0 + mv_t * 33.0 + ev_tick * 90.0
+        ach_t = alg_tick / (tick_us * 1e-6) / 1e9 if tick_us > 0 else 0.0
+        ncu_ok = args.workload == "regional1m" and not args.agents and world == 1 and TPS == 300
+        roof = dict(bound="hbm", kernel="k_tick_loop (persistent cooperative kernel: advance + resolve phases of "
+                                        "%d ticks per launch; in-kernel %%globaltimer phase clocks)" % TPS,
+                    achieved=ach_t, peak=peak, unit="GB/s", frac=ach_t / peak,
+                    traffic=10.2e9 if ncu_ok else None,
+                    traffic_source="dram__bytes_read+write of one 300-tick launch, ncu --set full capture of this kernel on "
+                                   "this workload (profiles/r1_k_tick_loop_set_full_raw.csv)" if ncu_ok else None,
+                    peak_source=peak_src, us_per_launch=tick_us * TPS, us_per_tick=tick_us,
+                    algorithmic_bytes_per_launch=alg_tick * TPS, algorithmic_bytes_per_tick=alg_tick,
+                    moving_agents=mv_t, events_per_tick=ev_tick, share_of_step=tick_us * TPS / (1e6 * dt / K),
+                    note="1 B per waiting + 33 B per moving agent-step + ~90 B per link event (SURVEY.md 8d); at 1 M "
+                         "agents a tick is latency-bound between grid barriers (profiles/r1_summary.md): the advance "
+                         "phase alone is in roofline_advance (standalone kernel) and roofline_advance_saturated")
     sat = None
     if rank == 0 and world == 1 and args.saturated_agents > 0:
         eng.close()

@@ -145,15 +145,10 @@ struct drift_engine {
   int64_t r_heap_cap = 0;
   // tree cache + tree builder scratch (batched router)
   DevBuf<int32_t> t_slot_of, t_next, t_job_dst, t_job_slot, t_ctl;  // t_ctl: n_slots, n_jobs, job_cursor
-  DevBuf<NodeRec> t_rec, tw_rec;   // per-block / per-warp search scratch
-  DevBuf<int32_t> tw_lists;
-  DevBuf<uint32_t> tw_iter;
-  int32_t tw_jobs = 0;             // concurrent warp searches
-  bool warp_search = false;  // measured slower than one block per search (profiles/r1_summary.md)
+  DevBuf<NodeRec> t_rec;   // per-block search scratch
   int32_t t_sides = 2;       // 2 = trees out of hot sources as well as into hot destinations
   DevBuf<int32_t> t_cnt;
   DevBuf<uint8_t> t_q_side;
-  int64_t warp_scratch_bytes = (int64_t)40 << 30;
   DevBuf<uint32_t> t_iter, t_slot_stamp;
   DevBuf<int32_t> t_slot_owner, t_slot_job, t_job_qhead, t_job_cnt, t_q_next;
   DevBuf<uint32_t> t_slot_job_batch;
@@ -398,16 +393,6 @@ int ensure_trees(drift_engine* e) {
   CU(e->t_lists.alloc(blocks * 5 * V, false));
   e->t_max_slots = (int32_t)slots;
   e->t_blocks = (int32_t)blocks;
-  if (e->warp_search) {  // scratch of the warp-per-search kernel: 36 B per node and concurrent search
-    int64_t wj = std::min<int64_t>((int64_t)e->num_sms * 16, e->warp_scratch_bytes / (36 * V));
-    wj = std::max<int64_t>(wj / 4 * 4, 4);
-    CU(e->tw_rec.alloc(wj * V, false));
-    k_init_noderecs<<<kSMs * 8, 256, 0, e->stream>>>(e->tw_rec.p, wj * V);
-    CU(cudaGetLastError());
-    CU(e->tw_iter.alloc(wj, true));
-    CU(e->tw_lists.alloc(wj * 5 * V, false));
-    e->tw_jobs = (int32_t)wj;
-  }
   return DRIFT_OK;
 }
 
@@ -502,19 +487,9 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
       cudaEventCreate(&tb1);
       cudaEventRecord(tb0, e->stream);
     }
-    const bool use_warp = e->warp_search && e->tw_jobs > 0 && tc.bounded_max > 0;
-    if (use_warp) {
-      TreeScratch tw;
-      tw.rec = e->tw_rec.p;
-      tw.lists = e->tw_lists.p;
-      tw.iter = e->tw_iter.p;
-      k_search_warp<<<e->tw_jobs / (kWarpSearchThreads / 32), kWarpSearchThreads, 0, e->stream>>>(
-          e->graph(), wb, wf, e->t_delta, tc, tw, e->tw_jobs, e->t_ctl.p + 3, qs, e->arena.p,
-          (unsigned long long)e->arena_cap, e->ctr.p, out, lc, lm);
-    }
     k_build_trees<<<e->t_blocks, e->t_threads, 0, e->stream>>>(e->graph(), wb, wf, e->t_delta, tc, ts, qs, e->arena.p,
                                                                (unsigned long long)e->arena_cap, e->ctr.p, out, lc, lm,
-                                                               use_warp ? 1 : 0);
+                                                               0);
     if (tb0) {
       cudaEventRecord(tb1, e->stream);
       e->tree_timers.push_back({tb0, tb1});
@@ -522,7 +497,7 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     k_extract_paths<<<gq, 256, 0, e->stream>>>(e->graph(), Q, n_dev, qs, qd, tc, e->arena.p,
                                                 (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
     CU(cudaGetLastError());
-    e->total_launches += use_warp ? 7 : 6;
+    e->total_launches += 6;
     return DRIFT_OK;
   }
   int rc = ensure_router(e, Q);
@@ -1747,12 +1722,6 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
   } else if (s == "tree_sides") {
     if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_sides must be set before the first batched route");
     e->t_sides = value >= 2 ? 2 : 1;
-  } else if (s == "warp_search") {
-    if (e->t_max_slots) return fail(DRIFT_ESTATE, "warp_search must be set before the first batched route");
-    e->warp_search = value != 0;
-  } else if (s == "warp_scratch_bytes") {
-    if (e->t_max_slots) return fail(DRIFT_ESTATE, "warp_scratch_bytes must be set before the first batched route");
-    e->warp_scratch_bytes = (int64_t)value;
   } else if (s == "tree_scratch_bytes") {
     if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_scratch_bytes must be set before the first batched route");
     e->tree_scratch_bytes = (int64_t)value;

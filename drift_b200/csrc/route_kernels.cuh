@@ -773,7 +773,7 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_tre
                                                               int32_t* __restrict__ arena, unsigned long long arena_cap,
                                                               Counters* ctr, RouteOut out,
                                                               const double* __restrict__ link_cost, Landmarks lm,
-                                                              int32_t skip_bounded) {
+                                                              int32_t reserved) {
   __shared__ int s_job, s_near_n, s_next_n, s_far_n, s_far2_n, s_done, s_touched, s_lmk[2], s_lmdir[2];
   __shared__ double s_lmref[2];
   __shared__ int s_e0[kTreeThreadsMax], s_off[kTreeThreadsMax], s_wsum[32];
@@ -808,7 +808,6 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_tre
     int32_t* next_link = tc.next_link + (int64_t)(slot < 0 ? 0 : slot) * V;
     const int nb = min(tc.job_cnt[job], kMaxBounded);
     const bool bounded = slot < 0;  // decided when the job was created (k_tree_requests)
-    if (bounded && skip_bounded) continue;  // k_search_warp takes it
     if (threadIdx.x == 0) ++c_jobs;
     if (bounded && threadIdx.x == 0) {
       int k = 0;
@@ -1077,270 +1076,6 @@ __global__ void k_init_noderecs(NodeRec* __restrict__ p, int64_t n) {
     r.stamp = 0;
     r.infar = 0;
     p[i] = r;
-  }
-}
-
-// -------------------------------------------------------------------------------------------------
-// One bounded search per WARP.  A goal-directed search on a road network has waves of a few dozen
-// nodes: a whole thread block per search spends half of its time in __syncthreads (ncu: 54 % barrier
-// stalls).  Here every warp runs its own search with warp-level synchronisation only; list pushes
-// are compacted with ballots, all counters live in registers.  Same arithmetic and same result as
-// the bounded branch of k_build_trees.  Jobs with more than tc.bounded_max queries (they keep a
-// tree) are left to k_build_trees.
-// -------------------------------------------------------------------------------------------------
-constexpr int kWarpSearchThreads = 128;
-
-__device__ __forceinline__ int warp_push(int32_t* list, int& count, bool pred, int32_t value, int lane) {
-  const unsigned m = __ballot_sync(0xffffffffu, pred);
-  if (pred) list[count + __popc(m & ((1u << lane) - 1u))] = value;
-  count += __popc(m);
-  return __popc(m);
-}
-
-__global__ void __launch_bounds__(kWarpSearchThreads) k_search_warp(
-    GraphArrays g, const double* __restrict__ w_bwd, const double* __restrict__ w_fwd, double delta, TreeCache tc,
-    TreeScratch sc, int32_t n_warp_jobs, int32_t* __restrict__ job_cursor, const int32_t* __restrict__ q_src,
-    int32_t* __restrict__ arena, unsigned long long arena_cap, Counters* ctr, RouteOut out,
-    const double* __restrict__ link_cost, Landmarks lm) {
-  const int lane = threadIdx.x & 31;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (gw >= n_warp_jobs) return;
-  const int64_t V = g.V;
-  NodeRec* rec = sc.rec + (int64_t)gw * V;
-  int32_t* nearA = sc.lists + ((int64_t)gw * 5 + 0) * V;
-  int32_t* nearB = sc.lists + ((int64_t)gw * 5 + 1) * V;
-  int32_t* farA = sc.lists + ((int64_t)gw * 5 + 2) * V;
-  int32_t* farB = sc.lists + ((int64_t)gw * 5 + 3) * V;
-  int32_t* touched = sc.lists + ((int64_t)gw * 5 + 4) * V;
-  uint32_t iter = sc.iter[gw];
-  const int n_jobs = *tc.n_jobs;
-  unsigned long long c_relaxed = 0, c_improved = 0, c_expanded = 0, c_iters = 0, c_far = 0, c_jobs = 0;
-  for (;;) {
-    int job = 0;
-    if (lane == 0) job = atomicAdd(job_cursor, 1);
-    job = __shfl_sync(0xffffffffu, job, 0);
-    if (job >= n_jobs) break;
-    const int nb = min(tc.job_cnt[job], kMaxBounded);
-    if (tc.job_slot[job] >= 0) continue;  // keeps a tree: k_build_trees
-    ++c_jobs;
-    const int32_t dest = tc.job_dst[job];
-    // lane k < nb holds query k of the job
-    int32_t my_q = -1, my_src = -1;
-    {
-      int32_t q = tc.job_qhead[job];
-      for (int k = 0; k < nb && q >= 0; ++k) {
-        if (lane == k) my_q = q;
-        q = tc.q_next[q];
-      }
-      if (my_q >= 0) my_src = q_src[my_q];
-    }
-    // goal direction (single source): the two landmark bounds that are largest at the destination
-    const double* lma0 = nullptr;
-    const double* lma1 = nullptr;
-    double lmr0 = 0.0, lmr1 = 0.0;
-    int lmd0 = 0, lmd1 = 0;
-    if (nb == 1 && lm.K > 0) {
-      const int32_t sn = __shfl_sync(0xffffffffu, my_src, 0);
-      if (sn >= 0 && sn < V) {
-        double b = -1.0, ref = 0.0;
-        const int k = lane >> 1, dir = lane & 1;
-        const double* arr = nullptr;
-        if (k < lm.K && k < 16) {
-          arr = (dir == 0 ? lm.from : lm.to) + (int64_t)k * V;
-          ref = arr[sn];
-          b = dir == 0 ? arr[dest] - ref : ref - arr[dest];
-          if (!(b > 0.0) || b > 1e300) b = -1.0;
-        }
-        for (int pick = 0; pick < 2; ++pick) {
-          double best = b;
-          int who = lane;
-          for (int o = 16; o; o >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int ow = __shfl_xor_sync(0xffffffffu, who, o);
-            if (ob > best || (ob == best && ow < who)) {
-              best = ob;
-              who = ow;
-            }
-          }
-          if (best > 0.0) {
-            const unsigned long long ap = __shfl_sync(0xffffffffu, (unsigned long long)arr, who);
-            const double rr = __shfl_sync(0xffffffffu, ref, who);
-            if (pick == 0) {
-              lma0 = (const double*)ap;
-              lmr0 = rr;
-              lmd0 = who & 1;
-            } else {
-              lma1 = (const double*)ap;
-              lmr1 = rr;
-              lmd1 = who & 1;
-            }
-          }
-          if (lane == who) b = -1.0;  // taken
-        }
-      }
-    }
-    auto pot = [&](int32_t v) -> double {
-      double h = 0.0;
-      if (lma0) {
-        const double b = lmd0 == 0 ? lma0[v] - lmr0 : lmr0 - lma0[v];
-        if (b > h && b < 1e300) h = b;
-      }
-      if (lma1) {
-        const double b = lmd1 == 0 ? lma1[v] - lmr1 : lmr1 - lma1[v];
-        if (b > h && b < 1e300) h = b;
-      }
-      return h;
-    };
-    const double jdelta = (lma0 != nullptr) ? delta * 0.25 : delta;
-    int near_n = 1, far_n = 0, touched_n = 1;
-    if (lane == 0) {
-      nearA[0] = dest;
-      touched[0] = dest;
-      rec[dest].dist = 0ULL;
-    }
-    __syncwarp();
-    double T_old = -1.0, T = pot(dest) + jdelta;
-    for (;;) {
-      if (near_n == 0) {
-        if (far_n == 0) break;
-        // every node with key <= T is final: stop once all sources are (pot(source) = 0)
-        bool ok = true;
-        if (my_q >= 0 && my_src >= 0 && my_src < V) ok = !(__longlong_as_double((long long)rec[my_src].dist) > T);
-        if (__all_sync(0xffffffffu, ok)) break;
-        unsigned long long m = kInfBits;
-        for (int i = lane; i < far_n; i += 32) {
-          const int32_t u = farA[i];
-          const double key = __dadd_rn(__longlong_as_double((long long)rec[u].dist), pot(u));
-          const unsigned long long kb = (unsigned long long)__double_as_longlong(key);
-          m = kb < m ? kb : m;
-        }
-        for (int o = 16; o; o >>= 1) {
-          const unsigned long long x = __shfl_xor_sync(0xffffffffu, m, o);
-          m = x < m ? x : m;
-        }
-        c_far += (unsigned long long)far_n;
-        const double minfar = __longlong_as_double((long long)m);
-        T_old = T;
-        T = (minfar > T ? minfar : T) + jdelta;
-        int far2_n = 0;
-        for (int base = 0; base < far_n; base += 32) {
-          const int i = base + lane;
-          int32_t u = -1;
-          double d = 0.0;
-          if (i < far_n) {
-            u = farA[i];
-            d = __dadd_rn(__longlong_as_double((long long)rec[u].dist), pot(u));
-          }
-          const bool stale = u >= 0 && d <= T_old;  // already expanded as a near node
-          const bool to_near = u >= 0 && !stale && d <= T;
-          const bool keep = u >= 0 && !stale && !to_near;
-          if (stale || to_near) rec[u].infar = 0;
-          warp_push(nearA, near_n, to_near, u, lane);
-          warp_push(farB, far2_n, keep, u, lane);
-        }
-        far_n = far2_n;
-        int32_t* t = farA;
-        farA = farB;
-        farB = t;
-        __syncwarp();
-        continue;
-      }
-      ++iter;
-      ++c_iters;
-      int next_n = 0;
-      for (int base = 0; base < near_n; base += 32) {
-        const int i = base + lane;
-        int deg = 0;
-        int32_t e0 = 0;
-        double dv = 0.0;
-        if (i < near_n) {
-          const int32_t v = nearA[i];
-          e0 = g.bwd_rowptr[v];
-          deg = g.bwd_rowptr[v + 1] - e0;
-          dv = __longlong_as_double((long long)rec[v].dist);
-          ++c_expanded;
-          c_relaxed += (unsigned long long)deg;
-        }
-        int incl = deg;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int x = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += x;
-        }
-        const int off = incl - deg;
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        for (int eb = 0; eb < total; eb += 32) {
-          const int k = eb + lane;
-          int j = 0;  // owner: largest lane j with off[j] <= k
-#pragma unroll
-          for (int step = 16; step; step >>= 1) {
-            const int cand_j = j + step;
-            const int pv = __shfl_sync(0xffffffffu, off, cand_j & 31);
-            if (cand_j < 32 && pv <= k) j = cand_j;
-          }
-          const int32_t e0j = __shfl_sync(0xffffffffu, e0, j);
-          const int offj = __shfl_sync(0xffffffffu, off, j);
-          const double dvj = __shfl_sync(0xffffffffu, dv, j);
-          bool first = false, to_near = false, to_far = false;
-          int32_t u = -1;
-          if (k < total) {
-            const int32_t e = e0j + (k - offj);
-            u = g.bwd_col[e];
-            const double cand = __dadd_rn(dvj, w_bwd[e]);
-            const unsigned long long cb = (unsigned long long)__double_as_longlong(cand);
-            const unsigned long long old = atomicMin(&rec[u].dist, cb);
-            if (cb < old) {
-              ++c_improved;
-              first = old == kInfBits;
-              if (__dadd_rn(cand, pot(u)) <= T) {
-                to_near = atomicExch(&rec[u].stamp, iter) != iter;
-              } else {
-                to_far = atomicExch(&rec[u].infar, 1u) == 0u;
-              }
-            }
-          }
-          warp_push(touched, touched_n, first, u, lane);
-          warp_push(nearB, next_n, to_near, u, lane);
-          warp_push(farA, far_n, to_far, u, lane);
-        }
-      }
-      near_n = next_n;
-      int32_t* t = nearA;
-      nearA = nearB;
-      nearB = t;
-      __syncwarp();
-    }
-    // routes of the sources, straight from dist[] (as in k_build_trees)
-    if (my_q >= 0) {
-      const int32_t tcap = (int32_t)(V / kMaxBounded);
-      route_from_labels(g, w_fwd, rec, my_src, dest, farB + (int64_t)lane * tcap, tcap, arena, arena_cap, ctr, link_cost,
-                        my_q, out);
-    }
-    if (lane == 0) tc.slot_of[dest] = -1;  // no tree was kept
-    __syncwarp();
-    for (int i = lane; i < touched_n; i += 32) {  // leave the scratch clean for the next job
-      rec[touched[i]].dist = kInfBits;
-      rec[touched[i]].infar = 0;
-    }
-    __syncwarp();
-  }
-  if (lane == 0) {
-    sc.iter[gw] = iter;
-    if (c_jobs) atomicAdd(&ctr->tree_jobs, c_jobs);
-    if (c_iters) {
-      atomicAdd(&ctr->tree_iters, c_iters);
-      atomicAdd(&ctr->tree_far_visits, c_far);
-    }
-  }
-  for (int o = 16; o; o >>= 1) {
-    c_relaxed += __shfl_down_sync(0xffffffffu, c_relaxed, o);
-    c_improved += __shfl_down_sync(0xffffffffu, c_improved, o);
-    c_expanded += __shfl_down_sync(0xffffffffu, c_expanded, o);
-  }
-  if (lane == 0 && c_expanded) {
-    atomicAdd(&ctr->tree_relaxed, c_relaxed);
-    atomicAdd(&ctr->tree_improved, c_improved);
-    atomicAdd(&ctr->tree_expanded, c_expanded);
   }
 }
 
