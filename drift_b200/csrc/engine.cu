@@ -144,7 +144,8 @@ struct drift_engine {
   int32_t r_workers = 0;
   int64_t r_heap_cap = 0;
   // tree cache + tree builder scratch (batched router)
-  DevBuf<int32_t> t_slot_of, t_next, t_job_dst, t_job_slot, t_ctl;  // t_ctl: n_slots, n_jobs, job_cursor
+  DevBuf<int32_t> t_slot_of, t_job_dst, t_job_slot, t_ctl;  // t_ctl: n_slots, n_jobs, job_cursor
+  DevBuf<int2> t_next;  // cached trees: {link, next node} per node
   DevBuf<NodeRec> t_rec;   // per-block search scratch
   int32_t t_sides = 2;       // 2 = trees out of hot sources as well as into hot destinations
   DevBuf<int32_t> t_cnt;
@@ -367,7 +368,7 @@ int ensure_trees(drift_engine* e) {
     if (!e->tree_budget_set) e->tree_budget_bytes = std::min<int64_t>((int64_t)48 << 30, (int64_t)(free_b * 0.30));
     if (!e->tree_scratch_set) e->tree_scratch_bytes = std::min<int64_t>((int64_t)64 << 30, (int64_t)(free_b * 0.40));
   }
-  int64_t slots = std::min<int64_t>(e->t_sides * V, e->tree_budget_bytes / (4 * V));
+  int64_t slots = std::min<int64_t>(e->t_sides * V, e->tree_budget_bytes / (8 * V));
   slots = std::max<int64_t>(slots, 1);
   // resident builder blocks: 32 B of scratch per node each
   int64_t blocks = std::min<int64_t>((int64_t)e->num_sms * std::min(32, 2048 / e->t_threads), e->tree_scratch_bytes / (36 * V));

@@ -512,7 +512,7 @@ struct TreeCache {
   int32_t* slot_of;      // [V] destination node -> slot, -1 = not cached
   int32_t* slot_owner;   // [max_slots] destination held by the slot, -1 = free
   uint32_t* slot_stamp;  // [max_slots] last batch that used the slot (never evicted within that batch)
-  int32_t* next_link;    // [slots][V] first link towards the destination, -1 = none
+  int2* next_link;       // [slots][V] {first link towards the root (-1 = none), node at its other end}: one load per hop
   int32_t* ring_cursor;  // FIFO allocation cursor (device counter)
   int32_t max_slots;
   int32_t* job_dst;      // [max_slots] trees to build
@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_tre
     const int32_t* __restrict__ x_col = out_tree ? g.fwd_col : g.bwd_col;
     const double* __restrict__ x_w = out_tree ? w_fwd : w_bwd;
     const int32_t slot = tc.job_slot[job];
-    int32_t* next_link = tc.next_link + (int64_t)(slot < 0 ? 0 : slot) * V;
+    int2* next_link = tc.next_link + (int64_t)(slot < 0 ? 0 : slot) * V;
     const int nb = min(tc.job_cnt[job], kMaxBounded);
     const bool bounded = slot < 0;  // decided when the job was created (k_tree_requests)
     if (threadIdx.x == 0) ++c_jobs;
@@ -1034,12 +1034,12 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_tre
       const double* __restrict__ y_w = out_tree ? w_bwd : w_fwd;
       const int32_t* __restrict__ y_link = out_tree ? g.bwd_link : g.fwd_link;
       for (int64_t u = threadIdx.x; u < V; u += blockDim.x) {
-        int32_t nl = -1;
+        int2 nl = make_int2(-1, -1);
         const unsigned long long du = rec[u].dist;
         if (u != dest && du != kInfBits) {
           unsigned long long dn = 0;
           const int32_t e = find_tight_entry(y_rowptr[u], y_rowptr[u + 1], du, rec, y_col, y_w, &dn);
-          if (e >= 0) nl = y_link[e];
+          if (e >= 0) nl = make_int2(y_link[e], y_col[e]);
         }
         next_link[u] = nl;
       }
@@ -1107,19 +1107,18 @@ __global__ void k_extract_paths(GraphArrays g, int64_t Q, const int32_t* __restr
       out.status[q] = DRIFT_ROUTE_NOPATH;
       continue;
     }
-    const int32_t* next_link = tc.next_link + (int64_t)slot * g.V;
-    const int32_t* step_to = out_tree ? g.link_u : g.link_v;
+    const int2* next_link = tc.next_link + (int64_t)slot * g.V;
     const int32_t from = out_tree ? t : s, to = out_tree ? s : t;
     int hops = 0;
     int32_t x = from;
     while (x != to) {
-      const int32_t l = next_link[x];
-      if (l < 0 || hops > g.V) {
+      const int2 en = next_link[x];
+      if (en.x < 0 || hops > g.V) {
         hops = -1;
         break;
       }
       ++hops;
-      x = step_to[l];
+      x = en.y;
     }
     if (hops < 0) {
       out.status[q] = DRIFT_ROUTE_NOPATH;
@@ -1135,16 +1134,16 @@ __global__ void k_extract_paths(GraphArrays g, int64_t Q, const int32_t* __restr
     x = from;
     if (!out_tree) {
       for (int k = 0; k < hops; ++k) {
-        const int32_t l = next_link[x];
-        arena[off + k] = l;
-        c = __dadd_rn(c, link_cost[l]);
-        x = g.link_v[l];
+        const int2 en = next_link[x];
+        arena[off + k] = en.x;
+        c = __dadd_rn(c, link_cost[en.x]);
+        x = en.y;
       }
     } else {
       for (int k = hops - 1; k >= 0; --k) {
-        const int32_t l = next_link[x];
-        arena[off + k] = l;
-        x = g.link_u[l];
+        const int2 en = next_link[x];
+        arena[off + k] = en.x;
+        x = en.y;
       }
       for (int k = 0; k < hops; ++k) c = __dadd_rn(c, link_cost[arena[off + k]]);
     }

@@ -207,7 +207,7 @@ def test_tree_cache_eviction():
     nodes = list(G.nodes)
     rng = random.Random(2)
     with Engine(lg, 8, route_arena_links=1 << 22) as eng:
-        eng.set_option("tree_cache_bytes", 8 * 4 * lg.V)
+        eng.set_option("tree_cache_bytes", 8 * 8 * lg.V)  # 8 slots of 8 B per node
         for rnd in range(12):
             dests = [rng.randrange(200) for _ in range(6)] + [0, 1]  # 0 and 1 stay hot, others churn
             pairs = [(rng.randrange(200), rng.choice(dests)) for _ in range(300)]
