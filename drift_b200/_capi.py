@@ -89,6 +89,7 @@ SIGNATURES = {
     "drift_phase_times": (C.c_int, [ENGINE, c_f64p, c_f64p, c_f64p, c_f64p, c_i64p, C.c_int32]),
     "drift_tree_stats": (C.c_int, [ENGINE, c_f64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, C.c_int32]),
     "drift_set_landmarks": (C.c_int, [ENGINE, C.c_int32, c_f64p, c_f64p]),
+    "drift_host_pow": (C.c_int, [c_f64p, C.c_double, c_f64p, C.c_int64]),
     "drift_set_option": (C.c_int, [ENGINE, C.c_char_p, C.c_double]),
     "drift_device_ptr": (C.c_int, [ENGINE, C.c_char_p, C.POINTER(C.c_void_p), c_i64p]),
 }

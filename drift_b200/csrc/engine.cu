@@ -1694,6 +1694,16 @@ int drift_set_landmarks(drift_engine* e, int32_t K, const double* dist_from, con
   return DRIFT_OK;
 }
 
+// Host utility (no device work): out[i] = pow(x[i], y) with the C library's pow -- the function CPython's
+// float ** float reaches (floatobject.c: float_pow -> pow), which NumPy's vectorised power does not
+// reproduce bit for bit.  Used by the vectorised s-t selectors (drift_b200/fast_selection.py) to keep
+// lib/st_selection.py:416 `(S_i * A_j) / (d_ij ** self.beta)` and :352 `(dx*dx + dy*dy)**0.5` exact.
+int drift_host_pow(const double* x, double y, double* out, int64_t n) {
+  if (n < 0 || (n && (!x || !out))) return fail(DRIFT_EINVAL, "drift_host_pow");
+  for (int64_t i = 0; i < n; ++i) out[i] = std::pow(x[i], y);
+  return DRIFT_OK;
+}
+
 int drift_set_option(drift_engine* e, const char* name, double value) {
   if (!e || !name) return fail(DRIFT_EINVAL, "drift_set_option");
   std::string s(name);

@@ -18,7 +18,7 @@ import numpy as np
 
 
 def run_headless(graph, agents, mode="random", hours=1, accel=10, seed=None, settings=None, st_selector=None,
-                 out_dir=".", on_tick=None, device=0, lowered=None):
+                 out_dir=".", on_tick=None, device=0, lowered=None, fast_selectors=False):
     """Returns (thread, wall_seconds).  One ``update_simulation_step`` per tick, no GUI pacing."""
     from .simulation_thread import SimulationThread
 
@@ -31,6 +31,7 @@ def run_headless(graph, agents, mode="random", hours=1, accel=10, seed=None, set
     try:
         th = SimulationThread(graph, agents, mode, duration_hours=hours, device=device, lowered=lowered)
         th.time_acceleration = accel
+        th.fast_selectors = bool(fast_selectors)
         if settings is not None:
             th.apply_settings(settings)
         if st_selector is not None:
@@ -61,6 +62,8 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--out", default=".")
     ap.add_argument("--json", action="store_true", help="also write the JSON export")
+    ap.add_argument("--fast-selectors", action="store_true",
+                    help="vectorised gravity / hub / zone models (drift_b200/fast_selection.py: same trips for the same seed)")
     ap.add_argument("--drift-root", default=os.environ.get("DRIFT_ROOT"), help="path of the DRIFT checkout")
     args = ap.parse_args(argv)
     if not args.drift_root:
@@ -72,7 +75,7 @@ def main(argv=None):
     np.random.seed(args.seed)
     G = GraphLoader().load_graph(args.graph)
     th, wall = run_headless(G, args.agents, args.mode, hours=args.hours, accel=args.accel, seed=args.seed,
-                            out_dir=args.out)
+                            out_dir=args.out, fast_selectors=args.fast_selectors)
     if args.json:
         th.data_logger.save_to_json()
     n = args.agents * th.step

@@ -155,6 +155,7 @@ class SimulationThread(QThread):
         self.agent_states = []
         self.settings = None
         self.st_selector = None
+        self.fast_selectors = False  # True: vectorised gravity / hub / zone models (same sequences, fast_selection.py)
         self._cached_agent_type_percentages = {}
         self._cached_network_stats = {}
         self._last_network_stats_step = 0
@@ -242,7 +243,8 @@ class SimulationThread(QThread):
                 self.log_message.emit("Using pre-computed ST selector model")
                 selector = self.st_selector
             else:
-                selector = make_selector(self.selection_mode, self.graph, self.settings)
+                selector = make_selector(self.selection_mode, self.graph, self.settings,
+                                         fast=getattr(self, "fast_selectors", False))
             nodes = lg.nodes
             self.agents = []
             if self.selection_mode == "activity":

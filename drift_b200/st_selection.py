@@ -38,9 +38,17 @@ class RandomSelection(SourceTargetSelection):
         return source, target
 
 
-def make_selector(mode, graph, settings=None):
+def make_selector(mode, graph, settings=None, fast=False):
     """Selector for ``selection_mode`` (config.py:174), built with the same arguments the reference
-    passes at lib/simulation_thread.py:201-261.  Non-random models come from the reference package."""
+    passes at lib/simulation_thread.py:201-261.  Non-random models come from the reference package;
+    ``fast=True`` takes the vectorised restatements of drift_b200/fast_selection.py (gravity, hub, zone:
+    same sequences for the same seed, no O(V) Python work per call, no O(V^2) set-up) where they exist."""
+    if fast:
+        from .fast_selection import make_fast_selector
+
+        sel = make_fast_selector(mode, graph, settings)
+        if sel is not None:
+            return sel
     if mode not in ("activity", "zone", "gravity", "hub"):
         try:
             from lib.st_selection import RandomSelection as RefRandom  # inside the DRIFT app

@@ -252,6 +252,10 @@ int drift_tree_stats(drift_engine* e, double* build_ms, int64_t* launches, int64
  * dist_from[K][V] = free-flow travel time landmark -> node, dist_to[K][V] = node -> landmark (+inf where
  * unreachable).  Only used while routing on the static travel times.  K = 0 switches it off. */
 int drift_set_landmarks(drift_engine* e, int32_t K, const double* dist_from, const double* dist_to);
+/* Host-side helper of the vectorised s-t selectors (drift_b200/fast_selection.py; replaces the Python loops
+ * of lib/st_selection.py:327-363 and :408-423): out[i] = pow(x[i], y) through the C library, i.e. exactly
+ * what CPython's `x ** y` computes.  No device is touched. */
+int drift_host_pow(const double* x, double y, double* out, int64_t n);
 /* Tunables: "tree_cache_bytes" (HBM budget of the destination-tree cache, before first use),
  * "tree_delta_scale" (multiplies the near-far bucket width). */
 int drift_set_option(drift_engine* e, const char* name, double value);

@@ -12,6 +12,9 @@ from oracle import golden
 
 pytestmark = pytest.mark.gpu
 LIVE = [n for n in golden.case_names() if "_random_" in n or "congested" in n]
+# recorded with the reference's own hub / zone / gravity selector objects; replayed here with the vectorised
+# restatements of drift_b200/fast_selection.py (the reference package does not exist on the GPU box)
+LIVE_FAST = [n for n in golden.case_names() if any(m in n for m in ("_hub_", "_zone_", "_gravity_"))]
 
 
 def _settings(case):
@@ -24,7 +27,7 @@ def _settings(case):
     return st
 
 
-@pytest.mark.parametrize("name", LIVE)
+@pytest.mark.parametrize("name", LIVE + LIVE_FAST)
 def test_thread_matches_reference_run(name, tmp_path):
     from drift_b200.headless import run_headless
     from drift_b200.simulation_thread import AgentView
@@ -48,7 +51,8 @@ def test_thread_matches_reference_run(name, tmp_path):
 
     AgentView._next_id = 1
     th, wall = run_headless(G, case.N, case.params["mode"], hours=case.hours, accel=case.accel,
-                            seed=case.params["seed"], settings=_settings(case), out_dir=str(tmp_path), on_tick=on_tick)
+                            seed=case.params["seed"], settings=_settings(case), out_dir=str(tmp_path), on_tick=on_tick,
+                            fast_selectors=name in LIVE_FAST)
     try:
         assert seen["max_tick"] == case.ticks
         assert [a.source for a in th.agents][:0] == []
