@@ -148,7 +148,8 @@ struct drift_engine {
   DevBuf<int2> t_next;  // cached trees: {link, next node} per node
   DevBuf<NodeRec> t_rec;   // per-block search scratch
   int32_t t_sides = 2;       // 2 = trees out of hot sources as well as into hot destinations
-  DevBuf<int32_t> t_cnt;
+  DevBuf<int32_t> t_cnt, t_pop;
+  int32_t t_pop_thresh = 16;  // destinations asked for more often than this over ~64 batches get a cached tree
   DevBuf<uint8_t> t_q_side;
   DevBuf<uint32_t> t_iter, t_slot_stamp;
   DevBuf<int32_t> t_slot_owner, t_slot_job, t_job_qhead, t_job_cnt, t_q_next;
@@ -376,6 +377,7 @@ int ensure_trees(drift_engine* e) {
   CU(e->t_slot_of.alloc(2 * V, false));  // keys: destination t, or V + source s
   CU(cudaMemset(e->t_slot_of.p, 0xff, sizeof(int32_t) * 2 * V));
   CU(e->t_cnt.alloc(2 * V, true));
+  CU(e->t_pop.alloc(V, true));
   CU(e->t_next.alloc(slots * V, false));
   CU(e->t_slot_owner.alloc(slots, false));
   CU(cudaMemset(e->t_slot_owner.p, 0xff, sizeof(int32_t) * slots));
@@ -450,6 +452,9 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
       CU(e->t_job_slot.alloc(need + e->t_max_slots));
     }
     tc.cnt = e->t_cnt.p;
+    tc.pop = e->t_pop.p;
+    tc.pop_thresh = e->t_pop_thresh;
+    if ((tc.batch & 63u) == 0) k_pop_decay<<<kSMs * 4, 256, 0, e->stream>>>(e->t_pop.p, e->V);
     tc.q_side = e->t_q_side.p;
     tc.V = e->V;
     tc.slot_job = e->t_slot_job.p;
@@ -1726,6 +1731,8 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
     e->route_window = (int32_t)value;
   } else if (s == "replan") {
     e->ticks_since_plan = 0;
+  } else if (s == "tree_pop_threshold") {
+    e->t_pop_thresh = (int32_t)value;
   } else if (s == "arena_compact_frac") {
     e->arena_compact_frac = std::min(0.95, std::max(0.05, value));
   } else if (s == "debug_mask") {

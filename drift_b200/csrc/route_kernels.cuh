@@ -531,6 +531,11 @@ struct TreeCache {
   // V + s = forward tree out of source s (return legs to scattered targets leave from few places:
   // depots, hubs, activity pools -- lib/st_selection.py).  cnt[key] = queries of this batch per key.
   int32_t* cnt;             // [2V], zero between batches
+  // Popularity of a destination across batches (halved every 64 batches): with small batches (lookahead
+  // planning) a mildly popular destination never collects bounded_max queries in ONE batch and would pay
+  // a bounded search per query for ever; once pop[t] exceeds pop_thresh its tree is built and cached.
+  int32_t* pop;             // [V]
+  int32_t pop_thresh;
   uint8_t* q_side;          // [Q] 0 = answered from the destination's tree, 1 = from the source's
   int32_t V;
   int32_t sides;            // 1 = destination trees only, 2 = both
@@ -541,6 +546,10 @@ constexpr int kMaxBounded = 8;
 constexpr unsigned long long kInfBits = 0x7FF0000000000000ULL;
 constexpr int kTreeThreadsMax = 256;
 constexpr int kTreeBlocksPerSM = 8;  // 32 registers per thread: searches are latency-bound, residency is what pays
+
+__global__ void k_pop_decay(int32_t* __restrict__ pop, int32_t V) {
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < V; i += gridDim.x * blockDim.x) pop[i] >>= 1;
+}
 
 __device__ __forceinline__ bool tree_query_ok(int32_t s, int32_t t, int32_t V) {
   return s >= 0 && t >= 0 && s < V && t < V && s != t;
@@ -554,6 +563,7 @@ __global__ void k_tree_count(int64_t Q, const int32_t* __restrict__ src, const i
     const int32_t s = src[q], t = dst[q];
     if (!tree_query_ok(s, t, tc.V)) continue;
     atomicAdd(&tc.cnt[t], 1);
+    atomicAdd(&tc.pop[t], 1);
     if (tc.sides > 1) atomicAdd(&tc.cnt[tc.V + s], 1);
   }
 }
@@ -593,9 +603,20 @@ __global__ void k_tree_requests(int64_t Q, const int32_t* __restrict__ src, cons
     if (!tree_query_ok(src[q], dst[q], tc.V)) continue;
     const int32_t t = tc.q_side[q] ? tc.V + src[q] : dst[q];
     if (atomicCAS(&tc.slot_of[t], -1, -2) != -1) continue;  // cached, or another thread is allocating it
-    if (t < tc.V && tc.bounded_max > 0 && tc.cnt[t] <= tc.bounded_max) {
-      // cold destination: a bounded search answers its few queries and keeps no tree -> no slot;
-      // slot_of[t] = -(job + 3) until the job is done
+    const bool may_bound = t < tc.V && tc.bounded_max > 0 && tc.cnt[t] <= tc.bounded_max;
+    int32_t s = -1;
+    if (!(may_bound && tc.pop[t] <= tc.pop_thresh)) {  // hot in this batch, or popular over the last batches: keep a tree
+      for (int tries = 0; tries < tc.max_slots; ++tries) {
+        const int32_t c = (int32_t)((uint32_t)atomicAdd(tc.ring_cursor, 1) % (uint32_t)tc.max_slots);
+        if (atomicExch(&tc.slot_stamp[c], tc.batch) != tc.batch) {  // not used by this batch: take it
+          s = c;
+          break;
+        }
+      }
+    }
+    if (s < 0 && may_bound) {
+      // cold destination (or no free slot for a merely popular one): a bounded search answers its few
+      // queries and keeps no tree -> no slot; slot_of[t] = -(job + 3) until the job is done
       const int32_t j = atomicAdd(tc.n_jobs, 1);
       tc.job_dst[j] = t;
       tc.job_slot[j] = -1;
@@ -603,14 +624,6 @@ __global__ void k_tree_requests(int64_t Q, const int32_t* __restrict__ src, cons
       tc.job_cnt[j] = 0;
       tc.slot_of[t] = -(j + 3);
       continue;
-    }
-    int32_t s = -1;
-    for (int tries = 0; tries < tc.max_slots; ++tries) {
-      const int32_t c = (int32_t)((uint32_t)atomicAdd(tc.ring_cursor, 1) % (uint32_t)tc.max_slots);
-      if (atomicExch(&tc.slot_stamp[c], tc.batch) != tc.batch) {  // not used by this batch: take it
-        s = c;
-        break;
-      }
     }
     if (s < 0) {  // more distinct hot keys in one batch than slots
       tc.slot_of[t] = -1;
