@@ -256,8 +256,27 @@ int drift_set_landmarks(drift_engine* e, int32_t K, const double* dist_from, con
  * of lib/st_selection.py:327-363 and :408-423): out[i] = pow(x[i], y) through the C library, i.e. exactly
  * what CPython's `x ** y` computes.  No device is touched. */
 int drift_host_pow(const double* x, double y, double* out, int64_t n);
-/* Tunables: "tree_cache_bytes" (HBM budget of the destination-tree cache, before first use),
- * "tree_delta_scale" (multiplies the near-far bucket width). */
+/* Options (name, value):
+ *   route_window        ticks between two route-planning batches (default 300)
+ *   plan_lookahead      1 = plan only the departures the coming window's draws allow (default 0 = keep the
+ *                       routes of every agent's next two trips ready)
+ *   plan_arrival_hops   lookahead: a moving agent with at most this many links to go may arrive within the
+ *                       window (-1 = window * fastest link / shortest link)
+ *   persistent          0 = one launch per phase and tick instead of the persistent tick kernel
+ *   coop_blocks_per_sm  blocks per SM of the persistent tick kernel (default 6)
+ *   tree_cache_bytes    HBM budget of the tree cache (default min(48 GB, 30 % of the free memory))
+ *   tree_scratch_bytes  HBM budget of the search scratch, 36 B per node and resident search (default
+ *                       min(64 GB, 40 % of the free memory))
+ *   tree_sides          1 = trees towards destinations only, 2 = also out of sources (default)
+ *   bounded_max         a destination wanted by at most this many queries of a batch is answered by a bounded
+ *                       search that keeps no tree (0..8; default 8, or 0 when every tree fits the cache)
+ *   tree_pop_threshold  a destination asked for more often than this over ~64 batches gets a cached tree anyway
+ *   tree_delta_scale    multiplies the near-far bucket width; tree_threads: 64 / 128 / 256 threads per search
+ *   arena_compact_frac  the live routes are compacted once this fraction of the route arena is used (0.75)
+ *   time_plan           1 = time the planning batches with CUDA events (drift_phase_times / drift_tree_stats)
+ *   debug_mask          timing probes only, results are then NOT the reference's: 1 = no departure draws,
+ *                       2 = crossers stay on their link, 4 = events are not emitted (tools/tick_probe.py)
+ * The tree_* budgets, tree_sides and tree_threads must be set before the first batched route. */
 int drift_set_option(drift_engine* e, const char* name, double value);
 /* Raw device pointers for PyTorch interop (tensor views of engine state). name in
  * {"occ","state","dist","speed","link_len","cur_link","events","travel_time"}. */
