@@ -120,3 +120,39 @@ def test_graph_cache_round_trip(tmp_path):
     u, v, k = next(iter(G2.edges(keys=True)))
     G2[u][v][k]["length"] += 1.0
     assert graph_cache.graph_digest(G2) != graph_cache.graph_digest(G)
+
+
+def test_departure_threshold_is_the_bernoulli_test():
+    """The tick kernel compares the 53 random bits with ceil(p * 2^53) instead of converting them to a
+    double and testing u < p (lib/agent.py:180): the two are the same predicate for every p, including
+    the values right next to a threshold."""
+    import math
+
+    from oracle.philox import uniform53
+
+    rng = np.random.default_rng(5)
+    agents = np.arange(20000, dtype=np.uint32)
+    u = uniform53(99, agents, 1234)
+    bits = np.round(u * 9007199254740992.0).astype(np.uint64)
+    assert np.array_equal(bits.astype(np.float64) / 9007199254740992.0, u)  # u = bits * 2^-53 exactly
+    ps = list(rng.random(20) * 1e-3) + [0.35 * 4 / 3600, 0.9 * 4 * 5 / 3600, 0.0, 1.0, 1.5, 2.0 ** -53, 3 * 2.0 ** -54]
+    ps += [float(x) for x in u[:40]] + [float(np.nextafter(x, 1.0)) for x in u[:40]]  # on / just above a draw
+    for p in ps:
+        if not p > 0.0:
+            thr = 0
+        else:
+            s = math.ceil(p * 9007199254740992.0)
+            thr = min(s, 2 ** 64 - 1)
+        assert np.array_equal(bits < np.uint64(thr) if thr < 2 ** 64 else np.ones_like(bits, bool), u < p), p
+
+
+def test_paired_philox_words():
+    """One Philox block serves the two agents of a pair: agents 2k and 2k+1 share a counter and take
+    different output words, so their draws differ and do not depend on the neighbour's presence."""
+    from oracle.philox import uniform53
+
+    a = uniform53(7, np.array([10, 11, 12, 13], dtype=np.uint32), 5)
+    assert len(set(a.tolist())) == 4
+    assert uniform53(7, np.array([11], dtype=np.uint32), 5)[0] == a[1]
+    assert uniform53(7, np.array([10], dtype=np.uint32), 6)[0] != a[0]
+    assert np.all((a >= 0) & (a < 1))
