@@ -112,3 +112,29 @@ def test_sharded_tick_semantics_gloo(world):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+def test_home_rank_arithmetic_matches_shard_bounds():
+    """k_tick_loop_p2p finds the home rank of a global agent id with two divisions (p2p_home in
+    csrc/tick_kernels.cuh); it must agree with the contiguous blocks ShardedEngine hands out."""
+    from drift_b200.dist import shard_bounds
+
+    def home(agent, n_total, world):  # transliteration of p2p_home
+        base, rem = n_total // world, n_total % world
+        big = (base + 1) * rem
+        if agent < big:
+            h = agent // (base + 1)
+            return h, agent - h * (base + 1)
+        r = agent - big
+        q = r // base
+        return rem + q, r - q * base
+
+    for n_total, world in [(10, 3), (1000, 8), (1001, 8), (7, 7), (40_000, 2), (999_999, 16), (16, 16)]:
+        owner = {}
+        for r in range(world):
+            lo, hi = shard_bounds(n_total, r, world)
+            for a in (lo, hi - 1, (lo + hi) // 2):
+                if lo <= a < hi:
+                    owner[a] = (r, a - lo)
+        for a, want in owner.items():
+            assert home(a, n_total, world) == want, (n_total, world, a)
