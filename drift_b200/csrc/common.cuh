@@ -95,6 +95,16 @@ struct AgentArrays {
   uint32_t base;  // global id of local agent 0
 };
 
+// What resolving an entry needs to know about a link, in one 32-byte sector: free speed, length and the
+// range of the link's capacity class in the BPR factor table (instead of cls -> cls_off -> factor).
+struct __align__(32) LinkRec {
+  double v0;
+  double len;
+  int32_t f_lo;  // first entry of the class in `factor`
+  int32_t f_hi;  // one past its last entry (the saturated 10 % floor)
+  int32_t pad[2];
+};
+
 struct LinkArrays {
   const double* len;
   const double* v0;
@@ -108,6 +118,7 @@ struct LinkArrays {
   const int32_t* cls;
   const double* factor;     // concatenated per-class tables
   const int64_t* cls_off;   // [n_class+1]
+  const LinkRec* rec;       // [L] packed copy of v0 / len / factor range (built by drift_set_bpr)
   int32_t L;
 };
 

@@ -85,6 +85,7 @@ struct drift_engine {
   DevBuf<int32_t> fwd_rowptr, fwd_col, fwd_link, bwd_rowptr, bwd_col, bwd_link, link_cap, link_u, link_v, link_cls;
   DevBuf<double> fwd_w, bwd_w, link_len, link_v0, link_t0, link_tt, factor, fwd_wc, bwd_wc;
   DevBuf<int64_t> cls_off;
+  DevBuf<LinkRec> link_rec;
   DevBuf<int32_t> occ, hist;
   DevBuf<unsigned long long> head;
   int64_t total_capacity = 0;
@@ -250,6 +251,7 @@ struct drift_engine {
     l.cls = link_cls.p;
     l.factor = factor.p;
     l.cls_off = cls_off.p;
+    l.rec = link_rec.p;
     l.L = L;
     return l;
   }
@@ -771,6 +773,11 @@ int drift_set_bpr(drift_engine* e, double alpha, double beta, const double* fact
   CU(e->factor.upload(factor_table, class_off[n_class]));
   CU(e->cls_off.upload(class_off, n_class + 1));
   CU(e->link_cls.upload(link_class, e->L));
+  if (class_off[n_class] >= ((int64_t)1 << 31)) return fail(DRIFT_EINVAL, "drift_set_bpr: factor table too large");
+  CU(e->link_rec.alloc(e->L, false));
+  k_pack_linkrec<<<grid_for(e->L, 256, kSMs * 8), 256, 0, e->stream>>>(e->links(), e->link_rec.p);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(e->stream));
   e->have_bpr = true;
   return DRIFT_OK;
 }

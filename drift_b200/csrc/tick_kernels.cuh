@@ -539,14 +539,14 @@ __device__ __forceinline__ void resolve_one(const LinkArrays& lk, const AgentArr
   int64_t f_lo = 0, f_hi = 1;
   int32_t next = -1;
   if (mine) {
-    const int32_t c = lk.cls[ev.link];
-    v0 = lk.v0[ev.link];
-    len = lk.len[ev.link];
+    const LinkRec r = lk.rec[ev.link];  // one sector: v0, len, factor range
+    v0 = r.v0;
+    len = r.len;
+    f_lo = r.f_lo;
+    f_hi = r.f_hi;
     const int32_t ri = a.route_idx[li] + 1;
     const int32_t rlen = a.route_len[li];
     const int64_t roff = a.route_off[li];
-    f_lo = lk.cls_off[c];
-    f_hi = lk.cls_off[c + 1];
     if (ri < rlen) next = arena[roff + ri];
   }
   int before = 0;  // sum of the deltas of events ordered before this one (agent-list order)
@@ -887,10 +887,10 @@ __device__ __forceinline__ bool resolve_one_p2p(const TickArgs& p, const P2PArgs
   double v0 = 0.0;
   int64_t f_lo = 0, f_hi = 1;
   if (ev.kind > 0) {  // loaded before the list walk: independent of it
-    const int32_t c = lk.cls[ev.link];
-    v0 = lk.v0[ev.link];
-    f_lo = lk.cls_off[c];
-    f_hi = lk.cls_off[c + 1];
+    const LinkRec r = lk.rec[ev.link];
+    v0 = r.v0;
+    f_lo = r.f_lo;
+    f_hi = r.f_hi;
   }
   int before = 0, net = 0, occ0 = 0;
   int j = first;
@@ -1014,6 +1014,19 @@ __global__ void k_recount(AgentArrays a, int32_t* __restrict__ hist) {
       const int32_t l = a.cur_link[i];
       if (l >= 0) atomicAdd(&hist[l], 1);
     }
+  }
+}
+
+__global__ void k_pack_linkrec(LinkArrays lk, LinkRec* __restrict__ rec) {
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < lk.L; l += gridDim.x * blockDim.x) {
+    const int32_t c = lk.cls[l];
+    LinkRec r;
+    r.v0 = lk.v0[l];
+    r.len = lk.len[l];
+    r.f_lo = (int32_t)lk.cls_off[c];
+    r.f_hi = (int32_t)lk.cls_off[c + 1];
+    r.pad[0] = r.pad[1] = 0;
+    rec[l] = r;
   }
 }
 
