@@ -467,11 +467,11 @@ def run_b200(args):
             data="synthetic",
             config=dict(workload=args.workload, description=w["desc"], agents_per_gpu=n_local, total_agents=total_agents,
                         nodes=lg.V, links=lg.L, demand=model, ticks_per_step=TPS, tick_seconds=delta,
-                        router="batched reverse-tree SSSP + destination cache", clock="08:00 peak",
-                        l2="no explicit flush: every step's route planning streams the tree-builder scratch, tree cache "
-                           "and route arena (GBs, >> 126 MB L2) between tick blocks; the per-tick agent state (%.0f MB "
-                           "hot) can stay L2-resident at this size, which is why roofline_advance_saturated uses 16 M "
-                           "agents (400 MB of hot state)" % (n_local * 25 / 1e6),
+                        router="batched SSSP: cached shortest-path trees on either end of a trip (destination / source), bounded goal-directed searches for cold pairs; planning: %s" % ("lookahead" if w.get("lookahead") else "prefetch-all"), clock="08:00 peak",
+                        l2="no explicit flush: a tick re-reads the same agent state by construction (%.0f MB hot + ~80 MB "
+                           "cold per-agent state at this size, L2 is 126 MB) and every step's route planning walks "
+                           "GBs of cached trees and route arena in between; roofline_advance_saturated uses 16 M "
+                           "agents (400 MB of hot state, >> L2) for the bandwidth-bound figure" % (n_local * 25 / 1e6),
                         multi_gpu=(("agents sharded by id block, graph replicated, links owned round-robin: events stored "
                                     "into the owner's inbox and entry speeds into the home rank's arrays over NVLink peer "
                                     "memory inside the persistent tick kernel (k_tick_loop_p2p), no collective call"
