@@ -77,3 +77,35 @@ class EventModel:
                 self.speed[i] = (float(self.pg.link_v0[link]) * f) * KPH_TO_MPS
                 self.elen[i] = float(self.pg.link_len[link])
         self.occ[run_link] = run
+
+    # ---- link-owner protocol (what k_tick_loop_p2p does over NVLink peer memory) ----------------
+    def resolve_owned(self, events, rank, world):
+        """Owner side: ``events`` = the events of ALL ranks on the links this rank owns (link % world ==
+        rank).  Updates the owned links' occupancy and returns [(global agent, speed)] for every entering
+        agent, to be delivered to the agent's home rank.  elen is not returned: the home rank knows the
+        link it entered (link tables are replicated)."""
+        out = []
+        if len(events) == 0:
+            return out
+        assert np.all(events[:, 0] % world == rank)
+        order = np.lexsort((events[:, 1], events[:, 0]))
+        ev = events[order]
+        run_link, run = -1, 0
+        for link, agent, kind, _ in ev.tolist():
+            if link != run_link:
+                if run_link >= 0:
+                    self.occ[run_link] = run
+                run_link, run = link, int(self.occ[link])
+            run += kind
+            if kind > 0:
+                f = bpr_factor(run, int(self.pg.link_cap[link]), self.alpha, self.beta)
+                out.append((agent, (float(self.pg.link_v0[link]) * f) * KPH_TO_MPS))
+        self.occ[run_link] = run
+        return out
+
+    def apply_speeds(self, results):
+        """Home side: entry speeds of this rank's agents as delivered by the owners of their links."""
+        for agent, sp in results:
+            i = agent - self.lo
+            self.speed[i] = sp
+            self.elen[i] = float(self.pg.link_len[self.cur_link[i]])

@@ -138,3 +138,74 @@ def test_home_rank_arithmetic_matches_shard_bounds():
                     owner[a] = (r, a - lo)
         for a, want in owner.items():
             assert home(a, n_total, world) == want, (n_total, world, a)
+
+
+def _worker_link_owner(rank, world, port, out):
+    """The link-owner protocol of the peer-memory exchange, host-level: every rank sends each event to the
+    owner of its link (link % world), the owner orders the events of its links and returns the entry
+    speeds to the agents' home ranks; owned volumes summed over the ranks and all agent state must
+    equal the sequential port."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from drift_b200.dist import shard_bounds
+        from oracle import golden
+        from oracle.event_model import EventModel
+        from oracle.port import PortSim
+
+        case = golden.GoldenCase("g40_congested_bpr")
+        pg = case.plain_graph()
+        trace = case.departure_trace()
+        ticks = 300
+        lo, hi = shard_bounds(case.N, rank, world)
+        bounds = [shard_bounds(case.N, r, world) for r in range(world)]
+        em = EventModel(pg, case.N, lo, hi, alpha=case.alpha, beta=case.beta)
+        ref = PortSim(pg, case.N, hourly=case.hourly, alpha=case.alpha, beta=case.beta, accel=case.accel,
+                      hours=case.hours, departure_trace=trace, init_nodes=case.init_nodes)
+        for k in range(1, ticks + 1):
+            deps = {a: v for a, v in trace.get(k, {}).items() if lo <= a < hi}
+            local = em.tick_begin(1.0, deps)
+            # exchange 1: events to the owners of their links
+            to_owner = [local[local[:, 0] % world == o].tolist() if len(local) else [] for o in range(world)]
+            # (gloo has no all-to-all for objects: gather everything, keep what is mine)
+            gathered = [None] * world
+            dist.all_gather_object(gathered, to_owner)
+            mine = [e for src in gathered for e in src[rank]]
+            results = em.resolve_owned(np.array(mine, dtype=np.int64).reshape(-1, 4), rank, world)
+            # exchange 2: entry speeds to the home ranks
+            to_home = [[(a, sp) for a, sp in results if bounds[h][0] <= a < bounds[h][1]] for h in range(world)]
+            gathered = [None] * world
+            dist.all_gather_object(gathered, to_home)
+            em.apply_speeds([x for src in gathered for x in src[rank]])
+            ref.tick()
+            occ = torch.from_numpy(em.occ.copy())
+            owned = torch.from_numpy((np.arange(pg.L) % world == rank).astype(np.int64))
+            assert bool(torch.all(occ * (1 - owned) == 0)), "a rank holds volume of a link it does not own"
+            dist.all_reduce(occ)
+            assert np.array_equal(occ.numpy(), np.asarray(ref.occ)), "volumes differ at tick %d" % k
+        st, d, sp, pi = ref.snapshot()
+        mv = st[lo:hi] == 1
+        assert np.array_equal(em.state, st[lo:hi])
+        assert np.array_equal(em.dist[mv], d[lo:hi][mv]) and np.array_equal(em.speed[mv], sp[lo:hi][mv])
+        out.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+
+        out.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_link_owner_protocol_gloo(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_link_owner, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
