@@ -11,7 +11,8 @@ from pinned host memory and reads back arrivals, departures and the link-volume 
 
 Workloads (BASELINE.json configs; the city networks of the reference are not shipped, so the
 graphs are synthetic):
-  regional1m   configs[2]: ~1.16 M-link regional road graph, activity-structured demand, 1 M agents
+  regional1m   configs[2]: ~1.16 M-link regional road graph, activity-based demand (the reference's trip law
+               per agent type, lib/st_selection.py:926-1050), 1 M agents
   brussels100k configs[1]: ~53 k-node city graph, gravity-structured demand, 100 k agents
   bundled      configs[0]-sized: 100-node graph, random demand, 300 agents (CPU-reference scale)
 """
@@ -37,6 +38,9 @@ WORKLOADS = {
     # name: (graph nodes, agents per GPU, demand model, description)
     "regional1m": dict(nodes=400_000, agents=1_000_000, model="activity",
                        desc="configs[2]: regional road graph ~1.16M links, activity-structured demand, 1M agents/GPU"),
+    "regional1m_pools": dict(nodes=400_000, agents=1_000_000, model="activity_pools",
+                             desc="regional1m with the pool-to-pool variant of the activity demand (every trip has an end "
+                                  "in a small pool: the best case for the tree cache)"),
     "brussels100k": dict(nodes=50_000, agents=100_000, model="gravity", reroute=True,
                          desc="configs[1]: city road graph ~53k nodes, gravity-structured demand, 100k agents/GPU, "
                               "congestion-aware reroute of en-route agents every step (5 simulated minutes; extension)"),

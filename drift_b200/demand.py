@@ -55,36 +55,85 @@ def hub_chains(rng, lg, start, k, hub_trip_probability=0.3, hub_percentage=0.1):
     return np.arange(N + 1, dtype=np.int64) * k, dst.reshape(-1)
 
 
-def activity_chains(rng, lg, start, k):
-    """ActivityBasedSelection (st_selection.py:650-1082) structure: trips run between small pools of
-    home / work / business / activity / distribution nodes whose sizes are capped by config.py:294-303
-    (100/100/80/50/20), picked by distance ring from the network centre; agent types commuter /
-    leisure / business / delivery with shares .4/.3/.2/.1 (config.py:323-328)."""
+def _activity_pools(rng, lg):
+    """The node pools of ActivityBasedSelection (st_selection.py:690-890): sizes capped by config.py:294-303
+    (activity 50 / business 80 / work 100 / home 100 / distribution 20), drawn by distance ring from the
+    network centre (centre <= 0.3, middle <= 0.7 of the largest distance)."""
     V = lg.V
     pos = lg.pos if lg.pos is not None else rng.random((V, 2))
-    c = pos.mean(axis=0)
+    c = 0.5 * (pos.min(axis=0) + pos.max(axis=0))
     r = np.hypot(pos[:, 0] - c[0], pos[:, 1] - c[1])
     rn = r / max(r.max(), 1e-12)
-    centre = np.nonzero(rn < 0.3)[0]
-    middle = np.nonzero((rn >= 0.3) & (rn < 0.7))[0]
-    border = np.nonzero(rn >= 0.7)[0]
+    centre = np.nonzero(rn <= 0.3)[0]
+    middle = np.nonzero((rn > 0.3) & (rn <= 0.7))[0]
+    border = np.nonzero(rn > 0.7)[0]
 
     def pick(pool, n):
         pool = pool if len(pool) else np.arange(V)
         return rng.choice(pool, size=min(n, len(pool)), replace=False)
 
-    homes = np.concatenate([pick(centre, 5), pick(middle, 35), pick(border, 60)])
-    works = np.concatenate([pick(centre, 20), pick(middle, 40), pick(border, 40)])
-    business = np.concatenate([pick(centre, 56), pick(middle, 24)])
-    leisure = np.concatenate([pick(centre, 40), pick(middle, 10)])
-    depots = np.concatenate([pick(middle, 10), pick(border, 10)])
+    return dict(homes=np.concatenate([pick(centre, 5), pick(middle, 35), pick(border, 60)]),
+                works=np.concatenate([pick(centre, 20), pick(middle, 40), pick(border, 40)]),
+                business=np.concatenate([pick(centre, 56), pick(middle, 24)]),
+                leisure=np.concatenate([pick(centre, 40), pick(middle, 10)]),
+                depots=np.concatenate([pick(middle, 10), pick(border, 10)]))
+
+
+def activity_chains(rng, lg, start, k, shares=(0.4, 0.3, 0.2, 0.1)):
+    """ActivityBasedSelection (st_selection.py:650-1082), trip law by agent type (shares commuter / leisure /
+    business / delivery = .4/.3/.2/.1, config.py:323-328), vectorised over the agents:
+      commuter  even trips -> a work node, odd trips -> a home node (:941-955)
+      delivery  70 % -> a distribution node, else any node (:972-975)
+      leisure   60 % -> an activity centre, else any node (:1000-1003)
+      business  80 % -> a business node, else any node (:1034-1037)
+    and a target equal to the source is redrawn (:978-984, 1006-1016, 1040-1048).  About a fifth of the
+    trips therefore end at an arbitrary node, and ~6 % run between two arbitrary nodes."""
+    V = lg.V
+    P = _activity_pools(rng, lg)
+    N = len(start)
+    typ = rng.choice(4, size=N, p=list(shares))  # 0 commuter, 1 leisure, 2 business, 3 delivery
+    com, lei, bus, dly = typ == 0, typ == 1, typ == 2, typ == 3
+    dst = np.empty((N, k), dtype=np.int32)
+    prev = np.asarray(start, dtype=np.int64).copy()
+
+    def mixed(mask, pool, p_pool):
+        n = int(mask.sum())
+        to_pool = rng.random(n) < p_pool
+        return np.where(to_pool, pool[rng.integers(0, len(pool), size=n)], rng.integers(0, V, size=n))
+
+    for j in range(k):
+        d = np.empty(N, dtype=np.int64)
+        pool = P["works"] if j % 2 == 0 else P["homes"]
+        d[com] = pool[rng.integers(0, len(pool), size=int(com.sum()))]
+        d[lei] = mixed(lei, P["leisure"], 0.6)
+        d[bus] = mixed(bus, P["business"], 0.8)
+        d[dly] = mixed(dly, P["depots"], 0.7)
+        for _ in range(100):  # redraws (commuters keep a target equal to the source, like the reference)
+            bad = (d == prev) & ~com
+            if not bad.any():
+                break
+            d[bad & lei] = mixed(bad & lei, P["leisure"], 0.6)
+            d[bad & bus] = mixed(bad & bus, P["business"], 0.8)
+            d[bad & dly] = rng.integers(0, V, size=int((bad & dly).sum()))  # :981: any node
+        dst[:, j] = d
+        prev = d
+    return np.arange(N + 1, dtype=np.int64) * k, dst.reshape(-1)
+
+
+def activity_pools_chains(rng, lg, start, k):
+    """Pool-to-pool variant of the activity model (every trip has at least one end in a small pool; only the
+    delivery out-legs go to arbitrary nodes): fixed home / work per agent, out legs on even trips, return legs
+    on odd ones.  The best case for the tree cache; kept as a separate workload for comparison."""
+    V = lg.V
+    P = _activity_pools(rng, lg)
+    homes, works, business, leisure, depots = P["homes"], P["works"], P["business"], P["leisure"], P["depots"]
     N = len(start)
     typ = rng.choice(4, size=N, p=[0.4, 0.3, 0.2, 0.1])
     home = homes[rng.integers(0, len(homes), size=N)]
     work = works[rng.integers(0, len(works), size=N)]
     dst = np.empty((N, k), dtype=np.int32)
     for j in range(k):
-        out = np.where(j % 2 == 0, 1, 0)  # even legs go out, odd legs return home
+        out = j % 2 == 0  # even legs go out, odd legs return home
         d = np.empty(N, dtype=np.int64)
         com, lei, bus, dly = typ == 0, typ == 1, typ == 2, typ == 3
         d[com] = work[com] if out else home[com]
@@ -153,6 +202,7 @@ MODELS = {
     "random": lambda rng, lg, start, k: random_chains(rng, lg.V, start, k),
     "hub": hub_chains,
     "activity": activity_chains,
+    "activity_pools": activity_pools_chains,
     "zone": zone_chains,
     "gravity": gravity_chains,
 }

@@ -68,3 +68,22 @@ def test_demand_chains_are_valid_targets(model):
     if model in ("random", "hub"):  # these models redraw a target equal to the trip's source (st_selection.py:47-49)
         d = dst.reshape(500, 6)
         assert np.all(d[:, 0] != start) and np.all(d[:, 1:] != d[:, :-1])
+
+
+def test_activity_law_matches_reference_shares():
+    """The vectorised activity demand follows the reference's trip law per agent type
+    (lib/st_selection.py:926-1050): share of targets drawn from the type's pool."""
+    lg = road_graph(6000, seed=3)
+    start = np.random.default_rng(1).integers(0, lg.V, size=40000).astype(np.int32)
+    rng = np.random.default_rng(9)
+    P = demand._activity_pools(np.random.default_rng(9), lg)  # same first draws as inside activity_chains
+    _, dst = demand.activity_chains(rng, lg, start, 6)
+    d = dst.reshape(-1, 6)
+    pools = np.unique(np.concatenate(list(P.values())))
+    share = np.isin(d, pools).mean()
+    # .4 commuter (always a pool) + .3 * .6 + .2 * .8 + .1 * .7 = 0.81, plus arbitrary nodes that happen to be pool nodes
+    assert 0.80 < share < 0.83
+    cold_cold = (~np.isin(d[:, 1:], pools) & ~np.isin(d[:, :-1], pools)).mean()
+    assert 0.05 < cold_cold < 0.08
+    _, dp = demand.activity_pools_chains(np.random.default_rng(9), lg, start, 6)
+    assert np.isin(dp.reshape(-1, 6)[:, 1::2], pools).all()  # return legs always end in a pool
