@@ -161,7 +161,7 @@ struct drift_engine {
   bool tree_budget_set = false, tree_scratch_set = false;
   uint32_t t_batch = 0;
   DevBuf<int32_t> t_lists;
-  DevBuf<double> lm_from, lm_to;
+  DevBuf<double> lm_tab;  // [V][2K] landmark distances interleaved per node
   int32_t lm_K = 0;
   int32_t t_max_slots = 0, t_blocks = 0;
   double t_delta = 1.0;
@@ -485,8 +485,7 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     k_tree_hits<<<gq, 256, 0, e->stream>>>(Q, qs, qd, tc, n_dev);
     k_tree_requests<<<gq, 256, 0, e->stream>>>(Q, qs, qd, tc, e->ctr.p, n_dev);
     Landmarks lm;
-    lm.from = e->lm_from.p;
-    lm.to = e->lm_to.p;
+    lm.tab = e->lm_tab.p;
     lm.K = use_congested ? 0 : e->lm_K;  // the landmark distances are free-flow distances
     k_link_queries<<<gq, 256, 0, e->stream>>>(Q, qs, qd, tc, n_dev);
     cudaEvent_t tb0 = nullptr, tb1 = nullptr;
@@ -1700,8 +1699,15 @@ int drift_set_landmarks(drift_engine* e, int32_t K, const double* dist_from, con
   CU(cudaStreamSynchronize(e->stream));
   e->lm_K = 0;
   if (K == 0) return DRIFT_OK;
-  CU(e->lm_from.upload(dist_from, (int64_t)K * e->V));
-  CU(e->lm_to.upload(dist_to, (int64_t)K * e->V));
+  if (K > kMaxLandmarks) return fail(DRIFT_EINVAL, "drift_set_landmarks: at most %d landmarks", kMaxLandmarks);
+  const int64_t V = e->V;
+  std::vector<double> tab((size_t)V * 2 * K);  // one row of 2K bounds per node: a potential reads one line
+  for (int32_t k = 0; k < K; ++k)
+    for (int64_t v = 0; v < V; ++v) {
+      tab[(size_t)v * 2 * K + k] = dist_from[(size_t)k * V + v];
+      tab[(size_t)v * 2 * K + K + k] = dist_to[(size_t)k * V + v];
+    }
+  CU(e->lm_tab.upload(tab.data(), (int64_t)tab.size()));
   e->lm_K = K;
   return DRIFT_OK;
 }

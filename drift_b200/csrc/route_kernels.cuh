@@ -503,10 +503,12 @@ struct TreeScratch {   // per resident block
 // Landmark lower bounds for goal-directed bounded searches (ALT: A*, landmarks, triangle inequality;
 // Goldberg & Harrelson 2005).  d(s,v) >= from[k][v] - from[k][s] and >= to[k][s] - to[k][v].
 struct Landmarks {
-  const double* from;  // [K][V] distance landmark -> node
-  const double* to;    // [K][V] distance node -> landmark
+  // [V][2K] interleaved per node: entries 0..K-1 = distance landmark k -> node, K..2K-1 = node -> landmark k
+  // (one 128-byte line per node for K = 8, so that a potential can use ALL bounds at the price of one line)
+  const double* tab;
   int32_t K;
 };
+constexpr int kMaxLandmarks = 16;
 
 struct TreeCache {
   int32_t* slot_of;      // [V] destination node -> slot, -1 = not cached
@@ -787,8 +789,8 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_tre
                                                               Counters* ctr, RouteOut out,
                                                               const double* __restrict__ link_cost, Landmarks lm,
                                                               int32_t reserved) {
-  __shared__ int s_job, s_near_n, s_next_n, s_far_n, s_far2_n, s_done, s_touched, s_lmk[2], s_lmdir[2];
-  __shared__ double s_lmref[2];
+  __shared__ int s_job, s_near_n, s_next_n, s_far_n, s_far2_n, s_done, s_touched, s_lm_on;
+  __shared__ double s_ref[2 * kMaxLandmarks];
   __shared__ int s_e0[kTreeThreadsMax], s_off[kTreeThreadsMax], s_wsum[32];
   __shared__ double s_dv[kTreeThreadsMax];
   __shared__ int s_bsrc[kMaxBounded], s_bq[kMaxBounded];
@@ -839,55 +841,39 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_tre
       nearA[0] = dest;
       touched[0] = dest;
       rec[dest].dist = 0ULL;
-      // goal direction for a single-source bounded job: the two landmarks with the best bound on d(s, dest)
-      s_lmk[0] = s_lmk[1] = -1;
+      // goal direction for a single-source bounded job: ALT potentials, the source's row of the landmark table
+      s_lm_on = 0;
       if (bounded && nb == 1 && lm.K > 0) {
         const int32_t sn = s_bsrc[0];
-        double best[2] = {0.0, 0.0};
         if (sn >= 0 && sn < V) {
-          for (int k = 0; k < lm.K; ++k) {
-            for (int dir = 0; dir < 2; ++dir) {
-              const double* arr = (dir == 0 ? lm.from : lm.to) + (int64_t)k * V;
-              const double b = dir == 0 ? arr[dest] - arr[sn] : arr[sn] - arr[dest];
-              if (!(b > 0.0) || b > 1e300) continue;  // useless or undefined (unreachable landmark)
-              const int slot = b > best[0] ? 0 : (b > best[1] ? 1 : -1);
-              if (slot < 0) continue;
-              if (slot == 0) {
-                best[1] = best[0];
-                s_lmk[1] = s_lmk[0];
-                s_lmdir[1] = s_lmdir[0];
-                s_lmref[1] = s_lmref[0];
-              }
-              best[slot] = b;
-              s_lmk[slot] = k;
-              s_lmdir[slot] = dir;
-              s_lmref[slot] = arr[sn];
-            }
-          }
+          for (int k = 0; k < 2 * lm.K; ++k) s_ref[k] = lm.tab[(int64_t)sn * (2 * lm.K) + k];
+          s_lm_on = 1;
         }
       }
     }
     __syncthreads();
-    const int lk0 = s_lmk[0], lk1 = s_lmk[1];
-    const double* lma0 = lk0 >= 0 ? (s_lmdir[0] == 0 ? lm.from : lm.to) + (int64_t)lk0 * V : nullptr;
-    const double* lma1 = lk1 >= 0 ? (s_lmdir[1] == 0 ? lm.from : lm.to) + (int64_t)lk1 * V : nullptr;
-    const double lmr0 = s_lmref[0], lmr1 = s_lmref[1];
-    const int lmd0 = s_lmdir[0], lmd1 = s_lmdir[1];
-    // feasible potential: lower bound on the remaining distance d(source, v); 0 without landmarks
+    const bool lm_on = s_lm_on != 0;
+    const int lmK = lm.K;
+    // feasible potential: lower bound on the remaining distance d(source, v), the maximum over ALL landmark
+    // bounds d(s,v) >= from[k][v] - from[k][s] and d(s,v) >= to[k][s] - to[k][v] (a maximum of consistent
+    // potentials is consistent).  With the two bounds that are best for the pair itself the search settles
+    // about twice as many nodes (tools/search_space_study.py).  0 without landmarks.
     auto pot = [&](int32_t v) -> double {
       double h = 0.0;
-      if (lma0) {
-        const double b = lmd0 == 0 ? lma0[v] - lmr0 : lmr0 - lma0[v];
-        if (b > h && b < 1e300) h = b;
-      }
-      if (lma1) {
-        const double b = lmd1 == 0 ? lma1[v] - lmr1 : lmr1 - lma1[v];
-        if (b > h && b < 1e300) h = b;
+      if (lm_on) {
+        const double* __restrict__ row = lm.tab + (int64_t)v * (2 * lmK);
+#pragma unroll 2
+        for (int k = 0; k < lmK; ++k) {
+          const double b0 = row[k] - s_ref[k];
+          const double b1 = s_ref[lmK + k] - row[lmK + k];
+          if (b0 > h && b0 < 1e300) h = b0;  // inf / NaN (unreachable landmark) never pass
+          if (b1 > h && b1 < 1e300) h = b1;
+        }
       }
       return h;
     };
     // goal-directed keys cluster just below d(source, dest): finer buckets keep the search inside the corridor
-    const double jdelta = (lma0 != nullptr) ? delta * 0.25 : delta;
+    const double jdelta = lm_on ? delta * 0.25 : delta;
     double T_old = -1.0, T = pot(dest) + jdelta;
     __syncthreads();
     for (;;) {
