@@ -36,20 +36,36 @@ def random_chains(rng, V, start, k):
 
 
 def hub_chains(rng, lg, start, k, hub_trip_probability=0.3, hub_percentage=0.1):
-    """HubAndSpokeSelection (st_selection.py:469-648) structure: hubs = top ``hub_percentage`` nodes
-    by degree; a trip goes to a hub with probability ``hub_trip_probability``, else anywhere."""
+    """HubAndSpokeSelection (st_selection.py:469-648), vectorised: hubs = top ``hub_percentage`` nodes by degree
+    (degree centrality only above 1 000 nodes, :498-511).  With probability ``hub_trip_probability`` a trip
+    involves a hub -- from a hub to any other node, from a non-hub to a hub (:566-582) -- otherwise it ends
+    at a non-hub (:584-606); the target never equals the source."""
     V = lg.V
     deg = np.diff(lg.fwd_rowptr) + np.diff(lg.bwd_rowptr)
     n_hubs = max(1, int(V * hub_percentage))
-    hubs = np.argsort(-deg, kind="stable")[:n_hubs]
+    order = np.argsort(-deg, kind="stable")
+    hubs, non_hubs = order[:n_hubs], order[n_hubs:]
+    is_hub = np.zeros(V, dtype=bool)
+    is_hub[hubs] = True
     N = len(start)
     dst = np.empty((N, k), dtype=np.int32)
     prev = np.asarray(start, dtype=np.int64).copy()
+
+    def draw(hub_trip, from_hub):
+        n = len(hub_trip)
+        anywhere = rng.integers(0, V, size=n)
+        to_hub = hubs[rng.integers(0, n_hubs, size=n)]
+        to_non = non_hubs[rng.integers(0, len(non_hubs), size=n)] if len(non_hubs) else anywhere
+        return np.where(hub_trip, np.where(from_hub, anywhere, to_hub), to_non)
+
     for j in range(k):
-        to_hub = rng.random(N) < hub_trip_probability
-        d = rng.integers(0, V, size=N)
-        d[to_hub] = hubs[rng.integers(0, n_hubs, size=int(to_hub.sum()))]
-        d = _no_self(rng, d, prev, V)
+        hub_trip = rng.random(N) < hub_trip_probability
+        from_hub = is_hub[prev]
+        d = draw(hub_trip, from_hub)
+        bad = d == prev
+        while bad.any():  # the reference removes the source from the candidate list before drawing
+            d[bad] = draw(hub_trip[bad], from_hub[bad])
+            bad = d == prev
         dst[:, j] = d
         prev = d
     return np.arange(N + 1, dtype=np.int64) * k, dst.reshape(-1)
@@ -146,25 +162,49 @@ def activity_pools_chains(rng, lg, start, k):
 
 
 def zone_chains(rng, lg, start, k, intra_zone_probability=0.7, grid=3):
-    """ZoneBasedSelection (st_selection.py:1084-1252) structure: 3 x 3 position zones; a trip stays
-    in the source's zone with probability 0.7 (config.py:283)."""
+    """ZoneBasedSelection (st_selection.py:1084-1252), vectorised: 3 x 3 position zones; a trip stays in the
+    source's zone with probability 0.7 (config.py:283, any other node of the zone, :1186-1197); otherwise it goes
+    to a uniformly chosen OTHER zone, with probability 0.7 to one of that zone's major nodes (its top third
+    by degree, :1142-1160) else to any of its nodes (:1199-1231).  The target never equals the source."""
     V = lg.V
     pos = lg.pos if lg.pos is not None else rng.random((V, 2))
     lo, hi = pos.min(axis=0), pos.max(axis=0)
     cell = np.minimum(((pos - lo) / np.maximum(hi - lo, 1e-12) * grid).astype(np.int64), grid - 1)
-    zone = cell[:, 1] * grid + cell[:, 0]
-    order = np.argsort(zone, kind="stable")
-    zstart = np.searchsorted(zone[order], np.arange(grid * grid + 1))
+    zone = cell[:, 0] * grid + cell[:, 1]  # :1134-1136: x cell * grid + y cell
+    Z = grid * grid
+    deg = np.diff(lg.fwd_rowptr) + np.diff(lg.bwd_rowptr)
+    order = np.lexsort((np.arange(V), -deg, zone))  # by zone, then degree (descending), then node id
+    zstart = np.searchsorted(zone[order], np.arange(Z + 1))
+    zsize = np.diff(zstart)
+    major = np.maximum(1, zsize // 3)
+    non_empty = np.nonzero(zsize > 0)[0]
     N = len(start)
     dst = np.empty((N, k), dtype=np.int32)
     prev = np.asarray(start, dtype=np.int64).copy()
+
+    def draw(src):
+        n = len(src)
+        zs = zone[src]
+        intra = (rng.random(n) < intra_zone_probability) & (zsize[zs] > 1)  # alone in its zone: inter-zone trip
+        other = non_empty[rng.integers(0, len(non_empty), size=n)]
+        for _ in range(64):  # a different, non-empty zone
+            same = other == zs
+            if not same.any() or len(non_empty) < 2:
+                break
+            other[same] = non_empty[rng.integers(0, len(non_empty), size=int(same.sum()))]
+        z = np.where(intra, zs, other)
+        to_major = ~intra & (rng.random(n) < 0.7)
+        span = np.where(to_major, major[z], zsize[z])
+        return order[zstart[z] + (rng.random(n) * span).astype(np.int64)]
+
     for j in range(k):
-        intra = rng.random(N) < intra_zone_probability
-        z = np.where(intra, zone[prev], rng.integers(0, grid * grid, size=N))
-        lo_i, hi_i = zstart[z], zstart[z + 1]
-        empty = hi_i <= lo_i
-        pick = lo_i + (rng.random(N) * np.maximum(hi_i - lo_i, 1)).astype(np.int64)
-        d = np.where(empty, rng.integers(0, V, size=N), order[np.minimum(pick, V - 1)])
+        d = draw(prev)
+        bad = d == prev
+        for _ in range(100):
+            if not bad.any():
+                break
+            d[bad] = draw(prev[bad])
+            bad = d == prev
         dst[:, j] = d
         prev = d
     return np.arange(N + 1, dtype=np.int64) * k, dst.reshape(-1)

@@ -87,3 +87,38 @@ def test_activity_law_matches_reference_shares():
     assert 0.05 < cold_cold < 0.08
     _, dp = demand.activity_pools_chains(np.random.default_rng(9), lg, start, 6)
     assert np.isin(dp.reshape(-1, 6)[:, 1::2], pools).all()  # return legs always end in a pool
+
+
+def test_hub_and_zone_laws():
+    """Vectorised hub / zone demand against the reference's rules (lib/st_selection.py:551-606, 1162-1231)."""
+    lg = road_graph(8000, seed=2)
+    start = np.random.default_rng(1).integers(0, lg.V, size=30000).astype(np.int32)
+    _, d = demand.hub_chains(np.random.default_rng(3), lg, start, 6)
+    d = d.reshape(-1, 6)
+    deg = np.diff(lg.fwd_rowptr) + np.diff(lg.bwd_rowptr)
+    is_hub = np.zeros(lg.V, dtype=bool)
+    is_hub[np.argsort(-deg, kind="stable")[:int(lg.V * 0.1)]] = True
+    src = np.concatenate([start[:, None], d[:, :-1]], axis=1)
+    assert not np.any(src == d)
+    # a trip ending at a hub from a non-hub source is a "hub trip" (30 %); non-hub trips (70 %) end at non-hubs
+    from_non = ~is_hub[src]
+    assert abs(is_hub[d][from_non].mean() - 0.3) < 0.02
+    # from a hub: 30 % anywhere (10 % of the nodes are hubs), 70 % non-hub
+    assert abs(is_hub[d][~from_non].mean() - 0.3 * 0.1) < 0.02
+
+    _, z = demand.zone_chains(np.random.default_rng(3), lg, start, 6)
+    z = z.reshape(-1, 6)
+    srcz = np.concatenate([start[:, None], z[:, :-1]], axis=1)
+    assert not np.any(srcz == z)
+    lo, hi = lg.pos.min(axis=0), lg.pos.max(axis=0)
+    cell = np.minimum(((lg.pos - lo) / (hi - lo) * 3).astype(np.int64), 2)
+    zone = cell[:, 0] * 3 + cell[:, 1]
+    intra = zone[z] == zone[srcz]
+    assert abs(intra.mean() - 0.7) < 0.02
+    # inter-zone trips prefer the destination zone's major nodes (top third by degree): 70 % + a third of the rest
+    major = np.zeros(lg.V, dtype=bool)
+    for zz in range(9):
+        members = np.nonzero(zone == zz)[0]
+        top = members[np.lexsort((members, -deg[members]))][:max(1, len(members) // 3)]
+        major[top] = True
+    assert abs(major[z][~intra].mean() - (0.7 + 0.3 / 3)) < 0.03
