@@ -501,6 +501,7 @@ def run_b200(args):
             line["cpu_baseline"] = dict(
                 value=cpu["agent_steps_per_s"], unit="agent-steps/s", cores=1, kind="port",
                 routes_per_s=cpu["routes_per_s"], host_cores=os.cpu_count(),
+                replicas_upper_bound=cpu["agent_steps_per_s"] * (os.cpu_count() or 1),  # one independent run per core
                 sample="oracle port (sequential Python restatement of the reference step incl. NetworkX-order "
                        "bidirectional Dijkstra), %d agents on a %d-node / %d-link road graph, %d ticks in %.1f s, %s demand"
                        % (cpu["agents"], cpu["nodes"], cpu["links"], cpu["ticks"], cpu["seconds"], model))
