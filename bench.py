@@ -194,7 +194,7 @@ def run_reference_arm(args):
         cpu_port_rate(w["model"], args.seed, budget_s=2.0, agents=2000, nodes=5000, ticks=50)
     t_all = time.perf_counter()
     for k in range(args.steps):
-        r = cpu_port_rate(w["model"], args.seed + k, budget_s=max(5.0, 120.0 / max(args.steps, 1)), agents=10_000,
+        r = cpu_port_rate(w["model"], args.seed + k, budget_s=args.ref_seconds or max(5.0, 120.0 / max(args.steps, 1)), agents=10_000,
                           nodes=20_000, ticks=args.ticks_per_step, reroute=bool(w.get("reroute")) and not args.no_reroute)
         vals.append(r["agent_steps_per_s"])
     wall = time.perf_counter() - t_all
@@ -526,6 +526,8 @@ def main():
     ap.add_argument("--ticks-per-step", type=int, default=0, help="ticks per step (default: the workload's, 300)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg (0 = skip)")
+    ap.add_argument("--ref-seconds", type=float, default=0.0,
+                    help="--impl reference: CPU seconds per step (default: 120 s spread over the steps, at least 5 s)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
     ap.add_argument("--landmarks", type=int, default=8, help="ALT landmarks for goal-directed bounded searches (0 = off)")
     ap.add_argument("--no-reroute", action="store_true", help="switch the periodic reroute extension off")
