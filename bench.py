@@ -461,6 +461,38 @@ def run_b200(args):
                    standalone_kernel_us=r["k_advance_us"], standalone_kernel_frac=r["k_advance_gbs"] / peak,
                    algorithmic_bytes_per_launch=r["algorithmic_bytes"], peak_source=peak_src)
 
+    # ---- multi-GPU: what a tick costs WITHOUT the exchange (same engine, same agents, peer exchange suspended:
+    # timing only, the state is not used afterwards), so that the exchange is visible separately from the
+    # embarrassingly parallel route planning
+    tick_only = None
+    if sharded is not None and args.exchange == "p2p":
+        barrier()
+        p2p_tick_us = phases["advance_us_per_tick"] + phases["inject_us_per_tick"] + phases["resolve_us_per_tick"]
+        eng.set_option("p2p_suspend", 1)
+        eng.phase_times(reset=True)
+        eng.run(TPS, delta, t_sim)
+        eng.sync()
+        loc = eng.phase_times(reset=True)
+        local_tick_us = loc["advance_us_per_tick"] + loc["inject_us_per_tick"] + loc["resolve_us_per_tick"]
+        tt = torch.tensor([local_tick_us, p2p_tick_us], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        local_tick_us, p2p_tick_us = float(tt[0].item()), float(tt[1].item())
+        tick_only = dict(local_tick_us=local_tick_us, exchange_tick_us=p2p_tick_us,
+                         tick_only_efficiency=local_tick_us / p2p_tick_us if p2p_tick_us > 0 else None,
+                         note="max over ranks; local = the same engine with the peer exchange suspended (k_tick_loop on "
+                              "this rank's agents only, timing probe), exchange = k_tick_loop_p2p in the timed region")
+        barrier()
+
+    # ---- multi-GPU: N-rank parity self-check (SURVEY.md 8e acceptance), after the timed regions
+    parity = None
+    if sharded is not None and not args.no_parity_check:
+        sharded.close()
+        dist.barrier()
+        from drift_b200.selfcheck import sharded_vs_single
+
+        parity = sharded_vs_single(local_rank, agents=args.parity_agents, nodes=20_000, ticks=100, blocks=3,
+                                   p2p=(args.exchange == "p2p"))
+
     line = None
     if rank == 0:
         cpu = cpu_port_rate(model, args.seed, budget_s=args.cpu_seconds, ticks=TPS, reroute=reroute) \
@@ -493,6 +525,7 @@ def run_b200(args):
                      phases={k: (round(v, 3) if isinstance(v, float) else v) for k, v in e2e_phases.items()}),
             gpu_launches=int(launches), router_stats={k: (round(v, 3) if isinstance(v, float) else v) for k, v in trees.items()},
             roofline=roof, roofline_advance=roof_adv, roofline_advance_saturated=sat,
+            parity_check=parity, tick_only=tick_only,
             clocks=clk.summary(),
             phases=dict(note="timed region: per-tick phase times of the persistent kernel (%globaltimer, barriers "
                              "included) and total ms in route-planning batches",
@@ -511,6 +544,9 @@ def run_b200(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.stderr.write("bench.py: N-rank parity check FAILED: %r\n" % (parity,))
+        return 3
     return 0
 
 
@@ -536,6 +572,9 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"],
                     help="multi-GPU: link events over NVLink peer memory inside the tick kernel, or per-tick NCCL all-gather")
     ap.add_argument("--coop-blocks", type=int, default=0, help="blocks per SM of the persistent tick kernel (0 = default)")
+    ap.add_argument("--no-parity-check", action="store_true",
+                    help="multi-GPU: skip the N-rank parity self-check (sharded run == one engine, bit for bit)")
+    ap.add_argument("--parity-agents", type=int, default=200_000, help="agents of the N-rank parity self-check")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -19,30 +19,52 @@ def factor(count: int, capacity: int, alpha: float, beta: float) -> float:
     return max(0.1, 1 / m)
 
 
-def build_tables(link_cap, alpha: float, beta: float, guard: int = 4):
+def _factor_row(counts, cap, alpha, beta):
+    """factor() for an int64 array of counts >= 1, bit for bit: true division of two ints, ``r ** beta``
+    through the C library's pow (what CPython's float.__pow__ calls; NumPy's power differs in the last bit),
+    then IEEE add / mul / div / max, which NumPy and CPython share."""
+    import ctypes as C
+
+    from . import _capi
+
+    r = counts.astype(np.float64) / float(cap)
+    pw = np.empty_like(r)
+    _capi.check(_capi.load().drift_host_pow(r.ctypes.data_as(C.POINTER(C.c_double)), float(beta),
+                                            pw.ctypes.data_as(C.POINTER(C.c_double)), len(r)))
+    return np.maximum(0.1, 1 / (1 + alpha * pw))
+
+
+def build_tables(link_cap, alpha: float, beta: float, guard: int = 4, max_count: int = 0):
     """Returns (table float64[], class_off int64[n_class+1], link_class int32[L]).
 
-    Class c covers counts 0..K_c where K_c is ``guard`` counts past the first saturated count; the
-    device clamps larger counts to the last entry (0.1).
+    Class c covers counts 0..K_c where K_c is ``guard`` counts past the first saturated count (the factor
+    is exactly 0.1 from ``1 + alpha*r**beta >= 10`` on), or ``max_count`` (no link can hold more agents than
+    exist) if that is smaller -- which also bounds the tables for parameters that saturate late or never
+    (alpha = 0.01, beta = 1 saturates at count = 900 x capacity).  The device clamps larger counts to the
+    last entry: exact in both cases.  Without ``max_count`` a row is cut 200 x capacity + 1000 counts out
+    (then the clamp is an approximation beyond that count; Engine always passes ``max_count``).
     """
     link_cap = np.asarray(link_cap, dtype=np.int64)
     caps, link_class = np.unique(link_cap, return_inverse=True)
     tables, off = [], [0]
     for cap in caps.tolist():
-        cap = int(cap)
-        row = [1.0]
-        n = 1
-        sat = 0
+        cap = max(int(cap), 1)
+        hard = 200 * cap + 1000 if max_count <= 0 else int(max_count)
+        # first saturated count, estimated (r_sat = (9/alpha)**(1/beta)); the loop below checks it on the real values
+        est = hard
+        if alpha > 0:
+            est = int(min(float(hard), np.ceil(cap * (9.0 / alpha) ** (1.0 / beta)))) + guard + 2
+        n = min(max(est, 8), hard)
         while True:
-            f = factor(n, cap, alpha, beta)
-            row.append(f)
-            sat = sat + 1 if f == 0.1 else 0
-            if sat >= guard:
+            row = _factor_row(np.arange(1, n + 1, dtype=np.int64), cap, alpha, beta)
+            sat = np.nonzero(row == 0.1)[0]
+            if len(sat) and sat[0] + guard <= n:
+                row = row[:sat[0] + guard]
                 break
-            n += 1
-            if n > 200 * max(cap, 1) + 1000:  # alpha ~ 0: never saturates; the tail keeps the last value
+            if n >= hard:
                 break
-        tables.append(np.array(row, dtype=np.float64))
-        off.append(off[-1] + len(row))
+            n = min(2 * n, hard)
+        tables.append(np.concatenate([[1.0], row]))
+        off.append(off[-1] + len(row) + 1)
     table = np.concatenate(tables) if tables else np.zeros(1)
-    return table, np.array(off, dtype=np.int64), link_class.astype(np.int32)
+    return np.ascontiguousarray(table, dtype=np.float64), np.array(off, dtype=np.int64), link_class.astype(np.int32)

@@ -67,6 +67,7 @@ constexpr int kOvfDepLog = 16;
 constexpr int kOvfEntries = 32;
 constexpr int kOvfStage = 64;
 constexpr int kOvfExchange = 128;
+constexpr int kOvfPending = 256;
 
 struct AgentArrays {
   uint8_t* state;       // [Npad] kWaiting / kMoving

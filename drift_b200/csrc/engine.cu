@@ -67,6 +67,12 @@ struct DevBuf {
   ~DevBuf() { release(); }
 };
 
+inline bool has_duplicates(const int32_t* a, int64_t n) {
+  std::vector<int32_t> v(a, a + n);
+  std::sort(v.begin(), v.end());
+  return std::adjacent_find(v.begin(), v.end()) != v.end();
+}
+
 inline int grid_for(int64_t n, int threads, int max_blocks) {
   int64_t b = (n + threads - 1) / threads;
   if (b < 1) b = 1;
@@ -126,6 +132,7 @@ struct drift_engine {
   // persistent tick loop
   bool persistent = true;
   int coop_blocks_per_sm = 6;
+  int occ_tick_loop = 0, occ_tick_loop_p2p = 0;  // resident blocks per SM of the two persistent kernels (queried once)
   int num_sms = kSMs;
   // pending departures + staged route batch
   DevBuf<int32_t> pend_agent, pend_len;
@@ -302,6 +309,7 @@ int check_overflow(drift_engine* e, const Counters& c) {
   if (c.overflow & kOvfEntries) what += " entry-trace";
   if (c.overflow & kOvfStage) what += " tree-cache";
   if (c.overflow & kOvfExchange) what += " event-exchange (raise the exchange capacity)";
+  if (c.overflow & kOvfPending) what += " pending-departures (more departures committed than agents)";
   return fail(DRIFT_EOVERFLOW, "device buffer overflow:%s", what.c_str());
 }
 
@@ -582,6 +590,7 @@ TickArgs make_tick_args(drift_engine* e, double delta, bool demand) {
   p.pend_agent = e->pend_agent.p;
   p.pend_off = e->pend_off.p;
   p.pend_len = e->pend_len.p;
+  p.pend_cap = (int32_t)e->pend_cap;
   p.delta = delta;
   p.kph_to_mps = kKphToMps;
   p.demand = demand ? 1 : 0;
@@ -632,7 +641,7 @@ int run_tick_loop(drift_engine* e, int32_t n_ticks, double delta, bool demand, d
   if (n_ticks <= 0) return DRIFT_OK;
   TickArgs p = make_tick_args(e, delta, demand);
   int32_t tick0 = (int32_t)e->tick + 1;
-  static int max_per_sm = 0;
+  int& max_per_sm = e->occ_tick_loop;  // per engine: occupancy belongs to the engine's device
   if (!max_per_sm) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_per_sm, k_tick_loop, kAdvThreads, 0));
     if (max_per_sm < 1) return fail(DRIFT_ECUDA, "k_tick_loop does not fit on an SM");
@@ -641,7 +650,7 @@ int run_tick_loop(drift_engine* e, int32_t n_ticks, double delta, bool demand, d
   int blocks = e->num_sms * std::min(max_per_sm, e->coop_blocks_per_sm);
   if (tiles < blocks) blocks = (int)std::max<int64_t>(tiles, 1);
   if (e->p2p_on) {
-    static int max_p2p = 0;
+    int& max_p2p = e->occ_tick_loop_p2p;
     if (!max_p2p) {
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_p2p, k_tick_loop_p2p, kAdvThreads, 0));
       if (max_p2p < 1) return fail(DRIFT_ECUDA, "k_tick_loop_p2p does not fit on an SM");
@@ -912,12 +921,14 @@ int drift_commit_departures(drift_engine* e, int64_t Q, const int32_t* agent) {
   if (Q == 0) return DRIFT_OK;
   for (int64_t q = 0; q < Q; ++q)
     if (agent[q] < 0 || agent[q] >= e->N) return fail(DRIFT_EINVAL, "drift_commit_departures: agent out of range");
+  if (has_duplicates(agent, Q)) return fail(DRIFT_EINVAL, "drift_commit_departures: an agent is listed twice");
   CU(cudaMemcpyAsync(e->q_agent.p, agent, sizeof(int32_t) * Q, cudaMemcpyHostToDevice, e->stream));
   k_commit<<<grid_for(Q, 256, kSMs), 256, 0, e->stream>>>(Q, e->q_agent.p, e->q_off.p, e->q_len.p, e->ctr.p,
                                                            e->pend_agent.p, e->pend_off.p, e->pend_len.p,
                                                            (int32_t)e->pend_cap, nullptr);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(e->stream));  // `agent` is a caller buffer
+  e->last_Q = 0;  // a staged batch is committed once: a second commit would inject its agents twice
   return DRIFT_OK;
 }
 
@@ -932,6 +943,7 @@ int drift_submit_departures(drift_engine* e, int64_t n, const int32_t* agent, co
     if (agent[q] < 0 || agent[q] >= e->N) return fail(DRIFT_EINVAL, "drift_submit_departures: agent out of range");
     if (route_off[q + 1] < route_off[q]) return fail(DRIFT_EINVAL, "drift_submit_departures: bad offsets");
   }
+  if (has_duplicates(agent, n)) return fail(DRIFT_EINVAL, "drift_submit_departures: an agent is listed twice");
   for (int64_t k = 0; k < total; ++k)
     if (route_links[k] < 0 || route_links[k] >= e->L) return fail(DRIFT_EINVAL, "drift_submit_departures: bad link id");
   int rc = ensure_qcap(e, n);
@@ -1087,8 +1099,10 @@ static int plan_window(drift_engine* e, double t_first, double delta) {
   if (rc) return rc;
   const int64_t Q = std::min<int64_t>(hc.n_plan, e->q_cap);
   e->routes_planned += Q;
-  rc = maybe_compact_arena(e, hc.arena_cursor);
-  if (rc) return rc;
+  if (hc.n_pending == 0) {  // committed, not yet injected departures point into the live arena (see maybe_compact_arena)
+    rc = maybe_compact_arena(e, hc.arena_cursor);
+    if (rc) return rc;
+  }
   int64_t chunk = Q;
   if (e->demand_router == DRIFT_ROUTER_BATCHED) {
     rc = ensure_trees(e);
@@ -1750,6 +1764,11 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
     e->arena_compact_frac = std::min(0.95, std::max(0.05, value));
   } else if (s == "debug_mask") {
     e->debug_mask = (int32_t)value;
+  } else if (s == "p2p_suspend") {
+    // timing probe of bench.py: run the next ticks on this rank's agents only (k_tick_loop) although the peer
+    // exchange is connected; the state is NOT the sharded run's afterwards
+    if (!e->p2p.world || !e->p2p_inbox.p) return fail(DRIFT_ESTATE, "p2p_suspend: no peer exchange to suspend");
+    e->p2p_on = value == 0;
   } else if (s == "tree_sides") {
     if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_sides must be set before the first batched route");
     e->t_sides = value >= 2 ? 2 : 1;

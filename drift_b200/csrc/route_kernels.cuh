@@ -254,6 +254,8 @@ __global__ void k_commit(int64_t Q, const int32_t* __restrict__ agent, const int
       pend_agent[p] = agent[q];
       pend_off[p] = q_off[q];
       pend_len[p] = q_len[q];
+    } else {
+      atomicOr(&ctr->overflow, kOvfPending);  // the injection clamps n_pending to pend_cap
     }
   }
 }

@@ -47,6 +47,7 @@ struct TickArgs {
   const int32_t* pend_agent;
   const int64_t* pend_off;
   const int32_t* pend_len;
+  int32_t pend_cap;         // entries of the pend_* arrays; ctr->n_pending may exceed it (flagged kOvfPending)
   double delta;
   double kph_to_mps;
   int32_t demand;           // device-driven departures on/off
@@ -406,7 +407,11 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
             *reinterpret_cast<int4*>(x->inbox[o] + ((int64_t)par * x->world + x->rank) * x->cap + pos) =
               *reinterpret_cast<const int4*>(&e);
           } else {
+            // The owner never sees this event.  For an entry nobody would deliver the speed and the agent's next
+            // advance would spin on kSpeedPending: give it the free-flow speed so that the launch ends and the host
+            // can raise DRIFT_EOVERFLOW (the run is invalid from here on; raise the exchange capacity).
             atomicOr(&p.ctr->overflow, kOvfExchange);
+            if (lkd >> 31) a.speed[sm.agent[w][k] - a.base] = __dmul_rn(p.lk.v0[link], p.kph_to_mps);
           }
         }
         if (n) __threadfence_system();  // this warp's peer stores are visible before the block reaches the grid barrier
@@ -434,6 +439,7 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
 // ---- phase A2 -----------------------------------------------------------------------------------
 __device__ __forceinline__ void start_on_route(const TickArgs& p, int32_t i, int64_t off, int32_t len, int32_t tick) {
   const AgentArrays& a = p.a;
+  if (a.state[i] == kMoving) return;  // committed while en route (caller error): the trip in progress wins
   const int32_t link = p.arena[off];
   a.state[i] = kMoving;
   a.route_off[i] = off;
@@ -598,7 +604,7 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_advance(const __grid_constan
 
 __global__ void __launch_bounds__(256) k_inject(const __grid_constant__ TickArgs p, int32_t tick) {
   const int par = tick & 1;
-  phase_inject(p, tick, p.ctr->n_pending, p.ctr->n_dep_req[par]);
+  phase_inject(p, tick, min(p.ctr->n_pending, p.pend_cap), p.ctr->n_dep_req[par]);
 }
 
 // Events that arrived from other ranks (link, agent, kind): push them on the link lists.
@@ -735,7 +741,7 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop(const __grid_const
       ctr->phase_ns[0] += t1 - t0;
       t0 = t1;
     }
-    const int n_pending = ctr->n_pending, n_urgent = ctr->n_dep_req[par];
+    const int n_pending = min(ctr->n_pending, p.pend_cap), n_urgent = ctr->n_dep_req[par];
     if (n_pending | n_urgent) {  // uniform across the grid
       phase_inject(p, tick, n_pending, n_urgent);
       grid.sync();
@@ -820,8 +826,9 @@ __device__ __forceinline__ void p2p_send_one(const TickArgs& p, const P2PArgs& x
     e.aux = 0;
     *reinterpret_cast<int4*>(x.inbox[o] + ((int64_t)par * x.world + x.rank) * x.cap + pos) = *reinterpret_cast<const int4*>(&e);
     __threadfence_system();
-  } else {
+  } else {  // see phase_advance: a dropped entry gets the free-flow speed so that nobody waits for its owner
     atomicOr(&p.ctr->overflow, kOvfExchange);
+    if (kind > 0) p.a.speed[agent - p.a.base] = __dmul_rn(p.lk.v0[link], p.kph_to_mps);
   }
 }
 
@@ -830,6 +837,7 @@ __device__ __noinline__ void phase_inject_p2p(const TickArgs& p, const P2PArgs& 
                                               int n_urgent) {
   const AgentArrays& a = p.a;
   auto start = [&](int32_t i, int64_t off, int32_t len) {
+    if (a.state[i] == kMoving) return;
     const int32_t link = p.arena[off];
     a.state[i] = kMoving;
     a.route_off[i] = off;
@@ -941,7 +949,7 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
     else
       phase_advance<false, true>(p, tick, p_dep, sm, &x, &xs);
     grid.sync();  // writers fenced their peer stores (system scope) before arriving here
-    const int n_pending = ctr->n_pending, n_urgent = ctr->n_dep_req[par];
+    const int n_pending = min(ctr->n_pending, p.pend_cap), n_urgent = ctr->n_dep_req[par];
     if (n_pending | n_urgent) {  // uniform across the grid
       phase_inject_p2p(p, x, tick, n_pending, n_urgent);
       grid.sync();

@@ -74,7 +74,7 @@ class ShardedEngine:
         self.n_total = n_total
         self.device = torch.device("cuda", device)
         self.engine = Engine(lg, self.hi - self.lo, alpha=alpha, beta=beta, device=device, agent_base=self.lo,
-                             route_arena_links=route_arena_links)
+                             route_arena_links=route_arena_links, total_agents=n_total)
         self.engine.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self.cap = 0
         self.p2p = False
@@ -131,7 +131,13 @@ class ShardedEngine:
                 self._set_cap(want)
 
     def step(self, delta):
-        """Trace / host-driven mode: pending departures were submitted to the local engine."""
+        """Trace / host-driven mode: pending departures were submitted to the local engine.  With the
+        peer-memory exchange the tick runs inside ``k_tick_loop_p2p`` (all ranks must call this together);
+        link volumes then live on the owner only -- read them with ``occupancy()``."""
+        if self.p2p:
+            self.engine.step(1, delta)
+            self.engine.max_events(reset=True)  # raises on overflow
+            return
         self._tick(delta, 0.0)
         self._after_block()
 

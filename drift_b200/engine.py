@@ -39,11 +39,13 @@ class Engine:
     """
 
     def __init__(self, lg: LoweredGraph, num_agents: int, alpha: float = 0.15, beta: float = 4.0, device: int = 0,
-                 agent_base: int = 0, route_arena_links: int = 0):
+                 agent_base: int = 0, route_arena_links: int = 0, total_agents: int = 0):
         self._lib = _capi.load()
         self.lg = lg
         self.N = int(num_agents)
         self.agent_base = int(agent_base)
+        # agents of the whole (possibly sharded) run: no link ever holds more -> bound of the BPR factor tables
+        self.total_agents = max(int(total_agents), self.agent_base + self.N)
         self._h = _capi.ENGINE()
         self._keep = dict(
             fwd_rowptr=_i32(lg.fwd_rowptr), fwd_col=_i32(lg.fwd_col), fwd_w=_f64(lg.fwd_w), fwd_link=_i32(lg.fwd_link),
@@ -91,7 +93,7 @@ class Engine:
 
     # ---- configuration ------------------------------------------------------------------------
     def set_bpr(self, alpha, beta):
-        table, off, cls = _bpr.build_tables(self.lg.link_cap, float(alpha), float(beta))
+        table, off, cls = _bpr.build_tables(self.lg.link_cap, float(alpha), float(beta), max_count=self.total_agents)
         self.alpha, self.beta = float(alpha), float(beta)
         _capi.check(self._lib.drift_set_bpr(self._h, self.alpha, self.beta, _p(table, C.c_double),
                                             _p(off, C.c_int64), len(off) - 1, _p(cls, C.c_int32)))

@@ -18,7 +18,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, name, out):
+def _worker(rank, world, port, name, out, p2p=False):
     import torch
     import torch.distributed as dist
 
@@ -37,6 +37,8 @@ def _worker(rank, world, port, name, out):
         snaps = case.snapshots()
         trace = case.departure_trace()
         se = ShardedEngine(lg, case.N, alpha=case.alpha, beta=case.beta, device=rank)
+        if p2p:  # the exchange inside k_tick_loop_p2p: link volumes live on the owner, occupancy() sums them
+            se.enable_p2p()
         lo, hi = se.lo, se.hi
         delta = 0.1 * case.accel
         ticks = min(case.ticks, 1200)
@@ -51,7 +53,7 @@ def _worker(rank, world, port, name, out):
                         assert lg.links_to_nodes(deps[a][0], ln) == deps[a][2]
                 se.engine.commit_departures([a - lo for a in agents])
             se.step(delta)
-            assert np.array_equal(se.engine.occupancy(), occ_ref[k - 1]), "rank %d: volumes differ at tick %d" % (rank, k)
+            assert np.array_equal(se.occupancy(), occ_ref[k - 1]), "rank %d: volumes differ at tick %d" % (rank, k)
             if k in snaps:
                 a = se.engine.agents()
                 st, d, sp, pi = snaps[k]
@@ -75,27 +77,38 @@ def _worker(rank, world, port, name, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["g40_congested", "g100_random_accel50"])
-def test_two_rank_replay_matches_reference(name):
+def _spawn(target, world, *args):
     import torch
     import torch.multiprocessing as mp
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, out)) for r in range(2)]
+    procs = [ctx.Process(target=target, args=(r, world, port) + args + (out,)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [out.get(timeout=600) for _ in procs]
+    res = [out.get(timeout=900) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
 
 
-def _worker_demand(rank, world, port, out, p2p=False):
-    """Device-driven demand sharded over 2 ranks == the same run on one engine (bit for bit)."""
+def _replay(rank, world, port, name, p2p, out):
+    _worker(rank, world, port, name, out, p2p)
+
+
+@pytest.mark.parametrize("world,p2p", [(2, False), (2, True), (3, True), (4, True), (8, True)])
+@pytest.mark.parametrize("name", ["g40_congested", "g100_random_accel50"])
+def test_sharded_replay_matches_reference(name, world, p2p):
+    """Recorded reference runs replayed over `world` ranks: link volumes at every tick, fp64 agent state
+    at the snapshots and the arrival ticks equal the single-process reference -- with the per-tick
+    all-gather (p2p=False) and with the peer-memory exchange inside the tick kernel (p2p=True)."""
+    _spawn(_replay, world, name, p2p)
+
+
+def _selfcheck(rank, world, port, p2p, agents, out):
     import torch
     import torch.distributed as dist
 
@@ -104,48 +117,11 @@ def _worker_demand(rank, world, port, out, p2p=False):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        from drift_b200.dist import ShardedEngine
-        from drift_b200.engine import Engine, ROUTER_BATCHED
-        from drift_b200.synth import road_graph
+        from drift_b200.selfcheck import sharded_vs_single
 
-        lg = road_graph(5000, seed=4)
-        N, blocks, ticks = 40_000, 4, 60
-        rng = np.random.default_rng(3)
-        start = rng.integers(0, lg.V, size=N).astype(np.int32)
-        cands = rng.integers(0, lg.V, size=(blocks, N, 2)).astype(np.int32)
-        first = rng.integers(0, lg.V, size=(N, 4)).astype(np.int32)
-        hourly = np.full(24, 0.9)
-
-        def drive(eng_like, eng, lo, hi):
-            eng.set_demand(77, hourly, start[lo:hi], chain_capacity=4, router=ROUTER_BATCHED)
-            eng.set_option("route_window", ticks)
-            eng.push_trips(first[lo:hi])
-            t, occs = 0.0, []
-            for b in range(blocks):
-                eng.push_trips(cands[b, lo:hi])
-                if eng_like is eng:
-                    eng.run(ticks, 1.0, t)
-                    t += ticks
-                else:
-                    t = eng_like.run(ticks, 1.0, t)
-                occs.append((eng if eng_like is eng else eng_like).occupancy().copy())
-            return occs, eng.agents(fields=("state", "dist", "speed", "route_idx", "trip_count"))
-
-        se = ShardedEngine(lg, N, device=rank, route_arena_links=N * 300)
-        if p2p:
-            se.enable_p2p()
-        occ_s, ag_s = drive(se, se.engine, se.lo, se.hi)
-        se.close()
-        if rank == 0:
-            eng = Engine(lg, N, device=0, route_arena_links=N * 300)
-            occ_1, ag_1 = drive(eng, eng, 0, N)
-            eng.close()
-            for a, b in zip(occ_s, occ_1):
-                assert np.array_equal(a, b), "sharded volumes differ from the single-engine run"
-            assert occ_1[-1].sum() > 1000
-            for k in ag_s:
-                assert np.array_equal(ag_s[k], ag_1[k][se.lo:se.hi]), k
-        dist.barrier()
+        r = sharded_vs_single(rank, agents=agents, nodes=5000, ticks=60, blocks=4, p2p=p2p)
+        assert r["ok"], r
+        assert r["completed_trips"] > 100 and r["on_roads_at_end"] > 1000, r
         out.put((rank, "ok"))
     except Exception:
         import traceback
@@ -155,22 +131,10 @@ def _worker_demand(rank, world, port, out, p2p=False):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("p2p", [False, True])
-def test_two_rank_device_demand_equals_single_engine(p2p):
-    """p2p=False: per-tick all-gather of the link events (NCCL); p2p=True: the exchange inside the
-    persistent tick kernel over NVLink peer memory (k_tick_loop_p2p, link-owner resolution)."""
-    import torch
-    import torch.multiprocessing as mp
-
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    ctx = mp.get_context("spawn")
-    out = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker_demand, args=(r, 2, port, out, p2p)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = [out.get(timeout=600) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+@pytest.mark.parametrize("world,p2p", [(2, False), (2, True), (3, True), (4, True), (8, True)])
+def test_sharded_device_demand_equals_single_engine(world, p2p):
+    """Device-driven demand sharded over `world` ranks == the same run on one engine, bit for bit (link
+    volumes at every block boundary, fp64 positions / speeds, route indices, trip counts, completed trips).
+    p2p=False: per-tick all-gather of the link events (NCCL); p2p=True: the exchange inside the persistent
+    tick kernel over NVLink peer memory (k_tick_loop_p2p, link-owner resolution) -- what bench.py uses."""
+    _spawn(_selfcheck, world, p2p, 40_000 + world)  # + world: uneven shards
