@@ -125,7 +125,7 @@ def build_workload(name, agents, seed, rank, nodes=None):
         lg = road_graph(nodes or w["nodes"], seed=seed, morton=os.environ.get("DRIFT_NO_MORTON") is None)
     rng = np.random.default_rng(seed * 1000 + 17 + rank)
     start = rng.integers(0, lg.V, size=agents).astype(np.int32)
-    return lg, start, w["model"], rng
+    return lg, start, w["model"], rng, kind
 
 
 def make_chains(model, rng, lg, start, k):
@@ -219,8 +219,20 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def progress(msg):
+    """Timestamped progress line on stderr (DRIFT_BENCH_VERBOSE=1): where a multi-rank run is, should it stall."""
+    if os.environ.get("DRIFT_BENCH_VERBOSE"):
+        sys.stderr.write("[bench %s rank %s] %s\n" % (time.strftime("%H:%M:%S"), os.environ.get("RANK", "0"), msg))
+        sys.stderr.flush()
+
+
 def run_b200(args):
     import torch
+
+    if os.environ.get("DRIFT_BENCH_VERBOSE"):  # where is a stalled rank? Python stacks every N seconds
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ.get("DRIFT_BENCH_WATCHDOG", "150")), repeat=True, file=sys.stderr)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,7 +255,7 @@ def run_b200(args):
 
     w = WORKLOADS[args.workload]
     n_local = args.agents or w["agents"]
-    lg, start, model, rng = build_workload(args.workload, n_local, args.seed, rank, nodes=args.nodes)
+    lg, start, model, rng, graph_kind = build_workload(args.workload, n_local, args.seed, rank, nodes=args.nodes)
     K, W, TPS = args.steps, args.warmup, args.ticks_per_step or w.get("tps", 300)
     arena_links = max(1 << 24, n_local * w.get("arena_per_agent", 2560))
     trips_per_step = 2
@@ -275,7 +287,29 @@ def run_b200(args):
     for kv in args.opt:
         k, v = kv.split("=")
         eng.set_option(k, float(v))
-    if args.landmarks > 0:
+    # static travel times -> contraction hierarchy (host, cached on disk: rank 0 contracts, the others load) + hub
+    # labels built on the device; graphs without a usable hierarchy (grids) keep the tree / bounded-search router
+    hier_info = None
+    if not args.no_labels and graph_kind == "road":
+        from drift_b200 import hierarchy
+        from drift_b200._capi import DriftError
+
+        try:
+            t_h = time.perf_counter()
+            if rank == 0:
+                hier, cached = hierarchy.build_cached(lg, time_limit_s=args.hier_seconds)
+            if dist is not None:
+                dist.barrier()
+            if rank != 0:
+                hier, cached = hierarchy.build_cached(lg, time_limit_s=args.hier_seconds)
+            t_h = time.perf_counter() - t_h
+            eng.set_hierarchy(hier)
+            hier_info = dict(hier.info(), host_seconds=t_h, from_cache=bool(cached), **eng.label_stats(reset=False))
+        except DriftError as ex:
+            hier_info = dict(unavailable=str(ex))
+        progress("hierarchy: %r" % (hier_info,))
+    labels_on = hier_info is not None and "unavailable" not in hier_info
+    if args.landmarks > 0 and not labels_on:
         eng.set_landmarks(args.landmarks)
     eng.set_demand(args.seed, HOURLY, start, chain_capacity=4, router=ROUTER_BATCHED)
     eng.set_option("route_window", TPS)
@@ -317,15 +351,18 @@ def run_b200(args):
             for _ in range(TPS):
                 t_sim += delta
 
+    progress("setup done, warm-up")
     for _ in range(W):
         run_block()
     barrier()
+    progress("timed region")
     launches0 = eng.kernel_times()["total_launches"]
     st0 = eng.stats()
     n_reroutes[0] = 0
     eng.set_option("time_plan", 1)
     eng.phase_times(reset=True)
     eng.tree_stats(reset=True)
+    eng.label_stats(reset=True)
     with ClockSampler(local_rank) as clk:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(bench_stream)
@@ -337,6 +374,7 @@ def run_b200(args):
     st1 = eng.stats()
     phases = eng.phase_times(reset=True)
     trees = eng.tree_stats(reset=True)
+    lab = eng.label_stats(reset=True)
     eng.set_option("time_plan", 0)
     launches = eng.kernel_times()["total_launches"] - launches0
     if dist is not None:
@@ -352,6 +390,7 @@ def run_b200(args):
         routes = int(rt.item())
     reroutes_timed = n_reroutes[0]
 
+    progress("timed region done: %.1f ms/step" % (1e3 * dt / K))
     # ---- e2e pass: per step H2D of the step's chains (pinned) + D2H of arrivals/departures/volumes
     dst_s = np.ascontiguousarray(dst_e2e).reshape(n_local, K + 1, trips_per_step)
     keep_t, blocks_p = zip(*[pinned(dst_s[:, b, :]) for b in range(K + 1)])
@@ -387,6 +426,7 @@ def run_b200(args):
         dt_e2e = float(tt.item())
     e2e_value = total_agents * TPS * K / dt_e2e
 
+    progress("e2e done")
     # ---- roofline pass: per-launch CUDA-event timing of the advance kernel on the engine stream
     stm0 = eng.stats()
     eng.set_profiling(True)
@@ -464,6 +504,7 @@ def run_b200(args):
     # ---- multi-GPU: what a tick costs WITHOUT the exchange (same engine, same agents, peer exchange suspended:
     # timing only, the state is not used afterwards), so that the exchange is visible separately from the
     # embarrassingly parallel route planning
+    progress("roofline pass done")
     tick_only = None
     if sharded is not None and args.exchange == "p2p":
         barrier()
@@ -484,6 +525,7 @@ def run_b200(args):
         barrier()
 
     # ---- multi-GPU: N-rank parity self-check (SURVEY.md 8e acceptance), after the timed regions
+    progress("tick-only probe done")
     parity = None
     if sharded is not None and not args.no_parity_check:
         sharded.close()
@@ -493,6 +535,7 @@ def run_b200(args):
         parity = sharded_vs_single(local_rank, agents=args.parity_agents, nodes=20_000, ticks=100, blocks=3,
                                    p2p=(args.exchange == "p2p"))
 
+    progress("parity check done: %r" % (parity,))
     line = None
     if rank == 0:
         cpu = cpu_port_rate(model, args.seed, budget_s=args.cpu_seconds, ticks=TPS, reroute=reroute) \
@@ -503,7 +546,12 @@ def run_b200(args):
             data="synthetic",
             config=dict(workload=args.workload, description=w["desc"], agents_per_gpu=n_local, total_agents=total_agents,
                         nodes=lg.V, links=lg.L, demand=model, ticks_per_step=TPS, tick_seconds=delta,
-                        router="batched SSSP: cached shortest-path trees on either end of a trip (destination / source), bounded goal-directed searches for cold pairs; planning: %s" % ("lookahead" if w.get("lookahead") else "prefetch-all"), clock="08:00 peak",
+                        router=("hub labels over a contraction hierarchy of the static travel times (labels built on the "
+                                "device, a route = intersection of two sorted labels + shortcut unpacking)" if labels_on else
+                                "batched SSSP: cached shortest-path trees on either end of a trip (destination / source), "
+                                "bounded goal-directed searches for cold pairs") +
+                               "; planning: %s" % ("lookahead" if w.get("lookahead") else "prefetch-all"),
+                        hierarchy=hier_info, clock="08:00 peak",
                         l2="no explicit flush: a tick re-reads the same agent state by construction (%.0f MB hot + ~80 MB "
                            "cold per-agent state at this size, L2 is 126 MB) and every step's route planning walks "
                            "GBs of cached trees and route arena in between; roofline_advance_saturated uses 16 M "
@@ -526,6 +574,12 @@ def run_b200(args):
             gpu_launches=int(launches), router_stats={k: (round(v, 3) if isinstance(v, float) else v) for k, v in trees.items()},
             roofline=roof, roofline_advance=roof_adv, roofline_advance_saturated=sat,
             parity_check=parity, tick_only=tick_only,
+            label_router=(dict(queries=lab["queries"], launches=lab["launches"], query_kernel_ms=round(lab["query_ms"], 4),
+                               entries_read=lab["entries_read"], algorithmic_bytes=12 * lab["entries_read"],
+                               achieved_gbs=(12e-9 * lab["entries_read"] / (lab["query_ms"] * 1e-3)) if lab["query_ms"] > 0 else None,
+                               note="k_label_query in the timed region: 12 B (hub id + fp64 distance) per label entry of "
+                                    "the two labels a query intersects; CUDA events on the engine stream")
+                          if labels_on else None),
             clocks=clk.summary(),
             phases=dict(note="timed region: per-tick phase times of the persistent kernel (%globaltimer, barriers "
                              "included) and total ms in route-planning batches",
@@ -572,6 +626,9 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"],
                     help="multi-GPU: link events over NVLink peer memory inside the tick kernel, or per-tick NCCL all-gather")
     ap.add_argument("--coop-blocks", type=int, default=0, help="blocks per SM of the persistent tick kernel (0 = default)")
+    ap.add_argument("--no-labels", action="store_true",
+                    help="do not build the contraction hierarchy / hub labels (route with trees + bounded searches)")
+    ap.add_argument("--hier-seconds", type=float, default=240.0, help="time limit of the host-side contraction")
     ap.add_argument("--no-parity-check", action="store_true",
                     help="multi-GPU: skip the N-rank parity self-check (sharded run == one engine, bit for bit)")
     ap.add_argument("--parity-agents", type=int, default=200_000, help="agents of the N-rank parity self-check")

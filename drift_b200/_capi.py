@@ -38,6 +38,19 @@ class StatsOut(C.Structure):
         "arrivals_total", "departures_total", "route_arena_used", "events_last_tick", "arena_compactions", "fallback_routes")]
 
 
+class HierDesc(C.Structure):
+    _fields_ = [
+        ("V", C.c_int32), ("max_level", C.c_int32), ("max_label", C.c_int32), ("pad0", C.c_int32),
+        ("mean_label", C.c_double), ("n_up", C.c_int64), ("n_down", C.c_int64),
+        ("level", c_i32p),
+        ("up_rowptr", c_i32p), ("up_other", c_i32p), ("up_w", c_f64p), ("up_a", c_i32p), ("up_b", c_i32p),
+        ("up_hops", c_i32p),
+        ("down_rowptr", c_i32p), ("down_other", c_i32p), ("down_w", c_f64p), ("down_a", c_i32p), ("down_b", c_i32p),
+        ("down_hops", c_i32p),
+    ]
+
+
+HIER = C.c_void_p
 # name -> (restype, argtypes); must list every symbol of include/drift_b200.h
 ENGINE = C.c_void_p
 SIGNATURES = {
@@ -88,7 +101,15 @@ SIGNATURES = {
     "drift_set_profiling": (C.c_int, [ENGINE, C.c_int32]),
     "drift_phase_times": (C.c_int, [ENGINE, c_f64p, c_f64p, c_f64p, c_f64p, c_i64p, C.c_int32]),
     "drift_tree_stats": (C.c_int, [ENGINE, c_f64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, C.c_int32]),
+    "drift_time_passes": (C.c_int, [ENGINE, C.c_int32, c_f64p, c_f64p]),
     "drift_set_landmarks": (C.c_int, [ENGINE, C.c_int32, c_f64p, c_f64p]),
+    "drift_hier_build": (C.c_int, [C.c_int32, C.c_int32, c_i32p, c_i32p, c_f64p, c_i32p, C.c_int32, C.c_double,
+                                   C.POINTER(HIER)]),
+    "drift_hier_info": (C.c_int, [HIER, c_i64p, c_i64p, c_i64p, c_i32p, c_i32p, c_f64p, c_f64p]),
+    "drift_hier_export": (C.c_int, [HIER, C.POINTER(HierDesc)]),
+    "drift_hier_free": (C.c_int, [HIER]),
+    "drift_set_hierarchy": (C.c_int, [ENGINE, C.POINTER(HierDesc)]),
+    "drift_label_stats": (C.c_int, [ENGINE, c_i64p, c_f64p, c_f64p, c_i64p, c_i64p, c_i64p, C.c_int32]),
     "drift_host_pow": (C.c_int, [c_f64p, C.c_double, c_f64p, C.c_int64]),
     "drift_set_option": (C.c_int, [ENGINE, C.c_char_p, C.c_double]),
     "drift_device_ptr": (C.c_int, [ENGINE, C.c_char_p, C.POINTER(C.c_void_p), c_i64p]),

@@ -57,6 +57,8 @@ struct Counters {
   unsigned long long tree_iters;      // near-list waves (block barriers) over all jobs
   unsigned long long tree_far_visits; // far-list entries scanned by threshold advances
   unsigned long long n_fallback;      // departures routed inside the tick because no planned route was ready
+  unsigned long long label_entries;   // hub-label router: label entries read by the queries (roofline accounting)
+  unsigned long long label_queries;
 };
 
 constexpr int kOvfEvents = 1;

@@ -5,11 +5,14 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "common.cuh"
+#include "hierarchy.hpp"
+#include "label_kernels.cuh"
 #include "route_kernels.cuh"
 #include "tick_kernels.cuh"
 
@@ -173,6 +176,21 @@ struct drift_engine {
   int32_t t_max_slots = 0, t_blocks = 0;
   double t_delta = 1.0;
   int64_t tree_budget_bytes = (int64_t)48 << 30;
+  // contraction hierarchy + hub labels (static travel times)
+  DevBuf<int32_t> h_level, h_order;
+  DevBuf<int32_t> hu_rowptr, hu_other, hu_a, hu_b, hu_hops, hd_rowptr, hd_other, hd_a, hd_b, hd_hops;
+  DevBuf<double> hu_w, hd_w;
+  DevBuf<long long> lab_off;        // [2][V]
+  DevBuf<int32_t> lab_cnt;          // [2][V]
+  DevBuf<int32_t> lab_hub, lab_par, lab_flag, q_hub;
+  DevBuf<double> lab_dist;
+  DevBuf<unsigned long long> lab_cursor;
+  bool labels_ready = false;
+  bool labels_enabled = true;   // option "use_labels"
+  int64_t label_entries = 0, label_cap = 0;
+  double label_build_ms = 0, label_ms = 0;
+  int64_t label_launches = 0, label_queries_host = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> label_timers;
   // rings
   DevBuf<int32_t> arr_agent, arr_tick;
   int64_t arr_cap = 0;
@@ -277,6 +295,11 @@ struct drift_engine {
     g.V = V;
     g.L = L;
     return g;
+  }
+  HierSide hier_up() { return HierSide{hu_rowptr.p, hu_other.p, hu_w.p, hu_a.p, hu_b.p, hu_hops.p}; }
+  HierSide hier_down() { return HierSide{hd_rowptr.p, hd_other.p, hd_w.p, hd_a.p, hd_b.p, hd_hops.p}; }
+  LabelSet labels(int side) {
+    return LabelSet{lab_off.p + (int64_t)side * V, lab_cnt.p + (int64_t)side * V, lab_hub.p, lab_par.p, lab_dist.p};
   }
   Rings rings() {
     Rings r;
@@ -440,6 +463,34 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
   const double* wf = use_congested ? e->fwd_wc.p : e->fwd_w.p;
   const double* wb = use_congested ? e->bwd_wc.p : e->bwd_w.p;
   const double* lc = use_congested ? e->link_tt.p : e->link_t0.p;
+  if (router == DRIFT_ROUTER_BATCHED && e->labels_ready && e->labels_enabled && !use_congested) {
+    // hub labels: every query is the intersection of two sorted labels + a walk through the parent arcs
+    if (e->q_hub.n < e->q_cap) {
+      CU(cudaStreamSynchronize(e->stream));
+      CU(e->q_hub.alloc(e->q_cap, false));
+    }
+    cudaEvent_t tb0 = nullptr, tb1 = nullptr;
+    if (e->time_plan) {
+      cudaEventCreate(&tb0);
+      cudaEventCreate(&tb1);
+      cudaEventRecord(tb0, e->stream);
+    }
+    const int gw = grid_for(Q * 32, 256, kSMs * 8);
+    k_label_query<<<gw, 256, 0, e->stream>>>(Q, n_dev, qs, qd, e->labels(0), e->labels(1), e->V, e->q_hub.p + q0, out,
+                                             &e->ctr.p->label_entries);
+    if (tb0) {
+      cudaEventRecord(tb1, e->stream);
+      e->label_timers.push_back({tb0, tb1});
+    }
+    k_label_paths<<<grid_for(Q, 128, kSMs * 16), 128, 0, e->stream>>>(Q, n_dev, qs, qd, e->labels(0), e->labels(1),
+                                                                     e->hier_up(), e->hier_down(), e->q_hub.p + q0,
+                                                                     e->arena.p, (unsigned long long)e->arena_cap,
+                                                                     e->ctr.p, out, lc);
+    CU(cudaGetLastError());
+    e->total_launches += 2;
+    e->label_queries_host += Q;
+    return DRIFT_OK;
+  }
   if (router == DRIFT_ROUTER_BATCHED) {
     int rc = ensure_trees(e);
     if (rc) return rc;
@@ -1103,8 +1154,9 @@ static int plan_window(drift_engine* e, double t_first, double delta) {
     rc = maybe_compact_arena(e, hc.arena_cursor);
     if (rc) return rc;
   }
-  int64_t chunk = Q;
-  if (e->demand_router == DRIFT_ROUTER_BATCHED) {
+  int64_t chunk = std::max<int64_t>(Q, 1);
+  const bool by_labels = e->labels_ready && e->labels_enabled && !e->use_congested;
+  if (e->demand_router == DRIFT_ROUTER_BATCHED && !by_labels) {
     rc = ensure_trees(e);
     if (rc) return rc;
     chunk = router_chunk(e, Q, e->use_congested);
@@ -1220,7 +1272,7 @@ int drift_tick_begin_demand(drift_engine* e, double delta, double t, int64_t* n_
 int drift_update_travel_times(drift_engine* e) {
   if (!e || !e->have_bpr) return fail(DRIFT_ESTATE, "drift_update_travel_times");
   CU(cudaSetDevice(e->device));
-  k_travel_times<<<grid_for(e->L, 256, kSMs * 8), 256, 0, e->stream>>>(e->links());
+  k_travel_times<<<grid_for((e->L + 3) / 4, 256, kSMs * 8), 256, 0, e->stream>>>(e->links());
   k_refresh_weights<<<grid_for(e->Ef, 256, kSMs * 8), 256, 0, e->stream>>>(e->Ef, e->link_tt.p, e->fwd_link.p,
                                                                            e->bwd_link.p, e->fwd_wc.p, e->bwd_wc.p);
   CU(cudaGetLastError());
@@ -1297,7 +1349,7 @@ int drift_recount_occupancy(drift_engine* e, int32_t* occ_out) {
   if (!e || !occ_out || !e->N) return fail(DRIFT_EINVAL, "drift_recount_occupancy");
   CU(cudaSetDevice(e->device));
   CU(cudaMemsetAsync(e->hist.p, 0, sizeof(int32_t) * e->L, e->stream));
-  k_recount<<<grid_for(e->N, 256, kSMs * 8), 256, 0, e->stream>>>(e->agents(), e->hist.p);
+  k_recount<<<grid_for(e->N, kRecThreads * kRecPerThread, kSMs * 8), kRecThreads, 0, e->stream>>>(e->agents(), e->hist.p);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(occ_out, e->hist.p, sizeof(int32_t) * e->L, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
@@ -1736,6 +1788,266 @@ int drift_host_pow(const double* x, double y, double* out, int64_t n) {
   return DRIFT_OK;
 }
 
+// ---- contraction hierarchy + hub labels ------------------------------------------------------------
+struct drift_hierarchy {
+  Hierarchy h;
+  int32_t max_label = 0;
+  double mean_label = 0;
+  double build_s = 0;
+};
+
+int drift_hier_build(int32_t V, int32_t Ef, const int32_t* fwd_rowptr, const int32_t* fwd_col, const double* fwd_w,
+                     const int32_t* fwd_link, int32_t witness_settled, double time_limit_s, drift_hierarchy** out) {
+  if (!out || V <= 0 || Ef < 0 || !fwd_rowptr || (Ef && (!fwd_col || !fwd_w || !fwd_link)))
+    return fail(DRIFT_EINVAL, "drift_hier_build: bad argument");
+  *out = nullptr;
+  if (fwd_rowptr[V] != Ef) return fail(DRIFT_EINVAL, "drift_hier_build: rowptr[V] != Ef");
+  for (int32_t k = 0; k < Ef; ++k)
+    if (fwd_col[k] < 0 || fwd_col[k] >= V || !(fwd_w[k] > 0.0) || !(fwd_w[k] < 1e300))
+      return fail(DRIFT_EINVAL, "drift_hier_build: travel times must be positive and finite");
+  drift_hierarchy* hh = new drift_hierarchy();
+  HierParams prm;
+  if (witness_settled > 0) prm.witness_settled = witness_settled;
+  prm.time_limit_s = time_limit_s;
+  const auto t0 = std::chrono::steady_clock::now();
+  if (!build_hierarchy(V, fwd_rowptr, fwd_col, fwd_w, fwd_link, prm, &hh->h)) {
+    delete hh;
+    return fail(DRIFT_ESTATE, "drift_hier_build: time limit of %.0f s hit (the graph has no hierarchy worth finding)",
+                time_limit_s);
+  }
+  hh->build_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  // label sizes on a sample (the device sizes its tables and the label arena from these)
+  std::vector<uint32_t> stamp(V, 0u);
+  std::vector<int32_t> stack;
+  uint32_t epoch = 0;
+  const int32_t samples = std::min<int32_t>(V, 4096);
+  uint64_t x = 0x9E3779B97F4A7C15ULL;
+  double sum = 0;
+  for (int32_t k = 0; k < samples; ++k) {
+    x ^= x << 13, x ^= x >> 7, x ^= x << 17;
+    const int32_t v = samples == V ? k : (int32_t)(x % (uint64_t)V);
+    const int32_t nf = closure_size(hh->h.up, v, stamp, ++epoch, stack);
+    const int32_t nb = closure_size(hh->h.down, v, stamp, ++epoch, stack);
+    hh->max_label = std::max(hh->max_label, std::max(nf, nb));
+    sum += nf + nb;
+  }
+  hh->mean_label = sum / (2.0 * samples);
+  *out = hh;
+  return DRIFT_OK;
+}
+
+int drift_hier_info(const drift_hierarchy* h, int64_t* n_up, int64_t* n_down, int64_t* shortcuts, int32_t* max_level,
+                    int32_t* max_label, double* mean_label, double* build_seconds) {
+  if (!h) return fail(DRIFT_EINVAL, "drift_hier_info");
+  if (n_up) *n_up = (int64_t)h->h.up.other.size();
+  if (n_down) *n_down = (int64_t)h->h.down.other.size();
+  if (shortcuts) *shortcuts = h->h.shortcuts;
+  if (max_level) *max_level = h->h.max_level;
+  if (max_label) *max_label = h->max_label;
+  if (mean_label) *mean_label = h->mean_label;
+  if (build_seconds) *build_seconds = h->build_s;
+  return DRIFT_OK;
+}
+
+int drift_hier_export(const drift_hierarchy* h, drift_hier_desc* d) {
+  if (!h || !d) return fail(DRIFT_EINVAL, "drift_hier_export");
+  const Hierarchy& H = h->h;
+  auto put = [](const auto& v, auto* dst) {
+    if (dst && !v.empty()) memcpy(dst, v.data(), v.size() * sizeof(v[0]));
+  };
+  put(H.level, const_cast<int32_t*>(d->level));
+  put(H.up.rowptr, const_cast<int32_t*>(d->up_rowptr));
+  put(H.up.other, const_cast<int32_t*>(d->up_other));
+  put(H.up.w, const_cast<double*>(d->up_w));
+  put(H.up.a, const_cast<int32_t*>(d->up_a));
+  put(H.up.b, const_cast<int32_t*>(d->up_b));
+  put(H.up.hops, const_cast<int32_t*>(d->up_hops));
+  put(H.down.rowptr, const_cast<int32_t*>(d->down_rowptr));
+  put(H.down.other, const_cast<int32_t*>(d->down_other));
+  put(H.down.w, const_cast<double*>(d->down_w));
+  put(H.down.a, const_cast<int32_t*>(d->down_a));
+  put(H.down.b, const_cast<int32_t*>(d->down_b));
+  put(H.down.hops, const_cast<int32_t*>(d->down_hops));
+  d->V = H.V;
+  d->n_up = (int64_t)H.up.other.size();
+  d->n_down = (int64_t)H.down.other.size();
+  d->max_level = H.max_level;
+  d->max_label = h->max_label;
+  d->mean_label = h->mean_label;
+  return DRIFT_OK;
+}
+
+int drift_hier_free(drift_hierarchy* h) {
+  delete h;
+  return DRIFT_OK;
+}
+
+int drift_set_hierarchy(drift_engine* e, const drift_hier_desc* d) {
+  if (!e || !d || d->V != e->V || !d->level || !d->up_rowptr || !d->down_rowptr)
+    return fail(DRIFT_EINVAL, "drift_set_hierarchy: bad argument (hierarchy of another graph?)");
+  if (d->n_up >= ((int64_t)1 << 30) || d->n_down >= ((int64_t)1 << 30))
+    return fail(DRIFT_EINVAL, "drift_set_hierarchy: too many arcs");
+  if (d->max_level + 4 > kUnpackStack)
+    return fail(DRIFT_EINVAL, "drift_set_hierarchy: %d levels, the unpacker handles %d", d->max_level, kUnpackStack - 4);
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  e->labels_ready = false;
+  const int32_t V = e->V;
+  // table size of the label builder: a power of two with head room over the largest sampled label
+  int32_t n_max = 512;
+  while (n_max < (int32_t)(1.5 * d->max_label) + 64) n_max <<= 1;
+  if (n_max > 4096)
+    return fail(DRIFT_EOVERFLOW, "drift_set_hierarchy: labels of up to ~%d hubs do not fit the builder's shared-memory "
+                                 "table (4096): this graph keeps the tree / bounded-search router", d->max_label);
+  int32_t log2H = 0;
+  while ((1 << log2H) < 2 * n_max) ++log2H;
+  const size_t smem = (size_t)40 * n_max;
+  CU(cudaFuncSetAttribute(k_build_labels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(e->h_level.upload(d->level, V));
+  CU(e->hu_rowptr.upload(d->up_rowptr, V + 1));
+  CU(e->hu_other.upload(d->up_other, d->n_up));
+  CU(e->hu_w.upload(d->up_w, d->n_up));
+  CU(e->hu_a.upload(d->up_a, d->n_up));
+  CU(e->hu_b.upload(d->up_b, d->n_up));
+  CU(e->hu_hops.upload(d->up_hops, d->n_up));
+  CU(e->hd_rowptr.upload(d->down_rowptr, V + 1));
+  CU(e->hd_other.upload(d->down_other, d->n_down));
+  CU(e->hd_w.upload(d->down_w, d->n_down));
+  CU(e->hd_a.upload(d->down_a, d->n_down));
+  CU(e->hd_b.upload(d->down_b, d->n_down));
+  CU(e->hd_hops.upload(d->down_hops, d->n_down));
+  // nodes by level, highest first
+  const int32_t nl = d->max_level + 1;
+  std::vector<int32_t> start(nl + 1, 0), order(V);
+  for (int32_t v = 0; v < V; ++v) {
+    if (d->level[v] < 0 || d->level[v] > d->max_level) return fail(DRIFT_EINVAL, "drift_set_hierarchy: bad level");
+    start[nl - 1 - d->level[v] + 1] += 1;
+  }
+  for (int32_t k = 0; k < nl; ++k) start[k + 1] += start[k];
+  {
+    std::vector<int32_t> fill(start.begin(), start.end() - 1);
+    for (int32_t v = 0; v < V; ++v) order[fill[nl - 1 - d->level[v]]++] = v;
+  }
+  CU(e->h_order.upload(order.data(), V));
+  CU(e->lab_off.alloc((int64_t)2 * V));
+  CU(e->lab_cnt.alloc((int64_t)2 * V));
+  CU(e->lab_flag.alloc(1));
+  CU(e->lab_cursor.alloc(1));
+  int64_t cap = (int64_t)(2.0 * d->mean_label * V * 1.25) + (1 << 20);
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    if ((double)cap * 16.0 > 0.6 * (double)free_b)
+      return fail(DRIFT_ENOMEM, "drift_set_hierarchy: %.1f GB of labels do not fit (%.1f GB free)", cap * 16.0 / 1e9,
+                  free_b / 1e9);
+    CU(e->lab_hub.alloc(cap, false));
+    CU(e->lab_par.alloc(cap, false));
+    CU(e->lab_dist.alloc(cap, false));
+    CU(cudaMemsetAsync(e->lab_flag.p, 0, sizeof(int32_t), e->stream));
+    CU(cudaMemsetAsync(e->lab_cursor.p, 0, sizeof(unsigned long long), e->stream));
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, e->stream);
+    for (int side = 0; side < 2; ++side)
+      for (int32_t k = 0; k < nl; ++k) {
+        const int32_t n = start[k + 1] - start[k];
+        if (n <= 0) continue;
+        k_build_labels<<<n, kLabelThreads, smem, e->stream>>>(side == 0 ? e->hier_up() : e->hier_down(), e->labels(side),
+                                                              e->h_order.p, start[k], n_max, log2H, e->lab_cursor.p,
+                                                              (unsigned long long)cap, e->lab_flag.p);
+      }
+    cudaEventRecord(ev1, e->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    e->label_build_ms = ms;
+    int32_t flag = 0;
+    unsigned long long used = 0;
+    CU(cudaMemcpy(&flag, e->lab_flag.p, sizeof(flag), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&used, e->lab_cursor.p, sizeof(used), cudaMemcpyDeviceToHost));
+    if (flag & 1) {
+      e->lab_hub.release(), e->lab_par.release(), e->lab_dist.release();
+      return fail(DRIFT_EOVERFLOW, "drift_set_hierarchy: a label outgrew the builder's table of %d hubs", n_max);
+    }
+    if (!(flag & 2)) {
+      e->label_entries = (int64_t)used;
+      e->label_cap = cap;
+      e->labels_ready = true;
+      return DRIFT_OK;
+    }
+    cap = (int64_t)((double)used * 1.05) + (1 << 20);  // the arena was too small: now the exact size is known
+  }
+  return fail(DRIFT_EOVERFLOW, "drift_set_hierarchy: label arena");
+}
+
+int drift_label_stats(drift_engine* e, int64_t* entries, double* build_ms, double* query_ms, int64_t* launches,
+                      int64_t* queries, int64_t* entries_read, int32_t reset) {
+  if (!e) return fail(DRIFT_EINVAL, "drift_label_stats");
+  CU(cudaSetDevice(e->device));
+  Counters c;
+  int rc = fetch_counters(e, &c);
+  if (rc) return rc;
+  for (auto& t : e->label_timers) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t.first, t.second);
+    e->label_ms += ms;
+    e->label_launches += 1;
+    cudaEventDestroy(t.first);
+    cudaEventDestroy(t.second);
+  }
+  e->label_timers.clear();
+  if (entries) *entries = e->labels_ready ? e->label_entries : 0;
+  if (build_ms) *build_ms = e->label_build_ms;
+  if (query_ms) *query_ms = e->label_ms;
+  if (launches) *launches = e->label_launches;
+  if (queries) *queries = e->label_queries_host;
+  if (entries_read) *entries_read = (int64_t)c.label_entries;
+  if (reset) {
+    CU(cudaMemsetAsync(&e->ctr.p->label_entries, 0, 2 * sizeof(unsigned long long), e->stream));
+    e->label_ms = 0;
+    e->label_launches = 0;
+    e->label_queries_host = 0;
+  }
+  return DRIFT_OK;
+}
+
+int drift_time_passes(drift_engine* e, int32_t iters, double* recount_us, double* travel_times_us) {
+  if (!e || iters <= 0 || !e->N || !e->have_bpr) return fail(DRIFT_EINVAL, "drift_time_passes");
+  CU(cudaSetDevice(e->device));
+  cudaEvent_t ev[4];
+  for (auto& x : ev) CU(cudaEventCreate(&x));
+  const int gr = grid_for(e->N, kRecThreads * kRecPerThread, kSMs * 8);
+  const int gt = grid_for((e->L + 3) / 4, 256, kSMs * 8);
+  for (int w = 0; w < 2; ++w) {  // warm-up
+    CU(cudaMemsetAsync(e->hist.p, 0, sizeof(int32_t) * e->L, e->stream));
+    k_recount<<<gr, kRecThreads, 0, e->stream>>>(e->agents(), e->hist.p);
+    k_travel_times<<<gt, 256, 0, e->stream>>>(e->links());
+  }
+  CU(cudaEventRecord(ev[0], e->stream));
+  for (int i = 0; i < iters; ++i) {
+    CU(cudaMemsetAsync(e->hist.p, 0, sizeof(int32_t) * e->L, e->stream));  // the zero-fill is part of the recount
+    k_recount<<<gr, kRecThreads, 0, e->stream>>>(e->agents(), e->hist.p);
+  }
+  CU(cudaEventRecord(ev[1], e->stream));
+  CU(cudaEventRecord(ev[2], e->stream));
+  for (int i = 0; i < iters; ++i) k_travel_times<<<gt, 256, 0, e->stream>>>(e->links());
+  CU(cudaEventRecord(ev[3], e->stream));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(e->stream));
+  float a = 0, b = 0;
+  CU(cudaEventElapsedTime(&a, ev[0], ev[1]));
+  CU(cudaEventElapsedTime(&b, ev[2], ev[3]));
+  for (auto& x : ev) cudaEventDestroy(x);
+  if (recount_us) *recount_us = 1e3 * a / iters;
+  if (travel_times_us) *travel_times_us = 1e3 * b / iters;
+  e->total_launches += 2 * iters;
+  return DRIFT_OK;
+}
+
 int drift_set_option(drift_engine* e, const char* name, double value) {
   if (!e || !name) return fail(DRIFT_EINVAL, "drift_set_option");
   std::string s(name);
@@ -1762,6 +2074,8 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
     e->t_pop_thresh = (int32_t)value;
   } else if (s == "arena_compact_frac") {
     e->arena_compact_frac = std::min(0.95, std::max(0.05, value));
+  } else if (s == "use_labels") {
+    e->labels_enabled = value != 0;
   } else if (s == "debug_mask") {
     e->debug_mask = (int32_t)value;
   } else if (s == "p2p_suspend") {

@@ -1015,13 +1015,58 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
 
 // ---- auxiliary passes -------------------------------------------------------------------------------
 // K3': per-link volume recount = histogram of cur_link over moving agents
-// (traffic_manager.py:122-135: total_agents_on_roads / per-link list lengths).
-__global__ void k_recount(AgentArrays a, int32_t* __restrict__ hist) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
-    if (a.state[i] == kMoving) {
-      const int32_t l = a.cur_link[i];
-      if (l >= 0) atomicAdd(&hist[l], 1);
+// (traffic_manager.py:122-135: total_agents_on_roads / per-link list lengths).  A tile of 1024 agents is staged in
+// a shared-memory histogram (open addressing on the link id) before it touches HBM: lanes of a warp that sit on
+// the same link are merged with __match_any_sync and only the group leader inserts, the block then issues ONE
+// global atomic per distinct link of the tile.  Agents on a hot link (a hub approach, a gridlocked arterial)
+// therefore cost a shared-memory add instead of a same-address L2 atomic, which serialises chip-wide.
+constexpr int kRecThreads = 256;
+constexpr int kRecPerThread = 4;
+constexpr int kRecSlots = 2048;  // >= 2 x agents of a tile: load factor <= 0.5
+
+__global__ void __launch_bounds__(kRecThreads) k_recount(AgentArrays a, int32_t* __restrict__ hist) {
+  __shared__ int32_t s_key[kRecSlots];
+  __shared__ int32_t s_cnt[kRecSlots];
+  const int64_t tile_agents = (int64_t)kRecThreads * kRecPerThread;
+  const int64_t tiles = (a.n + tile_agents - 1) / tile_agents;
+  const int lane = threadIdx.x & 31;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int i = threadIdx.x; i < kRecSlots; i += kRecThreads) {
+      s_key[i] = -1;
+      s_cnt[i] = 0;
     }
+    __syncthreads();
+    const int64_t i0 = (tile * kRecThreads + threadIdx.x) * kRecPerThread;  // arrays are padded to whole tiles
+    uint32_t st4 = 0;
+    int4 l4 = make_int4(-1, -1, -1, -1);
+    if (i0 < a.n) {
+      st4 = *reinterpret_cast<const uint32_t*>(a.state + i0);
+      if (st4) l4 = *reinterpret_cast<const int4*>(a.cur_link + i0);
+    }
+    const int32_t lk[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+    for (int j = 0; j < kRecPerThread; ++j) {
+      const bool on = ((st4 >> (8 * j)) & 0xffu) == kMoving && lk[j] >= 0 && i0 + j < a.n;
+      const unsigned active = __ballot_sync(0xffffffffu, on);
+      if (!on) continue;
+      const unsigned peers = __match_any_sync(active, lk[j]);
+      if ((peers & ((1u << lane) - 1u)) != 0) continue;  // not the lowest lane of its group
+      int slot = (int)(((uint32_t)lk[j] * 2654435761u) >> 21);  // 11 bits
+      for (;;) {
+        const int32_t k = s_key[slot];
+        if (k == lk[j]) break;
+        if (k == -1) {
+          const int32_t old = atomicCAS(&s_key[slot], -1, lk[j]);
+          if (old == -1 || old == lk[j]) break;
+        }
+        slot = (slot + 1) & (kRecSlots - 1);
+      }
+      atomicAdd(&s_cnt[slot], __popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kRecSlots; i += kRecThreads)
+      if (s_key[i] >= 0) atomicAdd(&hist[s_key[i]], s_cnt[i]);
+    __syncthreads();
   }
 }
 
@@ -1038,12 +1083,30 @@ __global__ void k_pack_linkrec(LinkArrays lk, LinkRec* __restrict__ rec) {
   }
 }
 
-// K4 (extension): tt[l] = t0[l] / factor(occ[l]) -- the BPR travel-time form of traffic_manager.py:92-107.
-__global__ void k_travel_times(LinkArrays lk) {
-  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < lk.L; l += gridDim.x * blockDim.x) {
-    const int32_t c = lk.occ[l];
-    const double f = (c == 0) ? 1.0 : bpr_factor_lookup(lk, l, c);
-    lk.tt[l] = __ddiv_rn(lk.t0[l], f);
+// K4 (extension): tt[l] = t0[l] / factor(occ[l]) -- the BPR travel-time form of traffic_manager.py:92-107, one
+// fused elementwise pass over the link arrays: 4 links per thread (one 16-byte load of the volumes, two of the
+// free-flow times, two 16-byte stores), the factor table is only touched for links that hold traffic
+// (an empty link has factor 1.0: traffic_manager.py:88-89).  24 B per link: occ 4 R + cap class 4 R + t0 8 R + tt 8 W.
+__global__ void __launch_bounds__(256) k_travel_times(LinkArrays lk) {
+  const int64_t quads = ((int64_t)lk.L + 3) / 4;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < quads; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l0 = q * 4;
+    if (l0 + 4 <= lk.L) {
+      const int4 c = *reinterpret_cast<const int4*>(lk.occ + l0);
+      const double2 t01 = *reinterpret_cast<const double2*>(lk.t0 + l0);
+      const double2 t23 = *reinterpret_cast<const double2*>(lk.t0 + l0 + 2);
+      const double f0 = c.x == 0 ? 1.0 : bpr_factor_lookup(lk, (int32_t)l0, c.x);
+      const double f1 = c.y == 0 ? 1.0 : bpr_factor_lookup(lk, (int32_t)l0 + 1, c.y);
+      const double f2 = c.z == 0 ? 1.0 : bpr_factor_lookup(lk, (int32_t)l0 + 2, c.z);
+      const double f3 = c.w == 0 ? 1.0 : bpr_factor_lookup(lk, (int32_t)l0 + 3, c.w);
+      *reinterpret_cast<double2*>(lk.tt + l0) = make_double2(__ddiv_rn(t01.x, f0), __ddiv_rn(t01.y, f1));
+      *reinterpret_cast<double2*>(lk.tt + l0 + 2) = make_double2(__ddiv_rn(t23.x, f2), __ddiv_rn(t23.y, f3));
+    } else {
+      for (int64_t l = l0; l < lk.L; ++l) {
+        const int32_t c = lk.occ[l];
+        lk.tt[l] = __ddiv_rn(lk.t0[l], c == 0 ? 1.0 : bpr_factor_lookup(lk, (int32_t)l, c));
+      }
+    }
   }
 }
 

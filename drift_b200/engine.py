@@ -352,6 +352,12 @@ class Engine:
         return dict(build_ms=ms.value, launches=v[0].value, trees=v[1].value, edges_relaxed=v[2].value,
                     improved=v[3].value, nodes_expanded=v[4].value, waves=v[5].value, far_visits=v[6].value)
 
+    def time_passes(self, iters=20):
+        """Per-launch microseconds of the volume recount (K3') and of the BPR travel-time pass (K4)."""
+        a, b = C.c_double(0), C.c_double(0)
+        _capi.check(self._lib.drift_time_passes(self._h, int(iters), C.byref(a), C.byref(b)))
+        return dict(recount_us=a.value, travel_times_us=b.value)
+
     def set_landmarks(self, K=8, seed=0):
         """Pick K far-apart landmarks and upload their free-flow distance arrays (host: scipy Dijkstra, a
         one-off setup cost of ~0.2 s per landmark on a 1 M-link graph)."""
@@ -385,6 +391,23 @@ class Engine:
         to = np.ascontiguousarray(np.stack(to), dtype=np.float64)
         _capi.check(self._lib.drift_set_landmarks(self._h, len(picks), _p(frm, C.c_double), _p(to, C.c_double)))
         return picks
+
+    def set_hierarchy(self, hier):
+        """Upload a contraction hierarchy (``drift_b200.hierarchy.build``) and build the hub labels on the device.
+        From then on ``ROUTER_BATCHED`` answers queries on the static travel times by label lookups.  Raises
+        ``_capi.DriftError`` when the graph has no usable hierarchy (labels too large): the engine keeps its
+        tree / bounded-search router."""
+        d = hier.desc()
+        self._hier_keep = hier
+        _capi.check(self._lib.drift_set_hierarchy(self._h, C.byref(d)))
+
+    def label_stats(self, reset=True):
+        ent, lau, q, rd = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        bms, qms = C.c_double(0), C.c_double(0)
+        _capi.check(self._lib.drift_label_stats(self._h, C.byref(ent), C.byref(bms), C.byref(qms), C.byref(lau),
+                                                C.byref(q), C.byref(rd), int(bool(reset))))
+        return dict(label_entries=ent.value, label_bytes=16 * ent.value, build_ms=bms.value, query_ms=qms.value,
+                    launches=lau.value, queries=q.value, entries_read=rd.value)
 
     def set_option(self, name, value):
         _capi.check(self._lib.drift_set_option(self._h, name.encode(), float(value)))

@@ -13,7 +13,9 @@ import numpy as np
 FIELDS = ("state", "dist", "speed", "route_idx", "trip_count")
 
 
-def _drive(run, eng, occupancy, lg, start, first, cands, hourly, ticks, seed, router):
+def _drive(run, eng, occupancy, lg, start, first, cands, hourly, ticks, seed, router, hier=None):
+    if hier is not None:
+        eng.set_hierarchy(hier)
     eng.set_demand(seed, hourly, start, chain_capacity=4, router=router)
     eng.set_option("route_window", ticks)
     eng.push_trips(first)
@@ -26,7 +28,8 @@ def _drive(run, eng, occupancy, lg, start, first, cands, hourly, ticks, seed, ro
     return occs, eng.agents(fields=FIELDS), arr
 
 
-def sharded_vs_single(device, agents=200_000, nodes=20_000, ticks=100, blocks=3, p2p=True, seed=77, group=None):
+def sharded_vs_single(device, agents=200_000, nodes=20_000, ticks=100, blocks=3, p2p=True, seed=77, group=None,
+                      labels=True):
     """Returns a dict ``{world, agents, nodes, links, ticks, exchange, ok, detail}``; ``ok`` is the AND over
     all ranks.  Needs an initialised ``torch.distributed`` process group with one CUDA device per rank."""
     import torch
@@ -46,13 +49,18 @@ def sharded_vs_single(device, agents=200_000, nodes=20_000, ticks=100, blocks=3,
     first = rng.integers(0, lg.V, size=(N, 4)).astype(np.int32)
     hourly = np.full(24, 0.9)
     arena = N * 300
+    hier = None
+    if labels:  # route by hub labels (what bench.py does on road graphs); every rank contracts the same graph
+        from . import hierarchy
+
+        hier = hierarchy.build(lg)
 
     se = ShardedEngine(lg, N, device=device, route_arena_links=arena, group=group)
     if p2p:
         se.enable_p2p()
     lo, hi = se.lo, se.hi
     occ_s, ag_s, arr_s = _drive(se.run, se.engine, se.occupancy, lg, start[lo:hi], first[lo:hi], cands[:, lo:hi],
-                                hourly, ticks, seed, ROUTER_BATCHED)
+                                hourly, ticks, seed, ROUTER_BATCHED, hier)
     se.close()
 
     # the same run on one engine (rank 0), broadcast to everybody
@@ -67,7 +75,7 @@ def sharded_vs_single(device, agents=200_000, nodes=20_000, ticks=100, blocks=3,
             eng.run(n, delta, t)
             return t + n * delta
 
-        o1, a1, arr1 = _drive(run1, eng, eng.occupancy, lg, start, first, cands, hourly, ticks, seed, ROUTER_BATCHED)
+        o1, a1, arr1 = _drive(run1, eng, eng.occupancy, lg, start, first, cands, hourly, ticks, seed, ROUTER_BATCHED, hier)
         eng.close()
         occ_1[:] = np.stack(o1)
         for k in FIELDS:
@@ -98,6 +106,6 @@ def sharded_vs_single(device, agents=200_000, nodes=20_000, ticks=100, blocks=3,
     dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
     moved = int(occ_1[-1].sum())
     return dict(world=world, agents=N, nodes=lg.V, links=lg.L, ticks=ticks * blocks, blocks=blocks,
-                exchange="p2p" if p2p else "allgather", completed_trips=int(n_arr_1[0]), on_roads_at_end=moved,
+                exchange="p2p" if p2p else "allgather", router="hub labels" if labels else "trees", completed_trips=int(n_arr_1[0]), on_roads_at_end=moved,
                 compared=["link volumes at every block boundary"] + list(FIELDS) + ["completed trips"],
                 ok=bool(ok.item()) and moved > 0, detail=bad)

@@ -248,10 +248,59 @@ int drift_phase_times(drift_engine* e, double* advance_ns, double* inject_ns, do
  * the CUDA-event time): trees built, edges relaxed, relaxations that improved a label, nodes expanded. */
 int drift_tree_stats(drift_engine* e, double* build_ms, int64_t* launches, int64_t* jobs, int64_t* relaxed,
                      int64_t* improved, int64_t* expanded, int64_t* iters, int64_t* far_visits, int32_t reset);
+/* Per-launch time (CUDA events on the engine stream, average of `iters` back-to-back launches after a warm-up) of
+ * the two auxiliary link passes on the engine's current state: the per-link volume recount (zero-fill +
+ * histogram of cur_link, traffic_manager.py:122-135) and the BPR travel-time pass (traffic_manager.py:92-107
+ * applied to every link).  For the roofline report of bench.py. */
+int drift_time_passes(drift_engine* e, int32_t iters, double* recount_us, double* travel_times_us);
 /* Landmark distances for goal-directed bounded searches in the batched router (ALT): K landmarks,
  * dist_from[K][V] = free-flow travel time landmark -> node, dist_to[K][V] = node -> landmark (+inf where
  * unreachable).  Only used while routing on the static travel times.  K = 0 switches it off. */
 int drift_set_landmarks(drift_engine* e, int32_t K, const double* dist_from, const double* dist_to);
+/* Contraction hierarchy + hub labels for the STATIC travel times (the reference never updates `travel_time`,
+ * lib/graph_loader.py:759-766, so the graph can be preprocessed once): replaces the search behind
+ * nx.shortest_path (lib/agent.py:94) by label lookups.  drift_hier_build runs on the host (no device is touched)
+ * from the forward CSR of drift_graph_desc; drift_hier_export copies the result into caller-owned arrays (sizes
+ * from drift_hier_info; e.g. to cache it on disk); drift_set_hierarchy uploads a hierarchy and builds the hub
+ * labels of every node on the device.  From then on DRIFT_ROUTER_BATCHED answers every query on the static
+ * travel times from the labels (queries on congested times keep the tree / bounded-search router).  Paths are
+ * shortest paths; they equal NetworkX's wherever the shortest path is unique (ties within ~1e-13 relative may
+ * resolve differently: shortcut weights are fp64 sums in contraction order).  Fails with DRIFT_EOVERFLOW /
+ * DRIFT_ENOMEM / DRIFT_ESTATE (time limit) on graphs without a usable hierarchy (e.g. uniform grids): the
+ * engine then keeps its other routers. */
+typedef struct drift_hierarchy drift_hierarchy;
+typedef struct drift_hier_desc {
+  int32_t V;
+  int32_t max_level;          /* arcs lead from a lower to a strictly higher level */
+  int32_t max_label;          /* largest label seen on a sample of nodes */
+  int32_t pad0;
+  double mean_label;          /* mean label size (hubs per node and side) on that sample */
+  int64_t n_up, n_down;
+  const int32_t* level;       /* [V] */
+  const int32_t* up_rowptr;   /* [V+1] arcs v -> w with w contracted later, stored at v */
+  const int32_t* up_other;    /* [n_up] w */
+  const double* up_w;
+  const int32_t* up_a;        /* original link id when up_b < 0, else position (down side) of the first half */
+  const int32_t* up_b;        /* -1, or position (up side) of the second half */
+  const int32_t* up_hops;     /* original links below the arc */
+  const int32_t* down_rowptr; /* [V+1] arcs u -> v with u contracted later, stored at v */
+  const int32_t* down_other;  /* [n_down] u */
+  const double* down_w;
+  const int32_t* down_a;
+  const int32_t* down_b;
+  const int32_t* down_hops;
+} drift_hier_desc;
+int drift_hier_build(int32_t V, int32_t Ef, const int32_t* fwd_rowptr, const int32_t* fwd_col, const double* fwd_w,
+                     const int32_t* fwd_link, int32_t witness_settled, double time_limit_s, drift_hierarchy** out);
+int drift_hier_info(const drift_hierarchy* h, int64_t* n_up, int64_t* n_down, int64_t* shortcuts, int32_t* max_level,
+                    int32_t* max_label, double* mean_label, double* build_seconds);
+int drift_hier_export(const drift_hierarchy* h, drift_hier_desc* d);
+int drift_hier_free(drift_hierarchy* h);
+int drift_set_hierarchy(drift_engine* e, const drift_hier_desc* d);
+/* Hub-label router since the last reset: label entries held, device time of the label build, time (needs option
+ * "time_plan") / launches / queries of the query kernel and label entries it read. */
+int drift_label_stats(drift_engine* e, int64_t* entries, double* build_ms, double* query_ms, int64_t* launches,
+                      int64_t* queries, int64_t* entries_read, int32_t reset);
 /* Host-side helper of the vectorised s-t selectors (drift_b200/fast_selection.py; replaces the Python loops
  * of lib/st_selection.py:327-363 and :408-423): out[i] = pow(x[i], y) through the C library, i.e. exactly
  * what CPython's `x ** y` computes.  No device is touched. */
@@ -274,6 +323,7 @@ int drift_host_pow(const double* x, double y, double* out, int64_t n);
  *   tree_delta_scale    multiplies the near-far bucket width; tree_threads: 64 / 128 / 256 threads per search
  *   arena_compact_frac  the live routes are compacted once this fraction of the route arena is used (0.75)
  *   time_plan           1 = time the planning batches with CUDA events (drift_phase_times / drift_tree_stats)
+ *   use_labels          0 = ignore an uploaded hierarchy (DRIFT_ROUTER_BATCHED falls back to trees / bounded searches)
  *   debug_mask          timing probes only, results are then NOT the reference's: 1 = no departure draws,
  *                       2 = crossers stay on their link, 4 = events are not emitted (tools/tick_probe.py)
  * The tree_* budgets, tree_sides and tree_threads must be set before the first batched route. */
