@@ -427,6 +427,54 @@ def run_b200(args):
     e2e_value = total_agents * TPS * K / dt_e2e
 
     progress("e2e done")
+    # ---- auxiliary link passes on the state the runs left behind: volume recount (K3') and BPR travel-time pass (K4)
+    peak, peak_src = peaks()
+    st_aux = eng.stats()
+    tp = eng.time_passes(20)
+    mv_aux, touched = st_aux["moving_agents"], st_aux["links_with_traffic"]
+    if sharded is not None:  # with the peer exchange a link's volume lives on its owner: ~1/world of the touched links here
+        touched = min(lg.L, mv_aux)
+    sc_bytes = 1.0 * n_local + 4.0 * mv_aux + 4.0 * lg.L + 8.0 * touched
+    bpr_bytes = 24.0 * lg.L
+    roof_scatter = dict(bound="hbm", kernel="zero-fill + k_recount (per-link volume = histogram of cur_link; warp-merged, "
+                                            "staged in a shared-memory histogram per 1024-agent tile)",
+                        us_per_launch=tp["recount_us"], algorithmic_bytes_per_launch=sc_bytes,
+                        achieved=sc_bytes / (tp["recount_us"] * 1e-6) / 1e9, peak=peak, unit="GB/s",
+                        frac=sc_bytes / (tp["recount_us"] * 1e-6) / 1e9 / peak, traffic=None, peak_source=peak_src,
+                        agents=n_local, moving_agents=mv_aux, links=lg.L, links_touched=touched,
+                        note="1 B state per agent + 4 B cur_link per moving agent + 4 B zero-fill per link + 8 B RMW per "
+                             "touched link (SURVEY.md 8d); %.1f MB at this size = %.1f us at peak: launch-latency-bound"
+                             % (sc_bytes / 1e6, sc_bytes / peak / 1e3))
+    roof_bpr = dict(bound="hbm", kernel="k_travel_times (tt = t0 / factor(occ), fused elementwise pass over the link arrays)",
+                    us_per_launch=tp["travel_times_us"], algorithmic_bytes_per_launch=bpr_bytes,
+                    achieved=bpr_bytes / (tp["travel_times_us"] * 1e-6) / 1e9, peak=peak, unit="GB/s",
+                    frac=bpr_bytes / (tp["travel_times_us"] * 1e-6) / 1e9 / peak, traffic=None, peak_source=peak_src,
+                    links=lg.L, note="24 B per link: occ 4 R + capacity class 4 R + t0 8 R + tt 8 W (SURVEY.md 8d)")
+    # ---- multi-GPU: north_star's dense per-tick all-reduce of the volume vector, as the labelled baseline next to
+    # the sparse event exchange the tick uses (SURVEY.md H6 "report both")
+    dense = None
+    if sharded is not None:
+        barrier()
+        vol = sharded.dense_volume_allreduce()
+        same = bool(np.array_equal(vol.cpu().numpy(), sharded.occupancy()))
+        iters = 50
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        d0.record(bench_stream)
+        for _ in range(iters):
+            sharded.dense_volume_allreduce()
+        d1.record(bench_stream)
+        barrier()
+        us = 1e3 * d0.elapsed_time(d1) / iters
+        tt = torch.tensor([us], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        us = float(tt.item())
+        payload = 4 * lg.L
+        dense = dict(us_per_tick=us, payload_bytes=payload, bus_gbs=2.0 * (world - 1) / world * payload / (us * 1e-6) / 1e9,
+                     equals_event_exchange_volumes=same,
+                     note="recount of this rank's agents + ncclAllReduce(int32[L], sum) per tick (max over ranks); "
+                          "volumes only: a sum cannot order one tick's entries across ranks (SURVEY.md 0-5), so the "
+                          "tick exchanges link events instead -- compare with tick_only.exchange_tick_us")
     # ---- roofline pass: per-launch CUDA-event timing of the advance kernel on the engine stream
     stm0 = eng.stats()
     eng.set_profiling(True)
@@ -442,7 +490,6 @@ def run_b200(args):
     waiting = n_local - moving
     adv_ms = kt["advance_ms"] / max(kt["advance_launches"], 1)
     alg_bytes = waiting * 1.0 + moving * 33.0  # 1 B per waiting, 33 B per moving agent-step
-    peak, peak_src = peaks()
     achieved = alg_bytes / (adv_ms * 1e-3) / 1e9 if adv_ms > 0 else 0.0
     roof_adv = dict(bound="hbm", kernel="k_advance (standalone launch, CUDA events on the engine stream)",
                     achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
@@ -573,6 +620,7 @@ def run_b200(args):
                      phases={k: (round(v, 3) if isinstance(v, float) else v) for k, v in e2e_phases.items()}),
             gpu_launches=int(launches), router_stats={k: (round(v, 3) if isinstance(v, float) else v) for k, v in trees.items()},
             roofline=roof, roofline_advance=roof_adv, roofline_advance_saturated=sat,
+            roofline_scatter=roof_scatter, roofline_bpr=roof_bpr, dense_allreduce=dense,
             parity_check=parity, tick_only=tick_only,
             label_router=(dict(queries=lab["queries"], launches=lab["launches"], query_kernel_ms=round(lab["query_ms"], 4),
                                entries_read=lab["entries_read"], algorithmic_bytes=12 * lab["entries_read"],

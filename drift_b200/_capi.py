@@ -35,7 +35,8 @@ class GraphDesc(C.Structure):
 class StatsOut(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "moving_agents", "total_agents_on_roads", "total_capacity", "links_with_traffic",
-        "arrivals_total", "departures_total", "route_arena_used", "events_last_tick", "arena_compactions", "fallback_routes")]
+        "arrivals_total", "departures_total", "route_arena_used", "events_last_tick", "arena_compactions", "fallback_routes",
+        "tie_fallbacks")]
 
 
 class HierDesc(C.Structure):
@@ -77,12 +78,16 @@ SIGNATURES = {
     "drift_invalidate_prefetch": (C.c_int, [ENGINE, C.c_double, C.c_double, C.c_int32]),
     "drift_read_occupancy": (C.c_int, [ENGINE, c_i32p]),
     "drift_recount_occupancy": (C.c_int, [ENGINE, c_i32p]),
+    "drift_recount_device": (C.c_int, [ENGINE]),
     "drift_read_travel_times": (C.c_int, [ENGINE, c_f64p]),
     "drift_read_agents": (C.c_int, [ENGINE, c_u8p, c_f64p, c_f64p, c_f64p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p]),
     "drift_read_agent_route": (C.c_int, [ENGINE, C.c_int64, c_i32p, C.c_int64, c_i64p]),
     "drift_export_routes": (C.c_int, [ENGINE, C.c_int64, c_i32p, c_i32p, c_f64p, c_i32p, C.c_int64]),
     "drift_drain_arrivals": (C.c_int, [ENGINE, c_i32p, c_i32p, C.c_int64, c_i64p]),
     "drift_drain_departures": (C.c_int, [ENGINE, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int64, c_i64p]),
+    "drift_drain_departures_routes": (C.c_int, [ENGINE, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i64p, c_i32p, c_i32p,
+                                                C.c_int64, c_i64p]),
+    "drift_export_logged_routes": (C.c_int, [ENGINE, C.c_int64, c_i64p, c_i32p, c_i32p, c_f64p, c_i32p, C.c_int64]),
     "drift_enable_entry_trace": (C.c_int, [ENGINE, C.c_int64]),
     "drift_drain_entries": (C.c_int, [ENGINE, c_i32p, c_i32p, c_i32p, c_f64p, C.c_int64, c_i64p]),
     "drift_stats": (C.c_int, [ENGINE, C.POINTER(StatsOut)]),

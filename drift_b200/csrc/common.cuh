@@ -59,6 +59,7 @@ struct Counters {
   unsigned long long n_fallback;      // departures routed inside the tick because no planned route was ready
   unsigned long long label_entries;   // hub-label router: label entries read by the queries (roofline accounting)
   unsigned long long label_queries;
+  unsigned long long n_tie_fallback;  // batched router: queries re-run by the NetworkX-exact router (possible ties)
 };
 
 constexpr int kOvfEvents = 1;
@@ -134,6 +135,10 @@ struct DemandArgs {  // device-driven demand (drift_run)
   int32_t* log_src;
   int32_t* log_dst;
   int32_t* log_status;
+  long long* log_off;          // where the departure's route sits in the arena (valid until the next compaction) ...
+  int32_t* log_len;            // ... its hops ...
+  int32_t* log_epoch;          // ... and the number of compactions so far (trip records: drift_export_logged_routes)
+  int32_t epoch;
   unsigned long long log_cap;
   unsigned long long log_drained;
 };

@@ -163,7 +163,8 @@ struct drift_engine {
   int32_t t_pop_thresh = 16;  // destinations asked for more often than this over ~64 batches get a cached tree
   DevBuf<uint8_t> t_q_side;
   DevBuf<uint32_t> t_iter, t_slot_stamp;
-  DevBuf<int32_t> t_slot_owner, t_slot_job, t_job_qhead, t_job_cnt, t_q_next;
+  DevBuf<int32_t> t_slot_owner, t_slot_job, t_job_qhead, t_job_cnt, t_q_next, t_tie_list;
+  int32_t detect_ties = 1;  // option "detect_ties": possible ties of the batched router go to the NetworkX-exact one
   DevBuf<uint32_t> t_slot_job_batch;
   int32_t t_bounded_max = -1;  // -1 = automatic: bounded search only when the cache cannot hold every destination
   int32_t t_threads = 256;
@@ -199,7 +200,8 @@ struct drift_engine {
   DevBuf<double> ent_speed;
   int64_t ent_cap = 0;
   unsigned long long ent_drained = 0;
-  DevBuf<int32_t> dl_agent, dl_tick, dl_src, dl_dst, dl_status;
+  DevBuf<int32_t> dl_agent, dl_tick, dl_src, dl_dst, dl_status, dl_len, dl_epoch;
+  DevBuf<long long> dl_off;
   int64_t dl_cap = 0;
   unsigned long long dl_drained = 0;
   // demand
@@ -506,6 +508,7 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
       const int64_t need = std::max<int64_t>(e->q_cap, Q + q0);
       CU(e->t_q_next.alloc(need, false));
       CU(e->t_q_side.alloc(need, false));
+      CU(e->t_tie_list.alloc(need, false));
       // per-batch job table: at most one job per query (bounded searches take no cache slot)
       CU(e->t_job_qhead.alloc(need + e->t_max_slots));
       CU(e->t_job_cnt.alloc(need + e->t_max_slots));
@@ -528,6 +531,7 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
                                            : ((e->t_max_slots >= e->V && !use_congested) ? 0 : kMaxBounded);
     // with full trees only, every key of a batch needs a slot: source-side keys only if all 2V fit
     tc.sides = (tc.bounded_max == 0 && e->t_max_slots < 2 * e->V) ? 1 : e->t_sides;
+    tc.detect_ties = e->detect_ties;
     CU(cudaMemsetAsync(out.status, 0xff, sizeof(int32_t) * Q, e->stream));  // -1 = not answered yet
     tc.n_jobs = e->t_ctl.p + 1;
     tc.job_cursor = e->t_ctl.p + 2;
@@ -564,6 +568,34 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
                                                 (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
     CU(cudaGetLastError());
     e->total_launches += 6;
+    if (tc.detect_ties) {
+      // queries whose shortest path may not be unique (exactly or within rounding) go through the NetworkX-exact
+      // router, which reproduces the reference's tie-breaking (nx:weighted.py:2387-2459); rare on continuous weights
+      k_collect_ties<<<gq, 256, 0, e->stream>>>(Q, n_dev, out.status, e->t_tie_list.p, e->t_ctl.p + 3, e->ctr.p);
+      int32_t n_ties = 0;
+      CU(cudaMemcpyAsync(&n_ties, e->t_ctl.p + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+      CU(cudaStreamSynchronize(e->stream));
+      e->total_launches += 1;
+      if (n_ties > 0) {
+        const int64_t per_worker = 2 * (int64_t)e->V * 16 + 2 * (int64_t)(e->Ef + 2) * (int64_t)sizeof(HeapItem);
+        const int64_t want = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n_ties, 256), ((int64_t)2 << 30) / per_worker));
+        rc = ensure_router(e, want);
+        if (rc) return rc;
+        RouteScratch sc;
+        sc.seen = e->r_seen.p;
+        sc.plink = e->r_plink.p;
+        sc.mark = e->r_mark.p;
+        sc.heap = e->r_heap.p;
+        sc.epoch = e->r_epoch.p;
+        sc.heap_cap = e->r_heap_cap;
+        sc.workers = (int32_t)std::min<int64_t>(e->r_workers, n_ties);
+        k_route_nx<<<(sc.workers + 31) / 32, 32, 0, e->stream>>>(e->graph(), wf, wb, n_ties, qs, qd, sc, e->arena.p,
+                                                                 (unsigned long long)e->arena_cap, e->ctr.p, out, lc,
+                                                                 nullptr, e->t_tie_list.p);
+        CU(cudaGetLastError());
+        e->total_launches += 1;
+      }
+    }
     return DRIFT_OK;
   }
   int rc = ensure_router(e, Q);
@@ -620,6 +652,10 @@ TickArgs make_tick_args(drift_engine* e, double delta, bool demand) {
     p.dm.log_src = e->dl_src.p;
     p.dm.log_dst = e->dl_dst.p;
     p.dm.log_status = e->dl_status.p;
+    p.dm.log_off = e->dl_off.p;
+    p.dm.log_len = e->dl_len.p;
+    p.dm.log_epoch = e->dl_epoch.p;
+    p.dm.epoch = (int32_t)e->compactions;
     p.dm.log_cap = (unsigned long long)e->dl_cap;
     p.dm.log_drained = e->dl_drained;
     p.fsc.seen = e->f_seen.p;
@@ -892,6 +928,9 @@ int drift_add_agents(drift_engine* e, int64_t n_agents, int64_t agent_base, int6
   CU(e->dl_src.alloc(e->dl_cap));
   CU(e->dl_dst.alloc(e->dl_cap));
   CU(e->dl_status.alloc(e->dl_cap));
+  CU(e->dl_off.alloc(e->dl_cap));
+  CU(e->dl_len.alloc(e->dl_cap));
+  CU(e->dl_epoch.alloc(e->dl_cap));
   CU(e->dep_req.alloc(n_agents));
   e->N = n_agents;
   e->Npad = Np;
@@ -1356,6 +1395,16 @@ int drift_recount_occupancy(drift_engine* e, int32_t* occ_out) {
   return DRIFT_OK;
 }
 
+int drift_recount_device(drift_engine* e) {
+  if (!e || !e->N) return fail(DRIFT_EINVAL, "drift_recount_device");
+  CU(cudaSetDevice(e->device));
+  CU(cudaMemsetAsync(e->hist.p, 0, sizeof(int32_t) * e->L, e->stream));
+  k_recount<<<grid_for(e->N, kRecThreads * kRecPerThread, kSMs * 8), kRecThreads, 0, e->stream>>>(e->agents(), e->hist.p);
+  CU(cudaGetLastError());
+  e->total_launches += 1;
+  return DRIFT_OK;
+}
+
 int drift_read_travel_times(drift_engine* e, double* tt_out) {
   if (!e || !tt_out) return fail(DRIFT_EINVAL, "drift_read_travel_times");
   CU(cudaSetDevice(e->device));
@@ -1490,6 +1539,61 @@ int drift_drain_departures(drift_engine* e, int32_t* agent, int32_t* tick, int32
                     {4, 4, 4, 4, 4});
 }
 
+int drift_drain_departures_routes(drift_engine* e, int32_t* agent, int32_t* tick, int32_t* src, int32_t* dst,
+                                  int32_t* status, int64_t* route_off, int32_t* route_len, int32_t* route_epoch,
+                                  int64_t cap, int64_t* n) {
+  if (!e || !n || cap < 0) return fail(DRIFT_EINVAL, "drift_drain_departures_routes");
+  CU(cudaSetDevice(e->device));
+  Counters c;
+  int rc = fetch_counters(e, &c);
+  if (rc) return rc;
+  rc = check_overflow(e, c);
+  if (rc) return rc;
+  return drain_ring(e, c.n_departures, &e->dl_drained, e->dl_cap, cap, n,
+                    {{agent, e->dl_agent.p}, {tick, e->dl_tick.p}, {src, e->dl_src.p}, {dst, e->dl_dst.p},
+                     {status, e->dl_status.p}, {route_off, e->dl_off.p}, {route_len, e->dl_len.p},
+                     {route_epoch, e->dl_epoch.p}},
+                    {4, 4, 4, 4, 4, 8, 4, 4});
+}
+
+int drift_export_logged_routes(drift_engine* e, int64_t n, const int64_t* route_off, const int32_t* route_len,
+                               const int32_t* route_epoch, double* metres, int32_t* links_out, int64_t cap) {
+  if (!e || n < 0 || (n && (!route_off || !route_len || !route_epoch || !metres)))
+    return fail(DRIFT_EINVAL, "drift_export_logged_routes");
+  CU(cudaSetDevice(e->device));
+  if (n == 0) return DRIFT_OK;
+  std::vector<int64_t> off(n + 1, 0);
+  for (int64_t r = 0; r < n; ++r) {
+    if (route_epoch[r] != (int32_t)e->compactions)
+      return fail(DRIFT_ESTATE, "drift_export_logged_routes: the route arena was compacted since departure %lld was "
+                                "logged; drain and export after every block of at most route_window ticks", (long long)r);
+    if (route_len[r] < 0 || route_off[r] < 0 || route_off[r] + route_len[r] > e->arena_cap)
+      return fail(DRIFT_EINVAL, "drift_export_logged_routes: bad arena range");
+    off[r + 1] = off[r] + route_len[r];
+  }
+  if (links_out && off[n] > cap) return fail(DRIFT_EINVAL, "drift_export_logged_routes: output buffer too small");
+  DevBuf<long long> d_off;
+  DevBuf<int32_t> d_len, d_links;
+  DevBuf<int64_t> d_out;
+  DevBuf<double> d_m;
+  CU(d_off.upload((const long long*)route_off, n));
+  CU(d_len.upload(route_len, n));
+  CU(d_m.alloc(n));
+  if (links_out && off[n] > 0) {
+    CU(d_out.upload(off.data(), n + 1));
+    CU(d_links.alloc(off[n], false));
+  }
+  CU(cudaStreamSynchronize(e->stream));
+  k_gather_logged<<<grid_for(n, 128, kSMs * 8), 128, 0, e->stream>>>(n, d_off.p, d_len.p, e->arena.p, e->link_len.p,
+                                                                     d_out.p, d_links.p, d_m.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(metres, d_m.p, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
+  if (links_out && off[n] > 0)
+    CU(cudaMemcpyAsync(links_out, d_links.p, sizeof(int32_t) * off[n], cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return DRIFT_OK;
+}
+
 int drift_enable_entry_trace(drift_engine* e, int64_t cap) {
   if (!e || cap < 0) return fail(DRIFT_EINVAL, "drift_enable_entry_trace");
   CU(cudaSetDevice(e->device));
@@ -1542,6 +1646,7 @@ int drift_stats(drift_engine* e, drift_stats_out* out) {
   out->route_arena_used = (int64_t)h.arena_cursor;
   out->arena_compactions = e->compactions;
   out->fallback_routes = (int64_t)h.n_fallback;
+  out->tie_fallbacks = (int64_t)h.n_tie_fallback;
   out->events_last_tick = 0;
   for (int sb = 0; sb < kEvSub; ++sb) out->events_last_tick += h.n_events[e->tick & 1][sb];
   return check_overflow(e, h);
@@ -2074,6 +2179,8 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
     e->t_pop_thresh = (int32_t)value;
   } else if (s == "arena_compact_frac") {
     e->arena_compact_frac = std::min(0.95, std::max(0.05, value));
+  } else if (s == "detect_ties") {
+    e->detect_ties = value != 0;
   } else if (s == "use_labels") {
     e->labels_enabled = value != 0;
   } else if (s == "debug_mask") {
@@ -2083,6 +2190,15 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
     // exchange is connected; the state is NOT the sharded run's afterwards
     if (!e->p2p.world || !e->p2p_inbox.p) return fail(DRIFT_ESTATE, "p2p_suspend: no peer exchange to suspend");
     e->p2p_on = value == 0;
+    if (!e->p2p_on) {
+      // with the peer exchange a link's volume lives on its owner; a local run needs the volumes of THIS rank's
+      // agents on every link: recount them (otherwise leaving agents would drive the local counts negative)
+      CU(cudaSetDevice(e->device));
+      CU(cudaMemsetAsync(e->hist.p, 0, sizeof(int32_t) * e->L, e->stream));
+      k_recount<<<grid_for(e->N, kRecThreads * kRecPerThread, kSMs * 8), kRecThreads, 0, e->stream>>>(e->agents(), e->hist.p);
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(e->occ.p, e->hist.p, sizeof(int32_t) * e->L, cudaMemcpyDeviceToDevice, e->stream));
+    }
   } else if (s == "tree_sides") {
     if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_sides must be set before the first batched route");
     e->t_sides = value >= 2 ? 2 : 1;
@@ -2111,6 +2227,7 @@ int drift_device_ptr(drift_engine* e, const char* name, void** ptr, int64_t* n_e
   int64_t n = 0;
   void* p = nullptr;
   if (s == "occ") p = e->occ.p, n = e->L;
+  else if (s == "volume_recount") p = e->hist.p, n = e->L;
   else if (s == "state") p = e->state.p, n = e->N;
   else if (s == "dist") p = e->dist.p, n = e->N;
   else if (s == "speed") p = e->speed.p, n = e->N;

@@ -204,12 +204,14 @@ __global__ void __launch_bounds__(32) k_route_nx(GraphArrays g, const double* __
                                                   RouteScratch sc, int32_t* __restrict__ arena,
                                                   unsigned long long arena_cap, Counters* ctr, RouteOut out,
                                                   const double* __restrict__ link_cost,
-                                                  const int32_t* __restrict__ n_dev) {
+                                                  const int32_t* __restrict__ n_dev,
+                                                  const int32_t* __restrict__ list = nullptr) {
   const int worker = blockIdx.x * blockDim.x + threadIdx.x;
   if (worker >= sc.workers) return;
   if (n_dev) Q = *n_dev;  // device-side batch size
   uint32_t epoch = sc.epoch[worker];
-  for (int64_t q = worker; q < Q; q += sc.workers) {
+  for (int64_t k = worker; k < Q; k += sc.workers) {
+    const int64_t q = list ? (int64_t)list[k] : k;  // list: only these queries of the batch (tie fallback)
     const RouteResult r = route_nx_one(g, w_fwd, w_bwd, src[q], dst[q], sc, worker, epoch, arena, arena_cap, ctr,
                                        link_cost);
     out.status[q] = r.status;
@@ -445,6 +447,23 @@ __global__ void k_gather_routes(int64_t n, const int32_t* __restrict__ agents, A
   }
 }
 
+// Trip-record export by arena position (routes logged at departure, drift_drain_departures_routes): metres
+// (left-to-right fp64 sum of the link lengths, data_logger.py:103-120) and, optionally, the links.
+__global__ void k_gather_logged(int64_t n, const long long* __restrict__ off, const int32_t* __restrict__ len,
+                                const int32_t* __restrict__ arena, const double* __restrict__ link_len,
+                                const int64_t* __restrict__ out_off, int32_t* __restrict__ out_links,
+                                double* __restrict__ out_metres) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    double m = 0.0;
+    for (int32_t k = 0; k < len[r]; ++k) {
+      const int32_t l = arena[off[r] + k];
+      m = __dadd_rn(m, link_len[l]);
+      if (out_links) out_links[out_off[r] + k] = l;
+    }
+    out_metres[r] = m;
+  }
+}
+
 // Waiting agents that will depart within the next n_ticks ticks (same Philox draws as the tick
 // kernel) drop their prefetched routes so that the next planning batch recomputes them on the
 // current travel times.
@@ -476,6 +495,7 @@ __global__ void k_store_prefetch(int64_t Q, const int32_t* __restrict__ q_agent,
 
 struct NodeRec;
 __global__ void k_init_noderecs(NodeRec* __restrict__ p, int64_t n);
+constexpr int32_t kStatusTie = -3;  // batched router: the shortest path may not be unique -> NetworkX-exact fallback
 
 // =====================================================================================
 // K5b: batched multi-source SSSP -- one reverse shortest-path tree per destination.
@@ -543,6 +563,7 @@ struct TreeCache {
   uint8_t* q_side;          // [Q] 0 = answered from the destination's tree, 1 = from the source's
   int32_t V;
   int32_t sides;            // 1 = destination trees only, 2 = both
+  int32_t detect_ties;      // 1 = flag queries whose shortest path may not be unique (kStatusTie)
 };
 
 constexpr int kMaxBounded = 8;
@@ -684,6 +705,39 @@ __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v
 // First entry e of [e0, e1) (CSR order) whose hop is tight: rec[col[e]].dist + w[e] == du.  The loads of
 // four entries are issued together (col/w, then the four labels), so a hop of the walk below costs
 // three dependent memory levels instead of two per entry.  Returns the entry, its label in *d_next.
+// A second entry whose hop is tight within kTieTol (relative) means the shortest path may not be unique -- or
+// unique only in one summation order: NetworkX sums forward labels from the source and backward labels from
+// the target (nx:weighted.py:2440-2452), this builder from the tree's root.  Such queries are re-run by the
+// NetworkX-exact router (k_route_nx), which reproduces the reference's tie-breaking.
+constexpr double kTieTol = 1e-12;
+
+__device__ __forceinline__ bool near_tight(double s, double du) { return fabs(s - du) <= kTieTol * du; }
+
+// Same, but scans every entry: returns the first exactly tight one and sets *tie when another entry is tight
+// within kTieTol.
+__device__ __forceinline__ int32_t find_tight_entry_ties(int32_t e0, int32_t e1, unsigned long long du,
+                                                         const NodeRec* __restrict__ rec,
+                                                         const int32_t* __restrict__ col, const double* __restrict__ w,
+                                                         unsigned long long* d_next, bool* tie) {
+  int32_t first = -1;
+  int near = 0;
+  const double dud = __longlong_as_double((long long)du);
+  for (int32_t e = e0; e < e1; ++e) {
+    const unsigned long long d = rec[col[e]].dist;
+    if (d == kInfBits) continue;
+    const double s = __dadd_rn(__longlong_as_double((long long)d), w[e]);
+    if (first < 0 && (unsigned long long)__double_as_longlong(s) == du) {
+      first = e;
+      *d_next = d;
+      ++near;
+    } else if (near_tight(s, dud)) {
+      ++near;
+    }
+  }
+  if (near > 1) *tie = true;
+  return first;
+}
+
 __device__ __forceinline__ int32_t find_tight_entry(int32_t e0, int32_t e1, unsigned long long du,
                                                     const NodeRec* __restrict__ rec, const int32_t* __restrict__ col,
                                                     const double* __restrict__ w, unsigned long long* d_next) {
@@ -721,11 +775,12 @@ __device__ __forceinline__ void route_from_labels(const GraphArrays& g, const do
                                                   int32_t* __restrict__ tmp, int32_t tmp_cap,
                                                   int32_t* __restrict__ arena, unsigned long long arena_cap,
                                                   Counters* ctr, const double* __restrict__ link_cost, int32_t q,
-                                                  const RouteOut& out) {
+                                                  const RouteOut& out, bool detect_ties) {
   const int64_t V = g.V;
   int32_t status = DRIFT_ROUTE_NOPATH, hops = 0;
   int64_t off = 0;
   double cost = 0.0;
+  bool tie = false;
   if (sn == dest) {
     status = DRIFT_ROUTE_TRIVIAL;
   } else if (sn >= 0 && sn < V && rec[sn].dist != kInfBits) {
@@ -734,7 +789,9 @@ __device__ __forceinline__ void route_from_labels(const GraphArrays& g, const do
     unsigned long long dx = rec[sn].dist;
     while (x != dest) {
       unsigned long long dn = 0;
-      const int32_t e = find_tight_entry(g.fwd_rowptr[x], g.fwd_rowptr[x + 1], dx, rec, g.fwd_col, w_fwd, &dn);
+      const int32_t e = detect_ties
+                            ? find_tight_entry_ties(g.fwd_rowptr[x], g.fwd_rowptr[x + 1], dx, rec, g.fwd_col, w_fwd, &dn, &tie)
+                            : find_tight_entry(g.fwd_rowptr[x], g.fwd_rowptr[x + 1], dx, rec, g.fwd_col, w_fwd, &dn);
       if (e < 0 || k > V) {
         k = -1;
         break;
@@ -744,7 +801,9 @@ __device__ __forceinline__ void route_from_labels(const GraphArrays& g, const do
       x = g.fwd_col[e];
       dx = dn;
     }
-    if (k > 0) {
+    if (tie) {
+      status = kStatusTie;  // answered by the NetworkX-exact router afterwards
+    } else if (k > 0) {
       hops = k;
       const unsigned long long o = atomicAdd(&ctr->arena_cursor, (unsigned long long)hops);
       if (o + hops > arena_cap) {
@@ -1016,7 +1075,7 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_tre
       if (threadIdx.x < nb) {
         const int32_t tcap = (int32_t)(V / kMaxBounded);
         route_from_labels(g, w_fwd, rec, s_bsrc[threadIdx.x], dest, farB + (int64_t)threadIdx.x * tcap, tcap, arena,
-                          arena_cap, ctr, link_cost, s_bq[threadIdx.x], out);
+                          arena_cap, ctr, link_cost, s_bq[threadIdx.x], out, tc.detect_ties != 0);
       }
       if (threadIdx.x == 0) tc.slot_of[dest] = -1;  // no tree was kept
       __syncthreads();
@@ -1039,8 +1098,12 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_tre
         const unsigned long long du = rec[u].dist;
         if (u != dest && du != kInfBits) {
           unsigned long long dn = 0;
-          const int32_t e = find_tight_entry(y_rowptr[u], y_rowptr[u + 1], du, rec, y_col, y_w, &dn);
-          if (e >= 0) nl = make_int2(y_link[e], y_col[e]);
+          bool tie = false;
+          const int32_t e = tc.detect_ties
+                                ? find_tight_entry_ties(y_rowptr[u], y_rowptr[u + 1], du, rec, y_col, y_w, &dn, &tie)
+                                : find_tight_entry(y_rowptr[u], y_rowptr[u + 1], du, rec, y_col, y_w, &dn);
+          // bit 31 of the node field: more than one (nearly) tight hop leaves this node
+          if (e >= 0) nl = make_int2(y_link[e], y_col[e] | (tie ? (int32_t)0x80000000 : 0));
         }
         next_link[u] = nl;
       }
@@ -1112,6 +1175,7 @@ __global__ void k_extract_paths(GraphArrays g, int64_t Q, const int32_t* __restr
     const int32_t from = out_tree ? t : s, to = out_tree ? s : t;
     int hops = 0;
     int32_t x = from;
+    int32_t tie = 0;
     while (x != to) {
       const int2 en = next_link[x];
       if (en.x < 0 || hops > g.V) {
@@ -1119,10 +1183,15 @@ __global__ void k_extract_paths(GraphArrays g, int64_t Q, const int32_t* __restr
         break;
       }
       ++hops;
-      x = en.y;
+      tie |= en.y;
+      x = en.y & 0x7fffffff;
     }
     if (hops < 0) {
       out.status[q] = DRIFT_ROUTE_NOPATH;
+      continue;
+    }
+    if (tie < 0) {  // some node on the way has several (nearly) tight hops: the NetworkX-exact router decides
+      out.status[q] = kStatusTie;
       continue;
     }
     const unsigned long long off = atomicAdd(&ctr->arena_cursor, (unsigned long long)hops);
@@ -1138,13 +1207,13 @@ __global__ void k_extract_paths(GraphArrays g, int64_t Q, const int32_t* __restr
         const int2 en = next_link[x];
         arena[off + k] = en.x;
         c = __dadd_rn(c, link_cost[en.x]);
-        x = en.y;
+        x = en.y & 0x7fffffff;
       }
     } else {
       for (int k = hops - 1; k >= 0; --k) {
         const int2 en = next_link[x];
         arena[off + k] = en.x;
-        x = en.y;
+        x = en.y & 0x7fffffff;
       }
       for (int k = 0; k < hops; ++k) c = __dadd_rn(c, link_cost[arena[off + k]]);
     }
@@ -1153,6 +1222,17 @@ __global__ void k_extract_paths(GraphArrays g, int64_t Q, const int32_t* __restr
     out.off[q] = (int64_t)off;
     out.cost[q] = c;
   }
+}
+
+// Queries the batched router left to the NetworkX-exact one (kStatusTie): their indices, compacted.
+__global__ void k_collect_ties(int64_t Q, const int32_t* __restrict__ n_dev, const int32_t* __restrict__ status,
+                               int32_t* __restrict__ list, int32_t* __restrict__ n_list, Counters* ctr) {
+  const int64_t n = n_dev ? (int64_t)*n_dev : Q;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
+    if (status[q] == kStatusTie) {
+      list[atomicAdd(n_list, 1)] = (int32_t)q;
+      atomicAdd(&ctr->n_tie_fallback, 1ULL);
+    }
 }
 
 }  // namespace drift

@@ -84,7 +84,9 @@ __device__ __forceinline__ double bpr_factor_lookup(const LinkArrays& lk, int32_
 __device__ __forceinline__ void emit_event(const LinkArrays& lk, Event* __restrict__ events, int slot, int32_t link,
                                            uint32_t agent, int32_t kind, uint32_t tag) {
   const unsigned long long mine = ((unsigned long long)tag << 32) | (uint32_t)slot;
-  const int32_t occ0 = lk.occ[link];  // issued alongside the exchange: only the first event needs it
+  // issued alongside the exchange: only the first event needs it.  Never negative in a consistent state; the clamp
+  // keeps the aux encoding (and so the list walks of phase C) well-formed whatever the state
+  const int32_t occ0 = max(lk.occ[link], 0);
   const unsigned long long prev = atomicExch(&lk.head[link], mine);
   Event e;
   e.link = link;
@@ -239,6 +241,9 @@ __device__ __noinline__ bool depart_agent(const TickArgs& p, int64_t i, int cnt,
     p.dm.log_src[k] = src;
     p.dm.log_dst[k] = dst;
     p.dm.log_status[k] = ns - 1;
+    p.dm.log_off[k] = noff;
+    p.dm.log_len[k] = go ? nlen : 0;
+    p.dm.log_epoch[k] = p.dm.epoch;
   } else {
     atomicOr(&ctr->overflow, kOvfDepLog);
   }
@@ -486,6 +491,9 @@ __device__ __noinline__ void phase_inject(const TickArgs& p, int32_t tick, int n
         p.dm.log_src[k] = s;
         p.dm.log_dst[k] = t;
         p.dm.log_status[k] = rr.status;
+        p.dm.log_off[k] = rr.off;
+        p.dm.log_len[k] = rr.n_links;
+        p.dm.log_epoch[k] = p.dm.epoch;
       } else {
         atomicOr(&p.ctr->overflow, kOvfDepLog);
       }
@@ -571,7 +579,7 @@ __device__ __forceinline__ void resolve_one(const LinkArrays& lk, const AgentArr
   }
   if (first == e) lk.occ[ev.link] = occ0 + net;
   if (mine) {
-    const int32_t count = occ0 + before + 1;  // includes the entering agent itself
+    const int32_t count = max(occ0 + before + 1, 0);  // includes the entering agent itself (>= 1 in a consistent state)
     // host-tabulated max(0.1, 1/(1+alpha*(count/cap)**beta)) (traffic_manager.py:88-107), saturated at the floor
     int64_t idx = f_lo + (int64_t)count;
     if (idx >= f_hi) idx = f_hi - 1;
@@ -876,6 +884,9 @@ __device__ __noinline__ void phase_inject_p2p(const TickArgs& p, const P2PArgs& 
         p.dm.log_src[k] = s;
         p.dm.log_dst[k] = t;
         p.dm.log_status[k] = rr.status;
+        p.dm.log_off[k] = rr.off;
+        p.dm.log_len[k] = rr.n_links;
+        p.dm.log_epoch[k] = p.dm.epoch;
       } else {
         atomicOr(&p.ctr->overflow, kOvfDepLog);
       }
@@ -917,7 +928,7 @@ __device__ __forceinline__ bool resolve_one_p2p(const TickArgs& p, const P2PArgs
     int home;
     uint32_t li;
     p2p_home(x, ev.agent, home, li);
-    const int32_t count = occ0 + before + 1;  // includes the entering agent itself
+    const int32_t count = max(occ0 + before + 1, 0);  // includes the entering agent itself
     int64_t idx = f_lo + (int64_t)count;
     if (idx >= f_hi) idx = f_hi - 1;
     x.speed[home][li] = __dmul_rn(__dmul_rn(v0, lk.factor[idx]), p.kph_to_mps);  // the home rank waits for it per agent

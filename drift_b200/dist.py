@@ -107,6 +107,18 @@ class ShardedEngine:
         dist.all_reduce(t, group=self.group)
         return t.cpu().numpy()
 
+    def dense_volume_allreduce(self):
+        """North_star's literal exchange ("report both"): every rank recounts the volumes of ITS agents
+        (histogram of cur_link) and the dense int32[L] vector is summed with one ``all_reduce`` (NCCL).  Returns the
+        global volume vector as a device tensor (valid until the next call).  This is a throughput / validation
+        mode: the sum alone cannot order the entries of one tick across ranks, so the tick itself
+        exchanges link events instead; the result equals ``occupancy()``."""
+        ptr, n = self.engine.device_ptr("volume_recount")
+        self.engine.recount_device()
+        t = torch.as_tensor(_DevPtr(ptr, n), device=self.device)
+        dist.all_reduce(t, group=self.group)
+        return t
+
     def _set_cap(self, cap):
         cap = int(cap)
         if cap == self.cap:

@@ -239,6 +239,10 @@ class Engine:
         _capi.check(self._lib.drift_recount_occupancy(self._h, _p(out, C.c_int32)))
         return out[:self.lg.L]
 
+    def recount_device(self):
+        """Volume recount left in the device buffer ``volume_recount`` (asynchronous)."""
+        _capi.check(self._lib.drift_recount_device(self._h))
+
     def travel_times(self):
         out = np.zeros(max(self.lg.L, 1))
         _capi.check(self._lib.drift_read_travel_times(self._h, _p(out, C.c_double)))
@@ -308,6 +312,28 @@ class Engine:
         """(agent, tick, src, dst, status) of device-driven departures since the last drain."""
         i32 = (np.int32, C.c_int32)
         return self._drain(self._lib.drift_drain_departures, [i32] * 5)
+
+    def drain_departures_routes(self):
+        """(agent, tick, src, dst, status, route_off, route_len, route_epoch): the departure log with the arena
+        position of every route, for ``export_logged_routes``."""
+        i32 = (np.int32, C.c_int32)
+        return self._drain(self._lib.drift_drain_departures_routes, [i32] * 5 + [(np.int64, C.c_int64), i32, i32])
+
+    def export_logged_routes(self, route_off, route_len, route_epoch, with_links=False):
+        """(metres float64[], links list-of-arrays | None) of routes logged at departure; call before the next
+        planning window can compact the arena (i.e. after every block of at most ``route_window`` ticks)."""
+        off, ln, ep = _i64(route_off), _i32(route_len), _i32(route_epoch)
+        n = len(off)
+        m = np.zeros(max(n, 1))
+        if n == 0:
+            return m[:0], ([] if with_links else None)
+        total = int(ln.sum()) if with_links else 0
+        flat = np.zeros(max(total, 1), dtype=np.int32)
+        _capi.check(self._lib.drift_export_logged_routes(self._h, n, _p(off, C.c_int64), _p(ln, C.c_int32),
+                                                         _p(ep, C.c_int32), _p(m, C.c_double),
+                                                         _p(flat, C.c_int32) if with_links else None, total))
+        links = np.split(flat[:total], np.cumsum(ln)[:-1]) if with_links else None
+        return m[:n], links
 
     def discard_logs(self):
         """Advance the arrival / departure rings past everything logged so far without copying it out

@@ -66,6 +66,11 @@ def graph_digest(lg):
 def build(lg, witness_settled=100, time_limit_s=0.0):
     """Contract the graph.  Raises ``_capi.DriftError`` (DRIFT_ESTATE) when ``time_limit_s`` is hit."""
     lib = _capi.load()
+    if len(lg.fwd_w) >= 64 and len(np.unique(lg.fwd_w)) < 0.5 * len(lg.fwd_w):
+        # e.g. the bundled graphs: one travel_time value for every link (SURVEY.md 0-7) -> most queries tie and the
+        # reference's answer depends on NetworkX's search order, which only the exact router reproduces
+        raise ValueError("tie-prone graph (few distinct travel times): the hub-label router needs unique shortest "
+                         "paths; use ROUTER_BATCHED without a hierarchy (tie detector + exact fallback) or ROUTER_NX_EXACT")
     rp = np.ascontiguousarray(lg.fwd_rowptr, dtype=np.int32)
     col = np.ascontiguousarray(lg.fwd_col, dtype=np.int32)
     w = np.ascontiguousarray(lg.fwd_w, dtype=np.float64)

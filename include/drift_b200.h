@@ -52,7 +52,10 @@ extern "C" {
 
 /* routing engines */
 #define DRIFT_ROUTER_NX_EXACT 0 /* bit-exact nx bidirectional_dijkstra order (nx:weighted.py:2387-2459) */
-#define DRIFT_ROUTER_BATCHED 1  /* batched multi-source label-correcting SSSP (unique-path graphs) */
+#define DRIFT_ROUTER_BATCHED 1  /* batched router: cached shortest-path trees / bounded searches (or hub labels, see
+                                  drift_set_hierarchy); a query whose shortest path may not be unique -- a second hop
+                                  tight within 1e-12 -- is re-run by the NetworkX-exact router, so the link sequences
+                                  equal NetworkX's on tie-prone graphs too (option "detect_ties", default 1) */
 
 typedef struct drift_engine drift_engine;
 
@@ -88,6 +91,7 @@ typedef struct drift_stats_out {
   int64_t events_last_tick;
   int64_t arena_compactions;     /* times the live routes were copied into the spare arena */
   int64_t fallback_routes;       /* departures routed inside a tick because no planned route was ready */
+  int64_t tie_fallbacks;         /* batched-router queries re-run by the NetworkX-exact router (possible ties) */
 } drift_stats_out;
 
 const char* drift_last_error(void);
@@ -178,6 +182,9 @@ int drift_invalidate_prefetch(drift_engine* e, double t0, double delta, int32_t 
 /* Readback.  Any output pointer may be NULL. */
 int drift_read_occupancy(drift_engine* e, int32_t* occ_out /* [L] */);
 int drift_recount_occupancy(drift_engine* e, int32_t* occ_out /* [L] */); /* histogram of cur_link (traffic_manager.py:122-135) */
+/* The same recount left on the device (asynchronous; buffer "volume_recount" of drift_device_ptr): the payload of
+ * the dense per-tick ncclAllReduce(int32[L]) mode of drift_b200/dist.py (north_star's literal design). */
+int drift_recount_device(drift_engine* e);
 int drift_read_travel_times(drift_engine* e, double* tt_out /* [L] */);
 int drift_read_agents(drift_engine* e, uint8_t* state, double* dist_on_link, double* speed, double* link_len,
                       int32_t* cur_link, int32_t* route_idx, int32_t* route_len, int32_t* trip_count,
@@ -190,6 +197,17 @@ int drift_export_routes(drift_engine* e, int64_t n, const int32_t* agents, int32
 int drift_drain_arrivals(drift_engine* e, int32_t* agent, int32_t* tick, int64_t cap, int64_t* n);
 int drift_drain_departures(drift_engine* e, int32_t* agent, int32_t* tick, int32_t* src, int32_t* dst,
                            int32_t* status, int64_t cap, int64_t* n);
+/* Same log with the arena position of each departure's route (offset, hops, compaction count at departure), and
+ * the export of such routes: metres (left-to-right fp64 sum of the link lengths, lib/data_logger.py:103-120) and,
+ * when links_out != NULL, the link ids concatenated in order (sum of route_len entries).  A logged position is
+ * valid until the next arena compaction (DRIFT_ESTATE afterwards): drain and export after every block of at most
+ * "route_window" ticks.  This is what keeps trip_distance_km / route_taken exact for agents that depart twice in a
+ * block or arrive before the block ends (drift_b200/block_runner.py). */
+int drift_drain_departures_routes(drift_engine* e, int32_t* agent, int32_t* tick, int32_t* src, int32_t* dst,
+                                  int32_t* status, int64_t* route_off, int32_t* route_len, int32_t* route_epoch,
+                                  int64_t cap, int64_t* n);
+int drift_export_logged_routes(drift_engine* e, int64_t n, const int64_t* route_off, const int32_t* route_len,
+                               const int32_t* route_epoch, double* metres, int32_t* links_out, int64_t cap);
 /* optional link-entry trace (tick, agent, link, speed) for parity tests */
 int drift_enable_entry_trace(drift_engine* e, int64_t cap);
 int drift_drain_entries(drift_engine* e, int32_t* tick, int32_t* agent, int32_t* link, double* speed,
@@ -323,13 +341,15 @@ int drift_host_pow(const double* x, double y, double* out, int64_t n);
  *   tree_delta_scale    multiplies the near-far bucket width; tree_threads: 64 / 128 / 256 threads per search
  *   arena_compact_frac  the live routes are compacted once this fraction of the route arena is used (0.75)
  *   time_plan           1 = time the planning batches with CUDA events (drift_phase_times / drift_tree_stats)
+ *   detect_ties         0 = the batched tree router returns A shortest path without the NetworkX-exact re-run of
+ *                       possible ties (default 1)
  *   use_labels          0 = ignore an uploaded hierarchy (DRIFT_ROUTER_BATCHED falls back to trees / bounded searches)
  *   debug_mask          timing probes only, results are then NOT the reference's: 1 = no departure draws,
  *                       2 = crossers stay on their link, 4 = events are not emitted (tools/tick_probe.py)
  * The tree_* budgets, tree_sides and tree_threads must be set before the first batched route. */
 int drift_set_option(drift_engine* e, const char* name, double value);
 /* Raw device pointers for PyTorch interop (tensor views of engine state). name in
- * {"occ","state","dist","speed","link_len","cur_link","events","travel_time"}. */
+ * {"occ","volume_recount","state","dist","speed","link_len","cur_link","events","travel_time"}. */
 int drift_device_ptr(drift_engine* e, const char* name, void** ptr, int64_t* n_elems);
 
 #ifdef __cplusplus

@@ -18,7 +18,11 @@ pytestmark = pytest.mark.gpu
     ("g40_congested", 0, 25, 1, 0), ("g100_random_s0", 0, 300, 1, 0), ("multi_random_s0", 0, 7, 1, 0),
     ("g40_congested", 0, 1, 1, 0), ("g40_congested", 0, 25, 0, 0), ("multi_random_s0", 0, 300, 0, 0),
     # lookahead planning: routes only for the departures the coming window's draws allow
-    ("g40_congested", 0, 25, 1, 1), ("g100_random_s0", 0, 50, 1, 1), ("multi_random_s0", 0, 7, 0, 1)])
+    ("g40_congested", 0, 25, 1, 1), ("g100_random_s0", 0, 50, 1, 1), ("multi_random_s0", 0, 7, 0, 1),
+    # the batched router (trees / bounded searches + tie detector -> NetworkX-exact fallback) on the bundled,
+    # tie-heavy graphs: the same link sequences as the reference's router, hence the same dynamics
+    ("g40_congested", 1, 25, 1, 0), ("g100_random_s0", 1, 300, 1, 0), ("multi_random_s0", 1, 7, 1, 1),
+    ("musicnet_random_s0", 1, 50, 1, 0)])
 def test_device_demand_matches_port(name, router, window, persistent, lookahead):
     from drift_b200.engine import Engine
     from drift_b200.graph import lower_graph

@@ -170,30 +170,54 @@ def test_batched_router_unique_paths_match_networkx():
     assert n_ok > Q // 2
 
 
+@pytest.mark.parametrize("bounded", [0, 8])
 @pytest.mark.parametrize("name", ["g100_random_s0", "musicnet_random_s0", "multi_random_s0"])
-def test_batched_router_costs_on_tie_graphs(name):
-    """With ties the batched router may pick another shortest path; its cost must be the optimum."""
-    from drift_b200.engine import Engine, ROUTE_OK, ROUTER_BATCHED, ROUTER_NX_EXACT
+def test_batched_router_equals_networkx_on_tie_graphs(name, bounded):
+    """Bundled graphs carry one travel_time value: most queries have several shortest paths and
+    the reference's answer depends on NetworkX's search order.  The batched router flags every query with a
+    second (nearly) tight hop and re-runs it through the NetworkX-exact router, so its link sequences equal
+    live nx.shortest_path -- from cached trees (bounded=0) and from bounded searches (bounded=8) alike."""
+    import networkx as nx
+    from drift_b200.engine import Engine, ROUTE_NOPATH, ROUTE_OK, ROUTE_TRIVIAL, ROUTER_BATCHED, ROUTER_NX_EXACT
     from drift_b200.graph import lower_graph
 
     case = golden.GoldenCase(name)
-    lg = lower_graph(case.nx_graph())
+    G = case.nx_graph()
+    lg = lower_graph(G)
+    nodes = list(G.nodes)
     rng = random.Random(1)
     Q = 800
     src = [rng.randrange(lg.V) for _ in range(Q)]
     dst = [rng.randrange(lg.V) for _ in range(Q)]
     with Engine(lg, 8, route_arena_links=1 << 22) as eng:
+        eng.set_option("bounded_max", bounded)
         st_b, nl_b, links_b = eng.route(src, dst, router=ROUTER_BATCHED)
         cost_b = eng.route_costs(Q)
+        ties = eng.stats()["tie_fallbacks"]
         st_x, nl_x, links_x = eng.route(src, dst, router=ROUTER_NX_EXACT)
         cost_x = eng.route_costs(Q)
-    assert np.array_equal(st_b, st_x)
+        # detector off: still optimal walks, but not necessarily NetworkX's
+        eng.set_option("detect_ties", 0)
+        st_o, nl_o, links_o = eng.route(src, dst, router=ROUTER_BATCHED)
+        cost_o = eng.route_costs(Q)
+    assert ties > Q // 10  # these graphs do tie
+    assert np.array_equal(st_b, st_x) and np.array_equal(nl_b, nl_x) and np.array_equal(cost_b, cost_x)
+    assert np.array_equal(st_o, st_x)
     ok = st_x == ROUTE_OK
-    assert np.all(np.abs(cost_b[ok] - cost_x[ok]) <= 1e-9 * np.abs(cost_x[ok]))
-    for q in np.nonzero(ok)[0]:  # a valid walk from src to dst
-        nodes = lg.links_to_nodes(src[q], links_b[q])
-        assert nodes[0] == src[q] and nodes[-1] == dst[q]
-        assert all(lg.link_u[l] == a for l, a in zip(links_b[q], nodes[:-1]))
+    assert np.all(np.abs(cost_o[ok] - cost_x[ok]) <= 1e-9 * np.abs(cost_x[ok]))
+    for q in range(Q):
+        s, t = src[q], dst[q]
+        if s == t:
+            assert st_b[q] == ROUTE_TRIVIAL
+            continue
+        try:
+            want = nx.shortest_path(G, nodes[s], nodes[t], weight="travel_time")
+        except nx.NetworkXNoPath:
+            assert st_b[q] == ROUTE_NOPATH
+            continue
+        assert [nodes[k] for k in lg.links_to_nodes(s, links_b[q])] == want, (s, t)
+        walk = lg.links_to_nodes(s, links_o[q])
+        assert walk[0] == s and walk[-1] == t and all(lg.link_u[l] == a for l, a in zip(links_o[q], walk[:-1]))
 
 
 def test_tree_cache_eviction():
