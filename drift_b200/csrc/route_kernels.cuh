@@ -1190,7 +1190,7 @@ __global__ void k_extract_paths(GraphArrays g, int64_t Q, const int32_t* __restr
       out.status[q] = DRIFT_ROUTE_NOPATH;
       continue;
     }
-    if (tie < 0) {  // some node on the way has several (nearly) tight hops: the NetworkX-exact router decides
+    if (tie < 0 && tc.detect_ties) {  // some node on the way has several (nearly) tight hops: the NetworkX-exact router decides
       out.status[q] = kStatusTie;
       continue;
     }
