@@ -126,6 +126,16 @@ constexpr int kMaxRanks = 16;
 // event and the next advance of that agent waits for a real (positive) speed -- per-agent hand-over
 // instead of a second all-rank barrier per tick.
 constexpr double kSpeedPending = -1.0;
+// Same, for an agent that CANNOT cross its new link in its first tick on it even at free-flow speed (the
+// common case: links are longer than one tick of travel): its first advance produces no event, so the home rank
+// does not wait for the owner at all -- it skips that advance (marking dist = -0.0) and applies it together with
+// the next one, when the owner's speed is guaranteed to have landed (the owner resolved tick k before it published
+// its events of tick k+1, which the home rank acquired before its own tick k+2).  Bit-exact: the two advances are
+// the same two fp64 operations, only later.
+constexpr double kSpeedDeferred = -2.0;
+constexpr long long kNegZeroBits = (long long)0x8000000000000000ULL;
+
+__device__ __forceinline__ bool owes_advance(double d) { return __double_as_longlong(d) == kNegZeroBits; }
 
 struct P2PArgs {
   int32_t rank, world;
@@ -162,6 +172,13 @@ __device__ __noinline__ double p2p_wait_speed(const double* p) {
   }
 }
 
+// kSpeedDeferred when even the free-flow speed (factor 1.0, the largest the BPR table holds) cannot carry the agent
+// over the whole link in one tick, else kSpeedPending.  Rounding is monotone, so the bound holds for every factor.
+__device__ __forceinline__ double first_tick_speed_marker(const LinkRec& r, double delta, double kph_to_mps) {
+  const double smax = __dmul_rn(__dmul_rn(r.v0, 1.0), kph_to_mps);
+  return __dadd_rn(0.0, __dmul_rn(smax, delta)) < r.len ? kSpeedDeferred : kSpeedPending;
+}
+
 __device__ __forceinline__ void stage_event(AdvSmem& sm, int32_t link, uint32_t agent, bool enter) {
   const int w = threadIdx.x >> 5;
   const int k = atomicAdd(&sm.n[w], 1);
@@ -181,8 +198,9 @@ __device__ __noinline__ bool cross_agent(const TickArgs& p, int64_t i, int32_t t
     // ... unless the link is resolved on another GPU (k_tick_loop_p2p): then the home rank does it here
     if (own_next) {
       a.next_link[i] = ri + 1 < a.route_len[i] ? p.arena[a.route_off[i] + ri + 1] : -1;
-      a.elen[i] = p.lk.len[nl];  // link tables are replicated: only the speed has to come from the owner
-      a.speed[i] = kSpeedPending;
+      const LinkRec r = p.lk.rec[nl];  // link tables are replicated: only the speed has to come from the owner
+      a.elen[i] = r.len;
+      a.speed[i] = first_tick_speed_marker(r, p.delta, p.kph_to_mps);
     }
     stage_event(sm, nl, a.base + (uint32_t)i, true);
     return false;
@@ -254,9 +272,10 @@ __device__ __noinline__ bool depart_agent(const TickArgs& p, int64_t i, int cnt,
   a.dist[i] = 0.0;
   a.cur_link[i] = fl;
   if (own_next) {
+    const LinkRec r = p.lk.rec[fl];
     a.next_link[i] = nl;
-    a.elen[i] = p.lk.len[fl];
-    a.speed[i] = kSpeedPending;
+    a.elen[i] = r.len;
+    a.speed[i] = first_tick_speed_marker(r, p.delta, p.kph_to_mps);
   }
   stage_event(sm, fl, a.base + (uint32_t)i, true);
   return true;
@@ -266,9 +285,10 @@ __device__ __noinline__ bool depart_agent(const TickArgs& p, int64_t i, int cnt,
 // its tile, when the owner of that link has had the time of a whole tile to deliver the entry speed.
 __device__ __noinline__ bool advance_late(const TickArgs& p, int64_t i, int32_t tick, AdvSmem& sm) {
   const AgentArrays& a = p.a;
-  const double d = a.dist[i];
+  double d = a.dist[i];
   const double el = __ldcg(a.elen + i);
   const double sp = p2p_wait_speed(a.speed + i);
+  if (owes_advance(d)) d = __dadd_rn(0.0, __dmul_rn(sp, p.delta));  // the advance skipped last tick (cannot cross)
   const double nd = __dadd_rn(d, __dmul_rn(sp, p.delta));  // agent.py:197-198
   if (nd >= el) {
     a.dist[i] = 0.0;
@@ -312,20 +332,30 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
         double d[4] = {d01.x, d01.y, d23.x, d23.y};
         double sp[4] = {s01.x, s01.y, s23.x, s23.y};
         const double el[4] = {e01.x, e01.y, e23.x, e23.y};
-        if (P2P) {  // entered a link last tick and the owner's speed has not landed yet: advanced last (below)
+        uint32_t skip = 0;  // P2P: first advance on a new link deferred to the next tick (kSpeedDeferred)
+        if (P2P) {  // entered a link last tick and the owner's speed has not landed yet
 #pragma unroll
           for (int j = 0; j < kAdvPerThread; ++j)
-            if (((st4 >> (8 * j)) & 0xffu) && sp[j] < 0.0) pend |= 1u << j;
+            if (((st4 >> (8 * j)) & 0xffu) && sp[j] < 0.0) {
+              if (sp[j] == kSpeedDeferred && !owes_advance(d[j]))
+                skip |= 1u << j;  // cannot cross this tick: no event, nothing to wait for
+              else
+                pend |= 1u << j;  // may cross at once (or already skipped once): advanced last (below)
+            }
         }
         uint32_t cross = 0;
 #pragma unroll
         for (int j = 0; j < kAdvPerThread; ++j) {
-          if (((st4 >> (8 * j)) & 0xffu) && !((pend >> j) & 1u)) {
+          if (((st4 >> (8 * j)) & 0xffu) && !(((pend | skip) >> j) & 1u)) {
             // two roundings, never contracted to an FMA (agent.py:197-198)
-            const double nd = __dadd_rn(d[j], __dmul_rn(sp[j], p.delta));
+            double dj = d[j];
+            if (P2P && owes_advance(dj)) dj = __dadd_rn(0.0, __dmul_rn(sp[j], p.delta));  // the skipped advance first
+            const double nd = __dadd_rn(dj, __dmul_rn(sp[j], p.delta));
             const bool c = nd >= el[j];  // agent.py:200-203: at most one link per tick, overshoot dropped
             d[j] = c ? 0.0 : nd;
             cross |= (c ? 1u : 0u) << j;
+          } else if (P2P && ((skip >> j) & 1u)) {
+            d[j] = __longlong_as_double(kNegZeroBits);  // owes this tick's advance
           }
         }
         *reinterpret_cast<double2*>(a.dist + i0) = make_double2(d[0], d[1]);
@@ -1009,7 +1039,10 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
       int r = 0;
       while (r + 1 < x.world && s_pref[r + 1] <= f) ++r;
       const bool remote = resolve_one_p2p(p, x, inbox, (par * x.world + r) * x.cap + (f - s_pref[r]));
-      if (remote && k == n_ticks - 1) __threadfence_system();  // landed before the launch-end barrier below
+      // system-scope fence by every thread that stored a speed into a peer: the speed is then ordered before this
+      // rank's next flag release, which is what lets the home rank defer an entrant's first advance by one tick
+      // without waiting (kSpeedDeferred), and before the launch-end barrier below
+      if (remote) __threadfence_system();
     }
     if (lead) ctr->phase_ns[2] += global_ns() - t0;
     // No all-rank barrier here: the next advance waits per agent for a pending entry speed, the inbox and
@@ -1022,6 +1055,14 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
   if (blockIdx.x == 0 && threadIdx.x < x.world)
     st_release_sys(x.flags[threadIdx.x] + 2 * kMaxRanks + x.rank, (unsigned long long)last << 32);
   p2p_wait(my_flags + 2 * kMaxRanks, x.world, last, nullptr);
+  // every entry speed has landed: apply the advances still owed (deferred at the last tick), so that the state a
+  // host reads between launches is the reference's
+  {
+    const AgentArrays& a = p.a;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x)
+      if (a.state[i] == kMoving && owes_advance(a.dist[i]))
+        a.dist[i] = __dadd_rn(0.0, __dmul_rn(__ldcg(a.speed + i), p.delta));
+  }
 }
 
 // ---- auxiliary passes -------------------------------------------------------------------------------
