@@ -449,7 +449,8 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
             if (lkd >> 31) a.speed[sm.agent[w][k] - a.base] = __dmul_rn(p.lk.v0[link], p.kph_to_mps);
           }
         }
-        if (n) __threadfence_system();  // this warp's peer stores are visible before the block reaches the grid barrier
+        // no fence here: ONE thread per block issues the system-scope fence after the block's last tile (see
+        // k_tick_loop_p2p) -- a membar.sys per warp and tile costs more than the whole local advance
       }
     } else if (n_blk && !(p.debug & 4)) {  // one global atomic per block and tile, spread over kEvSub counters
       const int sub = (int)(tile % kEvSub);
@@ -989,7 +990,11 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
       phase_advance<true, true>(p, tick, p_dep, sm, &x, &xs);
     else
       phase_advance<false, true>(p, tick, p_dep, sm, &x, &xs);
-    grid.sync();  // writers fenced their peer stores (system scope) before arriving here
+    // peer stores of the whole block -> system scope: block barrier, then one fence by one thread (cumulative over the
+    // barrier, the construction grid.sync() itself uses at gpu scope), then the grid barrier
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();
+    grid.sync();
     const int n_pending = min(ctr->n_pending, p.pend_cap), n_urgent = ctr->n_dep_req[par];
     if (n_pending | n_urgent) {  // uniform across the grid
       phase_inject_p2p(p, x, tick, n_pending, n_urgent);
@@ -1035,15 +1040,17 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
       ctr->phase_ns[1] += t1 - t0;  // exchange wait + list building
       t0 = t1;
     }
+    bool any_remote = false;
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
       int r = 0;
       while (r + 1 < x.world && s_pref[r + 1] <= f) ++r;
       const bool remote = resolve_one_p2p(p, x, inbox, (par * x.world + r) * x.cap + (f - s_pref[r]));
-      // system-scope fence by every thread that stored a speed into a peer: the speed is then ordered before this
-      // rank's next flag release, which is what lets the home rank defer an entrant's first advance by one tick
-      // without waiting (kSpeedDeferred), and before the launch-end barrier below
-      if (remote) __threadfence_system();
+      any_remote |= remote;
     }
+    // one system-scope fence per block for the speeds it stored into peers: they are then ordered before this rank's
+    // next flag release -- which is what lets a home rank defer an entrant's first advance by one tick without
+    // waiting (kSpeedDeferred) -- and before the launch-end barrier below
+    if (__syncthreads_or(any_remote ? 1 : 0) && threadIdx.x == 0) __threadfence_system();
     if (lead) ctr->phase_ns[2] += global_ns() - t0;
     // No all-rank barrier here: the next advance waits per agent for a pending entry speed, the inbox and
     // the event flags are double-buffered by tick parity, and a rank cannot run two ticks ahead of a peer

@@ -307,7 +307,138 @@ class GravitySelection(_Base):
                 "cache_valid": self._cache_valid}
 
 
-FAST_MODELS = {"gravity": GravitySelection, "hub": HubAndSpokeSelection, "zone": ZoneBasedSelection}
+class ActivityBasedSelection(_Base):
+    """lib/st_selection.py:650-1082 without the reference package (the GPU box does not have it) and without its
+    O(V x pool) list-membership filters (:763-764, :797-799, :842-845, :886-888 become set look-ups).
+
+    Set-up draws the five node pools with the reference's ``random.sample`` calls on the same lists in the same
+    order (activity centres, business, work, home, distribution: :732-900), so the pools -- and every later
+    (source, target) -- equal the reference's for the same seed.  A trip is one table row per agent type:
+    (pool a first trip starts from, pool the target is drawn from, probability of drawing from that pool,
+    whether a redraw keeps that probability) -- :926-1050."""
+
+    _DEFAULT_TYPES = {"commuter": 0.4, "leisure": 0.3, "business": 0.2, "delivery": 0.1}
+
+    def __init__(self, graph, config=None, agent_type_distributions=None):
+        super().__init__(graph)
+        if config is None:
+            try:
+                from config import MODELS as config  # inside the DRIFT application
+            except Exception:
+                config = None
+        self.config = config
+        cfg = lambda name, default: getattr(config, name, default) if config is not None else default  # noqa: E731
+        self.agent_type_distributions = agent_type_distributions if agent_type_distributions is not None else \
+            (cfg("DEFAULT_AGENT_TYPE_DISTRIBUTIONS", None) or dict(self._DEFAULT_TYPES))
+        self.center_threshold = cfg("ACTIVITY_CENTER_THRESHOLD", 0.3)
+        self.middle_threshold = cfg("ACTIVITY_MIDDLE_THRESHOLD", 0.7)
+        self.activity_size_factor, self.activity_max_size = cfg("ACTIVITY_SIZE_FACTOR", 6), cfg("ACTIVITY_MAX_SIZE", 50)
+        self.business_size_factor, self.business_max_size = cfg("BUSINESS_SIZE_FACTOR", 5), cfg("BUSINESS_MAX_SIZE", 80)
+        self.work_size_factor, self.work_max_size = cfg("WORK_SIZE_FACTOR", 4), cfg("WORK_MAX_SIZE", 100)
+        self.home_size_factor, self.home_max_size = cfg("HOME_SIZE_FACTOR", 4), cfg("HOME_MAX_SIZE", 100)
+        self.distribution_size_factor = cfg("DISTRIBUTION_SIZE_FACTOR", 10)
+        self.distribution_max_size = cfg("DISTRIBUTION_MAX_SIZE", 20)
+        self.activity_center_ratio = cfg("ACTIVITY_CENTER_RATIO", 0.8)
+        self.business_center_ratio = cfg("BUSINESS_CENTER_RATIO", 0.7)
+        self.work_ratios = cfg("WORK_RATIOS", (0.2, 0.4, 0.4))
+        self.home_ratios = cfg("HOME_RATIOS", (0.05, 0.35, 0.6))
+        self.distribution_ratios = cfg("DISTRIBUTION_RATIOS", (0.5, 0.5))
+        self._distribute_nodes_spatially(graph)
+
+    # ---- pools (:690-900) ----------------------------------------------------------------------
+    def _distribute_nodes_spatially(self, graph):
+        pos = [graph.nodes[n]["pos"] for n in self.nodes]
+        xs, ys = [p[0] for p in pos], [p[1] for p in pos]
+        cx, cy = (min(xs) + max(xs)) / 2, (min(ys) + max(ys)) / 2
+        dist = [((p[0] - cx) ** 2 + (p[1] - cy) ** 2) ** 0.5 for p in pos]  # the reference's float expression
+        far = max([0] + dist)
+        rel = [d / far for d in dist]  # ZeroDivisionError on a one-point layout, like the reference (:714)
+        rings = ([], [], [])  # centre, middle, border -- in self.nodes order
+        for n, r in zip(self.nodes, rel):
+            rings[0 if r <= self.center_threshold else (1 if r <= self.middle_threshold else 2)].append(n)
+        taken = set()
+
+        def pool(size, ring_ids, counts, filtered, fallback):
+            out = []
+            avail = [[n for n in rings[r] if n not in taken] if f else rings[r] for r, f in zip(ring_ids, filtered)]
+            for a, c in zip(avail, counts):
+                c = min(c, len(a))
+                if c > 0:
+                    out.extend(random.sample(a, c))
+            if not out:
+                rest = [n for n in self.nodes if n not in taken] if taken else []
+                out = random.sample(rest, min(fallback, len(rest))) if rest else \
+                    random.sample(self.nodes, min(fallback, len(self.nodes)))
+            return out
+
+        V = len(self.nodes)
+        centre, middle, border = rings
+        # activity centres (:732-755): counts are capped by the UNFILTERED ring sizes
+        size = min(V // self.activity_size_factor, self.activity_max_size)
+        c0 = min(int(size * self.activity_center_ratio), len(centre))
+        c1 = min(size - c0, len(middle))
+        self.activity_centers = pool(size, (0, 1), (c0, c1), (False, False), 3)
+        taken.update(self.activity_centers)
+        # business (:757-786): same capping first, then against the filtered rings
+        size = min(V // self.business_size_factor, self.business_max_size)
+        c0 = min(int(size * self.business_center_ratio), len(centre))
+        c1 = min(size - c0, len(middle))
+        self.business_nodes = pool(size, (0, 1), (c0, c1), (True, True), 5)
+        taken.update(self.business_nodes)
+        # work (:788-828): the border ring is NOT filtered (border_nodes.copy())
+        size = min(V // self.work_size_factor, self.work_max_size)
+        c0, c1 = int(size * self.work_ratios[0]), int(size * self.work_ratios[1])
+        self.work_nodes = pool(size, (0, 1, 2), (c0, c1, size - c0 - c1), (True, True, False), 5)
+        taken.update(self.work_nodes)
+        # home (:830-870)
+        size = min(V // self.home_size_factor, self.home_max_size)
+        c0, c1 = int(size * self.home_ratios[0]), int(size * self.home_ratios[1])
+        self.home_nodes = pool(size, (0, 1, 2), (c0, c1, size - c0 - c1), (True, True, True), 5)
+        taken.update(self.home_nodes)
+        # distribution (:872-900)
+        size = min(V // self.distribution_size_factor, self.distribution_max_size)
+        c1 = int(size * self.distribution_ratios[0])
+        self.distribution_nodes = pool(size, (1, 2), (c1, size - c1), (True, True), 3)
+
+    # ---- trips (:903-1068) ---------------------------------------------------------------------
+    def get_source_target(self, agent_type="random", current_location=None, trip_count=0):
+        if agent_type == "commuter":  # :926-954: alternates work / home, never redraws
+            if current_location is None:
+                source = random.choice(self.home_nodes or self.nodes)
+                return source, random.choice(self.work_nodes or self.nodes)
+            pool = self.work_nodes if trip_count % 2 == 0 else self.home_nodes
+            return current_location, random.choice(pool or self.nodes)
+        first, pool, p, keep = {"delivery": (self.distribution_nodes, self.distribution_nodes, 0.7, False),
+                                "leisure": (self.home_nodes, self.activity_centers, 0.6, True),
+                                "business": (self.business_nodes, self.business_nodes, 0.8, True)}.get(
+            agent_type, (None, None, None, False))
+        source = random.choice(first or self.nodes) if current_location is None else current_location
+
+        def target():
+            if p is not None and random.random() < p and pool:
+                return random.choice(pool)
+            return random.choice(self.nodes)
+
+        t = target()
+        attempts = 0
+        while t == source and attempts < 100:  # a redraw of the delivery / fallback pattern is uniform (:981, :1060)
+            attempts += 1
+            t = target() if keep else random.choice(self.nodes)
+            if len(self.nodes) <= 1:
+                break
+        return source, t
+
+    def get_agent_types_distribution(self):
+        return self.agent_type_distributions
+
+    def get_activity_nodes(self):
+        return {"activity_centers": self.activity_centers, "business_nodes": self.business_nodes,
+                "work_nodes": self.work_nodes, "home_nodes": self.home_nodes,
+                "distribution_nodes": self.distribution_nodes}
+
+
+FAST_MODELS = {"gravity": GravitySelection, "hub": HubAndSpokeSelection, "zone": ZoneBasedSelection,
+               "activity": ActivityBasedSelection}
 
 
 def make_fast_selector(mode, graph, settings=None):
@@ -321,4 +452,6 @@ def make_fast_selector(mode, graph, settings=None):
                                     hub_percentage=s.get("hub_percentage"))
     if mode == "zone":
         return ZoneBasedSelection(graph, intra_zone_probability=s.get("zone_intra_probability"))
+    if mode == "activity":
+        return ActivityBasedSelection(graph, agent_type_distributions=s.get("agent_type_distributions"))
     return None

@@ -58,10 +58,12 @@ def make_selector(mode, graph, settings=None, fast=False):
             return RandomSelection(graph)
     try:
         from lib import st_selection as ref
-    except Exception as exc:
-        raise RuntimeError(
-            "selection mode %r needs the reference's lib.st_selection on sys.path, or pass a ready "
-            "selector object via SimulationThread.st_selector" % mode) from exc
+    except Exception:
+        # outside the DRIFT application (headless box): the restatements of drift_b200/fast_selection.py give the
+        # same (source, target) sequences for the same seed (tests/test_fast_selection.py)
+        from .fast_selection import make_fast_selector
+
+        return make_fast_selector(mode, graph, settings)
     s = settings or {}
     if mode == "activity":
         if "agent_type_distributions" in s:

@@ -30,7 +30,14 @@ CASES = {
     "gravity_hops_beta": ("digeo200", "gravity", {"alpha": 2.0, "beta": 1.5}, 16, 30, 2000),
     "gravity_euclid": ("geo2500", "gravity", {"beta": 2.0}, 17, 60, 2500),
     "gravity_euclid_beta": ("geo2500", "gravity", {"alpha": 0.5, "beta": 2.5}, 18, 60, 1500),
+    # the selector is built AFTER seeding: its pools are drawn with random.sample (lib/st_selection.py:732-900)
+    "activity_small": ("geo300", "activity", {}, 19, 40, 3000),
+    "activity_large": ("geo2500", "activity", {"agent_type_distributions": {"commuter": 0.25, "leisure": 0.25,
+                                                                           "business": 0.25, "delivery": 0.25}},
+                       20, 60, 3000),
+    "activity_tiny": ("line40", "activity", {}, 21, 12, 1500),
 }
+SEED_BEFORE_BUILD = {"activity"}  # models whose constructor consumes the global generator
 
 
 def make_graph(kind):
@@ -62,13 +69,13 @@ def make_graph(kind):
 
 def ask(selector, n_agents, calls):
     """The questions lib/agent.py:47-53 asks, round-robin over the agents."""
-    types = ["commuter", "delivery", "leisure", "business"]
+    types = ["commuter", "delivery", "leisure", "business", "random"]
     where = [None] * n_agents
     trips = [0] * n_agents
     out = []
     for c in range(calls):
         a = c % n_agents
-        s, t = selector.get_source_target(types[a % 4], where[a], trips[a])
+        s, t = selector.get_source_target(types[a % 5], where[a], trips[a])
         where[a] = t
         trips[a] += 1
         out.append((s, t))
@@ -80,7 +87,8 @@ def reference_selector(model, graph, kwargs):
     os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
     from lib import st_selection as ref
 
-    cls = {"hub": ref.HubAndSpokeSelection, "zone": ref.ZoneBasedSelection, "gravity": ref.GravitySelection}[model]
+    cls = {"hub": ref.HubAndSpokeSelection, "zone": ref.ZoneBasedSelection, "gravity": ref.GravitySelection,
+           "activity": ref.ActivityBasedSelection}[model]
     return cls(graph, **kwargs)
 
 
@@ -88,8 +96,11 @@ def main():
     out = {}
     for name, (kind, model, kwargs, seed, agents, calls) in CASES.items():
         g = make_graph(kind)
+        if model in SEED_BEFORE_BUILD:
+            random.seed(seed)
         sel = reference_selector(model, g, kwargs)
-        random.seed(seed)
+        if model not in SEED_BEFORE_BUILD:
+            random.seed(seed)
         seq = ask(sel, agents, calls)
         idx = {n: i for i, n in enumerate(g.nodes())}
         out[name] = np.array([(idx[s], idx[t]) for s, t in seq], dtype=np.int32)

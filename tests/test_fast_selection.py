@@ -18,7 +18,7 @@ from oracle import make_golden_selectors as mg
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_selectors", "selectors.npz")
 FAST = {"hub": fast_selection.HubAndSpokeSelection, "zone": fast_selection.ZoneBasedSelection,
-        "gravity": fast_selection.GravitySelection}
+        "gravity": fast_selection.GravitySelection, "activity": fast_selection.ActivityBasedSelection}
 _graphs = {}
 
 
@@ -33,14 +33,17 @@ def test_sequences_match_recorded_reference(name):
     kind, model, kwargs, seed, agents, calls = mg.CASES[name]
     g = _graph(kind)
     want = np.load(GOLDEN)[name]
+    if model in mg.SEED_BEFORE_BUILD:  # the activity model draws its node pools in the constructor
+        random.seed(seed)
     sel = FAST[model](g, **kwargs)
-    random.seed(seed)
+    if model not in mg.SEED_BEFORE_BUILD:
+        random.seed(seed)
     seq = mg.ask(sel, agents, calls)
     idx = {n: i for i, n in enumerate(g.nodes())}
     got = np.array([(idx[s], idx[t]) for s, t in seq], dtype=np.int32)
     assert np.array_equal(got, want)
     # the draws consumed are the reference's too: the generator is left in the same state
-    assert all(s != t for s, t in seq) or model == "gravity"
+    assert all(s != t for s, t in seq) or model in ("gravity", "activity")  # commuters may stay (lib/st_selection.py:941-954)
 
 
 def _have_reference():
@@ -48,13 +51,21 @@ def _have_reference():
 
 
 @pytest.mark.skipif(not _have_reference(), reason="reference tree not present")
-@pytest.mark.parametrize("name", ["hub_small", "hub_large", "zone_small", "zone_sparse", "gravity_hops_beta"])
+@pytest.mark.parametrize("name", ["hub_small", "hub_large", "zone_small", "zone_sparse", "gravity_hops_beta",
+                                  "activity_small", "activity_large", "activity_tiny"])
 def test_live_against_reference_classes(name):
     kind, model, kwargs, seed, agents, calls = mg.CASES[name]
     g = _graph(kind)
+    random.seed(seed + 7)
     ref = mg.reference_selector(model, g, kwargs)
+    built_ref = random.getstate()
+    random.seed(seed + 7)
     fast = FAST[model](g, **kwargs)
-    if model == "hub":
+    assert random.getstate() == built_ref  # the constructors consume the same draws
+    if model == "activity":
+        assert ref.get_activity_nodes() == fast.get_activity_nodes()
+        assert ref.get_agent_types_distribution() == fast.get_agent_types_distribution()
+    elif model == "hub":
         assert ref.hubs == fast.hubs and ref.non_hubs == fast.non_hubs and ref.node_centrality == fast.node_centrality
     elif model == "zone":
         assert ref.zones == fast.zones and ref.node_to_zone == fast.node_to_zone
@@ -105,5 +116,9 @@ def test_make_selector_fast_switch():
     assert zone.__class__.__name__ == "ZoneBasedSelection" and zone.intra_zone_probability == 0.6  # lib/agent.py:57,61
     grav = make_selector("gravity", g, st, fast=True)
     assert type(grav) is fast_selection.GravitySelection and grav.alpha == 1.5 and grav.beta == 1.8
+    act = make_selector("activity", g, {"agent_type_distributions": {"commuter": 1.0}}, fast=True)
+    assert type(act) is fast_selection.ActivityBasedSelection and act.get_agent_types_distribution() == {"commuter": 1.0}
+    assert list(fast_selection.ActivityBasedSelection(g).get_agent_types_distribution()) == \
+        ["commuter", "leisure", "business", "delivery"]  # key order = config.py:326-331 (random.choices order)
     # models without a vectorised restatement fall through to the reference / built-in ones
     assert make_selector("random", g, None, fast=True).__class__.__name__ == "RandomSelection"

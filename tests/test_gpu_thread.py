@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 LIVE = [n for n in golden.case_names() if "_random_" in n or "congested" in n]
 # recorded with the reference's own hub / zone / gravity selector objects; replayed here with the vectorised
 # restatements of drift_b200/fast_selection.py (the reference package does not exist on the GPU box)
-LIVE_FAST = [n for n in golden.case_names() if any(m in n for m in ("_hub_", "_zone_", "_gravity_"))]
+LIVE_FAST = [n for n in golden.case_names() if any(m in n for m in ("_hub_", "_zone_", "_gravity_", "_activity_"))]
 
 
 def _settings(case):
