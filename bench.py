@@ -583,6 +583,26 @@ def run_b200(args):
                                    p2p=(args.exchange == "p2p"))
 
     progress("parity check done: %r" % (parity,))
+    # ---- the drop-in SimulationThread itself (exact mode: host MT19937 draws in the reference's order, the
+    # reference's selector interface, device step + NetworkX-exact device router) at the reference's own scale
+    thread_rate = None
+    if rank == 0 and world == 1 and args.cpu_seconds > 0:
+        import tempfile
+
+        from drift_b200.headless import run_headless
+        from oracle import golden
+
+        if sat is None:
+            eng.close()
+        case = golden.GoldenCase("liz_random_nopath")
+        th, wall = run_headless(case.nx_graph(), 10_000, "random", hours=0.25, accel=10, seed=0,
+                                out_dir=tempfile.mkdtemp())
+        thread_rate = dict(value=10_000 * th.step / wall, unit="agent-steps/s", agents=10_000, ticks=th.step,
+                           trips=len(th.data_logger.trips_data), seconds=wall,
+                           note="drift_b200.SimulationThread.update_simulation_step per tick (headless, no viz snapshot), "
+                                "random model, music-net digraph of the reference's example data (1 157 nodes)")
+        th.close()
+        progress("drop-in thread: %r" % (thread_rate,))
     line = None
     if rank == 0:
         cpu = cpu_port_rate(model, args.seed, budget_s=args.cpu_seconds, ticks=TPS, reroute=reroute) \
@@ -621,7 +641,7 @@ def run_b200(args):
             gpu_launches=int(launches), router_stats={k: (round(v, 3) if isinstance(v, float) else v) for k, v in trees.items()},
             roofline=roof, roofline_advance=roof_adv, roofline_advance_saturated=sat,
             roofline_scatter=roof_scatter, roofline_bpr=roof_bpr, dense_allreduce=dense,
-            parity_check=parity, tick_only=tick_only,
+            parity_check=parity, tick_only=tick_only, dropin_thread=thread_rate,
             label_router=(dict(queries=lab["queries"], launches=lab["launches"], query_kernel_ms=round(lab["query_ms"], 4),
                                entries_read=lab["entries_read"], algorithmic_bytes=12 * lab["entries_read"],
                                achieved_gbs=(12e-9 * lab["entries_read"] / (lab["query_ms"] * 1e-3)) if lab["query_ms"] > 0 else None,

@@ -183,7 +183,10 @@ struct drift_engine {
   DevBuf<double> hu_w, hd_w;
   DevBuf<long long> lab_off;        // [2][V]
   DevBuf<int32_t> lab_cnt;          // [2][V]
-  DevBuf<int32_t> lab_hub, lab_par, lab_flag, q_hub;
+  DevBuf<int32_t> lab_hub, lab_par, lab_flag;
+  DevBuf<uint32_t> lab_pnext;
+  DevBuf<uint2> q_ent;
+  DevBuf<int4> hu_rec, hd_rec;
   DevBuf<double> lab_dist;
   DevBuf<unsigned long long> lab_cursor;
   bool labels_ready = false;
@@ -298,10 +301,11 @@ struct drift_engine {
     g.L = L;
     return g;
   }
-  HierSide hier_up() { return HierSide{hu_rowptr.p, hu_other.p, hu_w.p, hu_a.p, hu_b.p, hu_hops.p}; }
-  HierSide hier_down() { return HierSide{hd_rowptr.p, hd_other.p, hd_w.p, hd_a.p, hd_b.p, hd_hops.p}; }
+  HierSide hier_up() { return HierSide{hu_rowptr.p, hu_other.p, hu_w.p, hu_a.p, hu_b.p, hu_hops.p, hu_rec.p}; }
+  HierSide hier_down() { return HierSide{hd_rowptr.p, hd_other.p, hd_w.p, hd_a.p, hd_b.p, hd_hops.p, hd_rec.p}; }
   LabelSet labels(int side) {
-    return LabelSet{lab_off.p + (int64_t)side * V, lab_cnt.p + (int64_t)side * V, lab_hub.p, lab_par.p, lab_dist.p};
+    return LabelSet{lab_off.p + (int64_t)side * V, lab_cnt.p + (int64_t)side * V, lab_hub.p, lab_par.p, lab_pnext.p,
+                    lab_dist.p};
   }
   Rings rings() {
     Rings r;
@@ -467,9 +471,9 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
   const double* lc = use_congested ? e->link_tt.p : e->link_t0.p;
   if (router == DRIFT_ROUTER_BATCHED && e->labels_ready && e->labels_enabled && !use_congested) {
     // hub labels: every query is the intersection of two sorted labels + a walk through the parent arcs
-    if (e->q_hub.n < e->q_cap) {
+    if (e->q_ent.n < e->q_cap) {
       CU(cudaStreamSynchronize(e->stream));
-      CU(e->q_hub.alloc(e->q_cap, false));
+      CU(e->q_ent.alloc(e->q_cap, false));
     }
     cudaEvent_t tb0 = nullptr, tb1 = nullptr;
     if (e->time_plan) {
@@ -478,16 +482,15 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
       cudaEventRecord(tb0, e->stream);
     }
     const int gw = grid_for(Q * 32, 256, kSMs * 8);
-    k_label_query<<<gw, 256, 0, e->stream>>>(Q, n_dev, qs, qd, e->labels(0), e->labels(1), e->V, e->q_hub.p + q0, out,
+    k_label_query<<<gw, 256, 0, e->stream>>>(Q, n_dev, qs, qd, e->labels(0), e->labels(1), e->V, e->q_ent.p + q0, out,
                                              &e->ctr.p->label_entries);
     if (tb0) {
       cudaEventRecord(tb1, e->stream);
       e->label_timers.push_back({tb0, tb1});
     }
-    k_label_paths<<<grid_for(Q, 128, kSMs * 16), 128, 0, e->stream>>>(Q, n_dev, qs, qd, e->labels(0), e->labels(1),
-                                                                     e->hier_up(), e->hier_down(), e->q_hub.p + q0,
-                                                                     e->arena.p, (unsigned long long)e->arena_cap,
-                                                                     e->ctr.p, out, lc);
+    k_label_paths<<<grid_for(Q * 32, kPathWarps * 32, kSMs * 16), kPathWarps * 32, 0, e->stream>>>(
+        Q, n_dev, e->labels(0), e->labels(1), e->hier_up(), e->hier_down(), e->q_ent.p + q0, e->arena.p,
+        (unsigned long long)e->arena_cap, e->ctr.p, out, lc);
     CU(cudaGetLastError());
     e->total_launches += 2;
     e->label_queries_host += Q;
@@ -549,7 +552,9 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     k_tree_requests<<<gq, 256, 0, e->stream>>>(Q, qs, qd, tc, e->ctr.p, n_dev);
     Landmarks lm;
     lm.tab = e->lm_tab.p;
-    lm.K = use_congested ? 0 : e->lm_K;  // the landmark distances are free-flow distances
+    // the landmark distances are free-flow distances; congested times are never shorter (tt = t0 / factor, factor <= 1,
+    // traffic_manager.py:92-107), so they remain valid lower bounds and the potentials stay feasible
+    lm.K = e->lm_K;
     k_link_queries<<<gq, 256, 0, e->stream>>>(Q, qs, qd, tc, n_dev);
     cudaEvent_t tb0 = nullptr, tb1 = nullptr;
     if (e->time_plan) {
@@ -1992,8 +1997,9 @@ int drift_set_hierarchy(drift_engine* e, const drift_hier_desc* d) {
     return fail(DRIFT_EINVAL, "drift_set_hierarchy: bad argument (hierarchy of another graph?)");
   if (d->n_up >= ((int64_t)1 << 30) || d->n_down >= ((int64_t)1 << 30))
     return fail(DRIFT_EINVAL, "drift_set_hierarchy: too many arcs");
-  if (d->max_level + 4 > kUnpackStack)
-    return fail(DRIFT_EINVAL, "drift_set_hierarchy: %d levels, the unpacker handles %d", d->max_level, kUnpackStack - 4);
+  if (d->max_level + 2 > kPathItems / 2)
+    return fail(DRIFT_EINVAL, "drift_set_hierarchy: %d levels, the route unpacker handles climbs of %d arcs",
+                d->max_level + 1, kPathItems / 2);
   CU(cudaSetDevice(e->device));
   CU(cudaStreamSynchronize(e->stream));
   e->labels_ready = false;
@@ -2006,7 +2012,7 @@ int drift_set_hierarchy(drift_engine* e, const drift_hier_desc* d) {
                                  "table (4096): this graph keeps the tree / bounded-search router", d->max_label);
   int32_t log2H = 0;
   while ((1 << log2H) < 2 * n_max) ++log2H;
-  const size_t smem = (size_t)40 * n_max;
+  const size_t smem = (size_t)48 * n_max;
   CU(cudaFuncSetAttribute(k_build_labels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CU(e->h_level.upload(d->level, V));
   CU(e->hu_rowptr.upload(d->up_rowptr, V + 1));
@@ -2021,6 +2027,21 @@ int drift_set_hierarchy(drift_engine* e, const drift_hier_desc* d) {
   CU(e->hd_a.upload(d->down_a, d->n_down));
   CU(e->hd_b.upload(d->down_b, d->n_down));
   CU(e->hd_hops.upload(d->down_hops, d->n_down));
+  {  // what unpacking needs about an arc in one record: {a, b, hops, hops of the first half (a down arc)}
+    std::vector<int4> rec((size_t)std::max<int64_t>(std::max(d->n_up, d->n_down), 1));
+    for (int side = 0; side < 2; ++side) {
+      const int64_t n = side == 0 ? d->n_up : d->n_down;
+      const int32_t* a = side == 0 ? d->up_a : d->down_a;
+      const int32_t* b = side == 0 ? d->up_b : d->down_b;
+      const int32_t* h = side == 0 ? d->up_hops : d->down_hops;
+      for (int64_t k = 0; k < n; ++k) {
+        if (b[k] >= 0 && (a[k] < 0 || a[k] >= d->n_down || b[k] >= d->n_up))
+          return fail(DRIFT_EINVAL, "drift_set_hierarchy: bad child arc");
+        rec[k] = make_int4(a[k], b[k], h[k], b[k] < 0 ? 0 : d->down_hops[a[k]]);
+      }
+      CU((side == 0 ? e->hu_rec : e->hd_rec).upload(rec.data(), n));
+    }
+  }
   // nodes by level, highest first
   const int32_t nl = d->max_level + 1;
   std::vector<int32_t> start(nl + 1, 0), order(V);
@@ -2042,11 +2063,13 @@ int drift_set_hierarchy(drift_engine* e, const drift_hier_desc* d) {
   for (int attempt = 0; attempt < 3; ++attempt) {
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    if ((double)cap * 16.0 > 0.6 * (double)free_b)
-      return fail(DRIFT_ENOMEM, "drift_set_hierarchy: %.1f GB of labels do not fit (%.1f GB free)", cap * 16.0 / 1e9,
+    if ((double)cap * 20.0 > 0.6 * (double)free_b)
+      return fail(DRIFT_ENOMEM, "drift_set_hierarchy: %.1f GB of labels do not fit (%.1f GB free)", cap * 20.0 / 1e9,
                   free_b / 1e9);
+    if (cap >= ((int64_t)1 << 32)) return fail(DRIFT_EOVERFLOW, "drift_set_hierarchy: more than 2^32 label entries");
     CU(e->lab_hub.alloc(cap, false));
     CU(e->lab_par.alloc(cap, false));
+    CU(e->lab_pnext.alloc(cap, false));
     CU(e->lab_dist.alloc(cap, false));
     CU(cudaMemsetAsync(e->lab_flag.p, 0, sizeof(int32_t), e->stream));
     CU(cudaMemsetAsync(e->lab_cursor.p, 0, sizeof(unsigned long long), e->stream));
@@ -2075,7 +2098,7 @@ int drift_set_hierarchy(drift_engine* e, const drift_hier_desc* d) {
     CU(cudaMemcpy(&flag, e->lab_flag.p, sizeof(flag), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(&used, e->lab_cursor.p, sizeof(used), cudaMemcpyDeviceToHost));
     if (flag & 1) {
-      e->lab_hub.release(), e->lab_par.release(), e->lab_dist.release();
+      e->lab_hub.release(), e->lab_par.release(), e->lab_pnext.release(), e->lab_dist.release();
       return fail(DRIFT_EOVERFLOW, "drift_set_hierarchy: a label outgrew the builder's table of %d hubs", n_max);
     }
     if (!(flag & 2)) {

@@ -150,8 +150,9 @@ struct P2PArgs {
 };
 
 struct P2PSmem {
-  int ocnt[kMaxRanks], obase[kMaxRanks];
+  int ocnt[kMaxRanks], obase[kMaxRanks], ooff[kMaxRanks + 1];
   uint16_t idx[kAdvWarps][kStageCap];
+  uint2 sorted[kAdvWarps * kStageCap];  // the tile's events grouped by owner: (link | enter bit, agent)
 };
 
 __device__ __noinline__ double p2p_wait_speed(const double* p) {
@@ -427,17 +428,35 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
         __syncthreads();
         if (threadIdx.x < x->world && xs->ocnt[threadIdx.x])
           xs->obase[threadIdx.x] = atomicAdd(&x->out_cnt[threadIdx.x], xs->ocnt[threadIdx.x]);
+        if (threadIdx.x == 0) {
+          int acc = 0;
+          for (int o = 0; o < x->world; ++o) {
+            xs->ooff[o] = acc;
+            acc += xs->ocnt[o];
+          }
+          xs->ooff[x->world] = acc;
+        }
         __syncthreads();
+        // group the events by owner in shared memory, then the whole block writes each owner's run with consecutive
+        // threads: the peer stores of a tile are contiguous 16-byte records (full 128-byte NVLink writes) instead of
+        // one scattered record per lane
         for (int k = lane; k < n; k += 32) {
           const uint32_t lkd = sm.link_kind[w][k];
-          const int32_t link = (int32_t)(lkd & 0x7fffffffu);
-          const int o = (int)((uint32_t)link % (uint32_t)x->world);
-          const int pos = xs->obase[o] + xs->idx[w][k];
+          const int o = (int)((lkd & 0x7fffffffu) % (uint32_t)x->world);
+          xs->sorted[xs->ooff[o] + xs->idx[w][k]] = make_uint2(lkd, sm.agent[w][k]);
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < n_blk; t += blockDim.x) {
+          int o = 0;
+          while (xs->ooff[o + 1] <= t) ++o;
+          const uint2 rec = xs->sorted[t];
+          const int32_t link = (int32_t)(rec.x & 0x7fffffffu);
+          const int pos = xs->obase[o] + (t - xs->ooff[o]);
           if (pos < x->cap) {
             Event e;
             e.link = link;
-            e.agent = sm.agent[w][k];
-            e.kind = (lkd >> 31) ? 1 : -1;
+            e.agent = rec.y;
+            e.kind = (rec.x >> 31) ? 1 : -1;
             e.aux = 0;
             *reinterpret_cast<int4*>(x->inbox[o] + ((int64_t)par * x->world + x->rank) * x->cap + pos) =
               *reinterpret_cast<const int4*>(&e);
@@ -446,7 +465,7 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
             // advance would spin on kSpeedPending: give it the free-flow speed so that the launch ends and the host
             // can raise DRIFT_EOVERFLOW (the run is invalid from here on; raise the exchange capacity).
             atomicOr(&p.ctr->overflow, kOvfExchange);
-            if (lkd >> 31) a.speed[sm.agent[w][k] - a.base] = __dmul_rn(p.lk.v0[link], p.kph_to_mps);
+            if (rec.x >> 31) a.speed[rec.y - a.base] = __dmul_rn(p.lk.v0[link], p.kph_to_mps);
           }
         }
         // no fence here: ONE thread per block issues the system-scope fence after the block's last tile (see

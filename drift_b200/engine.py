@@ -432,7 +432,7 @@ class Engine:
         bms, qms = C.c_double(0), C.c_double(0)
         _capi.check(self._lib.drift_label_stats(self._h, C.byref(ent), C.byref(bms), C.byref(qms), C.byref(lau),
                                                 C.byref(q), C.byref(rd), int(bool(reset))))
-        return dict(label_entries=ent.value, label_bytes=16 * ent.value, build_ms=bms.value, query_ms=qms.value,
+        return dict(label_entries=ent.value, label_bytes=20 * ent.value, build_ms=bms.value, query_ms=qms.value,
                     launches=lau.value, queries=q.value, entries_read=rd.value)
 
     def set_option(self, name, value):

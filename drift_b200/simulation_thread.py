@@ -292,12 +292,7 @@ class SimulationThread(QThread):
         # Agent.update for waiting agents (lib/agent.py:172-183): one MT19937 draw each, in agent order
         hour = int(((t + SIMULATION_START_OFFSET) / SECONDS_PER_HOUR) % 24)
         threshold = (self._hourly.get(hour, 0.05) * 4.0) * delta / SECONDS_PER_HOUR
-        draw = random.random
-        departing = []
-        for i in self._waiting:
-            if draw() < threshold:
-                departing.append(i)
-                self._start_new_journey(agents[i])
+        departing = self._draw_departures(threshold)
         started = []
         if departing:
             index = lg.node_index
@@ -359,6 +354,51 @@ class SimulationThread(QThread):
         if self.simulation_time - self.last_report_time >= 1800:
             self._emit_progress_report()
         return True
+
+    def _draw_departures(self, threshold):
+        """Agent.update for waiting agents (lib/agent.py:172-183): one ``random.random()`` per waiting agent in agent
+        order, a hit starts a journey (whose selector draws from the same generator before the next agent's draw).
+        The reference loops in Python; here the draws between two hits are produced in bulk: the MT19937 state of
+        ``random`` is handed to ``numpy.random.MT19937`` (same generator, same tempering), uniforms are built like
+        ``genrand_res53`` -- (a >> 5) * 2**26 + (b >> 6) over 2**53 -- the first hit is located, the generator is
+        advanced to just after that draw and handed back, the journey is started, and so on.  Same hits, same
+        (source, target) answers, same generator state afterwards (tests/test_host_cpu.py)."""
+        waiting, agents = self._waiting, self.agents
+        n = len(waiting)
+        if n < 64:  # not worth two state transfers
+            draw = random.random
+            departing = []
+            for i in waiting:
+                if draw() < threshold:
+                    departing.append(i)
+                    self._start_new_journey(agents[i])
+            return departing
+        departing = []
+        pos = 0
+        bg = np.random.MT19937()
+        chunk = 1 << 16
+        while pos < n:
+            version, internal, gauss = random.getstate()
+            key = np.array(internal[:-1], dtype=np.uint32)
+            start = {"bit_generator": "MT19937", "state": {"key": key, "pos": int(internal[-1])}}
+            bg.state = start
+            m = min(n - pos, chunk)
+            raw = bg.random_raw(2 * m)
+            u = ((raw[0::2] >> np.uint64(5)).astype(np.float64) * 67108864.0 +
+                 (raw[1::2] >> np.uint64(6)).astype(np.float64)) * (1.0 / 9007199254740992.0)
+            hits = np.nonzero(u < threshold)[0]
+            used = m if len(hits) == 0 else int(hits[0]) + 1
+            if used != m:  # rewind to just after the hit's draw
+                bg.state = start
+                bg.random_raw(2 * used)
+            st = bg.state["state"]
+            random.setstate((version, tuple(int(x) for x in st["key"]) + (int(st["pos"]),), gauss))
+            if len(hits):
+                i = waiting[pos + used - 1]
+                departing.append(i)
+                self._start_new_journey(agents[i])
+            pos += used
+        return departing
 
     def _reroute(self, t):
         """Extension step: congested travel times, re-plan en-route agents, keep the host paths in sync.

@@ -156,3 +156,37 @@ def test_paired_philox_words():
     assert uniform53(7, np.array([11], dtype=np.uint32), 5)[0] == a[1]
     assert uniform53(7, np.array([10], dtype=np.uint32), 6)[0] != a[0]
     assert np.all((a >= 0) & (a < 1))
+
+
+@pytest.mark.parametrize("n,threshold", [(10, 0.3), (500, 0.01), (5000, 0.0004), (70000, 0.0004), (3000, 0.0), (200, 1.0)])
+def test_bulk_departure_draws_equal_the_python_loop(n, threshold):
+    """SimulationThread._draw_departures (MT19937 state handed to numpy, bulk uniforms, rewind to the first hit) ==
+    the reference's loop of random.random() per waiting agent (lib/agent.py:180) with the selector's own draws in
+    between: same departures, same generator state afterwards."""
+    import random
+    import types
+
+    from drift_b200.simulation_thread import SimulationThread
+
+    def journeys(log):
+        def start(agent):  # a selector that consumes a varying number of draws, like random.choice's rejection loop
+            k = 1 + (agent % 3)
+            log.append((agent, [random.random() for _ in range(k)], random.randrange(1000)))
+        return start
+
+    waiting = sorted(random.Random(5).sample(range(2 * n), n))
+    for seed in (1, 2):
+        want_log, got_log = [], []
+        random.seed(seed)
+        want = []
+        start = journeys(want_log)
+        for i in waiting:
+            if random.random() < threshold:
+                want.append(i)
+                start(i)
+        state_want = random.getstate()
+        random.seed(seed)
+        fake = types.SimpleNamespace(_waiting=waiting, agents=list(range(2 * n)), _start_new_journey=journeys(got_log))
+        got = SimulationThread._draw_departures(fake, threshold)
+        assert got == want and got_log == want_log
+        assert random.getstate() == state_want
