@@ -149,10 +149,13 @@ struct P2PArgs {
   int32_t* out_cnt;                       // local [kMaxRanks]: events written to each owner in this tick
 };
 
+constexpr int kP2PSorted = 640;  // keeps the kernel at 6 blocks per SM (shared memory)
+
 struct P2PSmem {
   int ocnt[kMaxRanks], obase[kMaxRanks], ooff[kMaxRanks + 1];
   uint16_t idx[kAdvWarps][kStageCap];
-  uint2 sorted[kAdvWarps * kStageCap];  // the tile's events grouped by owner: (link | enter bit, agent)
+  uint2 sorted[kP2PSorted];  // the tile's events grouped by owner: (link | enter bit, agent); a tile with more events
+                             // than this (rare: every agent of the tile crossing at once) is written record by record
 };
 
 __device__ __noinline__ double p2p_wait_speed(const double* p) {
@@ -440,18 +443,30 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
         // group the events by owner in shared memory, then the whole block writes each owner's run with consecutive
         // threads: the peer stores of a tile are contiguous 16-byte records (full 128-byte NVLink writes) instead of
         // one scattered record per lane
-        for (int k = lane; k < n; k += 32) {
-          const uint32_t lkd = sm.link_kind[w][k];
-          const int o = (int)((lkd & 0x7fffffffu) % (uint32_t)x->world);
-          xs->sorted[xs->ooff[o] + xs->idx[w][k]] = make_uint2(lkd, sm.agent[w][k]);
+        const bool grouped = n_blk <= kP2PSorted;
+        if (grouped) {
+          for (int k = lane; k < n; k += 32) {
+            const uint32_t lkd = sm.link_kind[w][k];
+            const int o = (int)((lkd & 0x7fffffffu) % (uint32_t)x->world);
+            xs->sorted[xs->ooff[o] + xs->idx[w][k]] = make_uint2(lkd, sm.agent[w][k]);
+          }
+          __syncthreads();
         }
-        __syncthreads();
-        for (int t = threadIdx.x; t < n_blk; t += blockDim.x) {
+        // grouped: thread t writes the t-th record of the grouped tile; else every lane writes its own staged records
+        for (int t = grouped ? (int)threadIdx.x : lane; t < (grouped ? n_blk : n); t += grouped ? (int)blockDim.x : 32) {
           int o = 0;
-          while (xs->ooff[o + 1] <= t) ++o;
-          const uint2 rec = xs->sorted[t];
+          uint2 rec;
+          int pos;
+          if (grouped) {
+            while (xs->ooff[o + 1] <= t) ++o;
+            rec = xs->sorted[t];
+            pos = xs->obase[o] + (t - xs->ooff[o]);
+          } else {
+            rec = make_uint2(sm.link_kind[w][t], sm.agent[w][t]);
+            o = (int)((rec.x & 0x7fffffffu) % (uint32_t)x->world);
+            pos = xs->obase[o] + xs->idx[w][t];
+          }
           const int32_t link = (int32_t)(rec.x & 0x7fffffffu);
-          const int pos = xs->obase[o] + (t - xs->ooff[o]);
           if (pos < x->cap) {
             Event e;
             e.link = link;

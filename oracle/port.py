@@ -356,6 +356,22 @@ class PortSim:
                     a.trip["route"].append(node)
         return True
 
+    def viz_snapshot(self):
+        """simulation_thread.py:394-416 (_prepare_agent_data): what the reference does on EVERY tick as shipped
+        (UPDATE_FREQUENCY = 1, config.py:191) -- a throw-away class per agent carrying the fields the widget reads.
+        ~80 % of the reference's wall time; the headless rate switches it off."""
+        out = []
+        t = self.t
+        for a in self.agents:
+            rec = type("Agent", (), {
+                "id": a.idx + 1, "position": (0, 0), "state": "moving" if a.state else "waiting",
+                "agent_type": a.agent_type, "trip_count": a.trip_count, "speed": a.speed, "source": a.source,
+                "target": a.target, "path": a.path if a.has_path else [], "path_index": a.pidx,
+                "current_node": None, "distance_on_edge": a.d, "edge_length": a.elen})
+            rec.simulation_time = t  # :311-312
+            out.append(rec)
+        return out
+
     # ---- extension: congestion-aware rerouting (no reference behaviour; SURVEY.md 8c last row) -----
     # Composed from reference pieces: the BPR factor of traffic_manager.py:92-107 turned into a link
     # travel time tt = t0 / factor(occupancy), NetworkX-order bidirectional Dijkstra on those
