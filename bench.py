@@ -383,6 +383,8 @@ def run_b200(args):
     n_reroutes[0] = 0
     eng.set_option("time_plan", 1)
     eng.phase_times(reset=True)
+    if sharded is not None and args.exchange == "p2p":
+        eng.p2p_phase_detail(1)
     eng.tree_stats(reset=True)
     eng.label_stats(reset=True)
     with ClockSampler(local_rank) as clk:
@@ -395,6 +397,7 @@ def run_b200(args):
         dt = ev0.elapsed_time(ev1) * 1e-3  # device time on the engine's stream, host planning gaps included
     st1 = eng.stats()
     phases = eng.phase_times(reset=True)
+    p2p_detail = eng.p2p_phase_detail(phases["ticks"]) if (sharded is not None and args.exchange == "p2p") else None
     trees = eng.tree_stats(reset=True)
     lab = eng.label_stats(reset=True)
     eng.set_option("time_plan", 0)
@@ -587,7 +590,7 @@ def run_b200(args):
         tt = torch.tensor([local_tick_us, p2p_tick_us], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         local_tick_us, p2p_tick_us = float(tt[0].item()), float(tt[1].item())
-        tick_only = dict(local_tick_us=local_tick_us, exchange_tick_us=p2p_tick_us,
+        tick_only = dict(local_tick_us=local_tick_us, exchange_tick_us=p2p_tick_us, exchange_sections_us=p2p_detail,
                          tick_only_efficiency=local_tick_us / p2p_tick_us if p2p_tick_us > 0 else None,
                          note="max over ranks; local = the same engine with the peer exchange suspended (k_tick_loop on "
                               "this rank's agents only, timing probe), exchange = k_tick_loop_p2p in the timed region")

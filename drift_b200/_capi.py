@@ -105,6 +105,7 @@ SIGNATURES = {
     "drift_kernel_times": (C.c_int, [ENGINE, c_f64p, c_i64p, c_f64p, c_i64p]),
     "drift_set_profiling": (C.c_int, [ENGINE, C.c_int32]),
     "drift_phase_times": (C.c_int, [ENGINE, c_f64p, c_f64p, c_f64p, c_f64p, c_i64p, C.c_int32]),
+    "drift_p2p_phase_detail": (C.c_int, [ENGINE, c_f64p, C.c_int32]),
     "drift_tree_stats": (C.c_int, [ENGINE, c_f64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p, C.c_int32]),
     "drift_time_passes": (C.c_int, [ENGINE, C.c_int32, c_f64p, c_f64p]),
     "drift_set_landmarks": (C.c_int, [ENGINE, C.c_int32, c_f64p, c_f64p]),

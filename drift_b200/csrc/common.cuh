@@ -60,6 +60,9 @@ struct Counters {
   unsigned long long label_entries;   // hub-label router: label entries read by the queries (roofline accounting)
   unsigned long long label_queries;
   unsigned long long n_tie_fallback;  // batched router: queries re-run by the NetworkX-exact router (possible ties)
+  // k_tick_loop_p2p, block 0's clock per tick: advance | block fence | grid barrier | publish | wait for the peers'
+  // flags | list building | grid barrier | resolve + fence
+  unsigned long long p2p_ns[8];
 };
 
 constexpr int kOvfEvents = 1;

@@ -135,7 +135,7 @@ struct drift_engine {
   // persistent tick loop
   bool persistent = true;
   int coop_blocks_per_sm = 6;
-  int occ_tick_loop = 0, occ_tick_loop_p2p = 0;  // resident blocks per SM of the two persistent kernels (queried once)
+  int occ_tick_loop[2] = {0, 0}, occ_tick_loop_p2p[2] = {0, 0};  // resident blocks per SM: {6-, 7-block variant}
   int num_sms = kSMs;
   // pending departures + staged route batch
   DevBuf<int32_t> pend_agent, pend_len;
@@ -733,32 +733,34 @@ int run_tick_loop(drift_engine* e, int32_t n_ticks, double delta, bool demand, d
   if (n_ticks <= 0) return DRIFT_OK;
   TickArgs p = make_tick_args(e, delta, demand);
   int32_t tick0 = (int32_t)e->tick + 1;
-  int& max_per_sm = e->occ_tick_loop;  // per engine: occupancy belongs to the engine's device
-  if (!max_per_sm) {
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_per_sm, k_tick_loop, kAdvThreads, 0));
-    if (max_per_sm < 1) return fail(DRIFT_ECUDA, "k_tick_loop does not fit on an SM");
+  // resident blocks per SM of the 6- and 7-block variants of the two persistent kernels (queried once per engine)
+  if (!e->occ_tick_loop[0]) {
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_tick_loop[0], k_tick_loop<6>, kAdvThreads, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_tick_loop[1], k_tick_loop<7>, kAdvThreads, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_tick_loop_p2p[0], k_tick_loop_p2p<6>, kAdvThreads, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_tick_loop_p2p[1], k_tick_loop_p2p<7>, kAdvThreads, 0));
+    if (e->occ_tick_loop[0] < 1 || e->occ_tick_loop_p2p[0] < 1) return fail(DRIFT_ECUDA, "k_tick_loop does not fit on an SM");
   }
   const int64_t tiles = (e->N + (int64_t)kAdvThreads * kAdvPerThread - 1) / ((int64_t)kAdvThreads * kAdvPerThread);
-  int blocks = e->num_sms * std::min(max_per_sm, e->coop_blocks_per_sm);
+  const int* occ = e->p2p_on ? e->occ_tick_loop_p2p : e->occ_tick_loop;
+  // the 7-block variant only when it is what lets every tile run in one wave (and the caller did not ask for fewer)
+  int per_sm = std::min(occ[0], e->coop_blocks_per_sm);
+  bool seven = false;
+  if (e->coop_blocks_per_sm >= 6 && tiles > (int64_t)e->num_sms * per_sm && occ[1] >= 7 && tiles <= (int64_t)e->num_sms * 7) {
+    per_sm = 7;
+    seven = true;
+  }
+  int blocks = e->num_sms * per_sm;
   if (tiles < blocks) blocks = (int)std::max<int64_t>(tiles, 1);
   if (e->p2p_on) {
-    int& max_p2p = e->occ_tick_loop_p2p;
-    if (!max_p2p) {
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_p2p, k_tick_loop_p2p, kAdvThreads, 0));
-      if (max_p2p < 1) return fail(DRIFT_ECUDA, "k_tick_loop_p2p does not fit on an SM");
-    }
-    blocks = e->num_sms * std::min(max_p2p, e->coop_blocks_per_sm);
-    if (tiles < blocks) blocks = (int)std::max<int64_t>(tiles, 1);
     void* xargs[] = {(void*)&p, (void*)&e->p2p, (void*)&tick0, (void*)&n_ticks, (void*)&p_dep};
-    CU(cudaLaunchCooperativeKernel((void*)k_tick_loop_p2p, dim3(blocks), dim3(kAdvThreads), xargs, 0, e->stream));
-    e->tick += n_ticks;
-    e->loop_ticks += n_ticks;
-    e->total_launches += 1;
-    e->adv_launches += n_ticks;
-    return DRIFT_OK;
+    CU(cudaLaunchCooperativeKernel(seven ? (void*)k_tick_loop_p2p<7> : (void*)k_tick_loop_p2p<6>, dim3(blocks),
+                                   dim3(kAdvThreads), xargs, 0, e->stream));
+  } else {
+    void* args[] = {(void*)&p, (void*)&tick0, (void*)&n_ticks, (void*)&p_dep};
+    CU(cudaLaunchCooperativeKernel(seven ? (void*)k_tick_loop<7> : (void*)k_tick_loop<6>, dim3(blocks),
+                                   dim3(kAdvThreads), args, 0, e->stream));
   }
-  void* args[] = {(void*)&p, (void*)&tick0, (void*)&n_ticks, (void*)&p_dep};
-  CU(cudaLaunchCooperativeKernel((void*)k_tick_loop, dim3(blocks), dim3(kAdvThreads), args, 0, e->stream));
   e->tick += n_ticks;
   e->loop_ticks += n_ticks;
   e->total_launches += 1;
@@ -1866,6 +1868,17 @@ int drift_phase_times(drift_engine* e, double* advance_ns, double* inject_ns, do
     e->plan_ms = 0;
     e->loop_ticks = 0;
   }
+  return DRIFT_OK;
+}
+
+int drift_p2p_phase_detail(drift_engine* e, double ns_out[8], int32_t reset) {
+  if (!e || !ns_out) return fail(DRIFT_EINVAL, "drift_p2p_phase_detail");
+  CU(cudaSetDevice(e->device));
+  Counters c;
+  int rc = fetch_counters(e, &c);
+  if (rc) return rc;
+  for (int k = 0; k < 8; ++k) ns_out[k] = (double)c.p2p_ns[k];
+  if (reset) CU(cudaMemsetAsync(&e->ctr.p->p2p_ns[0], 0, 8 * sizeof(unsigned long long), e->stream));
   return DRIFT_OK;
 }
 

@@ -792,7 +792,13 @@ __global__ void k_resolve_gathered(const __grid_constant__ TickArgs p, const Eve
 
 // ---- the persistent tick loop ---------------------------------------------------------------------
 // One cooperative launch runs `n_ticks` ticks: 2 grid barriers per tick (3 when phase A2 has work).
-__global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop(const __grid_constant__ TickArgs p, int32_t tick0, int32_t n_ticks, double p_dep) {
+// kMinBlocks = resident blocks per SM the kernel is compiled for (6: 40 registers; 7: 32 registers, more spills in the
+// rare-event handlers).  A tick is latency-bound between grid barriers, so what matters is that every tile of a
+// phase runs in ONE wave: with 6 x 148 = 888 blocks, 1 M agents (977 tiles) leave 89 blocks with a second tile and
+// the whole grid waits a second tile time at the barrier (ncu: 73 % of the warp samples stalled on it); the engine
+// picks the variant with the fewest blocks per SM that holds all tiles at once.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kAdvThreads, kMinBlocks) k_tick_loop(const __grid_constant__ TickArgs p, int32_t tick0, int32_t n_ticks, double p_dep) {
   __shared__ AdvSmem sm;
   __shared__ int s_pref[kEvSub + 1];
   cg::grid_group grid = cg::this_grid();
@@ -1004,7 +1010,8 @@ __device__ __forceinline__ bool resolve_one_p2p(const TickArgs& p, const P2PArgs
 
 // One cooperative launch per rank runs `n_ticks` ticks; the ranks meet twice per tick through flags
 // in peer memory (events delivered / links resolved), never through the host.
-__global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_constant__ TickArgs p,
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kAdvThreads, kMinBlocks) k_tick_loop_p2p(const __grid_constant__ TickArgs p,
                                                                   const __grid_constant__ P2PArgs x, int32_t tick0,
                                                                   int32_t n_ticks, double p_dep) {
   __shared__ AdvSmem sm;
@@ -1019,16 +1026,27 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
   for (int32_t k = 0; k < n_ticks; ++k) {
     const int32_t tick = tick0 + k;
     const int par = tick & 1;
-    if (lead) t0 = global_ns();
+    unsigned long long d0 = 0;
+    auto lap = [&](int slot) {  // block 0's own clock, for the breakdown drift_p2p_phase_detail reports
+      if (lead) {
+        const unsigned long long now = global_ns();
+        ctr->p2p_ns[slot] += now - d0;
+        d0 = now;
+      }
+    };
+    if (lead) t0 = d0 = global_ns();
     if (p.demand)
       phase_advance<true, true>(p, tick, p_dep, sm, &x, &xs);
     else
       phase_advance<false, true>(p, tick, p_dep, sm, &x, &xs);
+    lap(0);
     // peer stores of the whole block -> system scope: block barrier, then one fence by one thread (cumulative over the
     // barrier, the construction grid.sync() itself uses at gpu scope), then the grid barrier
     __syncthreads();
     if (threadIdx.x == 0) __threadfence_system();
+    lap(1);
     grid.sync();
+    lap(2);
     const int n_pending = min(ctr->n_pending, p.pend_cap), n_urgent = ctr->n_dep_req[par];
     if (n_pending | n_urgent) {  // uniform across the grid
       phase_inject_p2p(p, x, tick, n_pending, n_urgent);
@@ -1048,7 +1066,9 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
       ctr->phase_ns[0] += t1 - t0;
       t0 = t1;
     }
+    lap(3);
     p2p_wait(my_flags + par * kMaxRanks, x.world, (uint32_t)tick, s_in);
+    lap(4);
     if (threadIdx.x == 0) {
       int acc = 0;
       for (int r = 0; r < x.world; ++r) {
@@ -1067,7 +1087,9 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
       const int4 raw = __ldcg(reinterpret_cast<const int4*>(inbox + e));  // written by a peer: bypass L1
       emit_event(p.lk, inbox, e, raw.x, (uint32_t)raw.y, raw.z, (uint32_t)tick);
     }
+    lap(5);
     grid.sync();
+    lap(6);
     if (lead) {
       ctr->n_pending = 0;
       const unsigned long long t1 = global_ns();
@@ -1086,6 +1108,7 @@ __global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_c
     // waiting (kSpeedDeferred) -- and before the launch-end barrier below
     if (__syncthreads_or(any_remote ? 1 : 0) && threadIdx.x == 0) __threadfence_system();
     if (lead) ctr->phase_ns[2] += global_ns() - t0;
+    lap(7);
     // No all-rank barrier here: the next advance waits per agent for a pending entry speed, the inbox and
     // the event flags are double-buffered by tick parity, and a rank cannot run two ticks ahead of a peer
     // (it needs that peer's events of the next tick first).

@@ -371,6 +371,14 @@ class Engine:
         return dict(ticks=n.value, advance_us_per_tick=a.value / t / 1e3, inject_us_per_tick=i.value / t / 1e3,
                     resolve_us_per_tick=r.value / t / 1e3, plan_ms=pl.value)
 
+    def p2p_phase_detail(self, ticks, reset=True):
+        """Microseconds per tick of the peer-exchange tick kernel's sections (block 0's clock)."""
+        out = np.zeros(8)
+        _capi.check(self._lib.drift_p2p_phase_detail(self._h, _p(out, C.c_double), int(bool(reset))))
+        names = ("advance", "block_fence", "grid_barrier_1", "publish", "wait_peer_flags", "link_events",
+                 "grid_barrier_2", "resolve_and_fence")
+        return {n: float(v) / max(int(ticks), 1) / 1e3 for n, v in zip(names, out)}
+
     def tree_stats(self, reset=True):
         ms = C.c_double(0)
         v = [C.c_int64(0) for _ in range(7)]

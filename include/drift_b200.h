@@ -262,6 +262,10 @@ int drift_set_profiling(drift_engine* e, int32_t on);
  * route-planning batches (CUDA events; needs option "time_plan" = 1). */
 int drift_phase_times(drift_engine* e, double* advance_ns, double* inject_ns, double* resolve_ns, double* plan_ms,
                       int64_t* ticks, int32_t reset);
+/* Peer-exchange tick kernel since the last reset: nanoseconds on block 0's clock spent in advance | block fence |
+ * grid barrier | flag publish | wait for the peers' flags | list building | grid barrier | resolve + fence
+ * (divide by the ticks of drift_phase_times). */
+int drift_p2p_phase_detail(drift_engine* e, double ns_out[8], int32_t reset);
 /* Work and time of the batched tree builder since the last reset (needs option "time_plan" = 1 for
  * the CUDA-event time): trees built, edges relaxed, relaxations that improved a label, nodes expanded. */
 int drift_tree_stats(drift_engine* e, double* build_ms, int64_t* launches, int64_t* jobs, int64_t* relaxed,

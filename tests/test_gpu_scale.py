@@ -10,7 +10,7 @@ HOURLY = np.array([0.05, 0.02, 0.01, 0.01, 0.02, 0.05, 0.15, 0.25, 0.35, 0.20, 0
                    0.22, 0.18, 0.16, 0.20, 0.25, 0.30, 0.35, 0.25, 0.15, 0.12, 0.08, 0.06])
 
 
-def _run(lg, N, seed, ticks, model="activity", blocks=3):
+def _run(lg, N, seed, ticks, model="activity", blocks=3, options=()):
     from drift_b200 import demand
     from drift_b200.engine import Engine, ROUTER_BATCHED
 
@@ -21,6 +21,8 @@ def _run(lg, N, seed, ticks, model="activity", blocks=3):
     eng = Engine(lg, N, route_arena_links=N * 600)
     eng.set_demand(seed, HOURLY * 3, start, chain_capacity=4, router=ROUTER_BATCHED)
     eng.set_option("route_window", ticks)
+    for name, value in options:
+        eng.set_option(name, value)
     eng.push_trips(dst[:, :4])
     t = 2 * 3600.0
     out = []
@@ -132,3 +134,23 @@ def test_route_arena_compaction_is_transparent():
         assert np.array_equal(o1, o2)
         for k in a1:
             assert np.array_equal(a1[k], a2[k])
+
+
+def test_one_wave_tick_kernel_variant_is_bit_identical():
+    """950 k agents = 928 tiles: more than the 6 x 148 blocks of the default persistent kernel can take in one wave, so
+    the engine launches the 7-blocks-per-SM variant (every tile in one wave).  Same results, bit for bit, as the
+    6-block variant run in two waves (coop_blocks_per_sm = 5 forces it)."""
+    from drift_b200.synth import road_graph
+
+    lg = road_graph(20_000, seed=5)
+    outs = []
+    for opts in ((), (("coop_blocks_per_sm", 5),)):
+        eng, out = _run(lg, 950_000, seed=11, ticks=60, model="hub", blocks=2, options=opts)
+        eng.close()
+        outs.append(out)
+    for (o1, a1, d1, r1, h1, s1), (o2, a2, d2, r2, h2, s2) in zip(*outs):
+        assert np.array_equal(o1, o2) and np.array_equal(h1, o1) and s1["moving_agents"] > 10_000
+        for k in a1:
+            assert np.array_equal(a1[k], a2[k]), k
+        assert sorted(zip(*[x.tolist() for x in d1])) == sorted(zip(*[x.tolist() for x in d2]))
+        assert sorted(zip(*[x.tolist() for x in r1])) == sorted(zip(*[x.tolist() for x in r2]))
