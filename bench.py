@@ -417,39 +417,43 @@ def run_b200(args):
 
     progress("timed region done: %.1f ms/step" % (1e3 * dt / K))
     # ---- e2e pass: per step H2D of the step's chains (pinned) + D2H of arrivals/departures/volumes
-    dst_s = np.ascontiguousarray(dst_e2e).reshape(n_local, K + 1, trips_per_step)
-    keep_t, blocks_p = zip(*[pinned(dst_s[:, b, :]) for b in range(K + 1)])
-    h2d = blocks_p[0].nbytes
-    d2h_total = 0
-    eng.push_trips(blocks_p[K])
-    run_block(False)  # warm the per-step path
-    eng.drain_arrivals(), eng.drain_departures(), (sharded.occupancy() if sharded is not None else eng.occupancy())
-    barrier()
-    st_e0 = eng.stats()
-    eng.phase_times(reset=True)
-    eng.tree_stats(reset=True)
-    eng.set_option("time_plan", 1)
-    ev0.record(bench_stream)
-    for b in range(K):
-        eng.push_trips(blocks_p[b])
-        run_block(False)
-        a = eng.drain_arrivals()
-        d = eng.drain_departures()
-        occ = sharded.occupancy() if sharded is not None else eng.occupancy()
-        d2h_total += sum(x.nbytes for x in a) + sum(x.nbytes for x in d) + occ.nbytes
-    ev1.record(bench_stream)
-    barrier()
-    dt_e2e = ev0.elapsed_time(ev1) * 1e-3
-    e2e_phases = eng.phase_times(reset=True)
-    e2e_trees = eng.tree_stats(reset=True)
-    eng.set_option("time_plan", 0)
-    st_e1 = eng.stats()
-    e2e_fallbacks = st_e1["fallback_routes"] - st_e0["fallback_routes"]
-    if dist is not None:
-        tt = torch.tensor([dt_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt_e2e = float(tt.item())
-    e2e_value = total_agents * TPS * K / dt_e2e
+    e2e_value = dt_e2e = None
+    h2d = d2h_total = e2e_fallbacks = 0
+    e2e_phases, e2e_trees, st_e1 = {}, {}, eng.stats()
+    if not args.skip_e2e:  # --skip-e2e: exploratory runs of the largest configs (the line then carries no e2e number)
+        dst_s = np.ascontiguousarray(dst_e2e).reshape(n_local, K + 1, trips_per_step)
+        keep_t, blocks_p = zip(*[pinned(dst_s[:, b, :]) for b in range(K + 1)])
+        h2d = blocks_p[0].nbytes
+        d2h_total = 0
+        eng.push_trips(blocks_p[K])
+        run_block(False)  # warm the per-step path
+        eng.drain_arrivals(), eng.drain_departures(), (sharded.occupancy() if sharded is not None else eng.occupancy())
+        barrier()
+        st_e0 = eng.stats()
+        eng.phase_times(reset=True)
+        eng.tree_stats(reset=True)
+        eng.set_option("time_plan", 1)
+        ev0.record(bench_stream)
+        for b in range(K):
+            eng.push_trips(blocks_p[b])
+            run_block(False)
+            a = eng.drain_arrivals()
+            d = eng.drain_departures()
+            occ = sharded.occupancy() if sharded is not None else eng.occupancy()
+            d2h_total += sum(x.nbytes for x in a) + sum(x.nbytes for x in d) + occ.nbytes
+        ev1.record(bench_stream)
+        barrier()
+        dt_e2e = ev0.elapsed_time(ev1) * 1e-3
+        e2e_phases = eng.phase_times(reset=True)
+        e2e_trees = eng.tree_stats(reset=True)
+        eng.set_option("time_plan", 0)
+        st_e1 = eng.stats()
+        e2e_fallbacks = st_e1["fallback_routes"] - st_e0["fallback_routes"]
+        if dist is not None:
+            tt = torch.tensor([dt_e2e], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt_e2e = float(tt.item())
+        e2e_value = total_agents * TPS * K / dt_e2e
 
     progress("e2e done")
     # ---- auxiliary link passes on the state the runs left behind: volume recount (K3') and BPR travel-time pass (K4)
@@ -659,7 +663,7 @@ def run_b200(args):
             reroutes_per_s=(reroutes_timed / dt) if reroute else None, reroutes_in_timed_region=int(reroutes_timed),
             moving_fraction=float(moving / n_local),
             e2e=dict(value=e2e_value, unit="agent-steps/s", h2d_bytes_per_step=int(h2d),
-                     d2h_bytes_per_step=int(d2h_total / K), ms_per_step=1e3 * dt_e2e / K,
+                     d2h_bytes_per_step=int(d2h_total / K), ms_per_step=(1e3 * dt_e2e / K) if dt_e2e else None,
                      fallback_routes=int(e2e_fallbacks), arena_compactions=int(st_e1["arena_compactions"]),
                      router_stats={k: (round(v, 3) if isinstance(v, float) else v) for k, v in e2e_trees.items()},
                      phases={k: (round(v, 3) if isinstance(v, float) else v) for k, v in e2e_phases.items()}),
@@ -723,6 +727,8 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"],
                     help="multi-GPU: link events over NVLink peer memory inside the tick kernel, or per-tick NCCL all-gather")
     ap.add_argument("--coop-blocks", type=int, default=0, help="blocks per SM of the persistent tick kernel (0 = default)")
+    ap.add_argument("--skip-e2e", action="store_true",
+                    help="skip the end-to-end pass (exploratory runs of the largest configs; e2e is then null)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="label of the line: weak = --agents per GPU is fixed as N grows (default), strong = the caller "
                          "divides a fixed total by N in --agents")

@@ -166,6 +166,7 @@ struct drift_engine {
   DevBuf<int32_t> t_slot_owner, t_slot_job, t_job_qhead, t_job_cnt, t_q_next, t_tie_list;
   int32_t detect_ties = 1;  // option "detect_ties": possible ties of the batched router go to the NetworkX-exact one
   DevBuf<uint32_t> t_slot_job_batch;
+  int64_t router_chunk_opt = 0;  // option "router_chunk": queries per batched-router launch (0 = from the cache slots)
   int32_t t_bounded_max = -1;  // -1 = automatic: bounded search only when the cache cannot hold every destination
   int32_t t_threads = 256;
   int64_t tree_scratch_bytes = (int64_t)64 << 30;
@@ -449,6 +450,7 @@ int invalidate_trees(drift_engine* e) {
 // Largest batch the tree cache can take in one go: every hot key needs a slot, and a key is hot only
 // if more than bounded_max queries of the batch share it.
 int64_t router_chunk(drift_engine* e, int64_t Q, bool congested) {
+  if (e->router_chunk_opt > 0) return e->router_chunk_opt;  // the caller knows its demand is cold (few shared ends)
   const int32_t bm = e->t_bounded_max >= 0 ? e->t_bounded_max : ((e->t_max_slots >= e->V && !congested) ? 0 : kMaxBounded);
   if (bm > 0) return std::max<int64_t>(1, (int64_t)e->t_max_slots * (bm + 1));
   return e->t_max_slots >= (int64_t)e->t_sides * e->V ? std::max<int64_t>(Q, 1) : std::max<int64_t>(1, e->t_max_slots);
@@ -2215,6 +2217,8 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
     e->t_pop_thresh = (int32_t)value;
   } else if (s == "arena_compact_frac") {
     e->arena_compact_frac = std::min(0.95, std::max(0.05, value));
+  } else if (s == "router_chunk") {
+    e->router_chunk_opt = std::max<int64_t>(0, (int64_t)value);
   } else if (s == "detect_ties") {
     e->detect_ties = value != 0;
   } else if (s == "use_labels") {

@@ -1153,7 +1153,7 @@ __global__ void k_extract_paths(GraphArrays g, int64_t Q, const int32_t* __restr
   const int64_t n = n_dev ? (int64_t)*n_dev : Q;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
     const int32_t s = src[q], t = dst[q];
-    if (out.status[q] >= 0) continue;  // answered by a bounded search
+    if (out.status[q] >= 0 || out.status[q] == kStatusTie) continue;  // answered (or left to the exact router) by a bounded search
     out.off[q] = 0;
     out.cost[q] = 0.0;
     out.n_links[q] = 0;

@@ -345,6 +345,9 @@ int drift_host_pow(const double* x, double y, double* out, int64_t n);
  *   tree_delta_scale    multiplies the near-far bucket width; tree_threads: 64 / 128 / 256 threads per search
  *   arena_compact_frac  the live routes are compacted once this fraction of the route arena is used (0.75)
  *   time_plan           1 = time the planning batches with CUDA events (drift_phase_times / drift_tree_stats)
+ *   router_chunk        queries per launch of the batched tree router (default 0 = as many as are guaranteed a cache slot
+ *                       should every key be hot; cold demand -- few trips share an end -- can take far larger chunks,
+ *                       an overflow of the cache is reported as DRIFT_EOVERFLOW)
  *   detect_ties         0 = the batched tree router returns A shortest path without the NetworkX-exact re-run of
  *                       possible ties (default 1)
  *   use_labels          0 = ignore an uploaded hierarchy (DRIFT_ROUTER_BATCHED falls back to trees / bounded searches)
