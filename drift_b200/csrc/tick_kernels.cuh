@@ -149,6 +149,14 @@ struct P2PArgs {
   int32_t* out_cnt;                       // local [kMaxRanks]: events written to each owner in this tick
 };
 
+// An event record travels to its owner WITHOUT a fence: its 4th word carries a check value over (tick, link, agent,
+// kind), and the owner polls each expected record until the check matches (a system-scope fence after the peer
+// stores costs ~6 us per block and tick on NVLink -- more than a quarter of the local tick).  A stale record of the
+// same slot (two ticks old, its 4th word since overwritten by the list link) or a torn one fails the check.
+__device__ __forceinline__ int32_t event_check(uint32_t tick, int32_t link, uint32_t agent, int32_t kind) {
+  return (int32_t)(tick * 2654435761u ^ (uint32_t)link * 0x85EBCA6Bu ^ agent * 0xC2B2AE35u ^ (uint32_t)kind ^ 0x5bd1e995u);
+}
+
 constexpr int kP2PSorted = 640;  // keeps the kernel at 6 blocks per SM (shared memory)
 
 struct P2PSmem {
@@ -472,7 +480,7 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
             e.link = link;
             e.agent = rec.y;
             e.kind = (rec.x >> 31) ? 1 : -1;
-            e.aux = 0;
+            e.aux = event_check((uint32_t)tick, link, rec.y, e.kind);
             *reinterpret_cast<int4*>(x->inbox[o] + ((int64_t)par * x->world + x->rank) * x->cap + pos) =
               *reinterpret_cast<const int4*>(&e);
           } else {
@@ -853,6 +861,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -893,8 +904,8 @@ __device__ __forceinline__ void p2p_home(const P2PArgs& x, uint32_t agent, int& 
   }
 }
 
-__device__ __forceinline__ void p2p_send_one(const TickArgs& p, const P2PArgs& x, int par, int32_t link, uint32_t agent,
-                                             int32_t kind) {
+__device__ __forceinline__ void p2p_send_one(const TickArgs& p, const P2PArgs& x, int par, uint32_t tick, int32_t link,
+                                             uint32_t agent, int32_t kind) {
   const int o = (int)((uint32_t)link % (uint32_t)x.world);
   const int pos = atomicAdd(&x.out_cnt[o], 1);
   if (pos < x.cap) {
@@ -902,9 +913,8 @@ __device__ __forceinline__ void p2p_send_one(const TickArgs& p, const P2PArgs& x
     e.link = link;
     e.agent = agent;
     e.kind = kind;
-    e.aux = 0;
+    e.aux = event_check(tick, link, agent, kind);
     *reinterpret_cast<int4*>(x.inbox[o] + ((int64_t)par * x.world + x.rank) * x.cap + pos) = *reinterpret_cast<const int4*>(&e);
-    __threadfence_system();
   } else {  // see phase_advance: a dropped entry gets the free-flow speed so that nobody waits for its owner
     atomicOr(&p.ctr->overflow, kOvfExchange);
     if (kind > 0) p.a.speed[agent - p.a.base] = __dmul_rn(p.lk.v0[link], p.kph_to_mps);
@@ -927,7 +937,7 @@ __device__ __noinline__ void phase_inject_p2p(const TickArgs& p, const P2PArgs& 
     a.next_link[i] = len > 1 ? p.arena[off + 1] : -1;
     a.elen[i] = p.lk.len[link];
     a.speed[i] = kSpeedPending;
-    p2p_send_one(p, x, tick & 1, link, a.base + (uint32_t)i, 1);
+    p2p_send_one(p, x, tick & 1, (uint32_t)tick, link, a.base + (uint32_t)i, 1);
   };
   const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
@@ -1040,10 +1050,7 @@ __global__ void __launch_bounds__(kAdvThreads, kMinBlocks) k_tick_loop_p2p(const
     else
       phase_advance<false, true>(p, tick, p_dep, sm, &x, &xs);
     lap(0);
-    // peer stores of the whole block -> system scope: block barrier, then one fence by one thread (cumulative over the
-    // barrier, the construction grid.sync() itself uses at gpu scope), then the grid barrier
-    __syncthreads();
-    if (threadIdx.x == 0) __threadfence_system();
+    // no fence for the peer stores: the records are self-validating (event_check), the owner polls them
     lap(1);
     grid.sync();
     lap(2);
@@ -1058,7 +1065,8 @@ __global__ void __launch_bounds__(kAdvThreads, kMinBlocks) k_tick_loop_p2p(const
       x.out_cnt[o] = 0;
       atomicMax(&ctr->max_events, cnt);
       if (cnt > x.cap) cnt = x.cap;  // overflow already flagged by the writers
-      st_release_sys(x.flags[o] + par * kMaxRanks + x.rank, ((unsigned long long)(uint32_t)tick << 32) | (uint32_t)cnt);
+      // the count only: a relaxed store, nothing is ordered behind it (the records carry their own check)
+      st_relaxed_sys(x.flags[o] + par * kMaxRanks + x.rank, ((unsigned long long)(uint32_t)tick << 32) | (uint32_t)cnt);
     }
     if (lead) {
       ctr->n_dep_req[par ^ 1] = 0;
@@ -1084,7 +1092,20 @@ __global__ void __launch_bounds__(kAdvThreads, kMinBlocks) k_tick_loop_p2p(const
       int r = 0;
       while (r + 1 < x.world && s_pref[r + 1] <= f) ++r;
       const int e = (par * x.world + r) * x.cap + (f - s_pref[r]);
-      const int4 raw = __ldcg(reinterpret_cast<const int4*>(inbox + e));  // written by a peer: bypass L1
+      // written by a peer, without a fence: poll (past L1) until the record of THIS tick has landed whole
+      int4 raw;
+      unsigned long long w0 = 0;
+      for (;;) {
+        asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "l"(inbox + e) : "memory");
+        if (raw.w == event_check((uint32_t)tick, raw.x, (uint32_t)raw.y, raw.z) && (raw.z == 1 || raw.z == -1)) break;
+        const unsigned long long now = global_ns();
+        if (!w0) w0 = now;
+        if (now - w0 > 60000000000ULL) {
+          printf("drift_b200: an event record of tick %d did not arrive within 60 s\n", tick);
+          __trap();
+        }
+      }
       emit_event(p.lk, inbox, e, raw.x, (uint32_t)raw.y, raw.z, (uint32_t)tick);
     }
     lap(5);
@@ -1103,10 +1124,10 @@ __global__ void __launch_bounds__(kAdvThreads, kMinBlocks) k_tick_loop_p2p(const
       const bool remote = resolve_one_p2p(p, x, inbox, (par * x.world + r) * x.cap + (f - s_pref[r]));
       any_remote |= remote;
     }
-    // one system-scope fence per block for the speeds it stored into peers: they are then ordered before this rank's
-    // next flag release -- which is what lets a home rank defer an entrant's first advance by one tick without
-    // waiting (kSpeedDeferred) -- and before the launch-end barrier below
-    if (__syncthreads_or(any_remote ? 1 : 0) && threadIdx.x == 0) __threadfence_system();
+    // the speeds stored into peers need no fence either: a home rank polls the value itself (kSpeedPending /
+    // kSpeedDeferred are not speeds).  Only the last tick of a launch fences them (one thread per block, after a block
+    // barrier), so that they have landed before the launch-end barrier below lets any rank return to its host
+    if (k == n_ticks - 1 && __syncthreads_or(any_remote ? 1 : 0) && threadIdx.x == 0) __threadfence_system();
     if (lead) ctr->phase_ns[2] += global_ns() - t0;
     lap(7);
     // No all-rank barrier here: the next advance waits per agent for a pending entry speed, the inbox and
