@@ -748,7 +748,10 @@ int run_tick_loop(drift_engine* e, int32_t n_ticks, double delta, bool demand, d
   // the 7-block variant only when it is what lets every tile run in one wave (and the caller did not ask for fewer)
   int per_sm = std::min(occ[0], e->coop_blocks_per_sm);
   bool seven = false;
-  if (e->coop_blocks_per_sm >= 6 && tiles > (int64_t)e->num_sms * per_sm && occ[1] >= 7 && tiles <= (int64_t)e->num_sms * 7) {
+  // (not for the peer-exchange kernel: its resolve phase keeps more values live and loses more to the 32-register
+  // build than the advance phase gains -- measured 6.6 -> 15.8 us per tick)
+  if (!e->p2p_on && e->coop_blocks_per_sm >= 6 && tiles > (int64_t)e->num_sms * per_sm && occ[1] >= 7 &&
+      tiles <= (int64_t)e->num_sms * 7) {
     per_sm = 7;
     seven = true;
   }
