@@ -353,7 +353,7 @@ def run_b200(args):
     t_sim = T_START
     launches0 = 0
 
-    reroute = bool(w.get("reroute")) and not args.no_reroute and sharded is None
+    reroute = bool(w.get("reroute")) and not args.no_reroute
     n_reroutes = [0]
 
     def run_block(resident=True):
@@ -363,7 +363,10 @@ def run_b200(args):
             step_no[0] += 1
             eng.discard_logs()  # nothing is read back in the resident pass: free the rings (no copy)
         if reroute and eng.tick > 0:  # K4 + reroute of en-route agents + fresh routes for this step's departures
-            eng.update_travel_times()
+            if sharded is not None:  # volumes of all ranks: dense all-reduce of the recount, then K4 on every rank
+                sharded.update_travel_times()
+            else:
+                eng.update_travel_times()
             n_reroutes[0] += eng.reroute_moving(ROUTER_BATCHED)
             eng.invalidate_prefetch(t_sim, delta, TPS)
         if sharded is not None:
@@ -414,6 +417,10 @@ def run_b200(args):
         dist.all_reduce(rt)
         routes = int(rt.item())
     reroutes_timed = n_reroutes[0]
+    if dist is not None and reroute:
+        rt = torch.tensor([reroutes_timed], device="cuda", dtype=torch.int64)
+        dist.all_reduce(rt)
+        reroutes_timed = int(rt.item())
 
     progress("timed region done: %.1f ms/step" % (1e3 * dt / K))
     # ---- e2e pass: per step H2D of the step's chains (pinned) + D2H of arrivals/departures/volumes

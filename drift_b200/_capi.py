@@ -74,6 +74,7 @@ SIGNATURES = {
     "drift_refill_from_pool": (C.c_int, [ENGINE, C.c_int32]),
     "drift_run": (C.c_int, [ENGINE, C.c_int32, C.c_double, C.c_double]),
     "drift_update_travel_times": (C.c_int, [ENGINE]),
+    "drift_update_travel_times_with": (C.c_int, [ENGINE, C.c_void_p]),
     "drift_reroute_moving": (C.c_int, [ENGINE, C.c_int32, c_i64p]),
     "drift_invalidate_prefetch": (C.c_int, [ENGINE, C.c_double, C.c_double, C.c_int32]),
     "drift_read_occupancy": (C.c_int, [ENGINE, c_i32p]),

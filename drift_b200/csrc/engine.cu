@@ -1320,10 +1320,23 @@ int drift_tick_begin_demand(drift_engine* e, double delta, double t, int64_t* n_
   return compact_for_exchange(e, n_events);
 }
 
+static int update_travel_times_from(drift_engine* e, const int32_t* volumes_dev);
+
 int drift_update_travel_times(drift_engine* e) {
   if (!e || !e->have_bpr) return fail(DRIFT_ESTATE, "drift_update_travel_times");
+  return update_travel_times_from(e, e->occ.p);
+}
+
+int drift_update_travel_times_with(drift_engine* e, const void* volumes_dev) {
+  if (!e || !e->have_bpr || !volumes_dev) return fail(DRIFT_ESTATE, "drift_update_travel_times_with");
+  return update_travel_times_from(e, (const int32_t*)volumes_dev);
+}
+
+static int update_travel_times_from(drift_engine* e, const int32_t* volumes_dev) {
   CU(cudaSetDevice(e->device));
-  k_travel_times<<<grid_for((e->L + 3) / 4, 256, kSMs * 8), 256, 0, e->stream>>>(e->links());
+  LinkArrays lk = e->links();
+  lk.occ = const_cast<int32_t*>(volumes_dev);  // read only by k_travel_times
+  k_travel_times<<<grid_for((e->L + 3) / 4, 256, kSMs * 8), 256, 0, e->stream>>>(lk);
   k_refresh_weights<<<grid_for(e->Ef, 256, kSMs * 8), 256, 0, e->stream>>>(e->Ef, e->link_tt.p, e->fwd_link.p,
                                                                            e->bwd_link.p, e->fwd_wc.p, e->bwd_wc.p);
   CU(cudaGetLastError());

@@ -119,6 +119,12 @@ class ShardedEngine:
         dist.all_reduce(t, group=self.group)
         return t
 
+    def update_travel_times(self):
+        """Extension (congestion-aware rerouting) on sharded agents: the link volumes of all ranks are summed with the
+        dense all-reduce, every rank then computes the same BPR travel times (K4) and re-plans its own agents."""
+        vol = self.dense_volume_allreduce()
+        self.engine.update_travel_times_with(vol.data_ptr())
+
     def _set_cap(self, cap):
         cap = int(cap)
         if cap == self.cap:

@@ -175,6 +175,10 @@ class Engine:
     def update_travel_times(self):
         _capi.check(self._lib.drift_update_travel_times(self._h))
 
+    def update_travel_times_with(self, volumes_dev_ptr):
+        """``update_travel_times`` from a device vector of link volumes (int32[L]; e.g. the all-reduced recount)."""
+        _capi.check(self._lib.drift_update_travel_times_with(self._h, C.c_void_p(volumes_dev_ptr)))
+
     def reroute_moving(self, router=ROUTER_NX_EXACT):
         """Extension: re-plan every en-route agent from the head of its current link on the congested
         travel times (call ``update_travel_times`` first).  Returns the number of agents rerouted."""

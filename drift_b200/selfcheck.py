@@ -13,7 +13,7 @@ import numpy as np
 FIELDS = ("state", "dist", "speed", "route_idx", "trip_count")
 
 
-def _drive(run, eng, occupancy, lg, start, first, cands, hourly, ticks, seed, router, hier=None):
+def _drive(run, eng, occupancy, lg, start, first, cands, hourly, ticks, seed, router, hier=None, reroute=None):
     if hier is not None:
         eng.set_hierarchy(hier)
     eng.set_demand(seed, hourly, start, chain_capacity=4, router=router)
@@ -22,6 +22,10 @@ def _drive(run, eng, occupancy, lg, start, first, cands, hourly, ticks, seed, ro
     t, occs = 0.0, []
     for b in range(len(cands)):
         eng.push_trips(cands[b])
+        if reroute is not None and b > 0:  # extension: BPR travel times from the global volumes, re-plan en-route agents
+            reroute()
+            eng.reroute_moving(router)
+            eng.invalidate_prefetch(t, 1.0, ticks)
         t = run(ticks, 1.0, t)
         occs.append(occupancy().copy())
     arr = eng.drain_arrivals()
@@ -29,7 +33,7 @@ def _drive(run, eng, occupancy, lg, start, first, cands, hourly, ticks, seed, ro
 
 
 def sharded_vs_single(device, agents=200_000, nodes=20_000, ticks=100, blocks=3, p2p=True, seed=77, group=None,
-                      labels=True):
+                      labels=True, reroute=False):
     """Returns a dict ``{world, agents, nodes, links, ticks, exchange, ok, detail}``; ``ok`` is the AND over
     all ranks.  Needs an initialised ``torch.distributed`` process group with one CUDA device per rank."""
     import torch
@@ -60,7 +64,8 @@ def sharded_vs_single(device, agents=200_000, nodes=20_000, ticks=100, blocks=3,
         se.enable_p2p()
     lo, hi = se.lo, se.hi
     occ_s, ag_s, arr_s = _drive(se.run, se.engine, se.occupancy, lg, start[lo:hi], first[lo:hi], cands[:, lo:hi],
-                                hourly, ticks, seed, ROUTER_BATCHED, hier)
+                                hourly, ticks, seed, ROUTER_BATCHED, hier,
+                                reroute=se.update_travel_times if reroute else None)
     se.close()
 
     # the same run on one engine (rank 0), broadcast to everybody
@@ -75,7 +80,8 @@ def sharded_vs_single(device, agents=200_000, nodes=20_000, ticks=100, blocks=3,
             eng.run(n, delta, t)
             return t + n * delta
 
-        o1, a1, arr1 = _drive(run1, eng, eng.occupancy, lg, start, first, cands, hourly, ticks, seed, ROUTER_BATCHED, hier)
+        o1, a1, arr1 = _drive(run1, eng, eng.occupancy, lg, start, first, cands, hourly, ticks, seed, ROUTER_BATCHED, hier,
+                              reroute=eng.update_travel_times if reroute else None)
         eng.close()
         occ_1[:] = np.stack(o1)
         for k in FIELDS:
@@ -106,6 +112,6 @@ def sharded_vs_single(device, agents=200_000, nodes=20_000, ticks=100, blocks=3,
     dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
     moved = int(occ_1[-1].sum())
     return dict(world=world, agents=N, nodes=lg.V, links=lg.L, ticks=ticks * blocks, blocks=blocks,
-                exchange="p2p" if p2p else "allgather", router="hub labels" if labels else "trees", completed_trips=int(n_arr_1[0]), on_roads_at_end=moved,
+                exchange="p2p" if p2p else "allgather", router="hub labels" if labels else "trees", reroute=bool(reroute), completed_trips=int(n_arr_1[0]), on_roads_at_end=moved,
                 compared=["link volumes at every block boundary"] + list(FIELDS) + ["completed trips"],
                 ok=bool(ok.item()) and moved > 0, detail=bad)

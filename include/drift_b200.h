@@ -173,6 +173,10 @@ int drift_run(drift_engine* e, int32_t n_ticks, double delta, double t0);
  * tt[l] = t0[l] / factor(occ[l]) (formula of lib/managers/traffic_manager.py:92-107 applied
  * per link) and rerouting of en-route agents from the head of their current link. */
 int drift_update_travel_times(drift_engine* e);
+/* Same from a caller-supplied device vector of link volumes (int32[L]): with agents sharded over several GPUs the
+ * volumes of all ranks are summed first (ncclAllReduce of the recount, drift_recount_device) -- north_star's "the
+ * per-link volume vector is all-reduced" feeding the BPR update -- so that every rank routes on the same times. */
+int drift_update_travel_times_with(drift_engine* e, const void* volumes_dev);
 int drift_reroute_moving(drift_engine* e, int32_t router, int64_t* n_rerouted);
 /* Device-driven demand + extension: waiting agents that will depart during the next n_ticks ticks
  * (clock t0, tick length delta) drop their prefetched routes; the next drift_run replans them on the

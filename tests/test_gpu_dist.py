@@ -108,7 +108,7 @@ def test_sharded_replay_matches_reference(name, world, p2p):
     _spawn(_replay, world, name, p2p)
 
 
-def _selfcheck(rank, world, port, p2p, agents, out):
+def _selfcheck(rank, world, port, p2p, agents, reroute, out):
     import torch
     import torch.distributed as dist
 
@@ -119,7 +119,7 @@ def _selfcheck(rank, world, port, p2p, agents, out):
     try:
         from drift_b200.selfcheck import sharded_vs_single
 
-        r = sharded_vs_single(rank, agents=agents, nodes=5000, ticks=60, blocks=4, p2p=p2p)
+        r = sharded_vs_single(rank, agents=agents, nodes=5000, ticks=60, blocks=4, p2p=p2p, reroute=reroute)
         assert r["ok"], r
         assert r["completed_trips"] > 100 and r["on_roads_at_end"] > 1000, r
         out.put((rank, "ok"))
@@ -137,4 +137,12 @@ def test_sharded_device_demand_equals_single_engine(world, p2p):
     volumes at every block boundary, fp64 positions / speeds, route indices, trip counts, completed trips).
     p2p=False: per-tick all-gather of the link events (NCCL); p2p=True: the exchange inside the persistent
     tick kernel over NVLink peer memory (k_tick_loop_p2p, link-owner resolution) -- what bench.py uses."""
-    _spawn(_selfcheck, world, p2p, 40_000 + world)  # + world: uneven shards
+    _spawn(_selfcheck, world, p2p, 40_000 + world, False)  # + world: uneven shards
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_reroute_equals_single_engine(world):
+    """The extension on sharded agents: every rank recounts the volumes of its agents, the dense int32[L] vector is
+    all-reduced (NCCL), every rank computes the same BPR travel times and re-plans its own en-route agents -- the run
+    stays bit-identical to one engine doing the same on all agents."""
+    _spawn(_selfcheck, world, True, 30_000 + world, True)
