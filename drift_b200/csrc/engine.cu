@@ -135,7 +135,8 @@ struct drift_engine {
   // persistent tick loop
   bool persistent = true;
   int coop_blocks_per_sm = 6;
-  int occ_tick_loop[2] = {0, 0}, occ_tick_loop_p2p[2] = {0, 0};  // resident blocks per SM: {6-, 7-block variant}
+  int occ_tick_loop = 0, occ_tick_loop_p2p = 0;  // resident blocks per SM of the two persistent kernels (queried once)
+  bool one_wave = true;  // option "one_wave_tiles"
   int num_sms = kSMs;
   // pending departures + staged route batch
   DevBuf<int32_t> pend_agent, pend_len;
@@ -735,36 +736,30 @@ int run_tick_loop(drift_engine* e, int32_t n_ticks, double delta, bool demand, d
   if (n_ticks <= 0) return DRIFT_OK;
   TickArgs p = make_tick_args(e, delta, demand);
   int32_t tick0 = (int32_t)e->tick + 1;
-  // resident blocks per SM of the 6- and 7-block variants of the two persistent kernels (queried once per engine)
-  if (!e->occ_tick_loop[0]) {
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_tick_loop[0], k_tick_loop<6>, kAdvThreads, 0));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_tick_loop[1], k_tick_loop<7>, kAdvThreads, 0));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_tick_loop_p2p[0], k_tick_loop_p2p<6>, kAdvThreads, 0));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_tick_loop_p2p[1], k_tick_loop_p2p<7>, kAdvThreads, 0));
-    if (e->occ_tick_loop[0] < 1 || e->occ_tick_loop_p2p[0] < 1) return fail(DRIFT_ECUDA, "k_tick_loop does not fit on an SM");
+  if (!e->occ_tick_loop) {  // resident blocks per SM of the two persistent kernels (queried once per engine)
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_tick_loop, k_tick_loop, kAdvThreads, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->occ_tick_loop_p2p, k_tick_loop_p2p, kAdvThreads, 0));
+    if (e->occ_tick_loop < 1 || e->occ_tick_loop_p2p < 1) return fail(DRIFT_ECUDA, "k_tick_loop does not fit on an SM");
   }
-  const int64_t tiles = (e->N + (int64_t)kAdvThreads * kAdvPerThread - 1) / ((int64_t)kAdvThreads * kAdvPerThread);
-  const int* occ = e->p2p_on ? e->occ_tick_loop_p2p : e->occ_tick_loop;
-  // the 7-block variant only when it is what lets every tile run in one wave (and the caller did not ask for fewer)
-  int per_sm = std::min(occ[0], e->coop_blocks_per_sm);
-  bool seven = false;
-  // (not for the peer-exchange kernel: its resolve phase keeps more values live and loses more to the 32-register
-  // build than the advance phase gains -- measured 6.6 -> 15.8 us per tick)
-  if (!e->p2p_on && e->coop_blocks_per_sm >= 6 && tiles > (int64_t)e->num_sms * per_sm && occ[1] >= 7 &&
-      tiles <= (int64_t)e->num_sms * 7) {
-    per_sm = 7;
-    seven = true;
-  }
+  const int per_sm = std::min(e->p2p_on ? e->occ_tick_loop_p2p : e->occ_tick_loop, e->coop_blocks_per_sm);
   int blocks = e->num_sms * per_sm;
+  // every tile of a phase in ONE wave where a few more agents per tile achieve it (see TickArgs::tile_singles)
+  int64_t tiles = (e->N + kAdvTileQuads - 1) / kAdvTileQuads;
+  p.tile_singles = 0;
+  if (tiles > blocks && e->one_wave)
+    for (int s = 32; s <= kAdvMaxSingles; s += 32)
+      if ((e->N + kAdvTileQuads + s - 1) / (kAdvTileQuads + s) <= blocks) {
+        p.tile_singles = s;
+        tiles = (e->N + kAdvTileQuads + s - 1) / (kAdvTileQuads + s);
+        break;
+      }
   if (tiles < blocks) blocks = (int)std::max<int64_t>(tiles, 1);
   if (e->p2p_on) {
     void* xargs[] = {(void*)&p, (void*)&e->p2p, (void*)&tick0, (void*)&n_ticks, (void*)&p_dep};
-    CU(cudaLaunchCooperativeKernel(seven ? (void*)k_tick_loop_p2p<7> : (void*)k_tick_loop_p2p<6>, dim3(blocks),
-                                   dim3(kAdvThreads), xargs, 0, e->stream));
+    CU(cudaLaunchCooperativeKernel((void*)k_tick_loop_p2p, dim3(blocks), dim3(kAdvThreads), xargs, 0, e->stream));
   } else {
     void* args[] = {(void*)&p, (void*)&tick0, (void*)&n_ticks, (void*)&p_dep};
-    CU(cudaLaunchCooperativeKernel(seven ? (void*)k_tick_loop<7> : (void*)k_tick_loop<6>, dim3(blocks),
-                                   dim3(kAdvThreads), args, 0, e->stream));
+    CU(cudaLaunchCooperativeKernel((void*)k_tick_loop, dim3(blocks), dim3(kAdvThreads), args, 0, e->stream));
   }
   e->tick += n_ticks;
   e->loop_ticks += n_ticks;
@@ -894,8 +889,9 @@ int drift_add_agents(drift_engine* e, int64_t n_agents, int64_t agent_base, int6
   if (e->N) return fail(DRIFT_ESTATE, "drift_add_agents: agents already created");
   if (agent_base + n_agents >= ((int64_t)1 << 32)) return fail(DRIFT_EINVAL, "agent ids must fit 32 bits");
   CU(cudaSetDevice(e->device));
+  // padded to whole tiles, with room for the widest tile shape of the persistent kernel (TickArgs::tile_singles)
   const int64_t tile = (int64_t)kAdvThreads * kAdvPerThread;
-  const int64_t Np = (n_agents + tile - 1) / tile * tile;
+  const int64_t Np = (n_agents + kAdvTileQuads + kAdvMaxSingles + tile - 1) / tile * tile;
   CU(e->state.alloc(Np));
   CU(e->dist.alloc(Np));
   CU(e->speed.alloc(Np));
@@ -2233,6 +2229,8 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
     e->t_pop_thresh = (int32_t)value;
   } else if (s == "arena_compact_frac") {
     e->arena_compact_frac = std::min(0.95, std::max(0.05, value));
+  } else if (s == "one_wave_tiles") {
+    e->one_wave = value != 0;
   } else if (s == "router_chunk") {
     e->router_chunk_opt = std::max<int64_t>(0, (int64_t)value);
   } else if (s == "detect_ties") {

@@ -50,6 +50,11 @@ struct TickArgs {
   int32_t pend_cap;         // entries of the pend_* arrays; ctr->n_pending may exceed it (flagged kOvfPending)
   double delta;
   double kph_to_mps;
+  // A tile = 1024 agents handled four per thread + `tile_singles` agents (a multiple of 32, <= 256) handled one per
+  // thread by the first threads of the block.  0 unless that is what lets every tile of the persistent kernel run in
+  // ONE wave: a tick is latency-bound between grid barriers, and a block with a second tile makes the whole grid wait
+  // a second tile time (1 M agents = 977 plain tiles on 888 resident blocks; 869 tiles of 1024 + 128).
+  int32_t tile_singles;
   int32_t demand;           // device-driven departures on/off
   int32_t debug;            // timing probes only (tools/tick_probe.py): 1 = no departure draws, 2 = crossers stay, 4 = events not emitted
 };
@@ -107,7 +112,9 @@ __device__ __forceinline__ void emit_event(const LinkArrays& lk, Event* __restri
 // reserves the slots with ONE global atomic (single-address L2 atomics serialise at ~1 op/cycle
 // chip-wide) and all threads write + link the staged events.
 constexpr int kAdvWarps = kAdvThreads / 32;
-constexpr int kStageCap = 2 * 32 * kAdvPerThread;  // every agent of a warp's slice emits <= 2 events
+constexpr int kAdvTileQuads = kAdvThreads * kAdvPerThread;  // agents of a tile that are processed four per thread
+constexpr int kAdvMaxSingles = kAdvThreads;                 // + at most one more agent per thread (TickArgs::tile_singles)
+constexpr int kStageCap = 2 * 32 * (kAdvPerThread + 1);     // every agent of a warp's slice emits <= 2 events
 
 struct AdvSmem {  // per-warp staging: warps do not wait for each other while they process agents
   int n[kAdvWarps];
@@ -316,13 +323,16 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
   const AgentArrays& a = p.a;
   const int par = tick & 1;
   const unsigned long long dep_thresh = DEMAND ? departure_threshold(p_dep) : 0ULL;
-  const int64_t tiles = (a.n + (int64_t)kAdvThreads * kAdvPerThread - 1) / ((int64_t)kAdvThreads * kAdvPerThread);
+  const int64_t tile_agents = (int64_t)kAdvTileQuads + p.tile_singles;
+  const int64_t tiles = (a.n + tile_agents - 1) / tile_agents;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     if (lane == 0) sm.n[w] = 0;
     if (P2P && threadIdx.x < kMaxRanks) xs->ocnt[threadIdx.x] = 0;
     __syncwarp();
-    const int64_t i0 = (tile * kAdvThreads + threadIdx.x) * kAdvPerThread;
+    const int64_t i0 = tile * tile_agents + (int64_t)threadIdx.x * kAdvPerThread;
+    // the thread's single agent of this tile (tile_singles > 0 only), handled after the quad
+    const int64_t is = (int)threadIdx.x < p.tile_singles ? tile * tile_agents + kAdvTileQuads + threadIdx.x : a.n;
     if (i0 < a.n) {
       const uint32_t st4 = *reinterpret_cast<const uint32_t*>(a.state + i0);
       uint32_t cn4 = 0;
@@ -423,6 +433,37 @@ __device__ __forceinline__ void phase_advance(const TickArgs& p, int32_t tick, d
         }
       }
       if (nst4 != st4) *reinterpret_cast<uint32_t*>(a.state + i0) = nst4;
+    }
+    if (is < a.n) {  // the same steps for the thread's single agent
+      const uint32_t st1 = a.state[is];
+      const uint32_t cn1 = DEMAND ? a.chain_cnt[is] : 0u;
+      uint32_t nst1 = st1;
+      bool pend1 = false;
+      if (st1) {
+        const double d1 = a.dist[is];
+        const double s1 = P2P ? __ldcg(a.speed + is) : a.speed[is];
+        const double e1 = P2P ? __ldcg(a.elen + is) : a.elen[is];
+        bool skip1 = false;
+        if (P2P && s1 < 0.0) {
+          if (s1 == kSpeedDeferred && !owes_advance(d1)) skip1 = true; else pend1 = true;
+        }
+        if (skip1) {
+          a.dist[is] = __longlong_as_double(kNegZeroBits);
+        } else if (!pend1) {
+          double dj = d1;
+          if (P2P && owes_advance(dj)) dj = __dadd_rn(0.0, __dmul_rn(s1, p.delta));
+          const double nd = __dadd_rn(dj, __dmul_rn(s1, p.delta));  // agent.py:197-198
+          const bool c = nd >= e1;
+          a.dist[is] = c ? 0.0 : nd;
+          if (c && !(p.debug & 2) && cross_agent(p, is, tick, sm, P2P)) nst1 = kWaiting;
+        }
+      }
+      if (DEMAND && st1 == kWaiting && cn1 != 0 && !(p.debug & 1) &&
+          philox_bits53(p.dm.seed, a.base + (uint32_t)is, (uint32_t)tick) < dep_thresh) {  // agent.py:180
+        if (depart_agent(p, is, (int)cn1, tick, sm, P2P)) nst1 = kMoving;
+      }
+      if (P2P && pend1 && advance_late(p, is, tick, sm)) nst1 = kWaiting;
+      if (nst1 != st1) a.state[is] = (uint8_t)nst1;
     }
     __syncthreads();  // all warps of the block have staged their events
     int n_blk = 0, my_off = 0;
@@ -800,13 +841,7 @@ __global__ void k_resolve_gathered(const __grid_constant__ TickArgs p, const Eve
 
 // ---- the persistent tick loop ---------------------------------------------------------------------
 // One cooperative launch runs `n_ticks` ticks: 2 grid barriers per tick (3 when phase A2 has work).
-// kMinBlocks = resident blocks per SM the kernel is compiled for (6: 40 registers; 7: 32 registers, more spills in the
-// rare-event handlers).  A tick is latency-bound between grid barriers, so what matters is that every tile of a
-// phase runs in ONE wave: with 6 x 148 = 888 blocks, 1 M agents (977 tiles) leave 89 blocks with a second tile and
-// the whole grid waits a second tile time at the barrier (ncu: 73 % of the warp samples stalled on it); the engine
-// picks the variant with the fewest blocks per SM that holds all tiles at once.
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kAdvThreads, kMinBlocks) k_tick_loop(const __grid_constant__ TickArgs p, int32_t tick0, int32_t n_ticks, double p_dep) {
+__global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop(const __grid_constant__ TickArgs p, int32_t tick0, int32_t n_ticks, double p_dep) {
   __shared__ AdvSmem sm;
   __shared__ int s_pref[kEvSub + 1];
   cg::grid_group grid = cg::this_grid();
@@ -1020,8 +1055,7 @@ __device__ __forceinline__ bool resolve_one_p2p(const TickArgs& p, const P2PArgs
 
 // One cooperative launch per rank runs `n_ticks` ticks; the ranks meet twice per tick through flags
 // in peer memory (events delivered / links resolved), never through the host.
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kAdvThreads, kMinBlocks) k_tick_loop_p2p(const __grid_constant__ TickArgs p,
+__global__ void __launch_bounds__(kAdvThreads, 6) k_tick_loop_p2p(const __grid_constant__ TickArgs p,
                                                                   const __grid_constant__ P2PArgs x, int32_t tick0,
                                                                   int32_t n_ticks, double p_dep) {
   __shared__ AdvSmem sm;

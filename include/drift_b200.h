@@ -349,6 +349,8 @@ int drift_host_pow(const double* x, double y, double* out, int64_t n);
  *   tree_delta_scale    multiplies the near-far bucket width; tree_threads: 64 / 128 / 256 threads per search
  *   arena_compact_frac  the live routes are compacted once this fraction of the route arena is used (0.75)
  *   time_plan           1 = time the planning batches with CUDA events (drift_phase_times / drift_tree_stats)
+ *   one_wave_tiles      0 = plain 1024-agent tiles in the persistent tick kernel even when a slightly larger tile
+ *                       (1024 + up to 256 agents) would let all tiles run in one wave of resident blocks (default 1)
  *   router_chunk        queries per launch of the batched tree router (default 0 = as many as are guaranteed a cache slot
  *                       should every key be hot; cold demand -- few trips share an end -- can take far larger chunks,
  *                       an overflow of the cache is reported as DRIFT_EOVERFLOW)

@@ -136,15 +136,15 @@ def test_route_arena_compaction_is_transparent():
             assert np.array_equal(a1[k], a2[k])
 
 
-def test_one_wave_tick_kernel_variant_is_bit_identical():
-    """950 k agents = 928 tiles: more than the 6 x 148 blocks of the default persistent kernel can take in one wave, so
-    the engine launches the 7-blocks-per-SM variant (every tile in one wave).  Same results, bit for bit, as the
-    6-block variant run in two waves (coop_blocks_per_sm = 5 forces it)."""
+def test_one_wave_tiles_are_bit_identical():
+    """950 k agents = 928 plain tiles of 1 024: more than the 6 x 148 resident blocks of the persistent tick kernel can
+    take in one wave, so the engine widens the tiles (1 024 agents four per thread + 64 one per thread = 874 tiles).
+    Same results, bit for bit, as plain tiles run in two waves (one_wave_tiles = 0)."""
     from drift_b200.synth import road_graph
 
     lg = road_graph(20_000, seed=5)
     outs = []
-    for opts in ((), (("coop_blocks_per_sm", 5),)):
+    for opts in ((), (("one_wave_tiles", 0),)):
         eng, out = _run(lg, 950_000, seed=11, ticks=60, model="hub", blocks=2, options=opts)
         eng.close()
         outs.append(out)
