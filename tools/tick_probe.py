@@ -22,7 +22,7 @@ def main():
     args = ap.parse_args()
     w = bench.WORKLOADS[args.workload]
     n = args.agents or w["agents"]
-    lg, start, model, rng = bench.build_workload(args.workload, n, 0, 0)
+    lg, start, model, rng, _kind = bench.build_workload(args.workload, n, 0, 0)
     eng = Engine(lg, n, route_arena_links=max(1 << 24, n * 1536))
     _, dst = bench.make_chains(model, rng, lg, start, 4 + 2 * 3)
     dst = dst.reshape(n, -1)
