@@ -476,7 +476,10 @@ def run_b200(args):
                                             "staged in a shared-memory histogram per 1024-agent tile)",
                         us_per_launch=tp["recount_us"], algorithmic_bytes_per_launch=sc_bytes,
                         achieved=sc_bytes / (tp["recount_us"] * 1e-6) / 1e9, peak=peak, unit="GB/s",
-                        frac=sc_bytes / (tp["recount_us"] * 1e-6) / 1e9 / peak, traffic=None, peak_source=peak_src,
+                        frac=sc_bytes / (tp["recount_us"] * 1e-6) / 1e9 / peak,
+                        traffic=8.57e6 if (args.workload == "regional1m" and not args.agents and sharded is None) else None,
+                        traffic_source="ncu --set full capture of k_recount on this workload "
+                                       "(profiles/r2_recount_travel_times_set_full_raw.csv)", peak_source=peak_src,
                         agents=n_local, moving_agents=mv_aux, links=lg.L, links_touched=touched,
                         note="1 B state per agent + 4 B cur_link per moving agent + 4 B zero-fill per link + 8 B RMW per "
                              "touched link (SURVEY.md 8d); %.1f MB at this size = %.1f us at peak: launch-latency-bound"
@@ -484,7 +487,10 @@ def run_b200(args):
     roof_bpr = dict(bound="hbm", kernel="k_travel_times (tt = t0 / factor(occ), fused elementwise pass over the link arrays)",
                     us_per_launch=tp["travel_times_us"], algorithmic_bytes_per_launch=bpr_bytes,
                     achieved=bpr_bytes / (tp["travel_times_us"] * 1e-6) / 1e9, peak=peak, unit="GB/s",
-                    frac=bpr_bytes / (tp["travel_times_us"] * 1e-6) / 1e9 / peak, traffic=None, peak_source=peak_src,
+                    frac=bpr_bytes / (tp["travel_times_us"] * 1e-6) / 1e9 / peak,
+                    traffic=18.0e6 if (args.workload == "regional1m" and not args.agents) else None,
+                    traffic_source="dram__bytes_read of the ncu --set full capture (the 9.3 MB of tt stores stay in L2 within "
+                                   "the capture; profiles/r2_recount_travel_times_set_full_raw.csv)", peak_source=peak_src,
                     links=lg.L, note="24 B per link: occ 4 R + capacity class 4 R + t0 8 R + tt 8 W (SURVEY.md 8d)")
     # ---- multi-GPU: north_star's dense per-tick all-reduce of the volume vector, as the labelled baseline next to
     # the sparse event exchange the tick uses (SURVEY.md H6 "report both")
@@ -529,9 +535,9 @@ def run_b200(args):
     achieved = alg_bytes / (adv_ms * 1e-3) / 1e9 if adv_ms > 0 else 0.0
     roof_adv = dict(bound="hbm", kernel="k_advance (standalone launch, CUDA events on the engine stream)",
                     achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                    traffic=43.5e6 if (args.workload == "regional1m" and not args.agents) else None,
-                    traffic_source="dram__bytes_read+write per launch, ncu --set full capture of this kernel on this "
-                                   "workload at 43 % moving (profiles/r1_k_advance_set_full_raw.csv)",
+                    traffic=43.9e6 if (args.workload == "regional1m" and not args.agents) else None,
+                    traffic_source="dram__bytes_read+write per launch: 100 launches of this kernel on this workload in the "
+                                   "ncu launch list profiles/r2_launches_regional1m_ncu.csv (4.39 GB + 2.5 MB)",
                     peak_source=peak_src, us_per_launch=adv_ms * 1e3, moving_agents=moving,
                     algorithmic_bytes_per_launch=alg_bytes,
                     note="1 B per waiting + 33 B per moving agent-step (SURVEY.md 8d); at this size the kernel is "
@@ -562,9 +568,10 @@ def run_b200(args):
         roof = dict(bound="hbm", kernel="k_tick_loop (persistent cooperative kernel: advance + resolve phases of "
                                         "%d ticks per launch; in-kernel %%globaltimer phase clocks)" % TPS,
                     achieved=ach_t, peak=peak, unit="GB/s", frac=ach_t / peak,
-                    traffic=10.2e9 if ncu_ok else None,
-                    traffic_source="dram__bytes_read+write of one 300-tick launch, ncu --set full capture of this kernel on "
-                                   "this workload (profiles/r1_k_tick_loop_set_full_raw.csv)" if ncu_ok else None,
+                    traffic=6.8e9 if ncu_ok else None,
+                    traffic_source="dram__bytes_read+write of one 300-tick launch (5.65 / 7.88 GB in the two captured "
+                                   "launches = 19-26 MB per tick), ncu --set full capture of this kernel on this workload "
+                                   "(profiles/r2_tick_loop_label_query_label_paths_set_full_raw.csv)" if ncu_ok else None,
                     peak_source=peak_src, us_per_launch=tick_us * TPS, us_per_tick=tick_us,
                     algorithmic_bytes_per_launch=alg_tick * TPS, algorithmic_bytes_per_tick=alg_tick,
                     moving_agents=mv_t, events_per_tick=ev_tick, share_of_step=tick_us * TPS / (1e6 * dt / K),

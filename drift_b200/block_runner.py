@@ -41,6 +41,7 @@ class BlockSimulation:
         self.engine = Engine(lg, self.N, alpha=alpha, beta=beta, device=device,
                              route_arena_links=route_arena_links or max(1 << 22, self.N * 1024))
         self.keep_log = keep_log
+        self.keep_rows = False  # set to keep the rows in self.rows when no CSV is written
         self.departure_log = []  # (tick, agent, src, dst, status) of every departure (keep_log only)
         if hierarchy is not None:  # static travel times: route by hub labels (drift_b200.hierarchy)
             self.engine.set_hierarchy(hierarchy)
@@ -63,6 +64,7 @@ class BlockSimulation:
         self._open = np.ones(self.N, dtype=bool)      # the reference opens a trip for every agent at init
         self._first = np.ones(self.N, dtype=bool)     # first-trip quirk still pending
         self._routes = {}                             # agent -> node list (record_routes only)
+        self.rows = []
         self._fh = self._csv = None
         if csv_path:
             self._fh = open(csv_path, "w", newline="", encoding="utf-8")
@@ -156,6 +158,11 @@ class BlockSimulation:
         return route
 
     def _close(self, agent, t, upto=None, moving=False):
+        if self._csv is None and not self.keep_rows:  # nobody reads the row: count it only (long-horizon runs)
+            self._routes.pop(agent, None)
+            self._open[agent] = False
+            self._first[agent] = False
+            return None
         minutes = (float(t) - float(self._open_t0[agent])) / 60.0
         km = float(self._open_m[agent]) / 1000.0
         nodes = self.lg.nodes
@@ -185,6 +192,8 @@ class BlockSimulation:
     def _write(self, rows):
         if self._csv is not None:
             self._csv.writerows(rows)
+        elif self.keep_rows:
+            self.rows.extend(rows)
         self.rows_written += len(rows)
 
     def finish(self):
