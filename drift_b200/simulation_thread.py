@@ -150,6 +150,7 @@ class SimulationThread(QThread):
         self.update_mutex = QMutex()
         self.batch_size = BATCH_SIZE
         self.update_frequency = UPDATE_FREQUENCY
+        self.snapshot_stride = 1  # agents_updated carries every k-th agent (1 = all, the reference's behaviour)
         self.last_visual_update = 0
         self.agent_positions = []
         self.agent_states = []
@@ -521,19 +522,22 @@ class SimulationThread(QThread):
         return pos[u] + direction * float(snap["dist"][i])
 
     def _prepare_agent_data(self):
+        """lib/simulation_thread.py:394-416.  ``snapshot_stride`` (default 1 = every agent, like the reference) thins
+        the snapshot for large runs: the untouched PyQt widget then draws every k-th agent."""
         snap = self._snapshot()
+        speed, ridx = snap["speed"].tolist(), snap["route_idx"].tolist()  # one bulk conversion, not one per agent
         out = []
-        for a in self.agents:
+        for a in self.agents[::max(1, int(getattr(self, "snapshot_stride", 1)))]:
             rec = _AgentSnapshot()
             rec.id = a.id
             rec.position = self._agent_position(a.index)
             rec.state = a.state
             rec.agent_type = a.agent_type
             rec.trip_count = a.trip_count
-            rec.speed = float(snap["speed"][a.index]) if a._departures else 0
+            rec.speed = speed[a.index] if a._departures else 0
             rec.source, rec.target = a.source, a.target
             rec.path = getattr(a, "path", [])
-            rec.path_index = a._pidx_base + int(snap["route_idx"][a.index]) if a._departures else 0
+            rec.path_index = a._pidx_base + ridx[a.index] if a._departures else 0
             rec.current_node = rec.target_node = None
             rec.progress = 0.0
             out.append(rec)
