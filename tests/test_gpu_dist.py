@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 
 def _free_port():
     s = socket.socket()
+    s.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
     s.bind(("127.0.0.1", 0))
     p = s.getsockname()[1]
     s.close()
@@ -84,14 +85,27 @@ def _spawn(target, world, *args):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     ctx = mp.get_context("spawn")
-    out = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=target, args=(r, world, port) + args + (out,)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = [out.get(timeout=900) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
+    res = []
+    for attempt in range(2):  # a rendezvous port can be taken between _free_port() and the store's bind: one retry
+        out = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=target, args=(r, world, port) + args + (out,)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = []
+        try:
+            for _ in procs:
+                res.append(out.get(timeout=600))
+                if res[-1][1] != "ok":  # fail fast: the other ranks would wait for this one until their timeout
+                    break
+        finally:
+            done = len(res) == world and all(r[1] == "ok" for r in res)
+            for p in procs:
+                if not done and p.is_alive():
+                    p.terminate()
+                p.join(timeout=60)
+        if done or not any("EADDRINUSE" in str(r[1]) or "address already in use" in str(r[1]) for r in res):
+            break
     assert sorted(res) == [(r, "ok") for r in range(world)], res
 
 
