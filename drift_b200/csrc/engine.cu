@@ -555,9 +555,10 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     k_tree_requests<<<gq, 256, 0, e->stream>>>(Q, qs, qd, tc, e->ctr.p, n_dev);
     Landmarks lm;
     lm.tab = e->lm_tab.p;
-    // the landmark distances are free-flow distances; congested times are never shorter (tt = t0 / factor, factor <= 1,
-    // traffic_manager.py:92-107), so they remain valid lower bounds and the potentials stay feasible
-    lm.K = e->lm_K;
+    // The landmark distances are free-flow distances.  They remain valid lower bounds on congested times (tt = t0 /
+    // factor >= t0), but weak ones: with them the goal-directed search keeps its four times finer buckets and loses its
+    // direction -- measured 10 x slower on the reroute workloads -- so congested routing runs without potentials.
+    lm.K = use_congested ? 0 : e->lm_K;
     k_link_queries<<<gq, 256, 0, e->stream>>>(Q, qs, qd, tc, n_dev);
     cudaEvent_t tb0 = nullptr, tb1 = nullptr;
     if (e->time_plan) {

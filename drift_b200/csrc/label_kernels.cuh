@@ -38,7 +38,6 @@ struct LabelSet {  // labels of one side: the label of v is entries [off[v], off
 };
 
 constexpr int kLabelThreads = 256;
-constexpr int kUnpackStack = 1024;  // most levels a hierarchy may have (shortcut nesting, length of a climb)
 constexpr int32_t kStatusPending = -2;
 
 __device__ __forceinline__ int label_hash_slot(int32_t* keys, int H, int shift, int32_t hub, int* s_n) {

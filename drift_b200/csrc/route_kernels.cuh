@@ -714,7 +714,7 @@ constexpr double kTieTol = 1e-12;
 __device__ __forceinline__ bool near_tight(double s, double du) { return fabs(s - du) <= kTieTol * du; }
 
 // Same, but scans every entry: returns the first exactly tight one and sets *tie when another entry is tight
-// within kTieTol.
+// within kTieTol.  Loads are issued four entries at a time like find_tight_entry.
 __device__ __forceinline__ int32_t find_tight_entry_ties(int32_t e0, int32_t e1, unsigned long long du,
                                                          const NodeRec* __restrict__ rec,
                                                          const int32_t* __restrict__ col, const double* __restrict__ w,
@@ -722,16 +722,29 @@ __device__ __forceinline__ int32_t find_tight_entry_ties(int32_t e0, int32_t e1,
   int32_t first = -1;
   int near = 0;
   const double dud = __longlong_as_double((long long)du);
-  for (int32_t e = e0; e < e1; ++e) {
-    const unsigned long long d = rec[col[e]].dist;
-    if (d == kInfBits) continue;
-    const double s = __dadd_rn(__longlong_as_double((long long)d), w[e]);
-    if (first < 0 && (unsigned long long)__double_as_longlong(s) == du) {
-      first = e;
-      *d_next = d;
-      ++near;
-    } else if (near_tight(s, dud)) {
-      ++near;
+  for (int32_t eb = e0; eb < e1; eb += 4) {
+    int32_t c[4];
+    double ww[4];
+    unsigned long long d[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int32_t e = eb + k < e1 ? eb + k : e1 - 1;
+      c[k] = col[e];
+      ww[k] = w[e];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d[k] = rec[c[k]].dist;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (eb + k >= e1 || d[k] == kInfBits) continue;
+      const double s = __dadd_rn(__longlong_as_double((long long)d[k]), ww[k]);
+      if (first < 0 && (unsigned long long)__double_as_longlong(s) == du) {
+        first = eb + k;
+        *d_next = d[k];
+        ++near;
+      } else if (near_tight(s, dud)) {
+        ++near;
+      }
     }
   }
   if (near > 1) *tie = true;

@@ -53,7 +53,8 @@ def main():
         t_h = time.perf_counter() - t0
     tpb = args.ticks_per_block
     sim = BlockSimulation(lg, start, bench.HOURLY, seed=args.seed, csv_path=args.csv, ticks_per_block=tpb,
-                          reroute=args.reroute, record_routes=False, route_arena_links=max(1 << 24, n * 1024),
+                          reroute=args.reroute, record_routes=False,
+                          route_arena_links=max(1 << 24, n * w.get("arena_per_agent", 2560)),  # as bench.py sizes it
                           hierarchy=hier)
     blocks = int(round(args.hours * 3600 / tpb))
     # the s-t model's trips for the whole horizon, generated in slabs of 64 blocks (the reference asks its selector
