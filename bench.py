@@ -674,6 +674,7 @@ def run_b200(args):
                                     "(NCCL), every rank resolves the global event set")) if world > 1 else "n/a"),
             routes_per_s=routes / dt, routes_in_timed_region=int(routes),
             fallback_routes_in_timed_region=int(st1["fallback_routes"] - st0["fallback_routes"]),
+            tie_fallbacks_in_timed_region=int(st1["tie_fallbacks"] - st0["tie_fallbacks"]),
             reroutes_per_s=(reroutes_timed / dt) if reroute else None, reroutes_in_timed_region=int(reroutes_timed),
             moving_fraction=float(moving / n_local),
             e2e=dict(value=e2e_value, unit="agent-steps/s", h2d_bytes_per_step=int(h2d),
