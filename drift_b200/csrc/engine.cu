@@ -165,7 +165,12 @@ struct drift_engine {
   DevBuf<uint8_t> t_q_side;
   DevBuf<uint32_t> t_iter, t_slot_stamp;
   DevBuf<int32_t> t_slot_owner, t_slot_job, t_job_qhead, t_job_cnt, t_q_next, t_tie_list;
-  int32_t detect_ties = 1;  // option "detect_ties": possible ties of the batched router go to the NetworkX-exact one
+  // option "detect_ties": possible ties of the batched router go to the NetworkX-exact one.  -1 = automatic: on for
+  // graphs of at most kTieAutoNodes nodes (the reference's scale: the bundled graphs tie on 56-98 % of the queries and
+  // an exact query costs microseconds), off above (one exact query on a 200 k-node graph takes ~0.2 s on one thread:
+  // 16 flagged queries cost the rgg_hub workload 1.7 s per step; ties are then measure-zero accidents of the
+  // synthetic weights, e.g. links clipped to the same minimum length)
+  int32_t detect_ties = -1;
   DevBuf<uint32_t> t_slot_job_batch;
   int64_t router_chunk_opt = 0;  // option "router_chunk": queries per batched-router launch (0 = from the cache slots)
   int32_t t_bounded_max = -1;  // -1 = automatic: bounded search only when the cache cannot hold every destination
@@ -328,6 +333,7 @@ struct drift_engine {
 namespace {
 
 constexpr double kKphToMps = 1000.0 / 3600.0;  // config.py:186
+constexpr int32_t kTieAutoNodes = 20000;       // "detect_ties" automatic: on up to this many nodes
 
 int check_overflow(drift_engine* e, const Counters& c) {
   if (!c.overflow) return DRIFT_OK;
@@ -537,7 +543,7 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
                                            : ((e->t_max_slots >= e->V && !use_congested) ? 0 : kMaxBounded);
     // with full trees only, every key of a batch needs a slot: source-side keys only if all 2V fit
     tc.sides = (tc.bounded_max == 0 && e->t_max_slots < 2 * e->V) ? 1 : e->t_sides;
-    tc.detect_ties = e->detect_ties;
+    tc.detect_ties = e->detect_ties < 0 ? (e->V <= kTieAutoNodes ? 1 : 0) : e->detect_ties;
     CU(cudaMemsetAsync(out.status, 0xff, sizeof(int32_t) * Q, e->stream));  // -1 = not answered yet
     tc.n_jobs = e->t_ctl.p + 1;
     tc.job_cursor = e->t_ctl.p + 2;
@@ -2235,7 +2241,7 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
   } else if (s == "router_chunk") {
     e->router_chunk_opt = std::max<int64_t>(0, (int64_t)value);
   } else if (s == "detect_ties") {
-    e->detect_ties = value != 0;
+    e->detect_ties = value < 0 ? -1 : (value != 0 ? 1 : 0);
   } else if (s == "use_labels") {
     e->labels_enabled = value != 0;
   } else if (s == "debug_mask") {

@@ -55,7 +55,7 @@ extern "C" {
 #define DRIFT_ROUTER_BATCHED 1  /* batched router: cached shortest-path trees / bounded searches (or hub labels, see
                                   drift_set_hierarchy); a query whose shortest path may not be unique -- a second hop
                                   tight within 1e-12 -- is re-run by the NetworkX-exact router, so the link sequences
-                                  equal NetworkX's on tie-prone graphs too (option "detect_ties", default 1) */
+                                  equal NetworkX's on tie-prone graphs too (option "detect_ties": automatic up to 20 000 nodes) */
 
 typedef struct drift_engine drift_engine;
 
@@ -354,8 +354,10 @@ int drift_host_pow(const double* x, double y, double* out, int64_t n);
  *   router_chunk        queries per launch of the batched tree router (default 0 = as many as are guaranteed a cache slot
  *                       should every key be hot; cold demand -- few trips share an end -- can take far larger chunks,
  *                       an overflow of the cache is reported as DRIFT_EOVERFLOW)
- *   detect_ties         0 = the batched tree router returns A shortest path without the NetworkX-exact re-run of
- *                       possible ties (default 1)
+ *   detect_ties         1 = the batched tree router re-runs possible ties through the NetworkX-exact router, 0 = it
+ *                       returns A shortest path; default -1 = on for graphs of at most 20 000 nodes (the reference's
+ *                       scale, where ties are the rule and an exact query is cheap), off above (an exact query on a
+ *                       200 k-node graph takes ~0.2 s on its one thread)
  *   use_labels          0 = ignore an uploaded hierarchy (DRIFT_ROUTER_BATCHED falls back to trees / bounded searches)
  *   debug_mask          timing probes only, results are then NOT the reference's: 1 = no departure draws,
  *                       2 = crossers stay on their link, 4 = events are not emitted (tools/tick_probe.py)
