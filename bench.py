@@ -311,8 +311,10 @@ def run_b200(args):
         eng.set_option(k, float(v))
     # static travel times -> contraction hierarchy (host, cached on disk: rank 0 contracts, the others load) + hub
     # labels built on the device; graphs without a usable hierarchy (grids) keep the tree / bounded-search router
+    # (the reroute extension routes on congested times from its first update on: labels of the static times would
+    # serve the initial batch only)
     hier_info = None
-    if not args.no_labels and graph_kind == "road":
+    if not args.no_labels and graph_kind == "road" and not (w.get("reroute") and not args.no_reroute):
         from drift_b200 import hierarchy
         from drift_b200._capi import DriftError
 

@@ -172,6 +172,7 @@ struct drift_engine {
   // synthetic weights, e.g. links clipped to the same minimum length)
   int32_t detect_ties = -1;
   DevBuf<uint32_t> t_slot_job_batch;
+  int32_t congested_landmarks = 0;  // option "congested_landmarks": experiment, see launch_router
   int64_t router_chunk_opt = 0;  // option "router_chunk": queries per batched-router launch (0 = from the cache slots)
   int32_t t_bounded_max = -1;  // -1 = automatic: bounded search only when the cache cannot hold every destination
   int32_t t_threads = 256;
@@ -561,10 +562,10 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     k_tree_requests<<<gq, 256, 0, e->stream>>>(Q, qs, qd, tc, e->ctr.p, n_dev);
     Landmarks lm;
     lm.tab = e->lm_tab.p;
-    // The landmark distances are free-flow distances.  They remain valid lower bounds on congested times (tt = t0 /
-    // factor >= t0), but weak ones: with them the goal-directed search keeps its four times finer buckets and loses its
-    // direction -- measured 10 x slower on the reroute workloads -- so congested routing runs without potentials.
-    lm.K = use_congested ? 0 : e->lm_K;
+    // The landmark distances are free-flow distances: valid lower bounds on congested times too (tt = t0 / factor >=
+    // t0).  Measured on the reroute workloads they change nothing (rgg_hub 105 vs 109 ms per step), so congested
+    // routing runs without them unless option "congested_landmarks" asks.
+    lm.K = (use_congested && !e->congested_landmarks) ? 0 : e->lm_K;
     k_link_queries<<<gq, 256, 0, e->stream>>>(Q, qs, qd, tc, n_dev);
     cudaEvent_t tb0 = nullptr, tb1 = nullptr;
     if (e->time_plan) {
@@ -2238,6 +2239,8 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
     e->arena_compact_frac = std::min(0.95, std::max(0.05, value));
   } else if (s == "one_wave_tiles") {
     e->one_wave = value != 0;
+  } else if (s == "congested_landmarks") {
+    e->congested_landmarks = value != 0;
   } else if (s == "router_chunk") {
     e->router_chunk_opt = std::max<int64_t>(0, (int64_t)value);
   } else if (s == "detect_ties") {

@@ -358,6 +358,8 @@ int drift_host_pow(const double* x, double y, double* out, int64_t n);
  *                       returns A shortest path; default -1 = on for graphs of at most 20 000 nodes (the reference's
  *                       scale, where ties are the rule and an exact query is cheap), off above (an exact query on a
  *                       200 k-node graph takes ~0.2 s on its one thread)
+ *   congested_landmarks 1 = keep the free-flow landmark potentials when routing on congested travel times (valid
+ *                       lower bounds, no measured gain; default 0)
  *   use_labels          0 = ignore an uploaded hierarchy (DRIFT_ROUTER_BATCHED falls back to trees / bounded searches)
  *   debug_mask          timing probes only, results are then NOT the reference's: 1 = no departure draws,
  *                       2 = crossers stay on their link, 4 = events are not emitted (tools/tick_probe.py)
