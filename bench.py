@@ -48,6 +48,10 @@ WORKLOADS = {
                     desc="configs[0]-sized: 100-node graph, random demand, 300 agents"),
     # cold demand (every trip has its own source and destination): routing is one bounded search per trip
     "grid_zone": dict(graph="grid", nodes=1_000_000, agents=1_000_000, model="zone", lookahead=True, arena_per_agent=768,
+                      # no end of a trip is shared by more than a few trips: no tree is worth caching (2 GB of slots for
+                      # the odd popular node), the memory goes to resident searches, and a launch takes 64 k queries
+                      # (tools/router_sweep.py: half the bucket width = 31 % fewer node expansions, 8 % less time)
+                      opts=dict(tree_cache_bytes=float(2 << 30), router_chunk=65536.0, tree_delta_scale=0.5),
                       desc="configs[3] at half linear scale (--nodes 4000000 --agents 10000000 = full size): 4-neighbour "
                            "grid, lengths U[50,300] m, 50 km/h, zone-structured demand, lookahead route planning"),
     "rgg_hub": dict(graph="rgg", nodes=200_000, agents=200_000, model="hub", reroute=True, lookahead=True, tps=30,
@@ -306,9 +310,12 @@ def run_b200(args):
     dst_all = dst_all[:, :4 + trips_per_step * total_steps]
     if w.get("lookahead"):
         eng.set_option("plan_lookahead", 1)
+    engine_opts = dict(w.get("opts", {}))
     for kv in args.opt:
         k, v = kv.split("=")
-        eng.set_option(k, float(v))
+        engine_opts[k] = float(v)
+    for k, v in engine_opts.items():
+        eng.set_option(k, v)
     # static travel times -> contraction hierarchy (host, cached on disk: rank 0 contracts, the others load) + hub
     # labels built on the device; graphs without a usable hierarchy (grids) keep the tree / bounded-search router
     # (the reroute extension routes on congested times from its first update on: labels of the static times would
@@ -663,7 +670,7 @@ def run_b200(args):
                                 "batched SSSP: cached shortest-path trees on either end of a trip (destination / source), "
                                 "bounded goal-directed searches for cold pairs") +
                                "; planning: %s" % ("lookahead" if w.get("lookahead") else "prefetch-all"),
-                        hierarchy=hier_info, clock="08:00 peak",
+                        hierarchy=hier_info, engine_options=engine_opts or None, clock="08:00 peak",
                         l2="no explicit flush: a tick re-reads the same agent state by construction (%.0f MB hot + ~80 MB "
                            "cold per-agent state at this size, L2 is 126 MB) and every step's route planning walks "
                            "GBs of cached trees and route arena in between; roofline_advance_saturated uses 16 M "

@@ -510,15 +510,33 @@ constexpr int32_t kStatusTie = -3;  // batched router: the shortest path may not
 // path equals NetworkX's wherever the shortest path is unique; cost parity 1e-9 relative.
 // =====================================================================================
 
+// 16 bytes per node and resident search: label, near-list stamp, and one word that holds the far-list flag (bit 31) and
+// the node's potential for the running goal-directed search as a non-negative float ROUNDED DOWN (bits 0..30).  A
+// relaxation used to fetch the 128-byte landmark line of its head node every time (4 in-links = 4 fetches per node on
+// a grid); now the first relaxation of a node computes the potential and the later ones find it in the sector they
+// read anyway.  Rounding down keeps the potential admissible, which is all the bounded search's stopping rule needs
+// (a node still in the far list has label + potential > T, so no path through it reaches a source below T); the
+// labels themselves stay fp64 sums.  The throughput of large graphs follows the number of resident searches, i.e.
+// the bytes of scratch per node: that is why the record is not wider.
 struct __align__(16) NodeRec {
   unsigned long long dist;  // fp64 bit pattern (non-negative doubles order like u64)
-  uint32_t stamp;           // near-list dedupe stamp
-  uint32_t infar;           // node is queued in the far list
+  uint32_t stamp;           // near-list dedupe stamp (running wave number, only ever compared for equality)
+  uint32_t potf;            // kFarBit | float bits of the cached potential, kPotUnset = not computed in this search
 };
+constexpr uint32_t kFarBit = 0x80000000u;
+constexpr uint32_t kPotUnset = 0x7FC00000u;  // a NaN pattern: no potential has it
+__device__ __forceinline__ void reset_noderec(NodeRec* r) {
+  *reinterpret_cast<uint4*>(r) = make_uint4(0u, 0x7FF00000u, 0u, kPotUnset);  // +inf, stamp 0, no flag, no potential
+}
 
 struct TreeScratch {   // per resident block
   NodeRec* rec;              // [blocks][V]
-  int32_t* lists;            // [blocks][5][V] nearA, nearB, farA, farB, touched
+  int32_t* lists;            // [blocks][list_stride]: touched [V], farA [V], farB [V], nearA, nearB [near_cap each]
+  int64_t list_stride;       // 3 V + 2 * near_cap
+  int32_t near_cap;          // entries of a near queue (one wave): V on small graphs, V / tree_list_div (>= 65536)
+                             // above; a search whose wave would overflow it stops and raises kOvfTreeQueues.  (The
+                             // far queue is NOT short: with noisy weights the open set of a goal-directed search is
+                             // porous, a fixed fraction of the searched area rather than its perimeter.)
   uint32_t* iter;            // [blocks] running stamp
 };
 
@@ -855,15 +873,19 @@ __device__ __forceinline__ void route_from_labels(const GraphArrays& g, const do
 // Jobs whose destination is wanted by at most tc.bounded_max queries of the batch ("cold"
 // destinations) stop as soon as all their sources are settled, write those routes themselves
 // (walking dist[] from the source) and do not keep a tree; the others build and cache the tree.
-__global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_trees(GraphArrays g, const double* __restrict__ w_bwd,
+// kBlocksPerSM = 8 / 6 / 4: 32 / 40 / 64 registers per thread; the engine launches the widest build whose residency the
+// scratch budget can fill (large graphs: memory, not the SM, limits the resident searches).  kFly = relaxations a
+// thread keeps in flight; 2 was measured on the 4 M-node grid and changes nothing (the waves are short), so 1 is built.
+template <int kBlocksPerSM, int kFly>
+__global__ void __launch_bounds__(kTreeThreadsMax, kBlocksPerSM) k_build_trees(GraphArrays g, const double* __restrict__ w_bwd,
                                                               const double* __restrict__ w_fwd, double delta,
                                                               TreeCache tc, TreeScratch sc,
                                                               const int32_t* __restrict__ q_src,
                                                               int32_t* __restrict__ arena, unsigned long long arena_cap,
                                                               Counters* ctr, RouteOut out,
                                                               const double* __restrict__ link_cost, Landmarks lm,
-                                                              int32_t reserved) {
-  __shared__ int s_job, s_near_n, s_next_n, s_far_n, s_far2_n, s_done, s_touched, s_lm_on;
+                                                              int32_t pot_cache) {
+  __shared__ int s_job, s_near_n, s_next_n, s_far_n, s_far2_n, s_done, s_touched, s_lm_on, s_ovf;
   __shared__ double s_ref[2 * kMaxLandmarks];
   __shared__ int s_e0[kTreeThreadsMax], s_off[kTreeThreadsMax], s_wsum[32];
   __shared__ double s_dv[kTreeThreadsMax];
@@ -872,15 +894,19 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_tre
   const int64_t V = g.V;
   // per-node scratch packed into one 16-byte record: a relaxation touches one sector, not three
   NodeRec* rec = sc.rec + (int64_t)blockIdx.x * V;
-  int32_t* nearA = sc.lists + ((int64_t)blockIdx.x * 5 + 0) * V;
-  int32_t* nearB = sc.lists + ((int64_t)blockIdx.x * 5 + 1) * V;
-  int32_t* farA = sc.lists + ((int64_t)blockIdx.x * 5 + 2) * V;
-  int32_t* farB = sc.lists + ((int64_t)blockIdx.x * 5 + 3) * V;
-  int32_t* touched = sc.lists + ((int64_t)blockIdx.x * 5 + 4) * V;
+  int32_t* touched = sc.lists + (int64_t)blockIdx.x * sc.list_stride;
+  const int qcap = sc.near_cap;
+  // the A / B halves of the far and near queues swap by parity (fewer live pointers than swapping them: registers)
+  int fpar = 0, npar = 0;
+#define FAR_Q(par) (touched + (int64_t)(1 + (par)) * V)
+#define NEAR_Q(par) (touched + 3 * V + (int64_t)(par) * qcap)
   uint32_t iter = sc.iter[blockIdx.x];
   const int n_jobs = *tc.n_jobs;
-  unsigned long long c_relaxed = 0, c_improved = 0, c_expanded = 0;  // per-thread work counters
-  unsigned long long c_iters = 0, c_far = 0, c_jobs = 0;
+  // work counters: per thread and launch 32 bits are plenty; the three that only thread 0 keeps live in shared memory
+  // (registers are what limits the residency of this kernel)
+  uint32_t c_relaxed = 0, c_improved = 0, c_expanded = 0;
+  __shared__ unsigned long long s_c_iters, s_c_far, s_c_jobs;
+  if (threadIdx.x == 0) s_c_iters = s_c_far = s_c_jobs = 0ULL;
   for (;;) {
     if (threadIdx.x == 0) s_job = atomicAdd(tc.job_cursor, 1);
     __syncthreads();
@@ -897,7 +923,7 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_tre
     int2* next_link = tc.next_link + (int64_t)(slot < 0 ? 0 : slot) * V;
     const int nb = min(tc.job_cnt[job], kMaxBounded);
     const bool bounded = slot < 0;  // decided when the job was created (k_tree_requests)
-    if (threadIdx.x == 0) ++c_jobs;
+    if (threadIdx.x == 0) ++s_c_jobs;
     if (bounded && threadIdx.x == 0) {
       int k = 0;
       for (int32_t q = tc.job_qhead[job]; q >= 0 && k < kMaxBounded; q = tc.q_next[q], ++k) {
@@ -912,7 +938,8 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_tre
       s_far_n = 0;
       s_far2_n = 0;
       s_touched = 1;
-      nearA[0] = dest;
+      s_ovf = 0;
+      NEAR_Q(npar)[0] = dest;
       touched[0] = dest;
       rec[dest].dist = 0ULL;
       // goal direction for a single-source bounded job: ALT potentials, the source's row of the landmark table
@@ -946,6 +973,11 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_tre
       }
       return h;
     };
+    // potential of a node that has been relaxed in this search (far-list scans): from its record when cached
+    const bool cached = lm_on && pot_cache != 0;
+    auto pot_seen = [&](int32_t v) -> double {
+      return cached ? (double)__uint_as_float(__ldcg(&rec[v].potf) & ~kFarBit) : pot(v);
+    };
     // goal-directed keys cluster just below d(source, dest): finer buckets keep the search inside the corridor
     const double jdelta = lm_on ? delta * 0.25 : delta;
     double T_old = -1.0, T = pot(dest) + jdelta;
@@ -973,55 +1005,59 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_tre
         if (threadIdx.x == 0) s_min = kInfBits;
         __syncthreads();
         unsigned long long m = kInfBits;
+        const int32_t* __restrict__ far_in = FAR_Q(fpar);
+        int32_t* __restrict__ far_out = FAR_Q(fpar ^ 1);
+        int32_t* __restrict__ near_out = NEAR_Q(npar);
         for (int i = threadIdx.x; i < nf; i += blockDim.x) {
-          const int32_t u = farA[i];
-          const double key = __dadd_rn(__longlong_as_double((long long)rec[u].dist), pot(u));
+          const int32_t u = far_in[i];
+          const double key = __dadd_rn(__longlong_as_double((long long)rec[u].dist), pot_seen(u));
           const unsigned long long kb = (unsigned long long)__double_as_longlong(key);
           m = kb < m ? kb : m;
         }
         const double minfar = __longlong_as_double((long long)block_min_u64(m, &s_min));
-        if (threadIdx.x == 0) c_far += (unsigned long long)nf;
+        if (threadIdx.x == 0) s_c_far += (unsigned long long)nf;
         T_old = T;
         T = (minfar > T ? minfar : T) + jdelta;
         for (int i = threadIdx.x; i < nf; i += blockDim.x) {
-          const int32_t u = farA[i];
-          const double d = __dadd_rn(__longlong_as_double((long long)rec[u].dist), pot(u));
+          const int32_t u = far_in[i];
+          const double d = __dadd_rn(__longlong_as_double((long long)rec[u].dist), pot_seen(u));
           if (d <= T_old) {
-            rec[u].infar = 0;  // already expanded as a near node
+            rec[u].potf &= ~kFarBit;  // already expanded as a near node (one thread per far entry, no relaxation runs)
           } else if (d <= T) {
-            rec[u].infar = 0;
-            nearA[atomicAdd(&s_near_n, 1)] = u;
+            rec[u].potf &= ~kFarBit;
+            const int at = atomicAdd(&s_near_n, 1);
+            if (at < qcap) near_out[at] = u; else s_ovf = 1;
           } else {
-            farB[atomicAdd(&s_far2_n, 1)] = u;
+            far_out[atomicAdd(&s_far2_n, 1)] = u;  // <= nf entries
           }
         }
         __syncthreads();
+        if (s_ovf) break;
         if (threadIdx.x == 0) {
           s_far_n = s_far2_n;
           s_far2_n = 0;
         }
-        int32_t* t = farA;
-        farA = farB;
-        farB = t;
+        fpar ^= 1;
         __syncthreads();
         continue;
       }
-      ++iter;
-      if (threadIdx.x == 0) ++c_iters;
+      if (++iter == 0u) iter = 1u;  // 0 is the stamp of a reset record
+      if (threadIdx.x == 0) ++s_c_iters;
       // Edge-parallel expansion: the block loads a chunk of frontier nodes, scans their degrees and
       // then every thread relaxes ONE edge, so the dependent-load chain of a wave does not grow with
       // the degree (a wave of a road network holds few nodes: latency, not bandwidth, is the cost).
+      const int32_t* __restrict__ near_in = NEAR_Q(npar);
       for (int base = 0; base < n; base += blockDim.x) {
         const int i = base + threadIdx.x;
         int deg = 0;
         if (i < n) {
-          const int32_t v = nearA[i];
+          const int32_t v = near_in[i];
           const int32_t e0 = x_rowptr[v];
           deg = x_rowptr[v + 1] - e0;
           s_e0[threadIdx.x] = e0;
           s_dv[threadIdx.x] = __longlong_as_double((long long)rec[v].dist);
           ++c_expanded;
-          c_relaxed += (unsigned long long)deg;
+          c_relaxed += (uint32_t)deg;
         }
         // block-wide exclusive scan of the degrees
         int incl = deg;
@@ -1048,53 +1084,108 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_tre
         const int total = s_wsum[((blockDim.x + 31) >> 5) - 1];
         const int cnt = min((int)blockDim.x, n - base);
         __syncthreads();
-        for (int k = threadIdx.x; k < total; k += blockDim.x) {
-          int lo = 0, hi = cnt - 1;  // owner j: largest j with s_off[j] <= k
-          while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (s_off[mid] <= k) lo = mid; else hi = mid - 1;
+        // kFly relaxations per thread in flight, in stages, so that their load chains (link -> head record ->
+        // landmark line -> atomics) overlap
+        for (int k0 = threadIdx.x; k0 < total; k0 += kFly * blockDim.x) {
+          bool on[kFly];
+          int32_t u[kFly];
+          double cand[kFly], pu[kFly];
+          unsigned long long cb[kFly], old[kFly];
+#pragma unroll
+          for (int j = 0; j < kFly; ++j) {  // stage 1: owner of the link, head node, candidate label
+            const int k = k0 + j * (int)blockDim.x;
+            on[j] = k < total;
+            const int kk = on[j] ? k : k0;
+            int lo = 0, hi = cnt - 1;  // owner: largest index with s_off[] <= kk
+            while (lo < hi) {
+              const int mid = (lo + hi + 1) >> 1;
+              if (s_off[mid] <= kk) lo = mid; else hi = mid - 1;
+            }
+            const int32_t e = s_e0[lo] + (kk - s_off[lo]);
+            u[j] = x_col[e];
+            cand[j] = __dadd_rn(s_dv[lo], x_w[e]);
+            cb[j] = (unsigned long long)__double_as_longlong(cand[j]);
           }
-          const int32_t e = s_e0[lo] + (k - s_off[lo]);
-          const int32_t u = x_col[e];
-          const double cand = __dadd_rn(s_dv[lo], x_w[e]);
-          const unsigned long long cb = (unsigned long long)__double_as_longlong(cand);
-          const double pu = pot(u);  // issued before the atomic: one dependent memory level less per wave
-          const unsigned long long old = atomicMin(&rec[u].dist, cb);
-          if (cb < old) {
-            ++c_improved;
-            if (old == kInfBits) touched[atomicAdd(&s_touched, 1)] = u;  // exactly one thread sees the first label
-            if (__dadd_rn(cand, pu) <= T) {
-              if (atomicExch(&rec[u].stamp, iter) != iter) nearB[atomicAdd(&s_next_n, 1)] = u;
-            } else if (atomicExch(&rec[u].infar, 1u) == 0u) {
-              farA[atomicAdd(&s_far_n, 1)] = u;  // at most one far entry per node: <= V entries
+          if (cached) {
+            // the node's sector first (L2, never a stale L1 line: the records are reset between jobs): label and
+            // cached potential; the landmark line only on the node's first relaxation, the atomic only if it can win
+#pragma unroll
+            for (int j = 0; j < kFly; ++j) {  // stage 2: head records
+              const ulonglong2 head = __ldcg(reinterpret_cast<const ulonglong2*>(&rec[u[j]]));
+              old[j] = head.x;
+              const uint32_t pf = (uint32_t)(head.y >> 32) & ~kFarBit;
+              pu[j] = pf == kPotUnset ? -1.0 : (double)__uint_as_float(pf);
+            }
+#pragma unroll
+            for (int j = 0; j < kFly; ++j) {  // stage 3: first relaxation of a node: its potential
+              if (pu[j] < 0.0) {
+                const float pf = __double2float_rd(pot(u[j]));
+                pu[j] = (double)pf;
+                // only the first store lands (the far flag is set after it, by a thread that has seen a potential)
+                atomicCAS(&rec[u[j]].potf, kPotUnset, __float_as_uint(pf));
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < kFly; ++j)  // stage 4: labels
+              if (on[j] && cb[j] < old[j]) old[j] = atomicMin(&rec[u[j]].dist, cb[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kFly; ++j) pu[j] = pot(u[j]);  // issued before the atomic: one dependent level less
+#pragma unroll
+            for (int j = 0; j < kFly; ++j) old[j] = on[j] ? atomicMin(&rec[u[j]].dist, cb[j]) : 0ULL;
+          }
+#pragma unroll
+          for (int j = 0; j < kFly; ++j) {  // stage 5: queues
+            if (on[j] && cb[j] < old[j]) {
+              ++c_improved;
+              if (old[j] == kInfBits) touched[atomicAdd(&s_touched, 1)] = u[j];  // exactly one thread sees the first label
+              if (__dadd_rn(cand[j], pu[j]) <= T) {
+                if (atomicExch(&rec[u[j]].stamp, iter) != iter) {
+                  const int at = atomicAdd(&s_next_n, 1);
+                  if (at < qcap) NEAR_Q(npar ^ 1)[at] = u[j]; else s_ovf = 1;
+                }
+              } else if ((atomicOr(&rec[u[j]].potf, kFarBit) & kFarBit) == 0u) {
+                FAR_Q(fpar)[atomicAdd(&s_far_n, 1)] = u[j];  // at most one far entry per node: <= V entries
+              }
             }
           }
         }
         __syncthreads();  // s_e0 / s_dv / s_off are reused by the next chunk
       }
       __syncthreads();
+      if (s_ovf) break;
       if (threadIdx.x == 0) {
         s_near_n = s_next_n;
         s_next_n = 0;
       }
-      int32_t* t = nearA;
-      nearA = nearB;
-      nearB = t;
+      npar ^= 1;
       __syncthreads();
+    }
+    if (s_ovf) {
+      // a near queue would have overflowed: the job is abandoned (its queries stay unanswered, the call fails with
+      // DRIFT_EOVERFLOW), the scratch is left clean and no tree is kept
+      if (threadIdx.x == 0) {
+        atomicOr(&ctr->overflow, kOvfTreeQueues);
+        tc.slot_of[key] = -1;
+        if (slot >= 0) tc.slot_owner[slot] = -1;
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < s_touched; i += blockDim.x) reset_noderec(&rec[touched[i]]);
+      __syncthreads();
+      continue;
     }
     if (bounded) {
       // routes of the few sources, straight from dist[] (route_from_labels); the far list of the finished
       // search is the scratch the links are collected in
       if (threadIdx.x < nb) {
         const int32_t tcap = (int32_t)(V / kMaxBounded);
-        route_from_labels(g, w_fwd, rec, s_bsrc[threadIdx.x], dest, farB + (int64_t)threadIdx.x * tcap, tcap, arena,
+        route_from_labels(g, w_fwd, rec, s_bsrc[threadIdx.x], dest, FAR_Q(fpar ^ 1) + (int64_t)threadIdx.x * tcap, tcap, arena,
                           arena_cap, ctr, link_cost, s_bq[threadIdx.x], out, tc.detect_ties != 0);
       }
       if (threadIdx.x == 0) tc.slot_of[dest] = -1;  // no tree was kept
       __syncthreads();
       for (int i = threadIdx.x; i < s_touched; i += blockDim.x) {  // leave the scratch clean for the next job
-        rec[touched[i]].dist = kInfBits;
-        rec[touched[i]].infar = 0;
+        reset_noderec(&rec[touched[i]]);
       }
       __syncthreads();
       continue;
@@ -1123,36 +1214,35 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kTreeBlocksPerSM) k_build_tre
     }
     __syncthreads();
     for (int i = threadIdx.x; i < s_touched; i += blockDim.x) {
-      rec[touched[i]].dist = kInfBits;
-      rec[touched[i]].infar = 0;
+      reset_noderec(&rec[touched[i]]);
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) sc.iter[blockIdx.x] = iter;
+  unsigned long long w_relaxed = c_relaxed, w_improved = c_improved, w_expanded = c_expanded;
   for (int o = 16; o; o >>= 1) {
-    c_relaxed += __shfl_down_sync(0xffffffffu, c_relaxed, o);
-    c_improved += __shfl_down_sync(0xffffffffu, c_improved, o);
-    c_expanded += __shfl_down_sync(0xffffffffu, c_expanded, o);
+    w_relaxed += __shfl_down_sync(0xffffffffu, w_relaxed, o);
+    w_improved += __shfl_down_sync(0xffffffffu, w_improved, o);
+    w_expanded += __shfl_down_sync(0xffffffffu, w_expanded, o);
   }
-  if ((threadIdx.x & 31) == 0 && c_expanded) {
-    atomicAdd(&ctr->tree_relaxed, c_relaxed);
-    atomicAdd(&ctr->tree_improved, c_improved);
-    atomicAdd(&ctr->tree_expanded, c_expanded);
+  if ((threadIdx.x & 31) == 0 && w_expanded) {
+    atomicAdd(&ctr->tree_relaxed, w_relaxed);
+    atomicAdd(&ctr->tree_improved, w_improved);
+    atomicAdd(&ctr->tree_expanded, w_expanded);
   }
-  if (threadIdx.x == 0 && c_jobs) atomicAdd(&ctr->tree_jobs, c_jobs);
-  if (threadIdx.x == 0 && c_iters) {
-    atomicAdd(&ctr->tree_iters, c_iters);
-    atomicAdd(&ctr->tree_far_visits, c_far);
+  if (threadIdx.x == 0 && s_c_jobs) atomicAdd(&ctr->tree_jobs, s_c_jobs);
+  if (threadIdx.x == 0 && s_c_iters) {
+    atomicAdd(&ctr->tree_iters, s_c_iters);
+    atomicAdd(&ctr->tree_far_visits, s_c_far);
   }
 }
 
+#undef FAR_Q
+#undef NEAR_Q
+
 __global__ void k_init_noderecs(NodeRec* __restrict__ p, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    NodeRec r;
-    r.dist = kInfBits;
-    r.stamp = 0;
-    r.infar = 0;
-    p[i] = r;
+    reset_noderec(&p[i]);
   }
 }
 

@@ -396,37 +396,14 @@ class Engine:
         _capi.check(self._lib.drift_time_passes(self._h, int(iters), C.byref(a), C.byref(b)))
         return dict(recount_us=a.value, travel_times_us=b.value)
 
-    def set_landmarks(self, K=8, seed=0):
+    def set_landmarks(self, K=8, seed=0, tables=None):
         """Pick K far-apart landmarks and upload their free-flow distance arrays (host: scipy Dijkstra, a
-        one-off setup cost of ~0.2 s per landmark on a 1 M-link graph)."""
-        from scipy.sparse import csr_matrix
-        from scipy.sparse.csgraph import dijkstra
-
-        lg = self.lg
-        V = lg.V
-        if K <= 0 or V < 2:
+        one-off setup cost of ~0.2 s per landmark on a 1 M-link graph).  ``tables`` = (from, to) of an earlier
+        ``landmark_tables`` call on the same graph skips the Dijkstras."""
+        if K <= 0 or self.lg.V < 2:
             _capi.check(self._lib.drift_set_landmarks(self._h, 0, None, None))
             return []
-        W = csr_matrix((lg.fwd_w, lg.fwd_col, lg.fwd_rowptr), shape=(V, V))
-        WT = csr_matrix((lg.bwd_w, lg.bwd_col, lg.bwd_rowptr), shape=(V, V))
-        rng = np.random.default_rng(seed)
-        first = int(rng.integers(0, V))
-        d0 = dijkstra(W, directed=True, indices=first)
-        d0[~np.isfinite(d0)] = -1.0
-        picks = [int(np.argmax(d0))]  # farthest node from a random one
-        frm, to = [], []
-        mind = None
-        for k in range(K):
-            f = dijkstra(W, directed=True, indices=picks[-1])
-            t = dijkstra(WT, directed=True, indices=picks[-1])
-            frm.append(f)
-            to.append(t)
-            reach = np.where(np.isfinite(f), f, -1.0)
-            mind = reach if mind is None else np.minimum(mind, reach)
-            if k + 1 < K:
-                picks.append(int(np.argmax(mind)))  # farthest-point sampling
-        frm = np.ascontiguousarray(np.stack(frm), dtype=np.float64)
-        to = np.ascontiguousarray(np.stack(to), dtype=np.float64)
+        picks, frm, to = tables if tables is not None else landmark_tables(self.lg, K, seed)
         _capi.check(self._lib.drift_set_landmarks(self._h, len(picks), _p(frm, C.c_double), _p(to, C.c_double)))
         return picks
 
@@ -463,3 +440,33 @@ class Engine:
         p, n = C.c_void_p(), C.c_int64(0)
         _capi.check(self._lib.drift_device_ptr(self._h, name.encode(), C.byref(p), C.byref(n)))
         return p.value, n.value
+
+
+def landmark_tables(lg, K=8, seed=0):
+    """(landmark nodes, distances landmark -> node [K][V], distances node -> landmark [K][V]) of K landmarks picked by
+    farthest-point sampling on the free-flow travel times."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import dijkstra
+
+    V = lg.V
+    W = csr_matrix((lg.fwd_w, lg.fwd_col, lg.fwd_rowptr), shape=(V, V))
+    WT = csr_matrix((lg.bwd_w, lg.bwd_col, lg.bwd_rowptr), shape=(V, V))
+    rng = np.random.default_rng(seed)
+    first = int(rng.integers(0, V))
+    d0 = dijkstra(W, directed=True, indices=first)
+    d0[~np.isfinite(d0)] = -1.0
+    picks = [int(np.argmax(d0))]  # farthest node from a random one
+    frm, to = [], []
+    mind = None
+    for k in range(K):
+        f = dijkstra(W, directed=True, indices=picks[-1])
+        t = dijkstra(WT, directed=True, indices=picks[-1])
+        frm.append(f)
+        to.append(t)
+        reach = np.where(np.isfinite(f), f, -1.0)
+        mind = reach if mind is None else np.minimum(mind, reach)
+        if k + 1 < K:
+            picks.append(int(np.argmax(mind)))  # farthest-point sampling
+    frm = np.ascontiguousarray(np.stack(frm), dtype=np.float64)
+    to = np.ascontiguousarray(np.stack(to), dtype=np.float64)
+    return picks, frm, to
