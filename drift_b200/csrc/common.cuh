@@ -74,7 +74,6 @@ constexpr int kOvfEntries = 32;
 constexpr int kOvfStage = 64;
 constexpr int kOvfExchange = 128;
 constexpr int kOvfPending = 256;
-constexpr int kOvfTreeQueues = 512;
 
 struct AgentArrays {
   uint8_t* state;       // [Npad] kWaiting / kMoving

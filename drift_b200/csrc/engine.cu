@@ -172,10 +172,6 @@ struct drift_engine {
   // synthetic weights, e.g. links clipped to the same minimum length)
   int32_t detect_ties = -1;
   DevBuf<uint32_t> t_slot_job_batch;
-  // option "tree_list_div": 1 = near queues of V entries.  Shorter ones (8: 29 instead of 36 B of scratch per node)
-  // buy more resident searches, but on the 4 M-node grid the gain ends at ~850 searches (32.4 vs 32.8 us per search
-  // at 1060 vs 854), so the default keeps the queues that cannot overflow.
-  int32_t t_list_div = 1, t_queue_cap = 0;
   int32_t tree_wide_regs = -1;  // option "tree_wide_regs": -1 automatic, see launch_router
   int32_t pot_cache = 1;  // option "pot_cache": goal-directed searches keep a node's potential in its record
   int32_t congested_landmarks = 0;  // option "congested_landmarks": experiment, see launch_router
@@ -354,7 +350,6 @@ int check_overflow(drift_engine* e, const Counters& c) {
   if (c.overflow & kOvfStage) what += " tree-cache";
   if (c.overflow & kOvfExchange) what += " event-exchange (raise the exchange capacity)";
   if (c.overflow & kOvfPending) what += " pending-departures (more departures committed than agents)";
-  if (c.overflow & kOvfTreeQueues) what += " search-queues (set option tree_list_div to 1 before the first route)";
   return fail(DRIFT_EOVERFLOW, "device buffer overflow:%s", what.c_str());
 }
 
@@ -418,9 +413,7 @@ int ensure_qcap(drift_engine* e, int64_t Q) {
 int ensure_trees(drift_engine* e) {
   if (e->t_max_slots) return DRIFT_OK;
   const int64_t V = e->V;
-  // near queues hold one wave, not the whole graph: V / tree_list_div entries on large graphs
-  e->t_queue_cap = (int32_t)(V <= 65536 ? V : std::max<int64_t>(V / std::max(1, e->t_list_div), 65536));
-  const int64_t search_bytes = 16 * V + 4 * (3 * V + 2 * (int64_t)e->t_queue_cap);
+  const int64_t search_bytes = 36 * V;  // a 16-byte record and five 4-byte list slots per node
   {  // budgets follow the free HBM unless set by option: up to 48 GB of cached trees; the search scratch takes what
      // full residency needs, up to 85 % of the free memory less the cache (on a 4 M-node graph a search owns 144 MB
      // and the throughput follows the number of resident searches: 148 / 296 / 444 / 591 / 854 searches took
@@ -436,8 +429,6 @@ int ensure_trees(drift_engine* e) {
   }
   int64_t slots = std::min<int64_t>(e->t_sides * V, e->tree_budget_bytes / (8 * V));
   slots = std::max<int64_t>(slots, 1);
-  // resident builder blocks: a 16-byte record, a slot of the touched list and of the two far queues per node, two near
-  // queues of t_queue_cap
   int64_t blocks = std::min<int64_t>((int64_t)e->num_sms * std::min(32, 2048 / e->t_threads), e->tree_scratch_bytes / search_bytes);
   blocks = std::max<int64_t>(blocks, 1);
   CU(e->t_slot_of.alloc(2 * V, false));  // keys: destination t, or V + source s
@@ -459,7 +450,7 @@ int ensure_trees(drift_engine* e) {
   k_init_noderecs<<<kSMs * 8, 256, 0, e->stream>>>(e->t_rec.p, blocks * V);  // jobs leave it at +inf / 0
   CU(cudaGetLastError());
   CU(e->t_iter.alloc(blocks, true));
-  CU(e->t_lists.alloc(blocks * (3 * V + 2 * (int64_t)e->t_queue_cap), false));
+  CU(e->t_lists.alloc(blocks * 5 * V, false));
   e->t_max_slots = (int32_t)slots;
   e->t_blocks = (int32_t)blocks;
   return DRIFT_OK;
@@ -572,8 +563,6 @@ int launch_router(drift_engine* e, int32_t router, int64_t Q, int32_t use_conges
     TreeScratch ts;
     ts.rec = e->t_rec.p;
     ts.lists = e->t_lists.p;
-    ts.list_stride = 3 * (int64_t)e->V + 2 * (int64_t)e->t_queue_cap;
-    ts.near_cap = e->t_queue_cap;
     ts.iter = e->t_iter.p;
     CU(cudaMemsetAsync(e->t_ctl.p + 1, 0, 3 * sizeof(int32_t), e->stream));
     const int gq = grid_for(Q, 256, kSMs * 4);
@@ -2272,9 +2261,6 @@ int drift_set_option(drift_engine* e, const char* name, double value) {
     e->arena_compact_frac = std::min(0.95, std::max(0.05, value));
   } else if (s == "one_wave_tiles") {
     e->one_wave = value != 0;
-  } else if (s == "tree_list_div") {
-    if (e->t_max_slots) return fail(DRIFT_ESTATE, "tree_list_div must be set before the first batched route");
-    e->t_list_div = std::max(1, (int32_t)value);
   } else if (s == "tree_wide_regs") {
     e->tree_wide_regs = value < 0 ? -1 : (value != 0 ? 1 : 0);
   } else if (s == "pot_cache") {

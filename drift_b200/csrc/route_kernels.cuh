@@ -531,12 +531,7 @@ __device__ __forceinline__ void reset_noderec(NodeRec* r) {
 
 struct TreeScratch {   // per resident block
   NodeRec* rec;              // [blocks][V]
-  int32_t* lists;            // [blocks][list_stride]: touched [V], farA [V], farB [V], nearA, nearB [near_cap each]
-  int64_t list_stride;       // 3 V + 2 * near_cap
-  int32_t near_cap;          // entries of a near queue (one wave): V on small graphs, V / tree_list_div (>= 65536)
-                             // above; a search whose wave would overflow it stops and raises kOvfTreeQueues.  (The
-                             // far queue is NOT short: with noisy weights the open set of a goal-directed search is
-                             // porous, a fixed fraction of the searched area rather than its perimeter.)
+  int32_t* lists;            // [blocks][5][V]: touched, farA, farB, nearA, nearB
   uint32_t* iter;            // [blocks] running stamp
 };
 
@@ -885,7 +880,7 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kBlocksPerSM) k_build_trees(G
                                                               Counters* ctr, RouteOut out,
                                                               const double* __restrict__ link_cost, Landmarks lm,
                                                               int32_t pot_cache) {
-  __shared__ int s_job, s_near_n, s_next_n, s_far_n, s_far2_n, s_done, s_touched, s_lm_on, s_ovf;
+  __shared__ int s_job, s_near_n, s_next_n, s_far_n, s_far2_n, s_done, s_touched, s_lm_on;
   __shared__ double s_ref[2 * kMaxLandmarks];
   __shared__ int s_e0[kTreeThreadsMax], s_off[kTreeThreadsMax], s_wsum[32];
   __shared__ double s_dv[kTreeThreadsMax];
@@ -894,19 +889,18 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kBlocksPerSM) k_build_trees(G
   const int64_t V = g.V;
   // per-node scratch packed into one 16-byte record: a relaxation touches one sector, not three
   NodeRec* rec = sc.rec + (int64_t)blockIdx.x * V;
-  int32_t* touched = sc.lists + (int64_t)blockIdx.x * sc.list_stride;
-  const int qcap = sc.near_cap;
+  int32_t* touched = sc.lists + (int64_t)blockIdx.x * 5 * V;
   // the A / B halves of the far and near queues swap by parity (fewer live pointers than swapping them: registers)
   int fpar = 0, npar = 0;
 #define FAR_Q(par) (touched + (int64_t)(1 + (par)) * V)
-#define NEAR_Q(par) (touched + 3 * V + (int64_t)(par) * qcap)
+#define NEAR_Q(par) (touched + (int64_t)(3 + (par)) * V)
   uint32_t iter = sc.iter[blockIdx.x];
   const int n_jobs = *tc.n_jobs;
   // work counters: per thread and launch 32 bits are plenty; the three that only thread 0 keeps live in shared memory
   // (registers are what limits the residency of this kernel)
-  uint32_t c_relaxed = 0, c_improved = 0, c_expanded = 0;
-  __shared__ unsigned long long s_c_iters, s_c_far, s_c_jobs;
-  if (threadIdx.x == 0) s_c_iters = s_c_far = s_c_jobs = 0ULL;
+  uint32_t c_improved = 0;
+  __shared__ unsigned long long s_c_iters, s_c_far, s_c_jobs, s_c_relaxed, s_c_expanded;
+  if (threadIdx.x == 0) s_c_iters = s_c_far = s_c_jobs = s_c_relaxed = s_c_expanded = 0ULL;
   for (;;) {
     if (threadIdx.x == 0) s_job = atomicAdd(tc.job_cursor, 1);
     __syncthreads();
@@ -938,7 +932,6 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kBlocksPerSM) k_build_trees(G
       s_far_n = 0;
       s_far2_n = 0;
       s_touched = 1;
-      s_ovf = 0;
       NEAR_Q(npar)[0] = dest;
       touched[0] = dest;
       rec[dest].dist = 0ULL;
@@ -1025,14 +1018,12 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kBlocksPerSM) k_build_trees(G
             rec[u].potf &= ~kFarBit;  // already expanded as a near node (one thread per far entry, no relaxation runs)
           } else if (d <= T) {
             rec[u].potf &= ~kFarBit;
-            const int at = atomicAdd(&s_near_n, 1);
-            if (at < qcap) near_out[at] = u; else s_ovf = 1;
+            near_out[atomicAdd(&s_near_n, 1)] = u;
           } else {
             far_out[atomicAdd(&s_far2_n, 1)] = u;  // <= nf entries
           }
         }
         __syncthreads();
-        if (s_ovf) break;
         if (threadIdx.x == 0) {
           s_far_n = s_far2_n;
           s_far2_n = 0;
@@ -1056,8 +1047,6 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kBlocksPerSM) k_build_trees(G
           deg = x_rowptr[v + 1] - e0;
           s_e0[threadIdx.x] = e0;
           s_dv[threadIdx.x] = __longlong_as_double((long long)rec[v].dist);
-          ++c_expanded;
-          c_relaxed += (uint32_t)deg;
         }
         // block-wide exclusive scan of the degrees
         int incl = deg;
@@ -1083,6 +1072,10 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kBlocksPerSM) k_build_trees(G
         s_off[threadIdx.x] = wbase + incl - deg;
         const int total = s_wsum[((blockDim.x + 31) >> 5) - 1];
         const int cnt = min((int)blockDim.x, n - base);
+        if (threadIdx.x == 0) {  // the block's totals of this chunk: nodes expanded, links relaxed
+          s_c_expanded += (unsigned long long)cnt;
+          s_c_relaxed += (unsigned long long)total;
+        }
         __syncthreads();
         // kFly relaxations per thread in flight, in stages, so that their load chains (link -> head record ->
         // landmark line -> atomics) overlap
@@ -1140,10 +1133,7 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kBlocksPerSM) k_build_trees(G
               ++c_improved;
               if (old[j] == kInfBits) touched[atomicAdd(&s_touched, 1)] = u[j];  // exactly one thread sees the first label
               if (__dadd_rn(cand[j], pu[j]) <= T) {
-                if (atomicExch(&rec[u[j]].stamp, iter) != iter) {
-                  const int at = atomicAdd(&s_next_n, 1);
-                  if (at < qcap) NEAR_Q(npar ^ 1)[at] = u[j]; else s_ovf = 1;
-                }
+                if (atomicExch(&rec[u[j]].stamp, iter) != iter) NEAR_Q(npar ^ 1)[atomicAdd(&s_next_n, 1)] = u[j];
               } else if ((atomicOr(&rec[u[j]].potf, kFarBit) & kFarBit) == 0u) {
                 FAR_Q(fpar)[atomicAdd(&s_far_n, 1)] = u[j];  // at most one far entry per node: <= V entries
               }
@@ -1153,26 +1143,12 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kBlocksPerSM) k_build_trees(G
         __syncthreads();  // s_e0 / s_dv / s_off are reused by the next chunk
       }
       __syncthreads();
-      if (s_ovf) break;
       if (threadIdx.x == 0) {
         s_near_n = s_next_n;
         s_next_n = 0;
       }
       npar ^= 1;
       __syncthreads();
-    }
-    if (s_ovf) {
-      // a near queue would have overflowed: the job is abandoned (its queries stay unanswered, the call fails with
-      // DRIFT_EOVERFLOW), the scratch is left clean and no tree is kept
-      if (threadIdx.x == 0) {
-        atomicOr(&ctr->overflow, kOvfTreeQueues);
-        tc.slot_of[key] = -1;
-        if (slot >= 0) tc.slot_owner[slot] = -1;
-      }
-      __syncthreads();
-      for (int i = threadIdx.x; i < s_touched; i += blockDim.x) reset_noderec(&rec[touched[i]]);
-      __syncthreads();
-      continue;
     }
     if (bounded) {
       // routes of the few sources, straight from dist[] (route_from_labels); the far list of the finished
@@ -1219,16 +1195,12 @@ __global__ void __launch_bounds__(kTreeThreadsMax, kBlocksPerSM) k_build_trees(G
     __syncthreads();
   }
   if (threadIdx.x == 0) sc.iter[blockIdx.x] = iter;
-  unsigned long long w_relaxed = c_relaxed, w_improved = c_improved, w_expanded = c_expanded;
-  for (int o = 16; o; o >>= 1) {
-    w_relaxed += __shfl_down_sync(0xffffffffu, w_relaxed, o);
-    w_improved += __shfl_down_sync(0xffffffffu, w_improved, o);
-    w_expanded += __shfl_down_sync(0xffffffffu, w_expanded, o);
-  }
-  if ((threadIdx.x & 31) == 0 && w_expanded) {
-    atomicAdd(&ctr->tree_relaxed, w_relaxed);
-    atomicAdd(&ctr->tree_improved, w_improved);
-    atomicAdd(&ctr->tree_expanded, w_expanded);
+  unsigned long long w_improved = c_improved;
+  for (int o = 16; o; o >>= 1) w_improved += __shfl_down_sync(0xffffffffu, w_improved, o);
+  if ((threadIdx.x & 31) == 0 && w_improved) atomicAdd(&ctr->tree_improved, w_improved);
+  if (threadIdx.x == 0 && s_c_expanded) {
+    atomicAdd(&ctr->tree_relaxed, s_c_relaxed);
+    atomicAdd(&ctr->tree_expanded, s_c_expanded);
   }
   if (threadIdx.x == 0 && s_c_jobs) atomicAdd(&ctr->tree_jobs, s_c_jobs);
   if (threadIdx.x == 0 && s_c_iters) {

@@ -340,7 +340,7 @@ int drift_host_pow(const double* x, double y, double* out, int64_t n);
  *   persistent          0 = one launch per phase and tick instead of the persistent tick kernel
  *   coop_blocks_per_sm  blocks per SM of the persistent tick kernel (default 6)
  *   tree_cache_bytes    HBM budget of the tree cache (default min(48 GB, 30 % of the free memory))
- *   tree_scratch_bytes  HBM budget of the search scratch, 36 B per node and resident search (28 B + 8 B per near-queue entry) (default: what full
+ *   tree_scratch_bytes  HBM budget of the search scratch, 36 B per node and resident search (default: what full
  *                       residency needs, at most 85 % of the free memory less the tree cache)
  *   tree_sides          1 = trees towards destinations only, 2 = also out of sources (default)
  *   bounded_max         a destination wanted by at most this many queries of a batch is answered by a bounded
@@ -358,11 +358,6 @@ int drift_host_pow(const double* x, double y, double* out, int64_t n);
  *                       returns A shortest path; default -1 = on for graphs of at most 20 000 nodes (the reference's
  *                       scale, where ties are the rule and an exact query is cheap), off above (an exact query on a
  *                       200 k-node graph takes ~0.2 s on its one thread)
- *   tree_list_div       the two near queues of a search (one wave each) hold V / tree_list_div node ids (at least
- *                       65 536; graphs of at most 65 536 nodes always get V).  A search whose wave would overflow
- *                       one is abandoned and the call fails with DRIFT_EOVERFLOW ("search-queues"); 1 = full-size
- *                       queues (the default: shorter queues were measured to gain nothing once ~850 searches are
- *                       resident; before the first route)
  *   tree_wide_regs      1 / 0 = force the 64-register (no spills, at most 4 searches of 256 threads per SM) / the
  *                       32-register build of the search kernel; default -1 = 64, 40 or 32 registers, whichever the
  *                       number of resident searches the scratch budget allows still fits
