@@ -16,7 +16,7 @@ import datetime
 
 import numpy as np
 
-from .data_logger import FIELDNAMES
+from .data_logger import FIELDNAMES, TripJsonStream
 from .engine import Engine, ROUTE_OK, ROUTER_BATCHED
 
 START = datetime.datetime(2025, 7, 10, 6, 0, 0)  # lib/simulation_thread.py:154
@@ -29,7 +29,7 @@ def _stamp(t):
 class BlockSimulation:
     def __init__(self, lg, start_nodes, hourly24, seed=0, csv_path=None, ticks_per_block=300, delta=1.0,
                  router=ROUTER_BATCHED, reroute=False, record_routes=False, device=0, alpha=0.15, beta=4.0,
-                 chain_capacity=4, route_arena_links=0, keep_log=False, hierarchy=None):
+                 chain_capacity=4, route_arena_links=0, keep_log=False, hierarchy=None, json_path=None):
         self.lg = lg
         self.N = len(start_nodes)
         self.start_nodes = np.asarray(start_nodes, dtype=np.int32)
@@ -66,6 +66,7 @@ class BlockSimulation:
         self._routes = {}                             # agent -> node list (record_routes only)
         self.rows = []
         self._fh = self._csv = None
+        self._json = TripJsonStream(json_path, START) if json_path else None  # the reference's JSON export, streamed
         if csv_path:
             self._fh = open(csv_path, "w", newline="", encoding="utf-8")
             self._csv = csv.DictWriter(self._fh, fieldnames=FIELDNAMES)
@@ -158,7 +159,7 @@ class BlockSimulation:
         return route
 
     def _close(self, agent, t, upto=None, moving=False):
-        if self._csv is None and not self.keep_rows:  # nobody reads the row: count it only (long-horizon runs)
+        if self._csv is None and self._json is None and not self.keep_rows:  # nobody reads the row: count it only (long-horizon runs)
             self._routes.pop(agent, None)
             self._open[agent] = False
             self._first[agent] = False
@@ -192,7 +193,9 @@ class BlockSimulation:
     def _write(self, rows):
         if self._csv is not None:
             self._csv.writerows(rows)
-        elif self.keep_rows:
+        if self._json is not None:
+            self._json.write(rows)
+        if self.keep_rows and self._csv is None:
             self.rows.extend(rows)
         self.rows_written += len(rows)
 
@@ -210,6 +213,8 @@ class BlockSimulation:
         if self._fh is not None:
             self._fh.close()
             self._fh = None
+        if self._json is not None:
+            self._json.close()
         return self.rows_written
 
     def status(self):
@@ -226,4 +231,6 @@ class BlockSimulation:
     def close(self):
         if self._fh is not None:
             self._fh.close()
+        if self._json is not None:
+            self._json.close()
         self.engine.close()

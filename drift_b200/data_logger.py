@@ -179,3 +179,50 @@ class SimulationDataLogger:
             "average_trip_distance_km": km / n,
             "average_trip_duration_min": minutes / n,
         }
+
+
+class TripJsonStream:
+    """The JSON export of lib/data_logger.py:260-306, written trip by trip for runs whose trips do not fit in host
+    memory as a list of dicts (``block_runner``): same two keys, same per-trip fields, same conversions
+    (``route_taken`` parsed back from its string form, 0.0 for missing numbers).  ``total_trips`` is only known at
+    the end, so "metadata" follows "trips" in the file -- a JSON object has no order; ``json.load`` returns the same
+    dict as for the reference's file."""
+
+    def __init__(self, filepath, simulation_start_time=None):
+        self.filepath = filepath
+        self.simulation_start_time = simulation_start_time or datetime.datetime.now().replace(
+            hour=6, minute=0, second=0, microsecond=0)
+        self.total = 0
+        self._fh = open(filepath, "w", encoding="utf-8")
+        self._fh.write('{\n  "trips": [')
+
+    @staticmethod
+    def _trip(trip):
+        route = trip.get("route_taken", [])
+        if isinstance(route, str):
+            try:
+                route = ast.literal_eval(route)
+            except Exception:
+                route = []
+        return {k: (route if k == "route_taken" else trip.get(k, 0.0 if k.startswith(("trip_d", "average")) else None))
+                for k in FIELDNAMES}
+
+    def write(self, rows):
+        for trip in rows:
+            text = json.dumps(self._trip(trip), indent=2, ensure_ascii=False)
+            self._fh.write(("," if self.total else "") + "\n    " + text.replace("\n", "\n    "))
+            self.total += 1
+
+    def close(self):
+        if self._fh is None:
+            return self.filepath
+        meta = {
+            "export_timestamp": datetime.datetime.now().isoformat(),
+            "simulation_start_time": self.simulation_start_time.isoformat(),
+            "total_trips": self.total,
+        }
+        self._fh.write(("\n  " if self.total else "") + '],\n  "metadata": '
+                       + json.dumps(meta, indent=2, ensure_ascii=False).replace("\n", "\n  ") + "\n}\n")
+        self._fh.close()
+        self._fh = None
+        return self.filepath

@@ -19,7 +19,9 @@ def test_block_runner_csv(tmp_path):
     start = rng.integers(0, lg.V, size=N).astype(np.int32)
     hourly = np.full(24, 0.9)
     path = tmp_path / "trips.csv"
-    sim = BlockSimulation(lg, start, hourly, seed=3, csv_path=str(path), ticks_per_block=200, record_routes=True)
+    jpath = tmp_path / "trips.json"
+    sim = BlockSimulation(lg, start, hourly, seed=3, csv_path=str(path), ticks_per_block=200, record_routes=True,
+                          json_path=str(jpath))
     n_dep = n_arr = 0
     for b in range(4):
         _, cand = demand.random_chains(rng, lg.V, start, 2)
@@ -34,6 +36,14 @@ def test_block_runner_csv(tmp_path):
         rows = list(csv.DictReader(fh))
     assert list(rows[0].keys()) == FIELDNAMES
     assert len(rows) == rows_total
+    # the streamed JSON export (lib/data_logger.py:260-306) carries the same trips, routes as lists
+    import json
+    js = json.load(open(jpath, encoding="utf-8"))
+    assert set(js) == {"metadata", "trips"} and js["metadata"]["total_trips"] == rows_total == len(js["trips"])
+    for r, j in zip(rows[:300] + rows[-300:], js["trips"][:300] + js["trips"][-300:]):
+        assert list(j.keys()) == FIELDNAMES
+        assert j["trip_id"] == r["trip_id"] and j["route_taken"] == eval(r["route_taken"])
+        assert j["trip_distance_km"] == float(r["trip_distance_km"])
     # every agent has exactly one first-trip row (origin == destination == its start node, 06:00:00)
     first = [r for r in rows if r["start_time"] == "06:00:00" and r["origin_node"] == r["destination_node"]]
     assert len(first) == N

@@ -190,3 +190,37 @@ def test_bulk_departure_draws_equal_the_python_loop(n, threshold):
         got = SimulationThread._draw_departures(fake, threshold)
         assert got == want and got_log == want_log
         assert random.getstate() == state_want
+
+
+def test_streamed_json_export_equals_the_logger_export(tmp_path):
+    """TripJsonStream (block_runner's trip writer) against SimulationDataLogger.export_to_json, which follows
+    lib/data_logger.py:260-306: same keys, same trips, same conversions; also the empty file."""
+    import json
+
+    from drift_b200.data_logger import FIELDNAMES, SimulationDataLogger, TripJsonStream
+
+    rows = []
+    for i in range(7):
+        rows.append({"trip_id": "T%06d" % (i + 1), "agent_id": "A%06d" % (i % 3 + 1), "start_time": "06:00:0%d" % i,
+                     "end_time": "06:10:0%d" % i, "origin_node": i, "destination_node": "n%d" % i,
+                     "route_taken": str([i, "n%d" % i]) if i != 4 else "not a list(",
+                     "trip_distance_km": 0.5 * i, "trip_duration_min": 1.5 * i,
+                     "average_speed_kmh": 20.0 if i else 0.0, "extra": "dropped"})
+    del rows[5]["trip_distance_km"]  # missing number -> 0.0, like trip.get(..., 0.0)
+    lg = SimulationDataLogger(output_dir=str(tmp_path))
+    lg.trips_data = [dict(r) for r in rows]
+    lg.export_to_json(str(tmp_path / "a.json"))
+    st = TripJsonStream(str(tmp_path / "b.json"), lg.simulation_start_time)
+    st.write(rows[:3])
+    st.write(rows[3:])
+    st.close()
+    a = json.load(open(tmp_path / "a.json", encoding="utf-8"))
+    b = json.load(open(tmp_path / "b.json", encoding="utf-8"))
+    assert a["trips"] == b["trips"] and [list(t.keys()) for t in b["trips"]] == [FIELDNAMES] * 7
+    assert b["trips"][4]["route_taken"] == [] and b["trips"][5]["trip_distance_km"] == 0.0
+    assert {k: v for k, v in a["metadata"].items() if k != "export_timestamp"} == \
+           {k: v for k, v in b["metadata"].items() if k != "export_timestamp"}
+    e = TripJsonStream(str(tmp_path / "c.json"), lg.simulation_start_time)
+    e.close()
+    c = json.load(open(tmp_path / "c.json", encoding="utf-8"))
+    assert c["trips"] == [] and c["metadata"]["total_trips"] == 0

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--agents", type=int, default=0)
     ap.add_argument("--ticks-per-block", type=int, default=300)
     ap.add_argument("--csv", default=None, help="stream the trip records to this CSV (reference format)")
+    ap.add_argument("--json", default=None, help="stream the trip records to this JSON file (reference format)")
     ap.add_argument("--reroute", action="store_true", help="congestion-aware reroute at every block (extension)")
     ap.add_argument("--no-labels", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
@@ -52,7 +53,8 @@ def main():
             hier = None
         t_h = time.perf_counter() - t0
     tpb = args.ticks_per_block
-    sim = BlockSimulation(lg, start, bench.HOURLY, seed=args.seed, csv_path=args.csv, ticks_per_block=tpb,
+    sim = BlockSimulation(lg, start, bench.HOURLY, seed=args.seed, csv_path=args.csv, json_path=args.json,
+                          ticks_per_block=tpb,
                           reroute=args.reroute, record_routes=False,
                           route_arena_links=max(1 << 24, n * w.get("arena_per_agent", 2560)),  # as bench.py sizes it
                           hierarchy=hier)
