@@ -16,7 +16,7 @@ import datetime
 
 import numpy as np
 
-from .data_logger import FIELDNAMES, TripJsonStream
+from .data_logger import FIELDNAMES, TripJsonStream, TripStatistics
 from .engine import Engine, ROUTE_OK, ROUTER_BATCHED
 
 START = datetime.datetime(2025, 7, 10, 6, 0, 0)  # lib/simulation_thread.py:154
@@ -64,6 +64,7 @@ class BlockSimulation:
         self._open = np.ones(self.N, dtype=bool)      # the reference opens a trip for every agent at init
         self._first = np.ones(self.N, dtype=bool)     # first-trip quirk still pending
         self._routes = {}                             # agent -> node list (record_routes only)
+        self.statistics = TripStatistics()            # get_statistics() without the list of trips
         self.rows = []
         self._fh = self._csv = None
         self._json = TripJsonStream(json_path, START) if json_path else None  # the reference's JSON export, streamed
@@ -159,13 +160,14 @@ class BlockSimulation:
         return route
 
     def _close(self, agent, t, upto=None, moving=False):
-        if self._csv is None and self._json is None and not self.keep_rows:  # nobody reads the row: count it only (long-horizon runs)
+        minutes = (float(t) - float(self._open_t0[agent])) / 60.0
+        km = float(self._open_m[agent]) / 1000.0
+        self.statistics.add(km, minutes, (km / minutes) * 60 if minutes > 0 else 0.0)
+        if self._csv is None and self._json is None and not self.keep_rows:  # nobody reads the row: count it only
             self._routes.pop(agent, None)
             self._open[agent] = False
             self._first[agent] = False
             return None
-        minutes = (float(t) - float(self._open_t0[agent])) / 60.0
-        km = float(self._open_m[agent]) / 1000.0
         nodes = self.lg.nodes
         o, d = int(self._open_src[agent]), int(self._open_dst[agent])
         route = self._route_taken(agent, upto) if self.record_routes else None
@@ -216,6 +218,10 @@ class BlockSimulation:
         if self._json is not None:
             self._json.close()
         return self.rows_written
+
+    def get_statistics(self):
+        """lib/data_logger.py:154-171 over every trip closed so far (running sums, no list of trips kept)."""
+        return self.statistics.result()
 
     def status(self):
         """Payload of the reference's ``status_updated`` signal (lib/simulation_thread.py:455-462)."""

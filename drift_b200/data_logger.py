@@ -10,7 +10,9 @@ import ast
 import csv
 import datetime
 import json
+import math
 import os
+import sys
 
 FIELDNAMES = ["trip_id", "agent_id", "start_time", "end_time", "origin_node", "destination_node",
               "route_taken", "trip_distance_km", "trip_duration_min", "average_speed_kmh"]
@@ -178,6 +180,62 @@ class SimulationDataLogger:
             "average_speed_kmh": speed,
             "average_trip_distance_km": km / n,
             "average_trip_duration_min": minutes / n,
+        }
+
+
+class _RunningSum:
+    """Left-to-right float sum that ends on the value the builtin ``sum`` returns for the same sequence: plain
+    additions before Python 3.12, Neumaier-compensated from 3.12 on (bltinmodule.c: the compensation is added once, at
+    the end, if it is finite and non-zero)."""
+
+    def __init__(self):
+        self.total = 0.0
+        self.comp = 0.0
+        self.compensated = sys.version_info >= (3, 12)
+
+    def add(self, x):
+        x = float(x)
+        if not self.compensated:
+            self.total += x
+            return
+        t = self.total + x
+        if abs(self.total) >= abs(x):
+            self.comp += (self.total - t) + x
+        else:
+            self.comp += (x - t) + self.total
+        self.total = t
+
+    def value(self):
+        if self.compensated and self.comp and math.isfinite(self.comp):
+            return self.total + self.comp
+        return self.total
+
+
+class TripStatistics:
+    """``SimulationDataLogger.get_statistics`` (lib/data_logger.py:154-171) for trips that are streamed out instead
+    of kept: the same six figures from running sums, equal to the list-based ones bit for bit."""
+
+    def __init__(self):
+        self.n = 0
+        self._km, self._min, self._kmh = _RunningSum(), _RunningSum(), _RunningSum()
+
+    def add(self, distance_km, duration_min, speed_kmh):
+        self.n += 1
+        self._km.add(distance_km)
+        self._min.add(duration_min)
+        self._kmh.add(speed_kmh)
+
+    def result(self):
+        if not self.n:
+            return {}
+        km, minutes = self._km.value(), self._min.value()
+        return {
+            "total_trips": self.n,
+            "total_distance_km": km,
+            "total_duration_hours": minutes / 60,
+            "average_speed_kmh": self._kmh.value() / self.n,
+            "average_trip_distance_km": km / self.n,
+            "average_trip_duration_min": minutes / self.n,
         }
 
 

@@ -36,6 +36,13 @@ def test_block_runner_csv(tmp_path):
         rows = list(csv.DictReader(fh))
     assert list(rows[0].keys()) == FIELDNAMES
     assert len(rows) == rows_total
+    # get_statistics() from running sums == the reference's expression over the rows (lib/data_logger.py:154-171)
+    stats = sim.get_statistics()
+    km = sum(float(r["trip_distance_km"]) for r in rows)
+    minutes = sum(float(r["trip_duration_min"]) for r in rows)
+    assert stats["total_trips"] == len(rows) and stats["total_distance_km"] == km
+    assert stats["total_duration_hours"] == minutes / 60
+    assert stats["average_speed_kmh"] == sum(float(r["average_speed_kmh"]) for r in rows) / len(rows)
     # the streamed JSON export (lib/data_logger.py:260-306) carries the same trips, routes as lists
     import json
     js = json.load(open(jpath, encoding="utf-8"))

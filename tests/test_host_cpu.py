@@ -224,3 +224,24 @@ def test_streamed_json_export_equals_the_logger_export(tmp_path):
     e.close()
     c = json.load(open(tmp_path / "c.json", encoding="utf-8"))
     assert c["trips"] == [] and c["metadata"]["total_trips"] == 0
+
+
+def test_running_trip_statistics_equal_the_list_based_ones():
+    """TripStatistics (streamed runs) against get_statistics over the kept list (lib/data_logger.py:154-171),
+    exact equality: the running sums end where the builtin sum does (compensated from Python 3.12 on)."""
+    import random
+
+    from drift_b200.data_logger import SimulationDataLogger, TripStatistics
+
+    rnd = random.Random(5)
+    lg = SimulationDataLogger(output_dir=".")
+    st = TripStatistics()
+    assert st.result() == {} == lg.get_statistics()
+    for i in range(20000):
+        km = rnd.random() * 10 ** rnd.randint(-3, 3) if i % 7 else 0.0
+        minutes = rnd.random() * 10 ** rnd.randint(-2, 2)
+        kmh = (km / minutes) * 60 if minutes > 0 else 0.0
+        lg.trips_data.append({"trip_distance_km": km, "trip_duration_min": minutes, "average_speed_kmh": kmh})
+        st.add(km, minutes, kmh)
+        if i in (0, 1, 17, 4999, 19999):
+            assert st.result() == lg.get_statistics()
