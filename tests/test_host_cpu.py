@@ -245,3 +245,33 @@ def test_running_trip_statistics_equal_the_list_based_ones():
         st.add(km, minutes, kmh)
         if i in (0, 1, 17, 4999, 19999):
             assert st.result() == lg.get_statistics()
+
+
+def test_landmark_tables_are_lower_bounds():
+    """engine.landmark_tables: the distance rows of the picked landmarks, and the ALT bounds the bounded searches
+    derive from them (d(s,v) >= from[k][v] - from[k][s] and >= to[k][s] - to[k][v]) never exceed the distance."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import dijkstra
+
+    from drift_b200.engine import landmark_tables
+    from drift_b200.synth import road_graph
+
+    lg = road_graph(1500, seed=4)
+    picks, frm, to = landmark_tables(lg, K=6, seed=1)
+    assert len(picks) == 6 == len(set(picks)) and frm.shape == to.shape == (6, lg.V)
+    W = csr_matrix((lg.fwd_w, lg.fwd_col, lg.fwd_rowptr), shape=(lg.V, lg.V))
+    d_from = dijkstra(W, directed=True, indices=picks)
+    assert np.array_equal(frm, d_from) and np.all(frm[np.arange(6), picks] == 0.0) and np.all(to[np.arange(6), picks] == 0.0)
+    rng = np.random.default_rng(0)
+    src = rng.integers(0, lg.V, size=40)
+    d = dijkstra(W, directed=True, indices=src)  # d[i][v] = d(src_i, v)
+    for i, s in enumerate(src):
+        b0 = frm - frm[:, s:s + 1]          # [K][V]
+        b1 = to[:, s:s + 1] - to
+        h = np.maximum(np.nanmax(np.where(np.isfinite(b0), b0, -np.inf), axis=0),
+                       np.nanmax(np.where(np.isfinite(b1), b1, -np.inf), axis=0))
+        ok = np.isfinite(d[i])
+        assert np.all(h[ok] <= d[i][ok] * (1 + 1e-12) + 1e-9)
+        # what the kernel stores: the bound as a float rounded DOWN stays a lower bound
+        hf = np.nextafter(np.maximum(h[ok], 0).astype(np.float32), np.float32(-np.inf)).astype(np.float64)
+        assert np.all(np.minimum(hf, np.maximum(h[ok], 0)) <= d[i][ok] * (1 + 1e-12) + 1e-9)
